@@ -1,0 +1,218 @@
+/*
+ * maniac_gpu.h -- C ABI of the B200 (sm_100a) energy engine for MANIAC-MC.
+ *
+ * This is the drop-in boundary between MANIAC's Fortran move drivers and the
+ * CUDA implementation of the per-trial-move energy change.  The reference has
+ * no FFI of its own: the seam is the set of energy routines that
+ * src/monte_carlo_utils.f90 (compute_old_energy :367-423, compute_new_energy
+ * :300-361, accept/reject :429-505, remove_molecule :642-657) and
+ * src/energy_utils.f90 (update_system_energy :22-39) call.  Each export below
+ * names the reference routine(s) it replaces; INTEGRATION.md shows the
+ * ISO_C_BINDING interface block and the Makefile lines a maintainer adds.
+ *
+ * Conventions
+ *   - plain C types only; every array is caller-owned and copied during the
+ *     call (the library keeps no host pointer after returning);
+ *   - indices are 0-based here; the Fortran shim subtracts 1;
+ *   - 3x3 matrices are passed as 9 doubles, element (i,j) at [i*3+j] with the
+ *     reference's own (i,j) meaning, i.e. box%cell%matrix(i+1,j+1);
+ *   - a molecule's geometry is com[3] + offset[natom][3] (offset(:,atom) is
+ *     contiguous, which is what the Fortran section guest%offset(:,res,mol,1:n)
+ *     becomes as a contiguous temporary);
+ *   - every function returns 0 on success, non-zero on error, with the text
+ *     available from mgpu_last_error(); the Fortran wrapper turns non-zero
+ *     into `call abort_run(msg, code)` (src/output_utils.f90:581-605);
+ *   - one global context per process, synchronous, not re-entrant (the
+ *     reference is single-threaded with module-level state); multi-GPU = one
+ *     process per device;
+ *   - there is NO CPU fallback: without a CUDA device mgpu_init fails.
+ *
+ * State model: the device always holds the last COMMITTED configuration of
+ * every walker.  A trial (mgpu_new_energy / mgpu_trial_batch) never mutates
+ * it; mgpu_commit applies the pending trial (coordinates, S(k), counts,
+ * running energies), mgpu_rollback drops it.  This replaces the reference's
+ * "mutate Ak in place, copy Ak_old back on reject" (src/ewald_phase.f90:17-125).
+ */
+#ifndef MANIAC_GPU_H
+#define MANIAC_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGPU_MAX_RES    8    /* residue types                                      */
+#define MGPU_MAX_SITES  16   /* atoms per guest molecule                           */
+
+/* energy_type, src/simulation_state.f90:61-69, same field order */
+enum { MGPU_E_NON_COULOMB = 0, MGPU_E_COULOMB = 1, MGPU_E_RECIP = 2,
+       MGPU_E_SELF = 3, MGPU_E_INTRA = 4, MGPU_E_TOTAL = 5 };
+
+/* is_creation / is_deletion flags of compute_old/new_energy */
+enum { MGPU_KIND_MOVE = 0, MGPU_KIND_CREATE = 1, MGPU_KIND_DELETE = 2 };
+
+/* move codes reported by mgpu_sweep traces (same numbering as the oracle) */
+enum { MGPU_MV_NONE = 0, MGPU_MV_TRANSLATE = 1, MGPU_MV_ROTATE = 2, MGPU_MV_CREATE = 3,
+       MGPU_MV_DELETE = 4, MGPU_MV_SWAP = 5, MGPU_MV_WIDOM = 6 };
+
+/* One residue type: res%atom, res%role / thermo%is_active, primary%atoms%charges,
+ * primary%atoms%types (src/simulation_state.f90:134-141,215-231). */
+typedef struct mgpu_residue {
+    int32_t natom;            /* res%atom(res)                                    */
+    int32_t is_active;        /* thermo%is_active(res): 1 guest, 0 host           */
+    int32_t nmol;             /* primary%num%residues(res) at init                */
+    int32_t capacity;         /* max molecules per walker (<= NB_MAX_MOLECULE)    */
+    const double  *charges;   /* [natom]                                          */
+    const int32_t *types;     /* [natom] atom type id, 0-based                    */
+    const double  *com;       /* [nmol][3]  coord%com(:,res,mol)                  */
+    const double  *offset;    /* [nmol][natom][3] coord%offset(:,res,mol,atom)    */
+    double mass;              /* res%mass(res) (g/mol), for the de Broglie length */
+    double fugacity;          /* thermo%fugacity(res); < 0 = use chemical_potential */
+    double chemical_potential;/* thermo%chemical_potential(res) (kcal/mol)        */
+} mgpu_residue;
+
+/* Everything setup_simulation_parameters (src/prepare_utils.f90:20-43) has
+ * produced by the time the MC loop starts. */
+typedef struct mgpu_system {
+    double matrix[9];         /* primary%cell%matrix                              */
+    double lo[3];             /* primary%cell%bounds(:,1)                         */
+    int32_t nres;
+    const mgpu_residue *residues;
+    int32_t ntypes;           /* atom types                                       */
+    const double *epsilon;    /* [ntypes*ntypes] per type pair, AFTER Lorentz-Berthelot */
+    const double *sigma;      /* (coeff%epsilon/sigma(res_i,res_j,atom_i,atom_j) collapsed on types, A16) */
+    double temperature;       /* thermo%temperature                               */
+    double ewald_tolerance;   /* ewald%param%tolerance (input)                    */
+    double real_space_cutoff; /* mc_input%real_space_cutoff (input)               */
+    double translation_step;  /* mc_input%translation_step                        */
+    double rotation_step_angle;
+    double p_translation, p_rotation, p_swap, p_insertion_deletion, p_widom; /* proba% */
+    int32_t n_walkers;        /* independent copies of the system on this device  */
+    int32_t device;           /* CUDA device ordinal                              */
+} mgpu_system;
+
+/* ---- lifecycle ---------------------------------------------------------------------
+ * mgpu_init replaces setup_ewald + allocate_array + precompute_valid_reciprocal_vectors
+ * + prepare_monte_carlo (src/prepare_utils.f90:20-43,141-259; src/ewald_kvectors.f90:24-65)
+ * and uploads the SoA image of host/guest coordinates, charges and the LJ table.
+ * Every walker starts as a copy of the configuration in `sys`. */
+int  mgpu_init(const mgpu_system *sys);
+void mgpu_finalize(void);
+const char *mgpu_last_error(void);
+int  mgpu_device_info(char *name, int name_len, int *sm_count, double *mem_gb);
+
+/* Ewald / box parameters the engine derived (to cross-check against the host's own) */
+int mgpu_get_ewald(double *alpha, int32_t kmax[3], int32_t *nkvec, double *rc_used);
+int mgpu_get_kvectors(int32_t *kx, int32_t *ky, int32_t *kz, double *k_squared_mag, double *form_factor_times_weight);
+int mgpu_get_box(double matrix[9], double reciprocal[9], double *volume, int32_t *is_triclinic);
+int mgpu_get_thermo(int32_t res, double *beta, double *lambda, double *mu_walker0);
+
+/* ---- per-walker state --------------------------------------------------------------- */
+/* coordinates of one molecule (mirror of guest%com / guest%offset); invalidates S(k) and
+ * the running energies of that walker until mgpu_total_energy is called */
+int mgpu_set_molecule(int32_t walker, int32_t res, int32_t mol, const double com[3], const double *offset);
+int mgpu_get_molecule(int32_t walker, int32_t res, int32_t mol, double com[3], double *offset);
+/* update_counts, src/monte_carlo_utils.f90:662-672 (absolute value) */
+int mgpu_set_count(int32_t walker, int32_t res, int32_t n);
+int mgpu_get_count(int32_t walker, int32_t res, int32_t *n);
+/* thermo%chemical_potential(res) / fugacity of one walker (isotherm points) */
+int mgpu_set_chemical_potential(int32_t walker, int32_t res, double mu);
+int mgpu_set_fugacity(int32_t walker, int32_t res, double fugacity);
+/* S(k) of a walker (ewald%Ak), interleaved re,im */
+int mgpu_get_Ak(int32_t walker, double *re_im);
+/* running totals `energy` of a walker */
+int mgpu_get_energy(int32_t walker, double out[6]);
+
+/* ---- energy routines (single walker, drop-in) -------------------------------------- */
+/* update_system_energy, src/energy_utils.f90:22-39: full recompute of the 5 components,
+ * rebuilds S(k) (compute_total_reciprocal_energy, src/ewald_energy.f90:20-58) */
+int mgpu_total_energy(int32_t walker, double out[6]);
+/* pairwise_energy_for_molecule, src/pairwise_energy_utils.f90:21-90, for a guest molecule.
+ * com/offset may be NULL = use the committed coordinates. */
+int mgpu_pairwise_energy_for_molecule(int32_t walker, int32_t res, int32_t mol, int32_t skip_ordering_check,
+                                      const double *com, const double *offset,
+                                      double *e_non_coulomb, double *e_coulomb);
+/* ewald_self_energy_single_mol :177-205 and intra_res_real_coulomb_energy :212-252 of
+ * src/ewald_energy.f90 */
+int mgpu_ewald_self_energy_single_mol(int32_t res, double *e);
+int mgpu_intra_res_real_coulomb_energy(int32_t walker, int32_t res, int32_t mol,
+                                       const double *com, const double *offset, double *e);
+/* reciprocal_ewald_energy :139-164 on the committed S(k) */
+int mgpu_reciprocal_ewald_energy(int32_t walker, double *e);
+/* compute_old_energy, src/monte_carlo_utils.f90:367-423 (committed coordinates) */
+int mgpu_old_energy(int32_t walker, int32_t res, int32_t mol, int32_t kind, double out[6]);
+/* compute_new_energy :300-361.  MOVE / CREATE: (com, offset) is the trial geometry the
+ * host proposed; DELETE: ignored (may be NULL).  Leaves a pending trial on the walker. */
+int mgpu_new_energy(int32_t walker, int32_t res, int32_t mol, int32_t kind,
+                    const double *com, const double *offset, double out[6]);
+/* accept_molecule_move :429-442 / accept_creation_move (creation.f90:82-116) /
+ * accept_deletion_move (deletion.f90:83-122) incl. remove_molecule + update_counts */
+int mgpu_commit(int32_t walker);
+/* reject_molecule_move :480-505 / reject_creation_move :579-591 / reject_deletion_move */
+int mgpu_rollback(int32_t walker);
+
+/* ---- batched host-driven trials (many walkers per call) ----------------------------- */
+/* One trial per listed walker: old and new energies in ONE launch.  com[n][3],
+ * offset[n][MGPU_MAX_SITES][3] (only the first natom rows are read).  e_old/e_new [n][6]. */
+int mgpu_trial_batch(int32_t n, const int32_t *walker, const int32_t *res, const int32_t *mol,
+                     const int32_t *kind, const double *com, const double *offset,
+                     double *e_old, double *e_new);
+int mgpu_commit_batch(int32_t n, const int32_t *walker, const int32_t *accept);
+
+/* ---- device-resident Monte Carlo (new capability; drivers of src/translation.f90,
+ * rotation.f90, creation.f90, deletion.f90, widom.f90 and the loop body of
+ * src/monte_carlo.f90:50-99 run on the GPU, one CTA per walker) ------------------------ */
+typedef struct mgpu_step_trace {
+    int32_t move, res, mol, accepted;
+    double  dE, prob;
+    double  e_old[6], e_new[6];
+} mgpu_step_trace;
+
+/* per-walker generator: xoshiro256** seeded by splitmix64(seed + 104729*walker) */
+int mgpu_seed(uint64_t seed);
+int mgpu_get_rng_state(int32_t walker, uint64_t st[4]);
+/* n_steps MC steps for every walker in [first_walker, first_walker+n_walkers).
+ * trace (optional) receives the steps of walker `trace_walker` only ([n_steps]). */
+int mgpu_sweep(int32_t first_walker, int32_t n_walkers, int64_t n_steps,
+               int32_t trace_walker, mgpu_step_trace *trace);
+/* counters%{translations,rotations,creations,deletions,swaps,widom}(1:2) of a walker */
+int mgpu_get_counters(int32_t walker, int64_t out[12]);
+/* statistic%weight / statistic%sample (src/widom.f90:74-92) accumulated by mgpu_sweep */
+int mgpu_get_widom(int32_t walker, int32_t res, double *sum_weight, int64_t *samples);
+/* block averages accumulated by mgpu_sweep: sum N, sum N^2, sum E_total, samples */
+int mgpu_get_averages(int32_t walker, int32_t res, double out[4]);
+int mgpu_reset_averages(void);
+
+/* Widom test-particle batch: n independent insertions of residue `res` into the
+ * committed configuration of `walker` (body of widom_trial, src/widom.f90:30-68, with
+ * insertion id -> 5 uniforms from a counter-based stream; state is never changed).
+ * dE_out may be NULL.  sum_w = sum of exp(-beta dU) over insertions with weight > 1e-10,
+ * n_ok = their number (accumulate_widom_weight :74-92). */
+int mgpu_widom_batch(int32_t walker, int32_t res, int64_t first_id, int64_t n, uint64_t seed,
+                     double *dE_out, double *sum_w, int64_t *n_ok);
+
+/* ---- multi-GPU: shard walkers over ranks, reduce averages at the end ---------------- */
+/* NCCL is bootstrapped by the caller: rank 0 obtains an id, every rank receives it
+ * (torch.distributed / MPI / a file) and calls mgpu_nccl_init.  mgpu_reduce_averages
+ * is an in-place sum over ranks of `count` doubles held in a HOST buffer (per
+ * isotherm point: sum N, sum N^2, sum E, samples, sum w, n_w).  nranks == 1: no-op. */
+int mgpu_nccl_unique_id(char id[128]);
+int mgpu_nccl_init(const char id[128], int32_t nranks, int32_t rank);
+int mgpu_reduce_averages(double *buf, int32_t count);
+void mgpu_nccl_finalize(void);
+const char *mgpu_nccl_last_error(void);
+
+/* ---- measurement helpers (bench.py) ------------------------------------------------- */
+/* average device time (ms) per launch of the named kernel class since the last reset,
+ * measured with CUDA events on the engine's stream; and the number of launches */
+int mgpu_timing_reset(void);
+int mgpu_timing_get(const char *kernel, double *total_ms, int64_t *launches);
+/* achieved FP64 FMA throughput of a register-resident DFMA loop (TFLOP/s) and the SM
+ * clock it ran at: the roofline denominator for the FP64-bound kernels */
+int mgpu_measure_fp64_peak(double *tflops, double *seconds);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MANIAC_GPU_H */

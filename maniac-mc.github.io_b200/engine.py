@@ -1,0 +1,343 @@
+"""Host-side mirror of the reference's energy interface on top of the C ABI.
+
+Method names follow the Fortran routines they stand for (``update_system_energy``,
+``pairwise_energy_for_molecule``, ``compute_old_energy`` / ``compute_new_energy``, ...),
+argument meaning is the same with 0-based indices, and errors surface the way the
+reference reports them: a non-zero status from the library becomes :class:`ManiacAbort`
+carrying the library's message (the Fortran shim calls ``abort_run(msg, code)``,
+``src/output_utils.f90:581-605``).
+
+Everything here calls the CUDA library; nothing falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import capi
+from .inputs import ERROR, System
+
+E_NON_COULOMB, E_COULOMB, E_RECIP, E_SELF, E_INTRA, E_TOTAL = range(6)
+KIND_MOVE, KIND_CREATE, KIND_DELETE = 0, 1, 2
+MV_NONE, MV_TRANSLATE, MV_ROTATE, MV_CREATE, MV_DELETE, MV_SWAP, MV_WIDOM = range(7)
+
+TRACE_DTYPE = np.dtype([("move", "i4"), ("res", "i4"), ("mol", "i4"), ("accepted", "i4"),
+                        ("dE", "f8"), ("prob", "f8"), ("e_old", "f8", 6), ("e_new", "f8", 6)])
+assert TRACE_DTYPE.itemsize == C.sizeof(capi.MgpuStepTrace)
+
+
+class ManiacAbort(RuntimeError):
+    """The engine reported an error (``abort_run`` in the reference)."""
+
+
+def lj_table(system: System):
+    """Per-type-pair epsilon / sigma after the Lorentz-Berthelot fill.
+
+    ``read_parameters`` + ``apply_lorentz_berthelot`` (src/parameters_parser.f90:19-178):
+    explicit ``pair_coeff i j eps sigma`` lines are stored symmetrically in file order; a
+    pair whose epsilon and sigma are both < 1e-10 afterwards receives
+    sigma = (s_ii + s_jj)/2, eps = sqrt(e_ii e_jj) if both results exceed 1e-10.  The
+    reference's 4-D arrays depend on the two atom types only, so the table is ntypes^2."""
+    n = system.ntypes
+    eps = np.zeros((n, n))
+    sig = np.zeros((n, n))
+    for ti, tj, e, s in system.pair_coeff:
+        if not (0 <= ti < n and 0 <= tj < n):
+            raise ManiacAbort("Failed to read pair_coeff value")
+        eps[ti, tj] = e
+        sig[ti, tj] = s
+        eps[tj, ti] = e
+        sig[tj, ti] = s
+    for ri in system.residues:
+        for ti in ri.types:
+            for rj in system.residues:
+                for tj in rj.types:
+                    if abs(eps[ti, tj]) < ERROR and abs(sig[ti, tj]) < ERROR:
+                        s = (sig[ti, ti] + sig[tj, tj]) / 2
+                        e = float(np.sqrt(eps[ti, ti] * eps[tj, tj]))
+                        if s > ERROR and e > ERROR:
+                            sig[ti, tj] = s
+                            eps[ti, tj] = e
+    return eps, sig
+
+
+def _pd(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _pi(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+class Engine:
+    """One process, one GPU, ``n_walkers`` independent copies of the system."""
+
+    def __init__(self, system: System, n_walkers: int = 1, capacity: Optional[int] = None, device: int = 0):
+        self.L = capi.lib()
+        self.system = system
+        self.n_walkers = int(n_walkers)
+        self.natom = [r.natom for r in system.residues]
+        self.active = [bool(r.active) for r in system.residues]
+        eps, sig = lj_table(system)
+        self._keep = [eps, sig]
+        res_arr = (capi.MgpuResidue * len(system.residues))()
+        self.capacity = []
+        for i, r in enumerate(system.residues):
+            cap = r.nmol if not r.active else max(r.nmol + 1, capacity or (r.nmol + 64))
+            cap = max(cap, 1)
+            self.capacity.append(cap)
+            ch = np.ascontiguousarray(r.charges, dtype=np.float64)
+            ty = np.ascontiguousarray(r.types, dtype=np.int32)
+            com = np.ascontiguousarray(r.com if r.nmol else np.zeros((1, 3)), dtype=np.float64)
+            off = np.ascontiguousarray(r.offset if r.nmol else np.zeros((1, r.natom, 3)), dtype=np.float64)
+            self._keep += [ch, ty, com, off]
+            res_arr[i] = capi.MgpuResidue(r.natom, int(r.active), r.nmol, cap, _pd(ch), _pi(ty), _pd(com), _pd(off),
+                                          float(r.mass), float(r.fugacity), float(r.chemical_potential))
+        s = capi.MgpuSystem()
+        s.matrix = (C.c_double * 9)(*np.asarray(system.matrix, dtype=np.float64).reshape(9))
+        s.lo = (C.c_double * 3)(*np.asarray(system.lo, dtype=np.float64))
+        s.nres = len(system.residues)
+        s.residues = res_arr
+        s.ntypes = system.ntypes
+        s.epsilon = _pd(eps)
+        s.sigma = _pd(sig)
+        s.temperature = system.temperature
+        s.ewald_tolerance = system.ewald_tolerance
+        s.real_space_cutoff = system.real_space_cutoff
+        s.translation_step = system.translation_step
+        s.rotation_step_angle = system.rotation_step_angle
+        s.p_translation, s.p_rotation, s.p_swap = system.p_translation, system.p_rotation, system.p_swap
+        s.p_insertion_deletion, s.p_widom = system.p_insertion_deletion, system.p_widom
+        s.n_walkers = self.n_walkers
+        s.device = device
+        self._ck(self.L.mgpu_init(C.byref(s)))
+        self._open = True
+
+    # -- plumbing -------------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc:
+            raise ManiacAbort(self.L.mgpu_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_open", False):
+            self.L.mgpu_finalize()
+            self._open = False
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- derived parameters -----------------------------------------------------------------
+    def ewald(self):
+        alpha, rc = C.c_double(), C.c_double()
+        kmax = (C.c_int32 * 3)()
+        nk = C.c_int32()
+        self._ck(self.L.mgpu_get_ewald(C.byref(alpha), kmax, C.byref(nk), C.byref(rc)))
+        return dict(alpha=alpha.value, kmax=list(kmax), nk=nk.value, rc=rc.value)
+
+    def kvectors(self):
+        nk = self.ewald()["nk"]
+        kx, ky, kz = (np.zeros(nk, dtype=np.int32) for _ in range(3))
+        k2, ffw = np.zeros(nk), np.zeros(nk)
+        self._ck(self.L.mgpu_get_kvectors(_pi(kx), _pi(ky), _pi(kz), _pd(k2), _pd(ffw)))
+        return kx, ky, kz, k2, ffw
+
+    def box(self):
+        m, r = np.zeros((3, 3)), np.zeros((3, 3))
+        v, t = C.c_double(), C.c_int32()
+        self._ck(self.L.mgpu_get_box(_pd(m), _pd(r), C.byref(v), C.byref(t)))
+        return dict(matrix=m, reciprocal=r, volume=v.value, triclinic=bool(t.value))
+
+    def thermo(self, res):
+        b, l, m = C.c_double(), C.c_double(), C.c_double()
+        self._ck(self.L.mgpu_get_thermo(res, C.byref(b), C.byref(l), C.byref(m)))
+        return dict(beta=b.value, lambda_=l.value, mu=m.value)
+
+    def device_info(self):
+        name = C.create_string_buffer(128)
+        sm, mem = C.c_int(), C.c_double()
+        self._ck(self.L.mgpu_device_info(name, 128, C.byref(sm), C.byref(mem)))
+        return dict(name=name.value.decode(), sm_count=sm.value, mem_gb=mem.value)
+
+    # -- state ---------------------------------------------------------------------------------
+    def set_molecule(self, res, mol, com, offset, walker=0):
+        com = np.ascontiguousarray(com, dtype=np.float64)
+        off = np.ascontiguousarray(offset, dtype=np.float64)
+        self._ck(self.L.mgpu_set_molecule(walker, res, mol, _pd(com), _pd(off)))
+
+    def get_molecule(self, res, mol, walker=0):
+        com, off = np.zeros(3), np.zeros((self.natom[res], 3))
+        self._ck(self.L.mgpu_get_molecule(walker, res, mol, _pd(com), _pd(off)))
+        return com, off
+
+    def set_count(self, res, n, walker=0):
+        self._ck(self.L.mgpu_set_count(walker, res, n))
+
+    def count(self, res, walker=0):
+        n = C.c_int32()
+        self._ck(self.L.mgpu_get_count(walker, res, C.byref(n)))
+        return n.value
+
+    def set_chemical_potential(self, res, mu, walker=0):
+        self._ck(self.L.mgpu_set_chemical_potential(walker, res, float(mu)))
+
+    def set_fugacity(self, res, f, walker=0):
+        self._ck(self.L.mgpu_set_fugacity(walker, res, float(f)))
+
+    def Ak(self, walker=0):
+        nk = self.ewald()["nk"]
+        a = np.zeros(2 * nk)
+        self._ck(self.L.mgpu_get_Ak(walker, _pd(a)))
+        return a[0::2] + 1j * a[1::2]
+
+    def energy(self, walker=0):
+        out = np.zeros(6)
+        self._ck(self.L.mgpu_get_energy(walker, _pd(out)))
+        return out
+
+    # -- the reference's energy routines ---------------------------------------------------------
+    def update_system_energy(self, walker=0):
+        out = np.zeros(6)
+        self._ck(self.L.mgpu_total_energy(walker, _pd(out)))
+        return out
+
+    def pairwise_energy_for_molecule(self, res, mol, skip_ordering_check=True, walker=0, com=None, offset=None):
+        a, b = C.c_double(), C.c_double()
+        pc = po = None
+        if com is not None:
+            com = np.ascontiguousarray(com, dtype=np.float64)
+            offset = np.ascontiguousarray(offset, dtype=np.float64)
+            pc, po = _pd(com), _pd(offset)
+        self._ck(self.L.mgpu_pairwise_energy_for_molecule(walker, res, mol, int(skip_ordering_check), pc, po,
+                                                          C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def ewald_self_energy_single_mol(self, res):
+        e = C.c_double()
+        self._ck(self.L.mgpu_ewald_self_energy_single_mol(res, C.byref(e)))
+        return e.value
+
+    def intra_res_real_coulomb_energy(self, res, mol, walker=0, com=None, offset=None):
+        e = C.c_double()
+        pc = po = None
+        if com is not None:
+            com = np.ascontiguousarray(com, dtype=np.float64)
+            offset = np.ascontiguousarray(offset, dtype=np.float64)
+            pc, po = _pd(com), _pd(offset)
+        self._ck(self.L.mgpu_intra_res_real_coulomb_energy(walker, res, mol, pc, po, C.byref(e)))
+        return e.value
+
+    def reciprocal_ewald_energy(self, walker=0):
+        e = C.c_double()
+        self._ck(self.L.mgpu_reciprocal_ewald_energy(walker, C.byref(e)))
+        return e.value
+
+    def compute_old_energy(self, res, mol, kind=KIND_MOVE, walker=0):
+        out = np.zeros(6)
+        self._ck(self.L.mgpu_old_energy(walker, res, mol, kind, _pd(out)))
+        return out
+
+    def compute_new_energy(self, res, mol, kind=KIND_MOVE, com=None, offset=None, walker=0):
+        out = np.zeros(6)
+        pc = po = None
+        if com is not None:
+            com = np.ascontiguousarray(com, dtype=np.float64)
+            offset = np.ascontiguousarray(offset, dtype=np.float64)
+            pc, po = _pd(com), _pd(offset)
+        self._ck(self.L.mgpu_new_energy(walker, res, mol, kind, pc, po, _pd(out)))
+        return out
+
+    def commit(self, walker=0):
+        self._ck(self.L.mgpu_commit(walker))
+
+    def rollback(self, walker=0):
+        self._ck(self.L.mgpu_rollback(walker))
+
+    # -- batched host-driven trials -----------------------------------------------------------------
+    def trial_batch(self, walkers, res, mol, kind, com, offset):
+        """``offset`` is (n, MAX_SITES, 3) or (n, natom, 3) (padded here)."""
+        walkers = np.ascontiguousarray(walkers, dtype=np.int32)
+        n = walkers.size
+        res = np.ascontiguousarray(np.broadcast_to(res, (n,)), dtype=np.int32)
+        mol = np.ascontiguousarray(mol, dtype=np.int32)
+        kind = np.ascontiguousarray(np.broadcast_to(kind, (n,)), dtype=np.int32)
+        com = np.ascontiguousarray(com, dtype=np.float64).reshape(n, 3)
+        offset = np.asarray(offset, dtype=np.float64)
+        if offset.shape[1] != capi.MAX_SITES:
+            pad = np.zeros((n, capi.MAX_SITES, 3))
+            pad[:, :offset.shape[1]] = offset
+            offset = pad
+        offset = np.ascontiguousarray(offset)
+        e_old, e_new = np.zeros((n, 6)), np.zeros((n, 6))
+        self._ck(self.L.mgpu_trial_batch(n, _pi(walkers), _pi(res), _pi(mol), _pi(kind), _pd(com), _pd(offset),
+                                         _pd(e_old), _pd(e_new)))
+        return e_old, e_new
+
+    def commit_batch(self, walkers, accept):
+        walkers = np.ascontiguousarray(walkers, dtype=np.int32)
+        accept = np.ascontiguousarray(accept, dtype=np.int32)
+        self._ck(self.L.mgpu_commit_batch(walkers.size, _pi(walkers), _pi(accept)))
+
+    # -- device-resident Monte Carlo ------------------------------------------------------------------
+    def seed(self, seed):
+        self._ck(self.L.mgpu_seed(int(seed) & 0xFFFFFFFFFFFFFFFF))
+
+    def rng_state(self, walker=0):
+        st = (C.c_uint64 * 4)()
+        self._ck(self.L.mgpu_get_rng_state(walker, st))
+        return list(st)
+
+    def sweep(self, n_steps, first_walker=0, n_walkers=None, trace_walker=None):
+        n = self.n_walkers - first_walker if n_walkers is None else n_walkers
+        tr = None
+        ptr = None
+        tw = -1
+        if trace_walker is not None:
+            tr = np.zeros(n_steps, dtype=TRACE_DTYPE)
+            ptr = tr.ctypes.data_as(C.c_void_p)
+            tw = trace_walker
+        self._ck(self.L.mgpu_sweep(first_walker, n, n_steps, tw, ptr))
+        return tr
+
+    def counters(self, walker=0):
+        out = (C.c_int64 * 12)()
+        self._ck(self.L.mgpu_get_counters(walker, out))
+        return np.array(out[:]).reshape(6, 2)
+
+    def widom(self, res, walker=0):
+        w, n = C.c_double(), C.c_int64()
+        self._ck(self.L.mgpu_get_widom(walker, res, C.byref(w), C.byref(n)))
+        return w.value, n.value
+
+    def averages(self, res, walker=0):
+        out = np.zeros(4)
+        self._ck(self.L.mgpu_get_averages(walker, res, _pd(out)))
+        return out
+
+    def reset_averages(self):
+        self._ck(self.L.mgpu_reset_averages())
+
+    def widom_batch(self, res, n, seed, first_id=0, walker=0, want_dE=False):
+        dE = np.zeros(n) if want_dE else None
+        sw, nok = C.c_double(), C.c_int64()
+        self._ck(self.L.mgpu_widom_batch(walker, res, first_id, n, int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                         _pd(dE) if want_dE else None, C.byref(sw), C.byref(nok)))
+        return dE, sw.value, nok.value
+
+    # -- measurement -----------------------------------------------------------------------------------
+    def timing_reset(self):
+        self.L.mgpu_timing_reset()
+
+    def timing(self, kernel):
+        ms, n = C.c_double(), C.c_int64()
+        self.L.mgpu_timing_get(kernel.encode(), C.byref(ms), C.byref(n))
+        return ms.value, n.value
+
+    def measure_fp64_peak(self):
+        tf, s = C.c_double(), C.c_double()
+        self._ck(self.L.mgpu_measure_fp64_peak(C.byref(tf), C.byref(s)))
+        return tf.value, s.value
