@@ -208,6 +208,11 @@ const char *mgpu_nccl_last_error(void);
  * measured with CUDA events on the engine's stream; and the number of launches */
 int mgpu_timing_reset(void);
 int mgpu_timing_get(const char *kernel, double *total_ms, int64_t *launches);
+/* work counters since the last reset, summed over all walkers: atom pairs evaluated,
+ * LJ terms inside the cutoff, erfc-Coulomb terms (the algorithmic-work figures of the
+ * roofline) */
+int mgpu_get_pair_counts(int64_t out[3]);
+int mgpu_reset_pair_counts(void);
 /* achieved FP64 FMA throughput of a register-resident DFMA loop (TFLOP/s) and the SM
  * clock it ran at: the roofline denominator for the FP64-bound kernels */
 int mgpu_measure_fp64_peak(double *tflops, double *seconds);

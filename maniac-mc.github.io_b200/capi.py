@@ -89,6 +89,8 @@ SIGNATURES = {
     "mgpu_nccl_last_error": (C.c_char_p, []),
     "mgpu_timing_reset": (C.c_int, []),
     "mgpu_timing_get": (C.c_int, [C.c_char_p, _pd, _pl]),
+    "mgpu_get_pair_counts": (C.c_int, [_pl]),
+    "mgpu_reset_pair_counts": (C.c_int, []),
     "mgpu_measure_fp64_peak": (C.c_int, [_pd, _pd]),
 }
 

@@ -352,7 +352,7 @@ int mgpu_init(const mgpu_system *sys)
     if (dalloc(&h.coords, W * (size_t)stride) || dalloc(&h.count, W * MGPU_MAX_RES) || dalloc(&h.S, W * 4 * nk1) || dalloc(&h.cur, W) ||
         dalloc(&h.energy, W * 6) || dalloc(&h.mu, W * MGPU_MAX_RES) || dalloc(&h.rng, W * 4) || dalloc(&h.counters, W * 12) ||
         dalloc(&h.widom_w, W * MGPU_MAX_RES) || dalloc(&h.widom_n, W * MGPU_MAX_RES) || dalloc(&h.avg, W * MGPU_MAX_RES * 4) ||
-        dalloc(&h.trial, W) || dalloc(&g.d_err, 1) || dalloc(&g.d_scratch, 64) || dalloc(&g.d_geom, 3 + 3 * MGPU_MAX_SITES)) return 1;
+        dalloc(&h.trial, W) || dalloc(&h.pair_count, 4) || dalloc(&g.d_err, 1) || dalloc(&g.d_scratch, 64) || dalloc(&g.d_geom, 3 + 3 * MGPU_MAX_SITES)) return 1;
     CK(cudaMallocHost(&g.h_scratch, sizeof(double) * 64));
     CK(cudaMemset(h.cur, 0, sizeof(int32_t) * W));
     CK(cudaMemset(h.S, 0, sizeof(double) * W * 4 * nk1));
@@ -363,6 +363,7 @@ int mgpu_init(const mgpu_system *sys)
     CK(cudaMemset(h.avg, 0, sizeof(double) * W * MGPU_MAX_RES * 4));
     CK(cudaMemset(h.trial, 0, sizeof(MgpuTrial) * W));
     CK(cudaMemset(g.d_err, 0, sizeof(int32_t)));
+    CK(cudaMemset(h.pair_count, 0, sizeof(unsigned long long) * 4));
     {
         // one walker image, replicated
         std::vector<double> img(stride ? stride : 1, 0.0); std::vector<int32_t> cnt(MGPU_MAX_RES, 0); std::vector<double> mu(MGPU_MAX_RES, 0.0);
@@ -819,6 +820,18 @@ int mgpu_widom_batch(int32_t w, int32_t res, int64_t first_id, int64_t n, uint64
 }
 
 // ---- measurement ----------------------------------------------------------------------
+int mgpu_get_pair_counts(int64_t out[3])
+{
+    NEED_READY();
+    CK(cudaMemcpy(out, g.h.pair_count, sizeof(int64_t) * 3, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int mgpu_reset_pair_counts(void)
+{
+    NEED_READY();
+    CK(cudaMemset(g.h.pair_count, 0, sizeof(unsigned long long) * 4));
+    return 0;
+}
 int mgpu_timing_reset(void) { g.timing.clear(); return 0; }
 int mgpu_timing_get(const char *kernel, double *total_ms, int64_t *launches)
 {

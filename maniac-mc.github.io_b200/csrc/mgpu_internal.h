@@ -64,4 +64,5 @@ struct DevSys {
     double  *widom_w; long long *widom_n;     // [W][MGPU_MAX_RES]
     double  *avg;                             // [W][MGPU_MAX_RES][4]
     MgpuTrial *trial;                         // [W]
+    unsigned long long *pair_count;           // [3] pairs evaluated, LJ terms, Coulomb terms (all walkers)
 };

@@ -126,9 +126,14 @@ __device__ __forceinline__ double min_image_r2(double dx, double dy, double dz)
 // One atom pair: LJ (pairwise_lj_energy, pairwise_energy_utils.f90:95-138) and erfc
 // Coulomb (pairwise_coulomb_energy :143-179, NO cutoff on the Coulomb term).
 // eps4 = 4*epsilon; qq = q_i*q_j or 0 when either |q| < 1e-10.
+// Work counters for the roofline accounting: pairs evaluated, LJ terms inside the
+// cutoff, erfc-Coulomb terms.  Integer adds on the otherwise idle ALU pipe.
+struct PairCount { unsigned geom, lj, coul; };
+
 __device__ __forceinline__ void pair_terms(double r2, double eps4, double sig, double qq, bool charged,
-                                           double &e_lj, double &e_coul)
+                                           double &e_lj, double &e_coul, PairCount &pc)
 {
+    pc.geom += 1u;
     const double rinv = rsqrt(r2);
     const double r = r2 * rinv;
     if (r < MGPU_ERR_TOL || !(r2 > 0.0)) {          // overlap sentinel (r = 0 gives rinv = inf)
@@ -141,8 +146,19 @@ __device__ __forceinline__ void pair_terms(double r2, double eps4, double sig, d
         const double s2 = s * s;
         const double s6 = s2 * s2 * s2;
         e_lj += eps4 * (s6 * s6 - s6);
+        pc.lj += (eps4 != 0.0);
     }
-    if (charged) e_coul += qq * erfc(c_sys.alpha * r) * rinv;
+    if (charged) { e_coul += qq * erfc(c_sys.alpha * r) * rinv; pc.coul += 1u; }
+}
+__device__ __forceinline__ void flush_pair_count(const PairCount &pc)
+{
+    const unsigned g = __reduce_add_sync(0xffffffffu, pc.geom), l = __reduce_add_sync(0xffffffffu, pc.lj),
+                   c = __reduce_add_sync(0xffffffffu, pc.coul);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(c_sys.pair_count + 0, (unsigned long long)g);
+        atomicAdd(c_sys.pair_count + 1, (unsigned long long)l);
+        atomicAdd(c_sys.pair_count + 2, (unsigned long long)c);
+    }
 }
 
 // ------------------------------------------------------------------------------------
@@ -163,7 +179,7 @@ struct Probe {
 template <bool TRI>
 __device__ __forceinline__ void probe_vs_atom(const Probe &P, const double *s_eps4, const double *s_sig,
                                               double tx, double ty, double tz, double tq, int ttype,
-                                              double (&acc)[4])
+                                              double (&acc)[4], PairCount &pc)
 {
     const bool tcharged = fabs(tq) >= MGPU_ERR_TOL;
     const int nt = c_sys.ntypes;
@@ -176,11 +192,11 @@ __device__ __forceinline__ void probe_vs_atom(const Probe &P, const double *s_ep
         if (eps4 == 0.0 && !charged) continue;
         if (P.has_old) {
             double r2 = min_image_r2<TRI>(tx - P.po[a][0], ty - P.po[a][1], tz - P.po[a][2]);
-            pair_terms(r2, eps4, sig, qq, charged, acc[0], acc[1]);
+            pair_terms(r2, eps4, sig, qq, charged, acc[0], acc[1], pc);
         }
         if (P.has_new) {
             double r2 = min_image_r2<TRI>(tx - P.pn[a][0], ty - P.pn[a][1], tz - P.pn[a][2]);
-            pair_terms(r2, eps4, sig, qq, charged, acc[2], acc[3]);
+            pair_terms(r2, eps4, sig, qq, charged, acc[2], acc[3], pc);
         }
     }
 }
@@ -192,6 +208,7 @@ __device__ void pair_sums_cta(const Probe &P, int w, const int32_t *s_count, con
                               const double *s_sig, double *red, double (&out)[4])
 {
     double acc[4] = { 0.0, 0.0, 0.0, 0.0 };
+    PairCount pc = { 0u, 0u, 0u };
     // host framework: one lane per host atom, coalesced 32-byte loads
     if (P.order_res < 0 || true) {
         const double4 *__restrict__ hx = c_sys.host_xyzq;
@@ -201,7 +218,7 @@ __device__ void pair_sums_cta(const Probe &P, int w, const int32_t *s_count, con
         // host atoms are handled by host_order_ok below.
         for (int j = threadIdx.x; j < c_sys.n_host; j += blockDim.x) {
             const double4 t = hx[j];
-            probe_vs_atom<TRI>(P, s_eps4, s_sig, t.x, t.y, t.z, t.w, ht[j], acc);
+            probe_vs_atom<TRI>(P, s_eps4, s_sig, t.x, t.y, t.z, t.w, ht[j], acc, pc);
         }
     }
     // guests of this walker: one lane per molecule
@@ -218,10 +235,11 @@ __device__ void pair_sums_cta(const Probe &P, int w, const int32_t *s_count, con
             for (int b = 0; b < na_g; ++b) {
                 const double *ob = off + (int64_t)b * 3 * cap;
                 const double tx = cx + ob[m], ty = cy + ob[cap + m], tz = cz + ob[2 * cap + m];
-                probe_vs_atom<TRI>(P, s_eps4, s_sig, tx, ty, tz, c_sys.charge[g][b], c_sys.type[g][b], acc);
+                probe_vs_atom<TRI>(P, s_eps4, s_sig, tx, ty, tz, c_sys.charge[g][b], c_sys.type[g][b], acc, pc);
             }
         }
     }
+    flush_pair_count(pc);
     block_sum<4>(acc, red);
 #pragma unroll
     for (int i = 0; i < 4; ++i) out[i] = acc[i];
@@ -536,6 +554,7 @@ __global__ void __launch_bounds__(128) k_commit(const int32_t *walker, const int
     MgpuTrial *tr = c_sys.trial + w;
     if (!tr->active) { if (threadIdx.x == 0) atomicExch(err, 1); return; }
     if (accept[t]) commit_trial(w, tr->kind, tr->res, tr->mol, tr->com, tr->off, tr->e_old, tr->e_new);
+    else if (tr->kind == MGPU_KIND_CREATE && tr->mol == 0) write_slot(w, tr->res, 0, tr->com, tr->off);
     __syncthreads();
     if (threadIdx.x == 0) tr->active = 0;
 }
@@ -649,6 +668,7 @@ __global__ void __launch_bounds__(MGPU_BLOCK) k_host_host(const int32_t *host_mo
 {
     __shared__ double red[2 * MGPU_WARPS];
     double acc[2] = { 0.0, 0.0 };
+    PairCount pc = { 0u, 0u, 0u };
     const int n = c_sys.n_host, nt = c_sys.ntypes;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double4 a = c_sys.host_xyzq[i];
@@ -659,7 +679,7 @@ __global__ void __launch_bounds__(MGPU_BLOCK) k_host_host(const int32_t *host_mo
             const int ti = ta * nt + c_sys.host_type[j];
             const bool charged = fabs(a.w) >= MGPU_ERR_TOL && fabs(b.w) >= MGPU_ERR_TOL;
             const double r2 = min_image_r2<TRI>(b.x - a.x, b.y - a.y, b.z - a.z);
-            pair_terms(r2, 4.0 * c_sys.eps[ti], c_sys.sig[ti], a.w * b.w, charged, acc[0], acc[1]);
+            pair_terms(r2, 4.0 * c_sys.eps[ti], c_sys.sig[ti], a.w * b.w, charged, acc[0], acc[1], pc);
         }
     }
     block_sum<2>(acc, red);
@@ -966,6 +986,7 @@ __global__ void __launch_bounds__(MGPU_WIDOM_BLOCK) k_widom_batch(int w, int res
     const unsigned long long id = (unsigned long long)(first_id + gid);
     double(*mypos)[3] = s_pos + (size_t)tid * natom_max;
     double e_lj = 0.0, e_c = 0.0, e_intra = 0.0;
+    PairCount pc = { 0u, 0u, 0u };
     const double *wc = c_sys.coords + (int64_t)w * c_sys.coord_stride;
     if (live) {
         double u[5];
@@ -1003,7 +1024,7 @@ __global__ void __launch_bounds__(MGPU_WIDOM_BLOCK) k_widom_batch(int w, int res
                 const double eps4 = s_eps4[ti];
                 if (eps4 == 0.0 && !charged) continue;
                 const double r2 = min_image_r2<TRI>(t.x - px, t.y - py, t.z - pz);
-                pair_terms(r2, eps4, s_sig[ti], qa * t.w, charged, e_lj, e_c);
+                pair_terms(r2, eps4, s_sig[ti], qa * t.w, charged, e_lj, e_c, pc);
             }
             for (int g = 0; g < c_sys.nres; ++g) {
                 if (!c_sys.active[g]) continue;
@@ -1020,11 +1041,12 @@ __global__ void __launch_bounds__(MGPU_WIDOM_BLOCK) k_widom_batch(int w, int res
                         const double eps4 = s_eps4[ti];
                         if (eps4 == 0.0 && !charged) continue;
                         const double r2 = min_image_r2<TRI>(tx - px, ty - py, tz - pz);
-                        pair_terms(r2, eps4, s_sig[ti], qa * tq, charged, e_lj, e_c);
+                        pair_terms(r2, eps4, s_sig[ti], qa * tq, charged, e_lj, e_c, pc);
                     }
             }
         }
     }
+    flush_pair_count(pc);
     s_e[tid] = e_lj + e_c * c_sys.eps0_inv_real + c_sys.e_self[res] + e_intra;   // non-recip part of new%total
     __syncthreads();
     // k space: warp `wid` handles the 32 insertions of its own lanes, one after the other

@@ -112,6 +112,8 @@ class Engine:
         s.p_insertion_deletion, s.p_widom = system.p_insertion_deletion, system.p_widom
         s.n_walkers = self.n_walkers
         s.device = device
+        self._sys_struct = s
+        self._keep.append(res_arr)
         self._ck(self.L.mgpu_init(C.byref(s)))
         self._open = True
 
@@ -336,6 +338,14 @@ class Engine:
         ms, n = C.c_double(), C.c_int64()
         self.L.mgpu_timing_get(kernel.encode(), C.byref(ms), C.byref(n))
         return ms.value, n.value
+
+    def pair_counts(self):
+        out = (C.c_int64 * 3)()
+        self._ck(self.L.mgpu_get_pair_counts(out))
+        return dict(pairs=out[0], lj=out[1], coulomb=out[2])
+
+    def reset_pair_counts(self):
+        self._ck(self.L.mgpu_reset_pair_counts())
 
     def measure_fp64_peak(self):
         tf, s = C.c_double(), C.c_double()

@@ -262,6 +262,11 @@ class Oracle:
     def seed(self, seed):
         self.L.orc_seed_rng(self.h, int(seed) & 0xFFFFFFFFFFFFFFFF)
 
+    def rng_state(self):
+        st = (C.c_uint64 * 4)()
+        self.L.orc_get_rng_state(self.h, st)
+        return [int(x) for x in st]
+
     def rand_uniform(self):
         return self.L.orc_rand_uniform(self.h)
 

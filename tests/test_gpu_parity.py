@@ -1,0 +1,401 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  GPU only.
+
+Tolerances are the north-star's: total / component energies within 1e-10 relative
+(|d| <= 1e-10 * max(1, |ref|)), per-move dE within 1e-9 (|d| <= 1e-9 * max(1, |dE_ref|)),
+identical accept / reject sequence over the first 10^4 moves on the shared RNG contract.
+"""
+import numpy as np
+import pytest
+
+from oracle.oracle import KIND_CREATE, KIND_DELETE, KIND_MOVE, Oracle
+
+pytestmark = pytest.mark.gpu
+
+REL_E = 1e-10
+REL_DE = 1e-9
+
+
+def close_e(a, b, rel=REL_E):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    return np.all(np.abs(a - b) <= rel * np.maximum(1.0, np.abs(b)))
+
+
+def assert_e(a, b, rel=REL_E, what=""):
+    assert close_e(a, b, rel), f"{what}: gpu={np.asarray(a)!r} ref={np.asarray(b)!r} diff={np.asarray(a) - np.asarray(b)!r}"
+
+
+@pytest.fixture
+def engine_cls():
+    from maniac_b200.engine import Engine
+    return Engine
+
+
+ALL = ["lj_gas", "zif8_h2o", "h2o_gas", "methanol", "two_atoms", "dipole", "two_dipole", "dipole_triclinic",
+       "zif8_co2_widom"]
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_total_energy_and_Sk(name, load, engine_cls):
+    s = load(name)
+    o = Oracle(s)
+    e_ref = o.update_system_energy()
+    with engine_cls(s, n_walkers=2) as eng:
+        ew_o, ew_g = o.ewald(), eng.ewald()
+        assert ew_o["nk"] == ew_g["nk"] and ew_o["kmax"] == ew_g["kmax"]
+        assert ew_o["alpha"] == ew_g["alpha"] and ew_o["rc"] == ew_g["rc"]      # same setup arithmetic, bit for bit
+        for w in (0, 1):
+            assert_e(eng.update_system_energy(w), e_ref, what=f"{name} total energy walker {w}")
+        ak_o, ak_g = o.Ak(), eng.Ak(0)
+        scale = max(1.0, np.abs(ak_o).max())
+        assert np.abs(ak_o - ak_g).max() <= 1e-11 * scale
+        bo, bg = o.box(), eng.box()
+        np.testing.assert_array_equal(bo["reciprocal"], bg["reciprocal"])
+        assert bo["volume"] == bg["volume"]
+
+
+def test_known_answers_on_gpu(load, kat, engine_cls):
+    """The reference's KATs, checked directly on the GPU path with the reference's tolerances."""
+    for name in ["lj_gas", "zif8_h2o", "h2o_gas", "methanol", "two_atoms", "dipole", "two_dipole"]:
+        ref = kat[name]["reference"]
+        with engine_cls(load(name)) as eng:
+            e = eng.update_system_energy()
+        assert abs(e[5] - ref["total"]) < ref["tol"], (name, e, ref)
+
+
+@pytest.mark.parametrize("name", ["zif8_h2o_gcmc", "h2o_gas", "dipole_triclinic"])
+def test_pairwise_energy_for_molecule(name, load, engine_cls):
+    s = load(name)
+    o = Oracle(s)
+    o.update_system_energy()
+    with engine_cls(s) as eng:
+        res = [i for i, r in enumerate(s.residues) if r.active][0]
+        n = s.residues[res].nmol
+        for mol in sorted(set([0, n // 2, n - 1])):
+            for skip in (True, False):
+                ref = o.pairwise_energy_for_molecule(res, mol, skip)
+                got = eng.pairwise_energy_for_molecule(res, mol, skip)
+                assert_e(got, ref, what=f"{name} pair energy mol {mol} skip {skip}")
+        assert eng.ewald_self_energy_single_mol(res) == pytest.approx(o.self_energy_single_mol(res), rel=1e-14)
+        assert_e(eng.intra_res_real_coulomb_energy(res, 0), o.intra_energy(res, 0), what="intra")
+
+
+def _rot(axis, theta, off):
+    c, s_ = np.cos(theta), np.sin(theta)
+    M = np.eye(3)
+    if axis == 0:
+        M[1, 1], M[1, 2], M[2, 1], M[2, 2] = c, -s_, s_, c
+    elif axis == 1:
+        M[0, 0], M[0, 2], M[2, 0], M[2, 2] = c, s_, -s_, c
+    else:
+        M[0, 0], M[0, 1], M[1, 0], M[1, 1] = c, -s_, s_, c
+    return off @ M.T
+
+
+@pytest.mark.parametrize("name", ["zif8_h2o_gcmc", "methanol", "dipole_triclinic", "lj_gas"])
+def test_old_new_energy_all_kinds(name, load, engine_cls):
+    """compute_old_energy / compute_new_energy for move, creation and deletion, then
+    commit / rollback, against the oracle doing the same through the reference's sequence."""
+    s = load(name)
+    rng = np.random.default_rng(5)
+    res = [i for i, r in enumerate(s.residues) if r.active][0]
+    na = s.residues[res].natom
+    o = Oracle(s, capacity=32)
+    o.update_system_energy()
+    with engine_cls(s, capacity=32) as eng:
+        eng.update_system_energy()
+        for it in range(6):
+            n = o.count(res)
+            mol = int(rng.integers(n))
+            com, off = o.get_molecule(res, mol)
+            # ---- translation / rotation
+            new_com = com + rng.uniform(-0.5, 0.5, 3)
+            new_off = _rot(int(rng.integers(3)), rng.uniform(-0.3, 0.3), off) if na > 1 else off
+            o.save_fourier(res, mol)
+            old_r = o.compute_old_energy(res, mol, KIND_MOVE)
+            o.set_molecule(res, mol, new_com, new_off)
+            new_r = o.compute_new_energy(res, mol, KIND_MOVE)
+            old_g = eng.compute_old_energy(res, mol, KIND_MOVE)
+            new_g = eng.compute_new_energy(res, mol, KIND_MOVE, new_com, new_off)
+            assert_e(old_g, old_r, what="old(move)")
+            assert_e(new_g, new_r, what="new(move)")
+            d_r, d_g = new_r[5] - old_r[5], new_g[5] - old_g[5]
+            assert abs(d_r - d_g) <= REL_DE * max(1.0, abs(d_r))
+            if it % 2 == 0:      # accept
+                eng.commit()
+                # oracle: accept_molecule_move bookkeeping == recompute
+                o.update_system_energy()
+            else:                # reject
+                eng.rollback()
+                o.set_molecule(res, mol, com, off)
+                o.restore_fourier(res, mol)
+            assert_e(eng.energy(), o.energy(), rel=1e-9, what="running energy after move")
+            ak_o, ak_g = o.Ak(), eng.Ak()
+            assert np.abs(ak_o - ak_g).max() <= 1e-10 * max(1.0, np.abs(ak_o).max())
+        # ---- creation (through the oracle's own driver, forced acceptance)
+        bx = o.box()
+        n = o.count(res)
+        o.set_chemical_potential(res, 50.0)
+        o.seed(99)
+        t = o.attempt_creation_move(res, n)
+        com_new, off_new = o.get_molecule(res, n)
+        old_g = eng.compute_old_energy(res, n, KIND_CREATE)
+        new_g = eng.compute_new_energy(res, n, KIND_CREATE, com_new, off_new)
+        assert_e(old_g, np.array(t.e_old[:]), what="old(create)")
+        assert_e(new_g, np.array(t.e_new[:]), rel=1e-9, what="new(create)")
+        assert abs((new_g[5] - old_g[5]) - t.dE) <= REL_DE * max(1.0, abs(t.dE))
+        if t.accepted:
+            eng.commit()
+            assert eng.count(res) == n + 1 == o.count(res)
+        else:
+            eng.rollback()
+        assert_e(eng.energy(), o.energy(), rel=1e-9, what="running energy after creation")
+        # ---- deletion
+        n = o.count(res)
+        mol = 0
+        o.set_chemical_potential(res, -50.0)
+        t = o.attempt_deletion_move(res, mol)
+        old_g = eng.compute_old_energy(res, mol, KIND_DELETE)
+        new_g = eng.compute_new_energy(res, mol, KIND_DELETE)
+        assert_e(old_g, np.array(t.e_old[:]), rel=1e-9, what="old(delete)")
+        assert_e(new_g, np.array(t.e_new[:]), rel=1e-9, what="new(delete)")
+        assert abs((new_g[5] - old_g[5]) - t.dE) <= REL_DE * max(1.0, abs(t.dE))
+        assert t.accepted == 1
+        eng.commit()
+        assert eng.count(res) == n - 1 == o.count(res)
+        for m in range(o.count(res)):           # swap-with-last compaction, remove_molecule
+            co, oo = o.get_molecule(res, m)
+            cg, og = eng.get_molecule(res, m)
+            np.testing.assert_array_equal(co, cg)
+            np.testing.assert_array_equal(oo, og)
+        full = eng.update_system_energy()
+        assert_e(full, o.update_system_energy(), what="full energy after create/delete")
+
+
+def test_trial_batch_many_walkers(load, engine_cls):
+    s = load("zif8_h2o_gcmc")
+    W = 12
+    rng = np.random.default_rng(1)
+    oracles = []
+    for w in range(W):
+        o = Oracle(s, capacity=16)
+        o.update_system_energy()
+        oracles.append(o)
+    with engine_cls(s, n_walkers=W, capacity=16) as eng:
+        mols = rng.integers(0, 3, W)
+        coms, offs, refs = [], [], []
+        for w in range(W):
+            com, off = oracles[w].get_molecule(0, int(mols[w]))
+            nc = com + rng.uniform(-0.5, 0.5, 3)
+            coms.append(nc)
+            offs.append(off)
+            oracles[w].save_fourier(0, int(mols[w]))
+            old = oracles[w].compute_old_energy(0, int(mols[w]), KIND_MOVE)
+            oracles[w].set_molecule(0, int(mols[w]), nc, off)
+            new = oracles[w].compute_new_energy(0, int(mols[w]), KIND_MOVE)
+            refs.append((old, new))
+        e_old, e_new = eng.trial_batch(np.arange(W), 0, mols, KIND_MOVE, np.array(coms), np.array(offs))
+        for w in range(W):
+            assert_e(e_old[w], refs[w][0], what=f"walker {w} old")
+            assert_e(e_new[w], refs[w][1], what=f"walker {w} new")
+        accept = (np.arange(W) % 2).astype(np.int32)
+        eng.commit_batch(np.arange(W), accept)
+        for w in range(W):
+            if accept[w]:
+                oracles[w].update_system_energy()
+                assert_e(eng.energy(w), oracles[w].energy(), rel=1e-9, what=f"walker {w} committed")
+                cg, _ = eng.get_molecule(0, int(mols[w]), walker=w)
+                np.testing.assert_array_equal(cg, coms[w])
+            else:
+                cg, _ = eng.get_molecule(0, int(mols[w]), walker=w)
+                assert not np.array_equal(cg, coms[w])
+        with pytest.raises(Exception):
+            eng.commit_batch([0], [1])          # nothing pending any more
+
+
+def _compare_traces(tr, ref, n_check=None):
+    n = len(ref) if n_check is None else n_check
+    assert (tr["move"][:n] == ref["move"][:n]).all()
+    assert (tr["res"][:n] == ref["res"][:n]).all()
+    assert (tr["mol"][:n] == ref["mol"][:n]).all()
+    assert (tr["accepted"][:n] == ref["accepted"][:n]).all(), np.nonzero(tr["accepted"][:n] != ref["accepted"][:n])
+    d = np.abs(tr["dE"][:n] - ref["dE"][:n])
+    lim = REL_DE * np.maximum(1.0, np.abs(ref["dE"][:n]))
+    assert (d <= lim).all(), (d.max(), np.argmax(d - lim))
+
+
+def test_sweep_10k_moves_accept_reject_sequence(load, engine_cls):
+    """North-star gate: identical accept/reject sequence over the first 10^4 moves and
+    per-move dE within 1e-9, GCMC mix of BASELINE configs[1] (0.4/0.4/0.2)."""
+    s = load("zif8_h2o_gcmc")
+    n = 10_000
+    o = Oracle(s, capacity=256)
+    o.update_system_energy()
+    o.seed(12345)
+    ref = o.monte_carlo_steps(n)
+    with engine_cls(s, n_walkers=3, capacity=256) as eng:
+        eng.seed(12345)
+        tr = eng.sweep(n, trace_walker=0)
+        _compare_traces(tr, ref)
+        assert eng.count(0, walker=0) == o.count(0)
+        assert_e(eng.energy(0), o.energy(), rel=1e-9, what="running energy after 10^4 moves")
+        np.testing.assert_array_equal(eng.counters(0), o.counters())
+        assert eng.rng_state(0) == o.rng_state()            # same number of draws consumed
+        # drift audit (output_utils.f90:258-275 analogue): incremental == full recompute
+        inc = eng.energy(0)
+        full = eng.update_system_energy(0)
+        assert_e(inc, full, rel=1e-9, what="incremental vs full after sweep")
+        # the other walkers ran their own streams
+        assert eng.counters(1).sum() > 0 and not np.array_equal(eng.counters(1), eng.counters(0))
+
+
+@pytest.mark.parametrize("name,steps", [("methanol", 3000), ("dipole_triclinic", 400), ("lj_gas", 2000)])
+def test_sweep_other_systems(name, steps, load, engine_cls):
+    s = load(name)
+    if name == "lj_gas":
+        s.p_translation, s.p_rotation, s.p_insertion_deletion = 0.5, 0.0, 0.5
+        for r in s.residues:
+            if r.active:
+                r.fugacity, r.chemical_potential = 50.0, 0.0
+    o = Oracle(s, capacity=128)
+    o.update_system_energy()
+    o.seed(777)
+    ref = o.monte_carlo_steps(steps)
+    with engine_cls(s, capacity=128) as eng:
+        eng.seed(777)
+        tr = eng.sweep(steps, trace_walker=0)
+        _compare_traces(tr, ref)
+        res = [i for i, r in enumerate(s.residues) if r.active][0]
+        assert eng.count(res) == o.count(res)
+        assert_e(eng.energy(), o.energy(), rel=1e-9)
+
+
+def test_sweep_from_empty_and_widom_moves(load, engine_cls):
+    """Edge cases: N = 0 (moves return early, creations use the slot-1 template) and Widom trials
+    inside the loop (state never changes; statistic%weight / sample)."""
+    s = load("zif8_co2_widom")
+    s.residues[1].fugacity = 5.0e4
+    s.p_translation, s.p_rotation, s.p_insertion_deletion, s.p_widom = 0.3, 0.3, 0.4, 0.0
+    o = Oracle(s, capacity=64)
+    o.set_count(1, 0)
+    o.update_system_energy()
+    o.seed(31)
+    ref = o.monte_carlo_steps(1500)
+    with engine_cls(s, capacity=64) as eng:
+        eng.set_count(1, 0)
+        eng.update_system_energy()
+        eng.seed(31)
+        tr = eng.sweep(1500, trace_walker=0)
+        _compare_traces(tr, ref)
+        assert eng.count(1) == o.count(1)
+    s.p_translation, s.p_rotation, s.p_insertion_deletion, s.p_widom = 0.25, 0.25, 0.0, 0.5
+    o = Oracle(s, capacity=64)
+    o.update_system_energy()
+    o.seed(32)
+    ref = o.monte_carlo_steps(800)
+    with engine_cls(s, capacity=64) as eng:
+        eng.seed(32)
+        tr = eng.sweep(800, trace_walker=0)
+        _compare_traces(tr, ref)
+        w_g, n_g = eng.widom(1)
+        w_o, n_o = o.widom(1)
+        assert n_g == n_o and w_g == pytest.approx(w_o, rel=1e-8)
+
+
+@pytest.mark.parametrize("loaded", [0, 6])
+def test_widom_batch(loaded, load, engine_cls):
+    """K3: per-insertion dE vs the oracle on the same counter-based draws, empty and loaded pore."""
+    s = load("zif8_co2_widom")
+    s.residues[1].fugacity = 1.0e5
+    s.p_translation, s.p_rotation, s.p_insertion_deletion, s.p_widom = 0.0, 0.0, 1.0, 0.0
+    o = Oracle(s, capacity=64)
+    o.set_count(1, 0)
+    o.update_system_energy()
+    o.seed(5)
+    with engine_cls(s, capacity=64) as eng:
+        eng.set_count(1, 0)
+        eng.update_system_energy()
+        if loaded:
+            # grow a loaded pore with creations only (device and oracle follow the same stream)
+            eng.seed(5)
+            steps = 0
+            while o.count(1) < loaded and steps < 4000:
+                o.monte_carlo_steps(50, trace=False)
+                eng.sweep(50)
+                steps += 50
+            assert eng.count(1) == o.count(1) >= 1
+        n = 300
+        dE_o, sw_o, ok_o = o.widom_batch(1, 1000, n, seed=424242)
+        dE_g, sw_g, ok_g = eng.widom_batch(1, n, seed=424242, first_id=1000, want_dE=True)
+        lim = REL_DE * np.maximum(1.0, np.abs(dE_o))
+        assert (np.abs(dE_g - dE_o) <= lim).all(), np.abs(dE_g - dE_o).max()
+        assert ok_g == ok_o and sw_g == pytest.approx(sw_o, rel=1e-9)
+        # state untouched
+        assert eng.count(1) == o.count(1)
+        assert_e(eng.update_system_energy(), o.update_system_energy())
+        # size-independent property: a batch equals the sum of its halves
+        _, a, na_ = eng.widom_batch(1, 5000, seed=9, first_id=0)
+        _, b, nb_ = eng.widom_batch(1, 5000, seed=9, first_id=5000)
+        _, c, nc_ = eng.widom_batch(1, 10000, seed=9, first_id=0)
+        assert na_ + nb_ == nc_ and (a + b) == pytest.approx(c, rel=1e-12)
+
+
+def test_error_behaviour(load, engine_cls):
+    from maniac_b200.engine import ManiacAbort
+    s = load("methanol")
+    with engine_cls(s, capacity=2) as eng:
+        with pytest.raises(ManiacAbort):
+            eng.update_system_energy(walker=5)
+        with pytest.raises(ManiacAbort):
+            eng.pairwise_energy_for_molecule(3, 0)
+        with pytest.raises(ManiacAbort):
+            eng.compute_new_energy(0, 0, KIND_MOVE)            # geometry missing
+        with pytest.raises(ManiacAbort):
+            eng.commit()                                       # nothing pending
+        com, off = eng.get_molecule(0, 0)
+        with pytest.raises(ManiacAbort):
+            eng.compute_new_energy(0, 7, KIND_CREATE, com, off)  # beyond capacity (check_molecule_index)
+        # the engine is still usable afterwards
+        assert np.isfinite(eng.update_system_energy()).all()
+    # capacity overflow inside the device-resident loop is reported, not ignored
+    s2 = load("methanol")
+    s2.residues[0].chemical_potential = 0.0
+    s2.residues[0].fugacity = 1.0e12
+    s2.p_translation, s2.p_rotation, s2.p_insertion_deletion = 0.0, 0.0, 1.0
+    with engine_cls(s2, capacity=3) as eng:
+        with pytest.raises(ManiacAbort):
+            eng.sweep(400)
+
+
+def test_host_driven_drivers_match_oracle_and_sweep(load, engine_cls):
+    """Third implementation of the drivers: C++ host drivers over the C ABI (the Fortran
+    drivers' role, include/maniac_host.h).  Same RNG contract => same trajectory as the
+    oracle and as the device-resident sweep."""
+    from maniac_b200.hostmc import HostMonteCarlo
+    s = load("zif8_h2o_gcmc")
+    n = 1500
+    o = Oracle(s, capacity=128)
+    o.update_system_energy()
+    o.seed(4242)
+    ref = o.monte_carlo_steps(n)
+    with engine_cls(s, n_walkers=4, capacity=128) as eng:
+        hm = HostMonteCarlo(eng, seed=4242)
+        tr = hm.run(n, trace_walker=0)
+        _compare_traces(tr, ref)
+        assert hm.count(0) == o.count(0) == eng.count(0)
+        assert_e(hm.energy(), o.energy(), rel=1e-9, what="host-side running energy")
+        assert_e(eng.energy(0), o.energy(), rel=1e-9, what="device running energy")
+        np.testing.assert_array_equal(hm.counters(), o.counters())
+        for m in range(o.count(0)):
+            co, oo = o.get_molecule(0, m)
+            ch, oh = hm.get_molecule(0, m)
+            cg, og = eng.get_molecule(0, m)
+            np.testing.assert_allclose(ch, co, rtol=0, atol=1e-12)
+            np.testing.assert_array_equal(ch, cg)
+            np.testing.assert_array_equal(oh, og)
+        t = hm.traffic()
+        assert t["trials"] > 0 and t["h2d_bytes"] > 0 and t["d2h_bytes"] == 96 * t["trials"]
+        hm.close()
+    with engine_cls(s, n_walkers=2, capacity=128) as eng:
+        eng.seed(4242)
+        tr2 = eng.sweep(n, trace_walker=0)
+        assert (tr2["accepted"] == tr["accepted"]).all() and (tr2["move"] == tr["move"]).all()

@@ -1,0 +1,143 @@
+"""Host-side logic that needs no GPU: input readers, LJ table semantics, the C-ABI library's
+symbol table, loud failure without a device."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_library_exports_every_declared_symbol():
+    from maniac_b200 import capi
+    hdr = (ROOT / "include" / "maniac_gpu.h").read_text()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(mgpu_[a-zA-Z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 40
+    L = capi.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/maniac_gpu.h but not exported"
+    assert declared == set(capi.SIGNATURES), declared ^ set(capi.SIGNATURES)
+
+
+def test_struct_layout_matches_header():
+    from maniac_b200 import capi
+    # mgpu_step_trace: 4 int32 + 2 double + 2*6 double
+    assert C.sizeof(capi.MgpuStepTrace) == 16 + 16 + 96
+    assert C.sizeof(capi.MgpuResidue) == 16 + 4 * 8 + 3 * 8
+    assert capi.MgpuSystem.residues.offset == 9 * 8 + 3 * 8 + 8
+
+
+def test_engine_fails_loudly_without_gpu(load):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from maniac_b200.engine import Engine, ManiacAbort
+    with pytest.raises(ManiacAbort, match="no CUDA device"):
+        Engine(load("methanol"))
+    from maniac_b200 import capi
+    L = capi.lib()
+    out = (C.c_double * 6)()
+    assert L.mgpu_total_energy(0, out) != 0 and b"not initialised" in L.mgpu_last_error()
+
+
+def test_lj_table_matches_oracle(load):
+    from maniac_b200.engine import lj_table
+    from oracle.oracle import Oracle
+    for name in ["zif8_h2o", "zif8_co2_widom", "lj_gas", "methanol", "dipole_triclinic"]:
+        s = load(name)
+        eps, sig = lj_table(s)
+        eo, so = Oracle(s).lj_table()
+        np.testing.assert_array_equal(eps, eo)
+        np.testing.assert_array_equal(sig, so)
+    # Lorentz-Berthelot fill for the CO2 / ZIF-8 cross terms (A16): sigma mean, eps geometric mean
+    s = load("zif8_co2_widom")
+    eps, sig = lj_table(s)
+    assert sig[7, 0] == (sig[7, 7] + sig[0, 0]) / 2 and eps[7, 0] == pytest.approx(np.sqrt(eps[7, 7] * eps[0, 0]))
+    # explicit "0 0" cross lines whose diagonals are zero stay zero (TIP4P M / H sites)
+    s = load("zif8_h2o")
+    eps, sig = lj_table(s)
+    assert eps[1, 5] == 0.0 and sig[1, 5] == 0.0 and eps[0, 3] == 0.115221
+
+
+def test_readers_roundtrip(tmp_path, load):
+    """.maniac / .data / .inc readers on a small synthetic case incl. residue sorting, the COM quirk
+    and unwrapping of a molecule that straddles the boundary."""
+    from maniac_b200.inputs import load_system
+    (tmp_path / "in.maniac").write_text("""
+nb_block 2
+nb_step 10
+temperature 300
+ewald_tolerance 1e-5
+real_space_cutoff 5
+translation_step 1
+rotation_step_angle 0.5
+translation_proba 0.6
+rotation_proba 0.6
+begin_residue
+  name wall
+  state inactif
+  types 3
+  names W
+  nb-atoms 1
+end_residue
+begin_residue
+  name ab
+  state actif
+  fugacity 2.0
+  types 1 2
+  names A B
+  nb-atoms 2
+end_residue
+""")
+    (tmp_path / "top.data").write_text("""test
+
+5 atoms
+3 atom types
+
+-5 5 xlo xhi
+-5 5 ylo yhi
+-5 5 zlo zhi
+
+Masses
+
+1 2.0
+2 4.0
+3 10.0
+
+Atoms # full
+
+3 2 3 0.0 1.0 1.0 1.0
+1 1 1 0.5 4.8 0.0 0.0
+2 1 2 -0.5 -4.8 0.0 0.0
+4 3 1 0.5 0.0 1.0 0.0
+5 3 2 -0.5 0.0 2.0 0.0
+""")
+    (tmp_path / "p.inc").write_text("pair_coeff 1 1 0.1 3.0\npair_coeff 2 2 0.2 2.0\npair_coeff 3 3 0.3 1.0\n")
+    s = load_system(tmp_path / "in.maniac", tmp_path / "top.data", tmp_path / "p.inc")
+    assert [r.name for r in s.residues] == ["ab", "wall"]          # sorted by smallest type id
+    assert s.p_translation == pytest.approx(0.5) and s.p_rotation == pytest.approx(0.5)   # rescaled to 1
+    ab = s.residues[0]
+    assert ab.nmol == 2 and ab.mass == pytest.approx(8.0)          # natom * mass(type of last atom)
+    # first molecule straddles the boundary: atom 2 is unwrapped to x = 5.2, centroid 5.0 -> wrapped to -5.0
+    np.testing.assert_allclose(ab.offset[0], [[-0.2, 0, 0], [0.2, 0, 0]], atol=1e-12)
+    assert ab.com[0][0] == pytest.approx(-5.0)
+    np.testing.assert_allclose(ab.com[1], [0.0, 1.5, 0.0])
+    assert list(ab.types) == [0, 1] and list(s.residues[1].types) == [2]
+    with pytest.raises(ValueError):
+        (tmp_path / "bad.maniac").write_text("nb_block 1\n")
+        load_system(tmp_path / "bad.maniac", tmp_path / "top.data", tmp_path / "p.inc")
+
+
+def test_snapshot_roundtrip(tmp_path, load):
+    from maniac_b200.snapshot import load_snapshot, save_snapshot
+    s = load("zif8_h2o")
+    save_snapshot(tmp_path / "x.npz", s)
+    t = load_snapshot(tmp_path / "x.npz")
+    assert t.pair_coeff == s.pair_coeff and t.ntypes == s.ntypes
+    for a, b in zip(s.residues, t.residues):
+        np.testing.assert_array_equal(a.com, b.com)
+        np.testing.assert_array_equal(a.offset, b.offset)
+        assert a.mass == b.mass and a.active == b.active
