@@ -216,6 +216,15 @@ int mgpu_reset_pair_counts(void);
 /* achieved FP64 FMA throughput of a register-resident DFMA loop (TFLOP/s) and the SM
  * clock it ran at: the roofline denominator for the FP64-bound kernels */
 int mgpu_measure_fp64_peak(double *tflops, double *seconds);
+/* accuracy of the two fast per-pair primitives on the device, measured against the exact
+ * forms over the whole tabulated range: max relative error of 1/r^2 (MUFU seed + Newton) and
+ * max error of the erfc(alpha r)/r table relative to the pair's Coulomb scale */
+int mgpu_selftest_math(double *max_rel_rcp, double *max_err_table);
+/* host-only (no GPU needed): builds the erfc(alpha r)/r table exactly as mgpu_init does for
+ * [r_lo, r_hi] and compares n log-spaced samples with long-double erfc.  Returns the number
+ * of samples inside the tabulated range. */
+int mgpu_coulomb_table_check(double alpha, double r_lo, double r_hi, int32_t n,
+                             double *max_rel_err, double *max_abs_err_times_r);
 
 #ifdef __cplusplus
 }

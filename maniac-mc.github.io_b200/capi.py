@@ -92,6 +92,8 @@ SIGNATURES = {
     "mgpu_get_pair_counts": (C.c_int, [_pl]),
     "mgpu_reset_pair_counts": (C.c_int, []),
     "mgpu_measure_fp64_peak": (C.c_int, [_pd, _pd]),
+    "mgpu_selftest_math": (C.c_int, [_pd, _pd]),
+    "mgpu_coulomb_table_check": (C.c_int, [D, D, D, I, _pd, _pd]),
 }
 
 

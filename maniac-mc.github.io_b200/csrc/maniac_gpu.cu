@@ -12,6 +12,7 @@
 #include <map>
 
 #include "mgpu_kernels.cuh"
+#include "mgpu_table.h"
 
 // ---- constants (src/constants.f90:8-21, src/parameters.f90:31-37) --------------------
 namespace {
@@ -44,7 +45,10 @@ struct Context {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     DevSys h{};                       // host copy of the constant block
     int natom_max = 1;
-    size_t smem = 0, smem_widom = 0, smem_buildS = 0;
+    size_t smem1 = 0, smem8 = 0, smem_buildS = 0;   // dynamic shared memory: 1 group (CTA) / MGPU_WARPS groups (warps) per CTA
+    int sm_count = 0, ctas_per_sm = 1;
+    int wgroups = MGPU_WGROUPS;        // walkers (warps) per CTA of the warp-per-task kernels
+    int tab_emin = 0, tab_noct = 0;
     std::vector<void *> allocs;
     // host-side mirrors needed by the API
     std::vector<int> natom, active, cap;
@@ -140,8 +144,8 @@ int rebuild(int first, int n)
     const int nk = g.h.nk;
     dim3 grid((nk + MGPU_BLOCK - 1) / MGPU_BLOCK, n);
     if (nk > 0) k_build_S<<<grid, MGPU_BLOCK, g.smem_buildS, g.stream>>>(1, nullptr, first);
-    if (g.h.triclinic) k_total_energy<true><<<n, MGPU_BLOCK, g.smem, g.stream>>>(first, g.natom_max);
-    else k_total_energy<false><<<n, MGPU_BLOCK, g.smem, g.stream>>>(first, g.natom_max);
+    if (g.h.triclinic) k_total_energy<true><<<n, MGPU_BLOCK, g.smem1, g.stream>>>(first, g.natom_max);
+    else k_total_energy<false><<<n, MGPU_BLOCK, g.smem1, g.stream>>>(first, g.natom_max);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(g.stream));
     for (int w = first; w < first + n; ++w) g.dirty[w] = 0;
@@ -238,7 +242,7 @@ int mgpu_init(const mgpu_system *sys)
     const double alpha = std::sqrt(std::fabs(std::log(tol * rc * screen))) / rc;
     const double t2 = 2.0 * screen * alpha;
     const double fprec = std::sqrt(-std::log(tol * rc * (t2 * t2)));
-    h.rc = rc; h.alpha = alpha;
+    h.rc = rc; h.rc2 = rc * rc; h.alpha = alpha;
     for (int d = 0; d < 3; ++d) h.kmax[d] = f_nint(0.25 + metrics[d] * alpha * fprec / PI);
     h.kmax_max = std::max(h.kmax[0], std::max(h.kmax[1], h.kmax[2]));
     h.eps0_inv_real = EPS0_INV_real(); h.twopi = TWOPI; h.overlap = OVERLAP();
@@ -316,7 +320,7 @@ int mgpu_init(const mgpu_system *sys)
     h.tstep = sys->translation_step; h.rstep = sys->rotation_step_angle;
 
     // ---- static arrays ----
-    std::vector<double4> hx(n_host ? n_host : 1); std::vector<int32_t> ht(n_host ? n_host : 1), hm(n_host ? n_host : 1);
+    std::vector<double4> hx(n_host ? n_host : 1); std::vector<int32_t> ht(n_host ? n_host : 1), hm(n_host ? n_host : 1); std::vector<double> hq(n_host ? n_host : 1);
     {
         int k = 0, molid = 0;
         for (int r = 0; r < sys->nres; ++r) {
@@ -325,27 +329,79 @@ int mgpu_init(const mgpu_system *sys)
             for (int m = 0; m < R.nmol; ++m, ++molid)
                 for (int a = 0; a < R.natom; ++a, ++k) {
                     const double *c = R.com + (size_t)m * 3, *o = R.offset + ((size_t)m * R.natom + a) * 3;
-                    hx[k] = make_double4(c[0] + o[0], c[1] + o[1], c[2] + o[2], R.charges[a]);   // geometry_utils.f90:235-241
-                    ht[k] = R.types[a]; hm[k] = molid;
+                    const double q = R.charges[a];
+                    hx[k] = make_double4(c[0] + o[0], c[1] + o[1], c[2] + o[2], std::fabs(q) < MGPU_ERR_TOL ? 0.0 : q);   // geometry_utils.f90:235-241; :157
+                    hq[k] = q; ht[k] = R.types[a]; hm[k] = molid;
                 }
         }
     }
-    double4 *d_hx; int32_t *d_ht, *d_hm; double *d_eps, *d_sig, *d_ffW, *d_Shost; int32_t *d_kx, *d_ky, *d_kz;
+    double4 *d_hx; int32_t *d_ht, *d_hm; double *d_eps, *d_sig, *d_ffW, *d_Shost, *d_hq, *d_ctab; int32_t *d_kx, *d_ky, *d_kz;
     const size_t nk1 = h.nk ? h.nk : 1, nt2 = (size_t)sys->ntypes * sys->ntypes;
     if (dalloc(&d_hx, hx.size()) || dalloc(&d_ht, ht.size()) || dalloc(&d_hm, hm.size()) || dalloc(&d_eps, nt2) || dalloc(&d_sig, nt2) ||
+        dalloc(&d_hq, hq.size()) || dalloc(&d_ctab, (size_t)MGPU_TAB_MAXOCT * (1 << MGPU_TAB_K) * MGPU_TAB_ROW) ||
         dalloc(&d_ffW, nk1) || dalloc(&d_kx, nk1) || dalloc(&d_ky, nk1) || dalloc(&d_kz, nk1) || dalloc(&d_Shost, 2 * nk1)) return 1;
     CK(cudaMemcpy(d_hx, hx.data(), sizeof(double4) * hx.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_ht, ht.data(), sizeof(int32_t) * ht.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_hm, hm.data(), sizeof(int32_t) * hm.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(d_eps, sys->epsilon, sizeof(double) * nt2, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(d_sig, sys->sigma, sizeof(double) * nt2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_hq, hq.data(), sizeof(double) * hq.size(), cudaMemcpyHostToDevice));
+    {
+        std::vector<double2> hxy(hx.size()), hzq(hx.size());
+        for (size_t i = 0; i < hx.size(); ++i) { hxy[i] = make_double2(hx[i].x, hx[i].y); hzq[i] = make_double2(hx[i].z, hx[i].w); }
+        double2 *d_xy, *d_zq;
+        if (dalloc(&d_xy, hxy.size()) || dalloc(&d_zq, hzq.size())) return 1;
+        CK(cudaMemcpy(d_xy, hxy.data(), sizeof(double2) * hxy.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_zq, hzq.data(), sizeof(double2) * hzq.size(), cudaMemcpyHostToDevice));
+        h.host_xy = d_xy; h.host_zq = d_zq;
+        // classes of guest atoms with respect to the framework
+        std::vector<char> type_present(sys->ntypes, 0);
+        bool host_charged = false;
+        for (int i = 0; i < n_host; ++i) { type_present[ht[i]] = 1; host_charged = host_charged || hx[i].w != 0.0; }
+        for (int r = 0; r < sys->nres; ++r) {
+            const mgpu_residue &R = sys->residues[r];
+            if (!R.is_active) continue;
+            for (int a = 0; a < R.natom; ++a) {
+                bool lj = false;
+                for (int t = 0; t < sys->ntypes; ++t)
+                    if (type_present[t] && sys->epsilon[(size_t)R.types[a] * sys->ntypes + t] != 0.0 && sys->sigma[(size_t)R.types[a] * sys->ntypes + t] != 0.0) lj = true;
+                const bool co = host_charged && std::fabs(R.charges[a]) >= MGPU_ERR_TOL;
+                const int mode = (lj ? 1 : 0) | (co ? 2 : 0);
+                h.hl_list[r][mode][h.hl_n[r][mode]++] = (int8_t)a;
+            }
+        }
+    }
+    {
+        // pairwise_lj_energy (pairwise_energy_utils.f90:131-136): 4 eps ((sigma/r)^12 - (sigma/r)^6) = A / s^6 - B / s^3
+        std::vector<double> A(nt2), B(nt2);
+        for (size_t i = 0; i < nt2; ++i) {
+            const double sg = sys->sigma[i], s2 = sg * sg, s6 = s2 * s2 * s2;
+            B[i] = 4.0 * sys->epsilon[i] * s6;
+            A[i] = B[i] * s6;
+        }
+        CK(cudaMemcpy(d_eps, A.data(), sizeof(double) * nt2, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_sig, B.data(), sizeof(double) * nt2, cudaMemcpyHostToDevice));
+    }
+    {
+        // Coulomb table over every minimum-image distance the box allows (orthorhombic: half the body
+        // diagonal; triclinic: the 27-image search is bounded by the same sum of cell-vector lengths)
+        double r_hi = h.triclinic ? 0.5 * (metrics[0] + metrics[1] + metrics[2]) + 1.0
+                                  : 0.5 * std::sqrt(metrics[0] * metrics[0] + metrics[1] * metrics[1] + metrics[2] * metrics[2]) + 1.0;
+        const double r_zero = MGPU_TAB_XCUT / alpha;         // erfc(7)/r < 1e-24: below the rounding of any sum it enters
+        h.s_zero = r_zero * r_zero;
+        if (r_hi > r_zero) r_hi = r_zero;
+        std::vector<double> tab;
+        mgpu_build_coulomb_table(alpha, 1.0, r_hi, &g.tab_emin, &g.tab_noct, tab);
+        CK(cudaMemcpy(d_ctab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
+        h.tab_ibase = (1023 + g.tab_emin) << MGPU_TAB_K;
+        h.tab_nint = g.tab_noct << MGPU_TAB_K;
+        h.ctab = d_ctab;
+    }
     if (h.nk) {
         CK(cudaMemcpy(d_ffW, ffW.data(), sizeof(double) * h.nk, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(d_kx, kx.data(), sizeof(int32_t) * h.nk, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(d_ky, ky.data(), sizeof(int32_t) * h.nk, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(d_kz, kz.data(), sizeof(int32_t) * h.nk, cudaMemcpyHostToDevice));
     }
-    h.host_xyzq = d_hx; h.host_type = d_ht; h.eps = d_eps; h.sig = d_sig; h.ffW = d_ffW; h.kx = d_kx; h.ky = d_ky; h.kz = d_kz; h.S_host = d_Shost;
+    h.host_xyzq = d_hx; h.host_type = d_ht; h.host_qraw = d_hq; h.ljA = d_eps; h.ljB = d_sig; h.ffW = d_ffW; h.kx = d_kx; h.ky = d_ky; h.kz = d_kz; h.S_host = d_Shost;
 
     // ---- per-walker arrays ----
     const size_t W = sys->n_walkers;
@@ -392,20 +448,29 @@ int mgpu_init(const mgpu_system *sys)
     g.dirty.assign(W, 0);
 
     // ---- shared-memory budgets ----
-    g.smem = smem_bytes(h.ntypes, h.kmax_max, g.natom_max);
+    g.smem1 = smem_bytes(h.ntypes, h.tab_nint, h.kmax_max, g.natom_max, 1);
+    g.wgroups = MGPU_WGROUPS;
+    while (g.wgroups > 1 && smem_bytes(h.ntypes, h.tab_nint, h.kmax_max, g.natom_max, g.wgroups) > 227 * 1024) --g.wgroups;
+    g.smem8 = smem_bytes(h.ntypes, h.tab_nint, h.kmax_max, g.natom_max, g.wgroups);
     g.smem_buildS = sizeof(double2) * (size_t)MGPU_STILE * 3 * (h.kmax_max + 1);
-    g.smem_widom = ((sizeof(double) * 2 * nt2 + 15) & ~size_t(15)) + sizeof(double2) * (MGPU_WIDOM_BLOCK / 32) * (size_t)g.natom_max * 3 * (h.kmax_max + 1)
-                 + sizeof(double) * 3 * (size_t)g.natom_max * MGPU_WIDOM_BLOCK + sizeof(double) * MGPU_WIDOM_BLOCK + 64;
-    const size_t smem_max = std::max(g.smem, std::max(g.smem_buildS, g.smem_widom));
-    if (smem_max > 227 * 1024) return fail("mgpu_init: kmax / ntypes need more than 227 KB of shared memory per CTA");
+    const size_t smem_max = std::max(g.smem8, g.smem_buildS);
+    if (smem_max > 227 * 1024) return fail("mgpu_init: kmax / ntypes / molecule size need more than 227 KB of shared memory per CTA");
+    CK(cudaDeviceGetAttribute(&g.sm_count, cudaDevAttrMultiProcessorCount, g.device));
 #define SET_SMEM(k, b) CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(b)))
-    SET_SMEM(k_trial<false>, g.smem); SET_SMEM(k_trial<true>, g.smem);
-    SET_SMEM(k_sweep<false>, g.smem); SET_SMEM(k_sweep<true>, g.smem);
-    SET_SMEM(k_total_energy<false>, g.smem); SET_SMEM(k_total_energy<true>, g.smem);
-    SET_SMEM(k_pair_molecule<false>, g.smem); SET_SMEM(k_pair_molecule<true>, g.smem);
-    SET_SMEM(k_widom_batch<false>, g.smem_widom); SET_SMEM(k_widom_batch<true>, g.smem_widom);
+    SET_SMEM((k_trial<false, 32>), g.smem8); SET_SMEM((k_trial<true, 32>), g.smem8);
+    SET_SMEM((k_trial<false, MGPU_BLOCK>), g.smem1); SET_SMEM((k_trial<true, MGPU_BLOCK>), g.smem1);
+    SET_SMEM(k_sweep<false>, g.smem8); SET_SMEM(k_sweep<true>, g.smem8);
+    SET_SMEM(k_total_energy<false>, g.smem1); SET_SMEM(k_total_energy<true>, g.smem1);
+    SET_SMEM(k_pair_molecule<false>, g.smem1); SET_SMEM(k_pair_molecule<true>, g.smem1);
+    SET_SMEM(k_widom_batch<false>, g.smem8); SET_SMEM(k_widom_batch<true>, g.smem8);
     SET_SMEM(k_build_S, g.smem_buildS);
 #undef SET_SMEM
+    {
+        int nb = 1;
+        if (h.triclinic) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_widom_batch<true>, 32 * g.wgroups, g.smem8));
+        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_widom_batch<false>, 32 * g.wgroups, g.smem8));
+        g.ctas_per_sm = nb > 0 ? nb : 1;
+    }
 
     if (upload_sys()) return 1;
     CK(cudaStreamSynchronize(g.stream));
@@ -599,8 +664,8 @@ int mgpu_pairwise_energy_for_molecule(int32_t w, int32_t res, int32_t mol, int32
     if (mol < 0 || mol >= g.h.cap[res]) return fail("pairwise_energy_for_molecule: molecule index out of range");
     const double *dg;
     if (upload_geom(res, com, offset, &dg)) return 1;
-    if (g.h.triclinic) k_pair_molecule<true><<<1, MGPU_BLOCK, g.smem, g.stream>>>(w, res, mol, skip, dg, g.d_scratch, g.natom_max);
-    else k_pair_molecule<false><<<1, MGPU_BLOCK, g.smem, g.stream>>>(w, res, mol, skip, dg, g.d_scratch, g.natom_max);
+    if (g.h.triclinic) k_pair_molecule<true><<<1, MGPU_BLOCK, g.smem1, g.stream>>>(w, res, mol, skip, dg, g.d_scratch, g.natom_max);
+    else k_pair_molecule<false><<<1, MGPU_BLOCK, g.smem1, g.stream>>>(w, res, mol, skip, dg, g.d_scratch, g.natom_max);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(g.h_scratch, g.d_scratch, sizeof(double) * 2, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
@@ -656,8 +721,15 @@ int mgpu_trial_batch(int32_t n, const int32_t *walker, const int32_t *res, const
     CK(cudaMemcpyAsync(g.d_task_off, g.h_task_off, sizeof(double) * 3 * MGPU_MAX_SITES * n, cudaMemcpyHostToDevice, g.stream));
     TaskArrays T{ reinterpret_cast<const int4 *>(g.d_task_i), g.d_task_com, g.d_task_off, g.d_task_out };
     Timer tm("trial");
-    if (g.h.triclinic) k_trial<true><<<n, MGPU_BLOCK, g.smem, g.stream>>>(T, g.natom_max);
-    else k_trial<false><<<n, MGPU_BLOCK, g.smem, g.stream>>>(T, g.natom_max);
+    // large batches: one warp per task (8 tasks per CTA); small ones: one CTA per task for latency
+    if (n >= g.sm_count * g.wgroups / 2) {
+        const int nb = (n + g.wgroups - 1) / g.wgroups;
+        if (g.h.triclinic) k_trial<true, 32><<<nb, 32 * g.wgroups, g.smem8, g.stream>>>(T, n, g.natom_max);
+        else k_trial<false, 32><<<nb, 32 * g.wgroups, g.smem8, g.stream>>>(T, n, g.natom_max);
+    } else {
+        if (g.h.triclinic) k_trial<true, MGPU_BLOCK><<<n, MGPU_BLOCK, g.smem1, g.stream>>>(T, n, g.natom_max);
+        else k_trial<false, MGPU_BLOCK><<<n, MGPU_BLOCK, g.smem1, g.stream>>>(T, n, g.natom_max);
+    }
     tm.stop();
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(g.h_task_out, g.d_task_out, sizeof(double) * 12 * n, cudaMemcpyDeviceToHost, g.stream));
@@ -743,8 +815,9 @@ int mgpu_sweep(int32_t first, int32_t n, int64_t n_steps, int32_t trace_walker, 
     mgpu_step_trace *d_trace = nullptr;
     if (trace) CK(cudaMalloc(&d_trace, sizeof(mgpu_step_trace) * n_steps));
     Timer tm("sweep");
-    if (g.h.triclinic) k_sweep<true><<<n, MGPU_BLOCK, g.smem, g.stream>>>(first, n_steps, g.natom_max, trace_walker, d_trace, g.d_err);
-    else k_sweep<false><<<n, MGPU_BLOCK, g.smem, g.stream>>>(first, n_steps, g.natom_max, trace_walker, d_trace, g.d_err);
+    const int nb_sweep = (n + g.wgroups - 1) / g.wgroups;
+    if (g.h.triclinic) k_sweep<true><<<nb_sweep, 32 * g.wgroups, g.smem8, g.stream>>>(first, n, n_steps, g.natom_max, trace_walker, d_trace, g.d_err);
+    else k_sweep<false><<<nb_sweep, 32 * g.wgroups, g.smem8, g.stream>>>(first, n, n_steps, g.natom_max, trace_walker, d_trace, g.d_err);
     tm.stop();
     cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess) { if (d_trace) cudaFree(d_trace); return fail(std::string("k_sweep: ") + cudaGetErrorString(le)); }
@@ -795,26 +868,30 @@ int mgpu_widom_batch(int32_t w, int32_t res, int64_t first_id, int64_t n, uint64
     NEED_READY();
     if (check_walker(w) || check_guest(res) || ensure_clean(w)) return 1;
     if (n <= 0) { *sum_w = 0.0; *n_ok = 0; return 0; }
-    const long long nb = (n + MGPU_WIDOM_BLOCK - 1) / MGPU_WIDOM_BLOCK;
+    // persistent warps: one insertion per warp at a time, grid = resident CTAs (or fewer for small n)
+    long long nb = (n + g.wgroups - 1) / g.wgroups;
+    const long long nb_max = (long long)g.sm_count * g.ctas_per_sm;
+    if (nb > nb_max) nb = nb_max;
+    const long long nw = nb * g.wgroups;
     double *d_dE = nullptr, *d_bw = nullptr; long long *d_bn = nullptr;
     if (dE_out) CK(cudaMalloc(&d_dE, sizeof(double) * n));
-    CK(cudaMalloc(&d_bw, sizeof(double) * nb));
-    CK(cudaMalloc(&d_bn, sizeof(long long) * nb));
+    CK(cudaMalloc(&d_bw, sizeof(double) * nw));
+    CK(cudaMalloc(&d_bn, sizeof(long long) * nw));
     Timer tm("widom");
-    if (g.h.triclinic) k_widom_batch<true><<<(unsigned)nb, MGPU_WIDOM_BLOCK, g.smem_widom, g.stream>>>(w, res, first_id, n, seed, d_dE, d_bw, d_bn, g.natom_max);
-    else k_widom_batch<false><<<(unsigned)nb, MGPU_WIDOM_BLOCK, g.smem_widom, g.stream>>>(w, res, first_id, n, seed, d_dE, d_bw, d_bn, g.natom_max);
+    if (g.h.triclinic) k_widom_batch<true><<<(unsigned)nb, 32 * g.wgroups, g.smem8, g.stream>>>(w, res, first_id, n, seed, d_dE, d_bw, d_bn, g.natom_max);
+    else k_widom_batch<false><<<(unsigned)nb, 32 * g.wgroups, g.smem8, g.stream>>>(w, res, first_id, n, seed, d_dE, d_bw, d_bn, g.natom_max);
     tm.stop();
     cudaError_t le = cudaGetLastError();
-    std::vector<double> bw(nb); std::vector<long long> bn(nb);
-    if (le == cudaSuccess) le = cudaMemcpyAsync(bw.data(), d_bw, sizeof(double) * nb, cudaMemcpyDeviceToHost, g.stream);
-    if (le == cudaSuccess) le = cudaMemcpyAsync(bn.data(), d_bn, sizeof(long long) * nb, cudaMemcpyDeviceToHost, g.stream);
+    std::vector<double> bw(nw); std::vector<long long> bn(nw);
+    if (le == cudaSuccess) le = cudaMemcpyAsync(bw.data(), d_bw, sizeof(double) * nw, cudaMemcpyDeviceToHost, g.stream);
+    if (le == cudaSuccess) le = cudaMemcpyAsync(bn.data(), d_bn, sizeof(long long) * nw, cudaMemcpyDeviceToHost, g.stream);
     if (le == cudaSuccess && dE_out) le = cudaMemcpyAsync(dE_out, d_dE, sizeof(double) * n, cudaMemcpyDeviceToHost, g.stream);
     if (le == cudaSuccess) le = cudaStreamSynchronize(g.stream);
     if (d_dE) cudaFree(d_dE);
     cudaFree(d_bw); cudaFree(d_bn);
     if (le != cudaSuccess) return fail(std::string("mgpu_widom_batch: ") + cudaGetErrorString(le));
     double sw = 0.0; long long ok = 0;
-    for (long long b = 0; b < nb; ++b) { sw += bw[b]; ok += bn[b]; }
+    for (long long b = 0; b < nw; ++b) { sw += bw[b]; ok += bn[b]; }
     *sum_w = sw; *n_ok = ok;
     return 0;
 }
@@ -839,6 +916,23 @@ int mgpu_timing_get(const char *kernel, double *total_ms, int64_t *launches)
     if (it == g.timing.end()) { if (total_ms) *total_ms = 0.0; if (launches) *launches = 0; return 0; }
     if (total_ms) *total_ms = it->second.ms;
     if (launches) *launches = it->second.launches;
+    return 0;
+}
+int mgpu_selftest_math(double *max_rel_rcp, double *max_err_table)
+{
+    NEED_READY();
+    double *d_out;
+    CK(cudaMalloc(&d_out, sizeof(double) * 2));
+    CK(cudaMemsetAsync(d_out, 0, sizeof(double) * 2, g.stream));
+    const double s_lo = std::ldexp(1.0, g.tab_emin) * 1.0000001, s_hi = std::ldexp(1.0, g.tab_emin + g.tab_noct) * 0.9999999;
+    k_selftest<<<g.sm_count * 4, 256, 0, g.stream>>>(s_lo, s_hi, 1 << 22, d_out);
+    CK(cudaGetLastError());
+    double out[2] = { 0.0, 0.0 };
+    CK(cudaMemcpyAsync(out, d_out, sizeof out, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    cudaFree(d_out);
+    if (max_rel_rcp) *max_rel_rcp = out[0];
+    if (max_err_table) *max_err_table = out[1];
     return 0;
 }
 int mgpu_measure_fp64_peak(double *tflops, double *seconds)

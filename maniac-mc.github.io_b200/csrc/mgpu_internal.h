@@ -2,8 +2,9 @@
 //
 // Layout in HBM (see DESIGN.md "Data layout"):
 //   * static, shared by all walkers: host-framework atoms as SoA-of-double4 {x,y,z,q} +
-//     type id, the per-type-pair LJ table, the k-vector list {kx,ky,kz} + ffW(k),
-//     S_host(k);
+//     type id, the per-type-pair LJ table (A = 4 eps sigma^12, B = 4 eps sigma^6), the
+//     piecewise-polynomial table of erfc(alpha r)/r in r^2, the k-vector list
+//     {kx,ky,kz} + ffW(k), S_host(k);
 //   * per walker: guest coordinates as SoA with the molecule index fastest
 //     (com[3][cap], offset[natom][3][cap] per guest residue type), two S(k) buffers
 //     (committed / trial, flipped on accept), running energies, counts, RNG state,
@@ -14,6 +15,24 @@
 
 #define MGPU_ERR_TOL 1.0e-10      // "error", src/parameters.f90:57
 #define MGPU_NB_MAX_MOLECULE 5000 // src/parameters.f90:10
+
+// Real-space Coulomb kernel g(s) = erfc(alpha sqrt(s)) / sqrt(s), s = r^2, tabulated as one
+// degree-6 polynomial per interval; intervals are the top MGPU_TAB_K mantissa bits of s inside
+// each binary octave, so the interval index is two integer instructions on the high word of s
+// and no sqrt / rsqrt / erfc is evaluated per pair.  A table row is 48 bytes:
+//   { c0, c1 | c2, c3 | c4, (float c5, float c6) }      (three 16-byte chunks)
+// c5, c6 only need single precision (their terms are < 2^-30 of g).  In shared memory the
+// table is replicated 8 times, replica r occupying 16-byte bank group r, and lane l reads
+// replica l & 7: each LDS.128 of a quarter-warp touches 8 distinct bank groups, i.e. the
+// gather is bank-conflict free whatever intervals the lanes need.  Error of the fit relative
+// to the pair's Coulomb scale 1/r is < 4e-15 (tests/test_host_logic.py::
+// test_coulomb_table_accuracy); pairs outside the tabulated range take the exact erfc path,
+// and g = 0 beyond alpha r > MGPU_TAB_XCUT where erfc(x)/r < 1e-24.
+#define MGPU_TAB_K 5
+#define MGPU_TAB_ROW 6            // doubles per row
+#define MGPU_TAB_REP 8            // shared-memory replicas
+#define MGPU_TAB_MAXOCT 11
+#define MGPU_TAB_XCUT 7.0
 
 struct MgpuTrial {
     int32_t active;               // 1 while a trial is pending on the walker
@@ -29,8 +48,13 @@ struct DevSys {
     double H[9], Hinv[9], lo[3], L[3], invL[3], volume;
     int32_t triclinic;
     // ewald / constants
-    double rc, alpha, eps0_inv_real, twopi, beta, overlap;
+    double rc, rc2, alpha, eps0_inv_real, twopi, beta, overlap;
     int32_t kmax[3], kmax_max, nk;
+    // Coulomb table
+    int32_t tab_ibase;            // (1023 + emin) << MGPU_TAB_K
+    int32_t tab_nint;             // number of intervals (octaves << MGPU_TAB_K)
+    const double *ctab;           // [tab_nint][MGPU_TAB_ROW]
+    double s_zero;                // g == 0 for s >= s_zero (alpha r > MGPU_TAB_XCUT)
     // residues
     int32_t nres, ntypes, nactive;
     int32_t natom[MGPU_MAX_RES], active[MGPU_MAX_RES], cap[MGPU_MAX_RES];
@@ -46,8 +70,13 @@ struct DevSys {
     // MC inputs
     double p_trans, p_rot, p_swap, p_insdel, p_widom, tstep, rstep;
     // static arrays
-    const double4 *host_xyzq; const int32_t *host_type; int32_t n_host;
-    const double *eps, *sig;                  // [ntypes*ntypes]
+    const double4 *host_xyzq; const int32_t *host_type; int32_t n_host;   // q stored as 0 when |q| < 1e-10
+    const double *host_qraw;                  // unthresholded charges (S_host build)
+    const double2 *host_xy, *host_zq;         // the same atoms as two coalesced 16-byte streams {x,y}, {z,q}
+    // guest atoms of each residue type by what they feel from the framework: 0 nothing, 1 LJ, 2 Coulomb, 3 both
+    int32_t hl_n[MGPU_MAX_RES][4];
+    int8_t  hl_list[MGPU_MAX_RES][4][MGPU_MAX_SITES];
+    const double *ljA, *ljB;                  // [ntypes*ntypes] 4 eps sigma^12, 4 eps sigma^6
     const int32_t *kx, *ky, *kz; const double *ffW;
     const double *S_host;                     // [2][nk] re, im
     // per-walker arrays

@@ -1,19 +1,28 @@
 // mgpu_kernels.cuh -- sm_100a kernels of the MANIAC per-trial-move energy path.
 //
-// K1  pair_sums_cta     fused real-space LJ + erfc-Coulomb of a trial molecule (old and
+// K1  pair_sums         fused real-space LJ + erfc-Coulomb of a trial molecule (old and
 //                       new geometry in one pass over the targets) vs the host framework
 //                       and the walker's guests            (pairwise_energy_utils.f90:21-179,
 //                                                           geometry_utils.f90:210-284)
-// K2  kspace_cta        1-D phase tables, dS(k), S_trial = S + dS, sum_k ffW |S_trial|^2
+// K2  kspace            1-D phase tables, dS(k), S_trial = S + dS, sum_k ffW |S_trial|^2
 //                                                          (ewald_phase.f90:205-312,
 //                                                           ewald_energy.f90:64-164)
-// K3  k_widom_batch     thread-per-insertion real space + warp-per-insertion k space
+// K3  k_widom_batch     one warp per test insertion, K1 + K2 read-only
 // K4  k_total_energy    full recompute (energy_utils.f90:22-134, ewald_energy.f90:20-58)
 //     k_sweep           device-resident move drivers + Metropolis (translation.f90,
 //                       rotation.f90, creation.f90, deletion.f90, widom.f90,
-//                       monte_carlo.f90:50-99), one CTA per walker
+//                       monte_carlo.f90:50-99), ONE WARP PER WALKER
+//     k_trial           host-driven trials (compute_old/new_energy of monte_carlo_utils.f90),
+//                       one warp per task for large batches, one CTA per task otherwise
+//
+// Every energy routine is written once for a cooperating "group" of NT threads
+// (NT = 32: a warp, synchronised with __syncwarp; NT = MGPU_BLOCK: a CTA, __syncthreads).
 //
 // All arithmetic is IEEE binary64.  No tensor cores: nothing here is a dense contraction.
+// The per-pair erfc(alpha r)/r comes from a piecewise degree-6 polynomial in r^2 staged in
+// shared memory, replicated per bank group so the gather is conflict free (error < 4e-15 of
+// 1/r, see mgpu_internal.h); 1/r^2 for the LJ term comes from MUFU.RCP64H + two Newton steps.
+// Out-of-range pairs use the exact forms.
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -21,8 +30,10 @@
 
 __constant__ DevSys c_sys;
 
-#define MGPU_BLOCK 256
+#define MGPU_BLOCK 256                    // CTA-per-task kernels (NT = MGPU_BLOCK)
 #define MGPU_WARPS (MGPU_BLOCK / 32)
+#define MGPU_WBLOCK 512                   // warp-per-task kernels (NT = 32): one CTA per SM
+#define MGPU_WGROUPS (MGPU_WBLOCK / 32)
 
 // ------------------------------------------------------------------------------------
 // small helpers
@@ -37,28 +48,43 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-// Block-wide sum of NV values per thread; result valid in every thread's out[].
-// red: shared scratch of NV*MGPU_WARPS doubles.
-template <int NV>
-__device__ __forceinline__ void block_sum(double (&v)[NV], double *red)
-{
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+// Thread-group abstraction: NT = 32 (one warp) or MGPU_BLOCK (the whole CTA).
+template <int NT> struct Grp;
+template <> struct Grp<32> {
+    static __device__ __forceinline__ int tid() { return threadIdx.x & 31; }
+    static __device__ __forceinline__ int id() { return threadIdx.x >> 5; }          // group index inside the CTA
+    static __device__ __forceinline__ void sync() { __syncwarp(); }
+    // sum of NV values over the group; result valid in every thread
+    template <int NV> static __device__ __forceinline__ void sum(double (&v)[NV], double *)
+    {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
-    __syncthreads();                       // protect red from a previous use
-    if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) red[i * MGPU_WARPS + wid] = v[i];
+        for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
     }
-    __syncthreads();
+};
+template <> struct Grp<MGPU_BLOCK> {
+    static __device__ __forceinline__ int tid() { return threadIdx.x; }
+    static __device__ __forceinline__ int id() { return 0; }
+    static __device__ __forceinline__ void sync() { __syncthreads(); }
+    template <int NV> static __device__ __forceinline__ void sum(double (&v)[NV], double *red)
+    {
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        double s = 0.0;
+        for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+        __syncthreads();                       // protect red from a previous use
+        if (lane == 0) {
 #pragma unroll
-        for (int w = 0; w < MGPU_WARPS; ++w) s += red[i * MGPU_WARPS + w];   // fixed order
-        v[i] = s;
+            for (int i = 0; i < NV; ++i) red[i * MGPU_WARPS + wid] = v[i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < MGPU_WARPS; ++w) s += red[i * MGPU_WARPS + w];   // fixed order
+            v[i] = s;
+        }
     }
-}
+};
 
 // gfortran MODULO(a,p) for reals (fmod + sign fix)
 __device__ __forceinline__ double f_modulo(double a, double p)
@@ -94,15 +120,19 @@ __device__ __forceinline__ void apply_PBC(double pos[3])
 // ------------------------------------------------------------------------------------
 // minimum image (geometry_utils.f90:210-284) -> squared distance
 // ------------------------------------------------------------------------------------
+#define MGPU_RINT_MAGIC 6755399441055744.0     // 1.5 * 2^52: (x + M) - M = rint(x) for |x| < 2^51
 template <bool TRI>
 __device__ __forceinline__ double min_image_r2(double dx, double dy, double dz)
 {
     if (!TRI) {
         // delta_d = modulo(delta_d + L/2, L) - L/2 restated as delta - L*rint(delta/L): the same
         // image except on the exact tie |delta| = L/2, where both images have the same length.
-        dx = fma(-c_sys.L[0], rint(dx * c_sys.invL[0]), dx);
-        dy = fma(-c_sys.L[1], rint(dy * c_sys.invL[1]), dy);
-        dz = fma(-c_sys.L[2], rint(dz * c_sys.invL[2]), dz);
+        const double nx = fma(dx, c_sys.invL[0], MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC;
+        const double ny = fma(dy, c_sys.invL[1], MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC;
+        const double nz = fma(dz, c_sys.invL[2], MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC;
+        dx = fma(-c_sys.L[0], nx, dx);
+        dy = fma(-c_sys.L[1], ny, dy);
+        dz = fma(-c_sys.L[2], nz, dz);
         return fma(dx, dx, fma(dy, dy, dz * dz));
     } else {
         // 27-image search with the COLUMNS of matrix as cell vectors, exactly like the reference
@@ -123,124 +153,348 @@ __device__ __forceinline__ double min_image_r2(double dx, double dy, double dz)
     }
 }
 
-// One atom pair: LJ (pairwise_lj_energy, pairwise_energy_utils.f90:95-138) and erfc
-// Coulomb (pairwise_coulomb_energy :143-179, NO cutoff on the Coulomb term).
-// eps4 = 4*epsilon; qq = q_i*q_j or 0 when either |q| < 1e-10.
 // Work counters for the roofline accounting: pairs evaluated, LJ terms inside the
 // cutoff, erfc-Coulomb terms.  Integer adds on the otherwise idle ALU pipe.
 struct PairCount { unsigned geom, lj, coul; };
 
-__device__ __forceinline__ void pair_terms(double r2, double eps4, double sig, double qq, bool charged,
-                                           double &e_lj, double &e_coul, PairCount &pc)
+// 1/s: MUFU.RCP64H seed + two Newton steps (s is a normal positive double here)
+__device__ __forceinline__ double rcp_fast(double s)
 {
-    pc.geom += 1u;
-    const double rinv = rsqrt(r2);
-    const double r = r2 * rinv;
-    if (r < MGPU_ERR_TOL || !(r2 > 0.0)) {          // overlap sentinel (r = 0 gives rinv = inf)
-        if (0.0 < c_sys.rc) e_lj += c_sys.overlap;
-        if (charged) e_coul += c_sys.overlap;
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(s));
+    double e = fma(-s, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-s, y, 1.0);
+    y = fma(y, fma(e, e, e), y);          // third-order step: error e^3
+    return y;
+}
+
+// The reference's pair formulas evaluated literally (pairwise_lj_energy :95-138,
+// pairwise_coulomb_energy :143-179); used off the hot path (host-host, intramolecular,
+// pairs outside the table range).  A = 4 eps sigma^12, B = 4 eps sigma^6.
+__device__ __noinline__ void pair_exact(double s, double A, double B, double qq, bool doC, double &e_lj, double &e_c)
+{
+    const double r = sqrt(s);
+    if (r < MGPU_ERR_TOL) {
+        if (r < c_sys.rc) e_lj += c_sys.overlap;
+        if (doC) e_c += c_sys.overlap;
         return;
     }
     if (r < c_sys.rc) {
-        const double s = sig * rinv;
-        const double s2 = s * s;
-        const double s6 = s2 * s2 * s2;
-        e_lj += eps4 * (s6 * s6 - s6);
-        pc.lj += (eps4 != 0.0);
+        const double y = 1.0 / s, y3 = y * y * y;
+        e_lj += (A * y3 - B) * y3;
     }
-    if (charged) { e_coul += qq * erfc(c_sys.alpha * r) * rinv; pc.coul += 1u; }
+    if (doC) e_c += qq * erfc(c_sys.alpha * r) / r;
 }
-__device__ __forceinline__ void flush_pair_count(const PairCount &pc)
+
+// One atom pair on the hot path.  tab = this lane's replica of the Coulomb table in shared
+// memory (double2 units, see mgpu_internal.h).  qq = q_i q_j with either factor already zeroed
+// when |q| < 1e-10 (:157).  AB = {4 eps sigma^12, 4 eps sigma^6}.
+__device__ __forceinline__ void pair_terms(double s, double2 AB, double qq, const double2 *__restrict__ tab,
+                                           double &e_lj, double &e_c, PairCount &pc)
 {
-    const unsigned g = __reduce_add_sync(0xffffffffu, pc.geom), l = __reduce_add_sync(0xffffffffu, pc.lj),
-                   c = __reduce_add_sync(0xffffffffu, pc.coul);
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(c_sys.pair_count + 0, (unsigned long long)g);
-        atomicAdd(c_sys.pair_count + 1, (unsigned long long)l);
-        atomicAdd(c_sys.pair_count + 2, (unsigned long long)c);
+    pc.geom += 1u;
+    const bool doL = (AB.x != 0.0) || (AB.y != 0.0), doC = (qq != 0.0);
+    const int hi = __double2hiint(s);
+    const int idx = (hi >> (20 - MGPU_TAB_K)) - c_sys.tab_ibase;
+    if ((unsigned)idx >= (unsigned)c_sys.tab_nint) {           // r < table start (incl. overlap) or beyond its end: rare
+        if (s >= c_sys.s_zero && s >= c_sys.rc2) { pc.coul += doC; return; }    // erfc(alpha r)/r < 1e-24: below the sum's rounding
+        pair_exact(s, AB.x, AB.y, qq, doC, e_lj, e_c);
+        pc.lj += (doL && s < c_sys.rc2); pc.coul += doC;
+        return;
+    }
+    if (doL) {
+        const double y = rcp_fast(s), y3 = y * y * y;
+        const double e = (AB.x * y3 - AB.y) * y3;
+        const bool in = s < c_sys.rc2;
+        e_lj += in ? e : 0.0;
+        pc.lj += in;
+    }
+    if (doC) {
+        const int chi = (hi & ~((1 << (20 - MGPU_TAB_K)) - 1)) | (1 << (19 - MGPU_TAB_K));
+        const double u = s - __hiloint2double(chi, 0);          // exact: same binade
+        const double2 *t = tab + idx * (3 * MGPU_TAB_REP);
+        const double2 c01 = t[0], c23 = t[MGPU_TAB_REP], c45 = t[2 * MGPU_TAB_REP];
+        const float uf = (float)u;
+        const float pf = fmaf(__int_as_float(__double2hiint(c45.y)), uf, __int_as_float(__double2loint(c45.y)));
+        double p = (double)pf;
+        p = fma(p, u, c45.x);
+        p = fma(p, u, c23.y);
+        p = fma(p, u, c23.x);
+        p = fma(p, u, c01.y);
+        p = fma(p, u, c01.x);
+        e_c = fma(qq, p, e_c);
+        pc.coul += 1u;
     }
 }
 
 // ------------------------------------------------------------------------------------
-// Probe: the trial molecule, staged in shared memory
+// Probe: the trial molecule, staged in shared memory (one per group)
 // ------------------------------------------------------------------------------------
 struct Probe {
     int32_t kind, res, mol, na;
     int32_t has_old, has_new;
     int32_t excl_res, excl_mol;              // target slot to skip (the molecule itself)
     int32_t order_res, order_mol;            // >= 0: only targets with (res,mol) > this (ordering check)
-    double q[MGPU_MAX_SITES];
+    int32_t pad[2];
+    double q[MGPU_MAX_SITES];                // 0 when |q| < 1e-10
     int32_t type[MGPU_MAX_SITES];
     double po[MGPU_MAX_SITES][3];            // old atom positions (com + offset)
     double pn[MGPU_MAX_SITES][3];            // new atom positions
 };
 
-// Accumulate the probe's pair energies against one target atom.
-template <bool TRI>
-__device__ __forceinline__ void probe_vs_atom(const Probe &P, const double *s_eps4, const double *s_sig,
-                                              double tx, double ty, double tz, double tq, int ttype,
-                                              double (&acc)[4], PairCount &pc)
+// Proposal / decision record of the device-resident drivers (one per group)
+struct SweepShared {
+    int32_t valid, move, kind, res, mol, accept, traced_accept, pad;
+    double com[3];
+    double off[MGPU_MAX_SITES][3];
+    double prob;
+    double e_old[6], e_new[6];
+};
+
+// Per-walker accumulators kept in shared memory during a sweep launch
+struct WalkerLocal {
+    unsigned long long rng[4];
+    long long cnt[12];
+    double avgN[MGPU_MAX_RES], avgN2[MGPU_MAX_RES];
+    double avgE;
+    long long n_samples;
+    unsigned long long pc[3];
+};
+
+// Fixed part of a group's workspace; the two phase tables follow it.
+struct GroupWS {
+    Probe probe;
+    double red[4 * MGPU_WARPS];
+    int32_t count[MGPU_MAX_RES];
+    SweepShared sh;
+    WalkerLocal loc;
+};
+
+// Shared-memory image of a CTA: replicated Coulomb table, LJ {A,B} pairs, then `groups` workspaces.
+struct Smem {
+    const double2 *ctab;        // this lane's replica: row i chunk c at ctab[(i*3 + c) * MGPU_TAB_REP]
+    const double2 *ljAB;        // [ntypes^2]
+    GroupWS *ws;
+    double2 *tab_old, *tab_new;
+};
+__host__ __device__ inline size_t smem_group_bytes(int kmax_max, int natom_max)
 {
-    const bool tcharged = fabs(tq) >= MGPU_ERR_TOL;
-    const int nt = c_sys.ntypes;
-    for (int a = 0; a < P.na; ++a) {
-        const double qa = P.q[a];
-        const bool charged = tcharged && (fabs(qa) >= MGPU_ERR_TOL);
-        const double qq = qa * tq;
-        const int ti = P.type[a] * nt + ttype;
-        const double eps4 = s_eps4[ti], sig = s_sig[ti];
-        if (eps4 == 0.0 && !charged) continue;
-        if (P.has_old) {
-            double r2 = min_image_r2<TRI>(tx - P.po[a][0], ty - P.po[a][1], tz - P.po[a][2]);
-            pair_terms(r2, eps4, sig, qq, charged, acc[0], acc[1], pc);
+    size_t b = (sizeof(GroupWS) + 15) & ~size_t(15);
+    b += sizeof(double2) * 2 * (size_t)natom_max * 3 * (kmax_max + 1);
+    return b;
+}
+__host__ __device__ inline size_t smem_common_bytes(int ntypes, int tab_nint)
+{
+    return sizeof(double2) * ((size_t)tab_nint * 3 * MGPU_TAB_REP + (size_t)ntypes * ntypes);
+}
+__host__ __device__ inline size_t smem_bytes(int ntypes, int tab_nint, int kmax_max, int natom_max, int groups)
+{
+    return smem_common_bytes(ntypes, tab_nint) + groups * smem_group_bytes(kmax_max, natom_max) + 16;
+}
+// Carve the CTA's dynamic shared memory and (cooperatively, whole CTA) load the common part.
+// Every thread of the CTA must call this; it ends with __syncthreads().
+__device__ __forceinline__ Smem smem_setup(unsigned char *base, int natom_max, int group)
+{
+    Smem s;
+    double2 *d = reinterpret_cast<double2 *>(base);
+    const int nt2 = c_sys.ntypes * c_sys.ntypes;
+    const int nchunk = c_sys.tab_nint * 3;
+    const double2 *src = reinterpret_cast<const double2 *>(c_sys.ctab);
+    for (int i = threadIdx.x; i < nchunk * MGPU_TAB_REP; i += blockDim.x) d[i] = src[i / MGPU_TAB_REP];
+    double2 *lj = d + (size_t)nchunk * MGPU_TAB_REP;
+    for (int i = threadIdx.x; i < nt2; i += blockDim.x) lj[i] = make_double2(c_sys.ljA[i], c_sys.ljB[i]);
+    s.ctab = d + (threadIdx.x & (MGPU_TAB_REP - 1));
+    s.ljAB = lj;
+    unsigned char *g = base + smem_common_bytes(c_sys.ntypes, c_sys.tab_nint) + (size_t)group * smem_group_bytes(c_sys.kmax_max, natom_max);
+    s.ws = reinterpret_cast<GroupWS *>(g);
+    s.tab_old = reinterpret_cast<double2 *>(g + ((sizeof(GroupWS) + 15) & ~size_t(15)));
+    s.tab_new = s.tab_old + (size_t)natom_max * 3 * (c_sys.kmax_max + 1);
+    __syncthreads();
+    return s;
+}
+
+// ---- host-framework passes --------------------------------------------------------------
+// The probe's atoms are sorted once per trial into lists by what they can feel from the
+// framework: LJ only (MODE 1), Coulomb only (MODE 2), both (MODE 3), nothing (MODE 0, geometry
+// only: the reference's overlap sentinel does not depend on eps or q).  Each list is swept in
+// chunks of N <= 4 atoms held in registers against U framework atoms per thread and
+// iteration; the body is branch free (N*U independent pair chains for the scheduler), pairs
+// that fall outside the Coulomb table are flagged and redone exactly afterwards.
+template <bool TRI, int MODE, int N, int U>
+struct HostPass {
+    double px[N], py[N], pz[N], q[N];
+    int trow[N];
+
+    __device__ __forceinline__ void load(const Probe &P, const double (*pos)[3], const int8_t *list)
+    {
+        const int nt = c_sys.ntypes;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const int a = list[i];
+            px[i] = pos[a][0]; py[i] = pos[a][1]; pz[i] = pos[a][2];
+            q[i] = P.q[a]; trow[i] = P.type[a] * nt;
         }
-        if (P.has_new) {
-            double r2 = min_image_r2<TRI>(tx - P.pn[a][0], ty - P.pn[a][1], tz - P.pn[a][2]);
-            pair_terms(r2, eps4, sig, qq, charged, acc[2], acc[3], pc);
+    }
+
+    template <int UU>
+    __device__ __forceinline__ void block(const Smem &S, int j, int stride, double &e_lj, double &e_c, PairCount &pc) const
+    {
+        const double2 *__restrict__ hxy = c_sys.host_xy;
+        const double2 *__restrict__ hzq = c_sys.host_zq;
+        const int32_t *__restrict__ ht = c_sys.host_type;
+        double2 txy[UU], tzq[UU]; int tt[UU];
+#pragma unroll
+        for (int u = 0; u < UU; ++u) {
+            txy[u] = __ldg(hxy + j + u * stride); tzq[u] = __ldg(hzq + j + u * stride);
+            tt[u] = (MODE & 1) ? __ldg(ht + j + u * stride) : 0;
         }
+        unsigned bad = 0u;
+        double sv[UU][N];
+#pragma unroll
+        for (int u = 0; u < UU; ++u) {
+            if (MODE & 2) pc.coul += (tzq[u].y != 0.0) ? N : 0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const double s = min_image_r2<TRI>(txy[u].x - px[i], txy[u].y - py[i], tzq[u].x - pz[i]);
+                sv[u][i] = s;
+                const int hi = __double2hiint(s);
+                const int idx = (hi >> (20 - MGPU_TAB_K)) - c_sys.tab_ibase;
+                const bool out = (unsigned)idx >= (unsigned)c_sys.tab_nint;
+                if (out) bad |= 1u << (u * N + i);
+                if (MODE & 1) {
+                    const double2 AB = S.ljAB[trow[i] + tt[u]];
+                    const double y = rcp_fast(out ? 1.0 : s), y3 = y * y * y;
+                    const double e = (AB.x * y3 - AB.y) * y3;
+                    const bool in = (s < c_sys.rc2) && !out;
+                    e_lj += in ? e : 0.0;
+                    pc.lj += (in && (AB.x != 0.0 || AB.y != 0.0));
+                }
+                if (MODE & 2) {
+                    const int chi = (hi & ~((1 << (20 - MGPU_TAB_K)) - 1)) | (1 << (19 - MGPU_TAB_K));
+                    const double uu = s - __hiloint2double(chi, 0);         // exact: same binade
+                    const double2 *t = S.ctab + (out ? 0 : idx) * (3 * MGPU_TAB_REP);
+                    const double2 c01 = t[0], c23 = t[MGPU_TAB_REP], c45 = t[2 * MGPU_TAB_REP];
+                    const float uf = (float)uu;
+                    const float pf = fmaf(__int_as_float(__double2hiint(c45.y)), uf, __int_as_float(__double2loint(c45.y)));
+                    double p = (double)pf;
+                    p = fma(p, uu, c45.x);
+                    p = fma(p, uu, c23.y);
+                    p = fma(p, uu, c23.x);
+                    p = fma(p, uu, c01.y);
+                    p = fma(p, uu, c01.x);
+                    e_c = fma(out ? 0.0 : q[i] * tzq[u].y, p, e_c);
+                }
+            }
+        }
+        pc.geom += UU * N;
+        if (bad) {                                                  // rare: r < 1 A (incl. overlap) or beyond the table
+#pragma unroll
+            for (int u = 0; u < UU; ++u)
+#pragma unroll
+                for (int i = 0; i < N; ++i)
+                    if (bad & (1u << (u * N + i))) {
+                        const double s = sv[u][i];
+                        if (s >= c_sys.s_zero && s >= c_sys.rc2) continue;   // erfc(alpha r)/r < 1e-24: below the sum's rounding
+                        double2 AB = make_double2(0.0, 0.0);
+                        if (MODE & 1) AB = S.ljAB[trow[i] + tt[u]];
+                        const double qq = (MODE & 2) ? q[i] * tzq[u].y : 0.0;
+                        pair_exact(s, AB.x, AB.y, qq, qq != 0.0, e_lj, e_c);
+                        if (MODE & 1) pc.lj += ((AB.x != 0.0 || AB.y != 0.0) && s < c_sys.rc2);
+                    }
+        }
+    }
+
+    __device__ __forceinline__ void run(const Smem &S, int t0, int stride, double &e_lj, double &e_c, PairCount &pc) const
+    {
+        const int n = c_sys.n_host;
+        int j = t0;
+        for (; j + (U - 1) * stride < n; j += U * stride) block<U>(S, j, stride, e_lj, e_c, pc);
+        for (; j < n; j += stride) block<1>(S, j, stride, e_lj, e_c, pc);
+    }
+};
+
+template <bool TRI, int MODE>
+__device__ __forceinline__ void host_list(const Smem &S, const Probe &P, const double (*pos)[3], const int8_t *list, int n,
+                                          int t0, int stride, double &e_lj, double &e_c, PairCount &pc)
+{
+    for (int base = 0; base < n; base += 4) {
+        const int m = min(4, n - base);
+        if (m == 4) { HostPass<TRI, MODE, 4, 1> hp; hp.load(P, pos, list + base); hp.run(S, t0, stride, e_lj, e_c, pc); }
+        else if (m == 3) { HostPass<TRI, MODE, 3, 1> hp; hp.load(P, pos, list + base); hp.run(S, t0, stride, e_lj, e_c, pc); }
+        else if (m == 2) { HostPass<TRI, MODE, 2, 2> hp; hp.load(P, pos, list + base); hp.run(S, t0, stride, e_lj, e_c, pc); }
+        else { HostPass<TRI, MODE, 1, 4> hp; hp.load(P, pos, list + base); hp.run(S, t0, stride, e_lj, e_c, pc); }
     }
 }
 
-// K1: block-cooperative pair sums of the probe against host atoms + the walker's guests.
-// Returns {lj_old, coul_old(e^2/A), lj_new, coul_new(e^2/A)} in every thread.
+// One target atom of a guest molecule against every probe atom (tq already zeroed if tiny).
 template <bool TRI>
-__device__ void pair_sums_cta(const Probe &P, int w, const int32_t *s_count, const double *s_eps4,
-                              const double *s_sig, double *red, double (&out)[4])
+__device__ __forceinline__ void probe_vs_guest_atom(const Probe &P, const double (*pos)[3], const Smem &S,
+                                                    double tx, double ty, double tz, double tq, int ttype,
+                                                    double &e_lj, double &e_c, PairCount &pc)
 {
-    double acc[4] = { 0.0, 0.0, 0.0, 0.0 };
-    PairCount pc = { 0u, 0u, 0u };
-    // host framework: one lane per host atom, coalesced 32-byte loads
-    if (P.order_res < 0 || true) {
-        const double4 *__restrict__ hx = c_sys.host_xyzq;
-        const int32_t *__restrict__ ht = c_sys.host_type;
-        // host residues have lower or higher res id than the probe: the ordering check of
-        // pairwise_energy_for_molecule (:60-62) only matters in the full-energy pass, where
-        // host atoms are handled by host_order_ok below.
-        for (int j = threadIdx.x; j < c_sys.n_host; j += blockDim.x) {
-            const double4 t = hx[j];
-            probe_vs_atom<TRI>(P, s_eps4, s_sig, t.x, t.y, t.z, t.w, ht[j], acc, pc);
-        }
+    const int nt = c_sys.ntypes;
+    const int na = P.na;
+    for (int a = 0; a < na; ++a) {
+        const double2 AB = S.ljAB[P.type[a] * nt + ttype];
+        pair_terms(min_image_r2<TRI>(tx - pos[a][0], ty - pos[a][1], tz - pos[a][2]), AB, P.q[a] * tq, S.ctab, e_lj, e_c, pc);
     }
-    // guests of this walker: one lane per molecule
+}
+
+// The two target loops for ONE geometry of the probe: host framework (passes above) and the
+// walker's guests (one thread per molecule).  Threads t0, t0 + stride, ... of the group take part.
+template <bool TRI>
+__device__ __forceinline__ void pair_loops(const Probe &P, const double (*pos)[3], const Smem &S, int w, int t0, int stride,
+                                           double &e_lj, double &e_c, PairCount &pc)
+{
+    if (c_sys.n_host > 0) {
+        const int r = P.res;
+        host_list<TRI, 1>(S, P, pos, c_sys.hl_list[r][1], c_sys.hl_n[r][1], t0, stride, e_lj, e_c, pc);
+        host_list<TRI, 2>(S, P, pos, c_sys.hl_list[r][2], c_sys.hl_n[r][2], t0, stride, e_lj, e_c, pc);
+        host_list<TRI, 3>(S, P, pos, c_sys.hl_list[r][3], c_sys.hl_n[r][3], t0, stride, e_lj, e_c, pc);
+        host_list<TRI, 0>(S, P, pos, c_sys.hl_list[r][0], c_sys.hl_n[r][0], t0, stride, e_lj, e_c, pc);
+    }
     const double *wc = c_sys.coords + (int64_t)w * c_sys.coord_stride;
     for (int g = 0; g < c_sys.nres; ++g) {
         if (!c_sys.active[g]) continue;
-        const int cap = c_sys.cap[g], na_g = c_sys.natom[g], n = s_count[g];
+        const int cap = c_sys.cap[g], na_g = c_sys.natom[g], n = S.ws->count[g];
         const double *com = wc + c_sys.goff[g];
         const double *off = com + 3 * (int64_t)cap;
-        for (int m = threadIdx.x; m < n; m += blockDim.x) {
+        for (int m = t0; m < n; m += stride) {
             if (g == P.excl_res && m == P.excl_mol) continue;
             if (P.order_res >= 0 && (g < P.order_res || (g == P.order_res && m <= P.order_mol))) continue;
             const double cx = com[m], cy = com[cap + m], cz = com[2 * cap + m];
             for (int b = 0; b < na_g; ++b) {
                 const double *ob = off + (int64_t)b * 3 * cap;
                 const double tx = cx + ob[m], ty = cy + ob[cap + m], tz = cz + ob[2 * cap + m];
-                probe_vs_atom<TRI>(P, s_eps4, s_sig, tx, ty, tz, c_sys.charge[g][b], c_sys.type[g][b], acc, pc);
+                double tq = c_sys.charge[g][b];
+                if (fabs(tq) < MGPU_ERR_TOL) tq = 0.0;
+                probe_vs_guest_atom<TRI>(P, pos, S, tx, ty, tz, tq, c_sys.type[g][b], e_lj, e_c, pc);
             }
         }
     }
-    flush_pair_count(pc);
-    block_sum<4>(acc, red);
+}
+
+// K1: group-cooperative pair sums of the probe against host atoms + the walker's guests.
+// A move needs the old AND the new geometry: the group splits in two halves, one per
+// geometry, so every thread works on a single geometry.  Creation / deletion / Widom use
+// the whole group on the one geometry there is.
+// Returns {lj_old, coul_old(e^2/A), lj_new, coul_new(e^2/A)} in every thread of the group.
+template <bool TRI, int NT>
+__device__ __noinline__ void pair_sums(const Smem &S, int w, double (&out)[4], PairCount &pc)
+{
+    const Probe &P = S.ws->probe;
+    const int gt = Grp<NT>::tid();
+    const bool both = P.has_old && P.has_new;
+    const bool new_set = both ? (gt >= NT / 2) : (P.has_new != 0);
+    const int stride = both ? NT / 2 : NT;
+    const int t0 = both ? (gt & (NT / 2 - 1)) : gt;
+    double e_lj = 0.0, e_c = 0.0;
+    pair_loops<TRI>(P, new_set ? P.pn : P.po, S, w, t0, stride, e_lj, e_c, pc);
+    double acc[4];
+    acc[0] = new_set ? 0.0 : e_lj; acc[1] = new_set ? 0.0 : e_c;
+    acc[2] = new_set ? e_lj : 0.0; acc[3] = new_set ? e_c : 0.0;
+    Grp<NT>::template sum<4>(acc, S.ws->red);
 #pragma unroll
     for (int i = 0; i < 4; ++i) out[i] = acc[i];
 }
@@ -268,22 +522,31 @@ __device__ double intra_energy(int res, const double (*pos)[3])
 // K2: reciprocal space
 // ------------------------------------------------------------------------------------
 // Fill the 1-D phase tables e^{i k theta_d}, k = 0..kmax_d, for n atoms at positions pos:
-// compute_atom_phase (ewald_phase.f90:255-280) + compute_phase_factor (:286-312).
-// tab layout: [atom][dim][k] (stride KW = kmax_max+1), as double2 {cos, sin}.
+// compute_atom_phase (ewald_phase.f90:255-280) + compute_phase_factor (:286-312).  One
+// sincos per (atom, dim); higher k by repeated complex multiplication (the reference calls
+// cos/sin per k; the two agree to ~k ulp).  tab layout: [atom][dim][k], stride KW = kmax_max+1.
 __device__ __forceinline__ void fill_phase_tables(double2 *tab, const double (*pos)[3], int n, int tid0, int nthreads)
 {
     const int KW = c_sys.kmax_max + 1;
-    const int total = n * 3 * KW;
-    for (int e = tid0; e < total; e += nthreads) {
-        const int k = e % KW, d = (e / KW) % 3, a = e / (3 * KW);
-        if (k > c_sys.kmax[d]) continue;
+    for (int e = tid0; e < n * 3; e += nthreads) {
+        const int d = e % 3, a = e / 3;
         double ph = 0.0;
 #pragma unroll
         for (int j = 0; j < 3; ++j) ph = __dadd_rn(ph, __dmul_rn(c_sys.Hinv[j * 3 + d], pos[a][j]));
         ph = c_sys.twopi * ph;
         double sn, cs;
-        sincos((double)k * ph, &sn, &cs);
-        tab[e] = make_double2(cs, sn);
+        sincos(ph, &sn, &cs);
+        double2 *t = tab + (int64_t)e * KW;
+        double cr = 1.0, ci = 0.0;
+        t[0] = make_double2(1.0, 0.0);
+        const int km = c_sys.kmax[d];
+        for (int k = 1; k <= km; ++k) {
+            const double nr = cr * cs - ci * sn, ni = cr * sn + ci * cs;
+            cr = nr; ci = ni;
+            // re-anchor every 8 steps so the recurrence error stays ~1e-16 for large kmax
+            if ((k & 7) == 0) sincos((double)k * ph, &ci, &cr);
+            t[k] = make_double2(cr, ci);
+        }
     }
 }
 
@@ -301,88 +564,50 @@ __device__ __forceinline__ cplx phase_product(const double2 *tab, int a, int kx,
 }
 
 // S_trial(k) = S(k) + dS(k) and E = sum_k ffW |S_trial|^2 * EPS0_INV_real * TWOPI / V.
-// tab_old / tab_new: phase tables of the probe's old / new geometry (shared memory).
 // S_out may be NULL (Widom: nothing is stored).
-__device__ double kspace_cta(const Probe &P, const double2 *tab_old, const double2 *tab_new,
-                             const double *__restrict__ S_in, double *__restrict__ S_out, double *red)
+template <int NT>
+__device__ double kspace(const Smem &S, const double *S_in, double *S_out)
 {
+    const Probe &P = S.ws->probe;
     const int nk = c_sys.nk;
     double part[1] = { 0.0 };
-    for (int i = threadIdx.x; i < nk; i += blockDim.x) {
+    const int kind = P.kind, na = P.na;
+    for (int i = Grp<NT>::tid(); i < nk; i += NT) {
         const int kx = c_sys.kx[i], ky = c_sys.ky[i], kz = c_sys.kz[i];
         double sr = 0.0, si = 0.0;
-        for (int a = 0; a < P.na; ++a) {
-            const double q = P.q[a];
-            cplx pn = { 0.0, 0.0 }, po = { 0.0, 0.0 };
-            if (P.has_new) pn = phase_product(tab_new, a, kx, ky, kz);
-            if (P.has_old) po = phase_product(tab_old, a, kx, ky, kz);
-            if (P.kind == MGPU_KIND_CREATE) { sr += q * pn.re; si += q * pn.im; }
-            else if (P.kind == MGPU_KIND_DELETE) { sr += q * po.re; si += q * po.im; }
-            else { sr += q * (pn.re - po.re); si += q * (pn.im - po.im); }
+        for (int a = 0; a < na; ++a) {
+            const double q = c_sys.charge[P.res][a];
+            if (kind != MGPU_KIND_DELETE) { const cplx pn = phase_product(S.tab_new, a, kx, ky, kz); sr += q * pn.re; si += q * pn.im; }
+            if (kind != MGPU_KIND_CREATE) { const cplx po = phase_product(S.tab_old, a, kx, ky, kz); sr -= q * po.re; si -= q * po.im; }
         }
-        double re = S_in[i], im = S_in[nk + i];
-        if (P.kind == MGPU_KIND_DELETE) { re -= sr; im -= si; } else { re += sr; im += si; }
+        const double re = S_in[i] + sr, im = S_in[nk + i] + si;
         if (S_out) { S_out[i] = re; S_out[nk + i] = im; }
         part[0] += c_sys.ffW[i] * (re * re + im * im);
     }
-    block_sum<1>(part, red);
+    Grp<NT>::template sum<1>(part, S.ws->red);
     return part[0] * c_sys.eps0_inv_real * c_sys.twopi / c_sys.volume;
 }
 
 // reciprocal_ewald_energy (ewald_energy.f90:139-164) of a stored S(k)
-__device__ double recip_energy_cta(const double *__restrict__ S, double *red)
+template <int NT>
+__device__ double recip_energy(const double *Sk, double *red)
 {
     const int nk = c_sys.nk;
     double part[1] = { 0.0 };
-    for (int i = threadIdx.x; i < nk; i += blockDim.x) {
-        const double re = S[i], im = S[nk + i];
+    for (int i = Grp<NT>::tid(); i < nk; i += NT) {
+        const double re = Sk[i], im = Sk[nk + i];
         part[0] += c_sys.ffW[i] * (re * re + im * im);
     }
-    block_sum<1>(part, red);
+    Grp<NT>::template sum<1>(part, red);
     return part[0] * c_sys.eps0_inv_real * c_sys.twopi / c_sys.volume;
 }
 
 // ------------------------------------------------------------------------------------
-// shared-memory carve-up used by the trial / sweep / total kernels
+// trial evaluation
 // ------------------------------------------------------------------------------------
-struct SmemLayout {
-    Probe   *probe;
-    double  *red;        // 4*MGPU_WARPS
-    int32_t *count;      // MGPU_MAX_RES
-    double  *eps4, *sig; // ntypes^2 each
-    double2 *tab_old, *tab_new;
-};
-__host__ __device__ inline size_t smem_bytes(int ntypes, int kmax_max, int natom_max)
+template <int NT> __device__ __forceinline__ void stage_counts(const Smem &S, int w)
 {
-    size_t b = 0;
-    b += (sizeof(Probe) + 15) & ~size_t(15);
-    b += sizeof(double) * 4 * MGPU_WARPS;
-    b += sizeof(double) * 8;                                  // count (int32 x MGPU_MAX_RES) + pad
-    b += sizeof(double) * 2 * (size_t)ntypes * ntypes;
-    b += sizeof(double2) * 2 * (size_t)natom_max * 3 * (kmax_max + 1);
-    return b + 64;
-}
-__device__ __forceinline__ SmemLayout carve(unsigned char *base, int natom_max)
-{
-    SmemLayout s;
-    size_t o = 0;
-    s.probe = reinterpret_cast<Probe *>(base + o); o += (sizeof(Probe) + 15) & ~size_t(15);
-    s.red = reinterpret_cast<double *>(base + o); o += sizeof(double) * 4 * MGPU_WARPS;
-    s.count = reinterpret_cast<int32_t *>(base + o); o += sizeof(double) * 8;
-    const int nt2 = c_sys.ntypes * c_sys.ntypes;
-    s.eps4 = reinterpret_cast<double *>(base + o); o += sizeof(double) * nt2;
-    s.sig = reinterpret_cast<double *>(base + o); o += sizeof(double) * nt2;
-    o = (o + 15) & ~size_t(15);
-    const size_t tab = (size_t)natom_max * 3 * (c_sys.kmax_max + 1);
-    s.tab_old = reinterpret_cast<double2 *>(base + o); o += sizeof(double2) * tab;
-    s.tab_new = reinterpret_cast<double2 *>(base + o);
-    return s;
-}
-__device__ __forceinline__ void stage_common(const SmemLayout &s, int w)
-{
-    const int nt2 = c_sys.ntypes * c_sys.ntypes;
-    for (int i = threadIdx.x; i < nt2; i += blockDim.x) { s.eps4[i] = 4.0 * c_sys.eps[i]; s.sig[i] = c_sys.sig[i]; }
-    if (threadIdx.x < MGPU_MAX_RES) s.count[threadIdx.x] = c_sys.count[(int64_t)w * MGPU_MAX_RES + threadIdx.x];
+    if (Grp<NT>::tid() < MGPU_MAX_RES) S.ws->count[Grp<NT>::tid()] = c_sys.count[(int64_t)w * MGPU_MAX_RES + Grp<NT>::tid()];
 }
 
 // load the committed geometry of (res, mol) of walker w as absolute atom positions
@@ -395,23 +620,49 @@ __device__ __forceinline__ void load_positions(int w, int res, int mol, double (
     for (int d = 0; d < 3; ++d) pos[a][d] = wc[d * cap + mol] + off[d * cap + mol];
 }
 
-// Evaluate one trial held in s.probe (positions staged): fills e_old / e_new (6 each) in
-// thread 0's registers and writes S_trial into the walker's non-committed buffer.
-// compute_old_energy / compute_new_energy, monte_carlo_utils.f90:300-423.
-template <bool TRI>
-__device__ void evaluate_trial(const SmemLayout &s, int w, int natom_max, double e_old[6], double e_new[6])
+// Stage the probe for a trial of `kind` on (res, mol) with new geometry (com, off).
+template <int NT>
+__device__ __forceinline__ void stage_probe(const Smem &S, int w, int kind, int res, int mol,
+                                            const double *com, const double (*off)[3])
 {
-    const Probe &P = *s.probe;
+    Probe &P = S.ws->probe;
+    const int na = c_sys.natom[res];
+    const int t = Grp<NT>::tid();
+    if (t == 0) {
+        P.kind = kind; P.res = res; P.mol = mol; P.na = na;
+        P.has_old = (kind != MGPU_KIND_CREATE);
+        P.has_new = (kind != MGPU_KIND_DELETE);
+        P.excl_res = res; P.excl_mol = mol;
+        P.order_res = -1; P.order_mol = -1;
+    }
+    if (t < na) {
+        const double q = c_sys.charge[res][t];
+        P.q[t] = (fabs(q) < MGPU_ERR_TOL) ? 0.0 : q;
+        P.type[t] = c_sys.type[res][t];
+        if (kind != MGPU_KIND_CREATE) load_positions(w, res, mol, P.po, t);
+        if (kind != MGPU_KIND_DELETE) {
+#pragma unroll
+            for (int d = 0; d < 3; ++d) P.pn[t][d] = com[d] + off[t][d];
+        }
+    }
+}
+
+// Evaluate one trial held in the group's probe (positions staged): fills e_old / e_new
+// (6 each, valid in every thread) and writes S_trial into the walker's non-committed buffer
+// (store_S) -- compute_old_energy / compute_new_energy, monte_carlo_utils.f90:300-423.
+template <bool TRI, int NT>
+__device__ void evaluate_trial(const Smem &S, int w, bool store_S, double e_old[6], double e_new[6], PairCount &pc)
+{
+    const Probe &P = S.ws->probe;
     double ps[4];
-    pair_sums_cta<TRI>(P, w, s.count, s.eps4, s.sig, s.red, ps);
-    // phase tables
-    if (P.has_old) fill_phase_tables(s.tab_old, P.po, P.na, threadIdx.x, blockDim.x);
-    if (P.has_new) fill_phase_tables(s.tab_new, P.pn, P.na, threadIdx.x, blockDim.x);
-    __syncthreads();
+    pair_sums<TRI, NT>(S, w, ps, pc);
+    if (P.has_old) fill_phase_tables(S.tab_old, P.po, P.na, Grp<NT>::tid(), NT);
+    if (P.has_new) fill_phase_tables(S.tab_new, P.pn, P.na, Grp<NT>::tid(), NT);
+    Grp<NT>::sync();
     const int cur = c_sys.cur[w];
     const double *S_in = c_sys.S + ((int64_t)w * 2 + cur) * 2 * c_sys.nk;
-    double *S_out = c_sys.S + ((int64_t)w * 2 + (cur ^ 1)) * 2 * c_sys.nk;
-    const double recip_new = kspace_cta(P, s.tab_old, s.tab_new, S_in, S_out, s.red);
+    double *S_out = store_S ? c_sys.S + ((int64_t)w * 2 + (cur ^ 1)) * 2 * c_sys.nk : nullptr;
+    const double recip_new = kspace<NT>(S, S_in, S_out);
     const double recip_cur = c_sys.energy[(int64_t)w * 6 + MGPU_E_RECIP];
 #pragma unroll
     for (int i = 0; i < 6; ++i) { e_old[i] = 0.0; e_new[i] = 0.0; }
@@ -425,62 +676,43 @@ __device__ void evaluate_trial(const SmemLayout &s, int w, int natom_max, double
         e_new[MGPU_E_NON_COULOMB] = ps[2];
         e_new[MGPU_E_COULOMB] = ps[3] * c_sys.eps0_inv_real;
     }
-    if (P.kind == MGPU_KIND_CREATE) {
-        e_new[MGPU_E_SELF] = c_sys.e_self[P.res];
-        e_new[MGPU_E_INTRA] = intra_energy<TRI>(P.res, P.pn);
-    } else if (P.kind == MGPU_KIND_DELETE) {
-        e_old[MGPU_E_SELF] = c_sys.e_self[P.res];
-        e_old[MGPU_E_INTRA] = intra_energy<TRI>(P.res, P.po);
+    if (P.kind != MGPU_KIND_MOVE) {
+        // rigid molecule: one thread evaluates the 1/2 na (na-1) intramolecular pairs, then broadcast
+        double intra = 0.0;
+        if (Grp<NT>::tid() == 0) intra = intra_energy<TRI>(P.res, P.kind == MGPU_KIND_CREATE ? P.pn : P.po);
+        if (NT == 32) intra = __shfl_sync(0xffffffffu, intra, 0);
+        else {
+            Grp<NT>::sync();
+            if (Grp<NT>::tid() == 0) S.ws->red[0] = intra;
+            Grp<NT>::sync();
+            intra = S.ws->red[0];
+        }
+        if (P.kind == MGPU_KIND_CREATE) { e_new[MGPU_E_SELF] = c_sys.e_self[P.res]; e_new[MGPU_E_INTRA] = intra; }
+        else { e_old[MGPU_E_SELF] = c_sys.e_self[P.res]; e_old[MGPU_E_INTRA] = intra; }
     }
     e_old[MGPU_E_TOTAL] = e_old[0] + e_old[1] + e_old[2] + e_old[3] + e_old[4];
     e_new[MGPU_E_TOTAL] = e_new[0] + e_new[1] + e_new[2] + e_new[3] + e_new[4];
 }
 
-// Stage the probe for a trial of `kind` on (res, mol) with new geometry (com, off).
-__device__ __forceinline__ void stage_probe(const SmemLayout &s, int w, int kind, int res, int mol,
-                                            const double *com, const double (*off)[3])
-{
-    Probe &P = *s.probe;
-    const int na = c_sys.natom[res];
-    if (threadIdx.x == 0) {
-        P.kind = kind; P.res = res; P.mol = mol; P.na = na;
-        P.has_old = (kind != MGPU_KIND_CREATE);
-        P.has_new = (kind != MGPU_KIND_DELETE);
-        P.excl_res = res; P.excl_mol = mol;
-        P.order_res = -1; P.order_mol = -1;
-    }
-    if (threadIdx.x < na) {
-        const int a = threadIdx.x;
-        P.q[a] = c_sys.charge[res][a];
-        P.type[a] = c_sys.type[res][a];
-        if (kind != MGPU_KIND_CREATE) load_positions(w, res, mol, P.po, a);
-        if (kind != MGPU_KIND_DELETE) {
-#pragma unroll
-            for (int d = 0; d < 3; ++d) P.pn[a][d] = com[d] + off[a][d];
-        }
-    }
-}
-
-// Apply an accepted trial to the walker (block-cooperative).
+// Apply an accepted trial to the walker (group-cooperative).
 // accept_molecule_move / accept_creation_move / accept_deletion_move + remove_molecule +
 // update_counts (monte_carlo_utils.f90:429-442,642-672; creation.f90:82-116; deletion.f90:83-122).
 __device__ void commit_trial(int w, int kind, int res, int mol, const double *com, const double (*off)[3],
-                             const double e_old[6], const double e_new[6])
+                             const double e_old[6], const double e_new[6], int tid, int nthreads)
 {
     double *wc = c_sys.coords + (int64_t)w * c_sys.coord_stride + c_sys.goff[res];
     const int cap = c_sys.cap[res], na = c_sys.natom[res];
     double *offs = wc + 3 * (int64_t)cap;
     const int n = c_sys.count[(int64_t)w * MGPU_MAX_RES + res];
-    const int tid = threadIdx.x;
     if (kind == MGPU_KIND_DELETE) {
         const int last = n - 1;
         if (mol != last) {
             if (tid < 3) wc[tid * cap + mol] = wc[tid * cap + last];
-            for (int e = tid; e < na * 3; e += blockDim.x) offs[(int64_t)e * cap + mol] = offs[(int64_t)e * cap + last];
+            for (int e = tid; e < na * 3; e += nthreads) offs[(int64_t)e * cap + mol] = offs[(int64_t)e * cap + last];
         }
     } else {
         if (tid < 3) wc[tid * cap + mol] = com[tid];
-        for (int e = tid; e < na * 3; e += blockDim.x) offs[(int64_t)e * cap + mol] = off[e / 3][e % 3];
+        for (int e = tid; e < na * 3; e += nthreads) offs[(int64_t)e * cap + mol] = off[e / 3][e % 3];
     }
     if (tid == 0) {
         if (kind == MGPU_KIND_CREATE) c_sys.count[(int64_t)w * MGPU_MAX_RES + res] = n + 1;
@@ -502,17 +734,28 @@ __device__ void commit_trial(int w, int kind, int res, int mol, const double *co
 // molecule into slot N+1 before the accept test and does not undo it on reject
 // (reject_creation_move, monte_carlo_utils.f90:579-591); that is observable when N = 0,
 // because slot 1 is the geometry template of the next insertion (:563-564).
-__device__ __forceinline__ void write_slot(int w, int res, int mol, const double *com, const double (*off)[3])
+__device__ __forceinline__ void write_slot(int w, int res, int mol, const double *com, const double (*off)[3], int tid, int nthreads)
 {
     double *wc = c_sys.coords + (int64_t)w * c_sys.coord_stride + c_sys.goff[res];
     const int cap = c_sys.cap[res], na = c_sys.natom[res];
     double *offs = wc + 3 * (int64_t)cap;
-    if (threadIdx.x < 3) wc[threadIdx.x * cap + mol] = com[threadIdx.x];
-    for (int e = threadIdx.x; e < na * 3; e += blockDim.x) offs[(int64_t)e * cap + mol] = off[e / 3][e % 3];
+    if (tid < 3) wc[tid * cap + mol] = com[tid];
+    for (int e = tid; e < na * 3; e += nthreads) offs[(int64_t)e * cap + mol] = off[e / 3][e % 3];
+}
+
+__device__ __forceinline__ void flush_pair_count(const PairCount &pc)
+{
+    const unsigned g = __reduce_add_sync(0xffffffffu, pc.geom), l = __reduce_add_sync(0xffffffffu, pc.lj),
+                   c = __reduce_add_sync(0xffffffffu, pc.coul);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(c_sys.pair_count + 0, (unsigned long long)g);
+        atomicAdd(c_sys.pair_count + 1, (unsigned long long)l);
+        atomicAdd(c_sys.pair_count + 2, (unsigned long long)c);
+    }
 }
 
 // ------------------------------------------------------------------------------------
-// host-driven trial batch: one CTA per task
+// host-driven trial batch: one group per task (NT = 32: MGPU_WARPS tasks per CTA)
 // ------------------------------------------------------------------------------------
 struct TaskArrays {
     const int4 *meta;      // [n] {walker, res, mol, kind}
@@ -521,30 +764,34 @@ struct TaskArrays {
     double *out;           // [n][12] e_old, e_new
 };
 
-template <bool TRI>
-__global__ void __launch_bounds__(MGPU_BLOCK) k_trial(TaskArrays T, int natom_max)
+template <bool TRI, int NT>
+__global__ void __launch_bounds__(NT == 32 ? MGPU_WBLOCK : MGPU_BLOCK, 1) k_trial(TaskArrays T, int n_tasks, int natom_max)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    const SmemLayout s = carve(smem, natom_max);
-    const int t = blockIdx.x;
+    const Smem S = smem_setup(smem, natom_max, Grp<NT>::id());
+    const int t = blockIdx.x * (NT == 32 ? (int)(blockDim.x >> 5) : 1) + Grp<NT>::id();
+    if (t >= n_tasks) return;                       // whole groups leave together (no later CTA barrier for NT = 32)
     const int4 meta = T.meta[t];
     const int w = meta.x, res = meta.y, mol = meta.z, kind = meta.w;
-    stage_common(s, w);
+    const int gt = Grp<NT>::tid();
+    stage_counts<NT>(S, w);
     const double *com = T.com + (int64_t)t * 3;
     const double(*off)[3] = reinterpret_cast<const double(*)[3]>(T.off + (int64_t)t * MGPU_MAX_SITES * 3);
-    stage_probe(s, w, kind, res, mol, com, off);
-    __syncthreads();
+    stage_probe<NT>(S, w, kind, res, mol, com, off);
+    Grp<NT>::sync();
     double e_old[6], e_new[6];
-    evaluate_trial<TRI>(s, w, natom_max, e_old, e_new);
+    PairCount pc = { 0u, 0u, 0u };
+    evaluate_trial<TRI, NT>(S, w, true, e_old, e_new, pc);
+    flush_pair_count(pc);
     // record the pending trial
     MgpuTrial *tr = c_sys.trial + w;
-    if (threadIdx.x == 0) {
+    if (gt == 0) {
         tr->active = 1; tr->kind = kind; tr->res = res; tr->mol = mol;
         for (int d = 0; d < 3; ++d) tr->com[d] = (kind == MGPU_KIND_DELETE) ? 0.0 : com[d];
         for (int i = 0; i < 6; ++i) { tr->e_old[i] = e_old[i]; tr->e_new[i] = e_new[i]; T.out[(int64_t)t * 12 + i] = e_old[i]; T.out[(int64_t)t * 12 + 6 + i] = e_new[i]; }
     }
     if (kind != MGPU_KIND_DELETE)
-        for (int e = threadIdx.x; e < c_sys.natom[res] * 3; e += blockDim.x) tr->off[e / 3][e % 3] = off[e / 3][e % 3];
+        for (int e = gt; e < c_sys.natom[res] * 3; e += NT) tr->off[e / 3][e % 3] = off[e / 3][e % 3];
 }
 
 __global__ void __launch_bounds__(128) k_commit(const int32_t *walker, const int32_t *accept, int32_t *err)
@@ -553,8 +800,8 @@ __global__ void __launch_bounds__(128) k_commit(const int32_t *walker, const int
     const int w = walker[t];
     MgpuTrial *tr = c_sys.trial + w;
     if (!tr->active) { if (threadIdx.x == 0) atomicExch(err, 1); return; }
-    if (accept[t]) commit_trial(w, tr->kind, tr->res, tr->mol, tr->com, tr->off, tr->e_old, tr->e_new);
-    else if (tr->kind == MGPU_KIND_CREATE && tr->mol == 0) write_slot(w, tr->res, 0, tr->com, tr->off);
+    if (accept[t]) commit_trial(w, tr->kind, tr->res, tr->mol, tr->com, tr->off, tr->e_old, tr->e_new, threadIdx.x, blockDim.x);
+    else if (tr->kind == MGPU_KIND_CREATE && tr->mol == 0) write_slot(w, tr->res, 0, tr->com, tr->off, threadIdx.x, blockDim.x);
     __syncthreads();
     if (threadIdx.x == 0) tr->active = 0;
 }
@@ -566,9 +813,9 @@ __global__ void __launch_bounds__(MGPU_BLOCK) k_pair_molecule(int w, int res, in
                                                               double *out2, int natom_max)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    const SmemLayout s = carve(smem, natom_max);
-    stage_common(s, w);
-    Probe &P = *s.probe;
+    const Smem S = smem_setup(smem, natom_max, 0);
+    stage_counts<MGPU_BLOCK>(S, w);
+    Probe &P = S.ws->probe;
     const int na = c_sys.natom[res];
     if (threadIdx.x == 0) {
         P.kind = MGPU_KIND_DELETE; P.res = res; P.mol = mol; P.na = na; P.has_old = 1; P.has_new = 0;
@@ -577,13 +824,15 @@ __global__ void __launch_bounds__(MGPU_BLOCK) k_pair_molecule(int w, int res, in
     }
     if (threadIdx.x < na) {
         const int a = threadIdx.x;
-        P.q[a] = c_sys.charge[res][a]; P.type[a] = c_sys.type[res][a];
+        const double q = c_sys.charge[res][a];
+        P.q[a] = (fabs(q) < MGPU_ERR_TOL) ? 0.0 : q; P.type[a] = c_sys.type[res][a];
         if (geom) { for (int d = 0; d < 3; ++d) P.po[a][d] = geom[d] + geom[3 + a * 3 + d]; }
         else load_positions(w, res, mol, P.po, a);
     }
     __syncthreads();
     double ps[4];
-    pair_sums_cta<TRI>(P, w, s.count, s.eps4, s.sig, s.red, ps);
+    PairCount pc = { 0u, 0u, 0u };
+    pair_sums<TRI, MGPU_BLOCK>(S, w, ps, pc);
     if (threadIdx.x == 0) { out2[0] = ps[0]; out2[1] = ps[1] * c_sys.eps0_inv_real; }
 }
 
@@ -624,7 +873,7 @@ __global__ void __launch_bounds__(MGPU_BLOCK) k_build_S(int mode, double *S_host
             __syncthreads();
             if (threadIdx.x < n) {
                 const double4 t = c_sys.host_xyzq[base + threadIdx.x];
-                pos[threadIdx.x][0] = t.x; pos[threadIdx.x][1] = t.y; pos[threadIdx.x][2] = t.z; qs[threadIdx.x] = t.w;
+                pos[threadIdx.x][0] = t.x; pos[threadIdx.x][1] = t.y; pos[threadIdx.x][2] = t.z; qs[threadIdx.x] = c_sys.host_qraw[base + threadIdx.x];
             }
             __syncthreads();
             fill_phase_tables(tab, pos, n, threadIdx.x, blockDim.x);
@@ -657,18 +906,18 @@ __global__ void __launch_bounds__(MGPU_BLOCK) k_build_S(int mode, double *S_host
         }
     }
     if (live) {
-        double *S = c_sys.S + ((int64_t)w * 2 + c_sys.cur[w]) * 2 * nk;
-        S[i] = re; S[nk + i] = im;
+        double *Sk = c_sys.S + ((int64_t)w * 2 + c_sys.cur[w]) * 2 * nk;
+        Sk[i] = re; Sk[nk + i] = im;
     }
 }
 
-// static host-host pair energy (pairs of host atoms that belong to different molecules)
+// static host-host pair energy (pairs of host atoms that belong to different molecules),
+// exact formulas, once at init
 template <bool TRI>
 __global__ void __launch_bounds__(MGPU_BLOCK) k_host_host(const int32_t *host_mol, double *partial /* [grid][2] */)
 {
     __shared__ double red[2 * MGPU_WARPS];
     double acc[2] = { 0.0, 0.0 };
-    PairCount pc = { 0u, 0u, 0u };
     const int n = c_sys.n_host, nt = c_sys.ntypes;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double4 a = c_sys.host_xyzq[i];
@@ -677,12 +926,12 @@ __global__ void __launch_bounds__(MGPU_BLOCK) k_host_host(const int32_t *host_mo
             if (host_mol[j] == ma) continue;
             const double4 b = c_sys.host_xyzq[j];
             const int ti = ta * nt + c_sys.host_type[j];
-            const bool charged = fabs(a.w) >= MGPU_ERR_TOL && fabs(b.w) >= MGPU_ERR_TOL;
+            const double qq = a.w * b.w;
             const double r2 = min_image_r2<TRI>(b.x - a.x, b.y - a.y, b.z - a.z);
-            pair_terms(r2, 4.0 * c_sys.eps[ti], c_sys.sig[ti], a.w * b.w, charged, acc[0], acc[1], pc);
+            pair_exact(r2, c_sys.ljA[ti], c_sys.ljB[ti], qq, qq != 0.0, acc[0], acc[1]);
         }
     }
-    block_sum<2>(acc, red);
+    Grp<MGPU_BLOCK>::sum<2>(acc, red);
     if (threadIdx.x == 0) { partial[blockIdx.x * 2] = acc[0]; partial[blockIdx.x * 2 + 1] = acc[1]; }
 }
 
@@ -694,15 +943,16 @@ template <bool TRI>
 __global__ void __launch_bounds__(MGPU_BLOCK) k_total_energy(int first_walker, int natom_max)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    const SmemLayout s = carve(smem, natom_max);
+    const Smem S = smem_setup(smem, natom_max, 0);
     const int w = first_walker + blockIdx.x;
-    stage_common(s, w);
+    stage_counts<MGPU_BLOCK>(S, w);
     __syncthreads();
-    Probe &P = *s.probe;
+    Probe &P = S.ws->probe;
     double e_lj = c_sys.hh_lj, e_c = 0.0, e_intra = 0.0, e_self = c_sys.self_host_total;
+    PairCount pc = { 0u, 0u, 0u };
     for (int g = 0; g < c_sys.nres; ++g) {
         if (!c_sys.active[g]) continue;
-        const int n = s.count[g], na = c_sys.natom[g];
+        const int n = S.ws->count[g], na = c_sys.natom[g];
         for (int m = 0; m < n; ++m) {
             __syncthreads();
             if (threadIdx.x == 0) {
@@ -710,19 +960,20 @@ __global__ void __launch_bounds__(MGPU_BLOCK) k_total_energy(int first_walker, i
                 P.excl_res = g; P.excl_mol = m; P.order_res = g; P.order_mol = m;
             }
             if (threadIdx.x < na) {
-                P.q[threadIdx.x] = c_sys.charge[g][threadIdx.x]; P.type[threadIdx.x] = c_sys.type[g][threadIdx.x];
+                const double q = c_sys.charge[g][threadIdx.x];
+                P.q[threadIdx.x] = (fabs(q) < MGPU_ERR_TOL) ? 0.0 : q; P.type[threadIdx.x] = c_sys.type[g][threadIdx.x];
                 load_positions(w, g, m, P.po, threadIdx.x);
             }
             __syncthreads();
             double ps[4];
-            pair_sums_cta<TRI>(P, w, s.count, s.eps4, s.sig, s.red, ps);
+            pair_sums<TRI, MGPU_BLOCK>(S, w, ps, pc);
             e_lj += ps[0]; e_c += ps[1];
             if (threadIdx.x == 0) e_intra += intra_energy<TRI>(g, P.po);
         }
         e_self += c_sys.e_self[g] * n;
     }
-    const double *S = c_sys.S + ((int64_t)w * 2 + c_sys.cur[w]) * 2 * c_sys.nk;
-    const double recip = recip_energy_cta(S, s.red);
+    const double *Sk = c_sys.S + ((int64_t)w * 2 + c_sys.cur[w]) * 2 * c_sys.nk;
+    const double recip = recip_energy<MGPU_BLOCK>(Sk, S.ws->red);
     if (threadIdx.x == 0) {
         double *E = c_sys.energy + (int64_t)w * 6;
         E[MGPU_E_NON_COULOMB] = e_lj;
@@ -744,18 +995,20 @@ __host__ __device__ __forceinline__ uint64_t splitmix64_mix(uint64_t z)
     return z ^ (z >> 31);
 }
 #define MGPU_GOLDEN 0x9E3779B97F4A7C15ULL
-struct Rng {
-    uint64_t s[4];
-    __device__ __forceinline__ double uniform()
-    {
-        const uint64_t r = rotl(s[1] * 5u, 7) * 9u;
-        const uint64_t t = s[1] << 17;
-        s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3];
-        s[2] ^= t; s[3] = rotl(s[3], 45);
-        return (double)(r >> 11) * 0x1.0p-53;
-    }
-    static __device__ __forceinline__ uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
-};
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+// state lives in shared memory (WalkerLocal::rng); only the group's thread 0 draws
+__device__ __forceinline__ double rng_uniform(unsigned long long *s)
+{
+    const uint64_t s0 = s[0], s1 = s[1];
+    uint64_t s2 = s[2], s3 = s[3];
+    const uint64_t r = rotl64(s1 * 5u, 7) * 9u;
+    const uint64_t t = s1 << 17;
+    s2 ^= s0; s3 ^= s1;
+    s[1] = s1 ^ s2; s[0] = s0 ^ s3;
+    s2 ^= t; s3 = rotl64(s3, 45);
+    s[2] = s2; s[3] = s3;
+    return (double)(r >> 11) * 0x1.0p-53;
+}
 
 // return_rotation_matrix (helper_utils.f90:30-75) applied to offsets (matmul, j = 1..3 in order)
 __device__ __forceinline__ void rotate_offsets(int axis, double theta, double (*off)[3], int na)
@@ -775,158 +1028,168 @@ __device__ __forceinline__ void rotate_offsets(int axis, double theta, double (*
 }
 
 // ------------------------------------------------------------------------------------
-// device-resident Monte Carlo: one CTA per walker, n_steps iterations of the body of
+// device-resident Monte Carlo: ONE WARP PER WALKER, n_steps iterations of the body of
 // monte_carlo_loop (monte_carlo.f90:50-99).  Draw order per step:
 // residue pick, molecule pick (if count > 0), move select, [create/delete coin],
-// proposal draws, accept draw.
+// proposal draws, accept draw.  Lane 0 plays the Fortran driver (RNG, proposal,
+// Metropolis); all 32 lanes evaluate the energies.  Warps never meet at a CTA barrier
+// after set-up, so a walker's serial section only idles its own warp.
 // ------------------------------------------------------------------------------------
-struct SweepShared {
-    int32_t valid, move, kind, res, mol, accept;
-    double com[3];
-    double off[MGPU_MAX_SITES][3];
-    double prob;
-};
-
-template <bool TRI>
-__global__ void __launch_bounds__(MGPU_BLOCK) k_sweep(int first_walker, long long n_steps, int natom_max,
-                                                      int trace_walker, mgpu_step_trace *trace, int32_t *err)
+// lane 0: draw and propose one step into sh (move drivers' proposal halves)
+__device__ __noinline__ void propose_step(int w, GroupWS &ws, int32_t *err)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const SmemLayout s = carve(smem, natom_max);
-    __shared__ SweepShared sh;
-    const int w = first_walker + blockIdx.x;
-    const int tid = threadIdx.x;
-    stage_common(s, w);
-    Rng rng;
-    if (tid == 0) for (int i = 0; i < 4; ++i) rng.s[i] = c_sys.rng[(int64_t)w * 4 + i];
-    long long cnt[12];
-    double acc_avg[MGPU_MAX_RES][3];
-    long long n_samples = 0;
-    if (tid == 0) {
-        for (int i = 0; i < 12; ++i) cnt[i] = 0;
-        for (int g = 0; g < MGPU_MAX_RES; ++g) acc_avg[g][0] = acc_avg[g][1] = acc_avg[g][2] = 0.0;
-    }
-    __syncthreads();
+    SweepShared &sh = ws.sh;
+    unsigned long long *rng = ws.loc.rng;
     const double cumul_translation = c_sys.p_trans;
     const double cumul_rotation = cumul_translation + c_sys.p_rot;
     const double cumul_swap = cumul_rotation + c_sys.p_swap;
-
-    for (long long step = 0; step < n_steps; ++step) {
-        if (tid == 0) {
-            sh.valid = 0; sh.move = MGPU_MV_NONE; sh.accept = 0; sh.prob = 0.0;
-            // pick_random_residue_type / pick_random_molecule_index, monte_carlo_utils.f90:140-201
-            const int res = c_sys.active_list[(int)(rng.uniform() * c_sys.nactive)];
-            const int n = s.count[res];
-            int mol = -1;
-            if (n > 0) { mol = (int)(rng.uniform() * n) + 1; if (mol > n) mol = n; mol -= 1; }
-            const double draw = rng.uniform();
-            const int na = c_sys.natom[res];
-            sh.res = res; sh.mol = mol;
-            const double *wc = c_sys.coords + (int64_t)w * c_sys.coord_stride + c_sys.goff[res];
-            const int cap = c_sys.cap[res];
-            const double *offs = wc + 3 * (int64_t)cap;
-            if (draw <= cumul_translation) {
-                if (mol >= 0) {                                           // translation.f90:21-97
-                    sh.valid = 1; sh.move = MGPU_MV_TRANSLATE; sh.kind = MGPU_KIND_MOVE;
-                    double tp[3];
-                    for (int d = 0; d < 3; ++d) tp[d] = rng.uniform();
-                    for (int d = 0; d < 3; ++d) sh.com[d] = wc[d * cap + mol] + (tp[d] - 0.5) * c_sys.tstep;
-                    apply_PBC(sh.com);
-                    for (int e = 0; e < na * 3; ++e) sh.off[e / 3][e % 3] = offs[(int64_t)e * cap + mol];
-                }
-            } else if (draw <= cumul_rotation) {
-                if (na != 1 && mol >= 0) {                                // rotation.f90:22-60
-                    sh.valid = 1; sh.move = MGPU_MV_ROTATE; sh.kind = MGPU_KIND_MOVE;
-                    for (int d = 0; d < 3; ++d) sh.com[d] = wc[d * cap + mol];
-                    for (int e = 0; e < na * 3; ++e) sh.off[e / 3][e % 3] = offs[(int64_t)e * cap + mol];
-                    const double theta = (rng.uniform() - 0.5) * c_sys.rstep;
-                    const int axis = (int)(rng.uniform() * 3.0) + 1;
+    sh.valid = 0; sh.move = MGPU_MV_NONE; sh.accept = 0; sh.traced_accept = 0; sh.prob = 0.0;
+    // pick_random_residue_type / pick_random_molecule_index, monte_carlo_utils.f90:140-201
+    const int res = c_sys.active_list[(int)(rng_uniform(rng) * c_sys.nactive)];
+    const int n = ws.count[res];
+    int mol = -1;
+    if (n > 0) { mol = (int)(rng_uniform(rng) * n) + 1; if (mol > n) mol = n; mol -= 1; }
+    const double draw = rng_uniform(rng);
+    const int na = c_sys.natom[res];
+    sh.res = res; sh.mol = mol;
+    const double *wc = c_sys.coords + (int64_t)w * c_sys.coord_stride + c_sys.goff[res];
+    const int cap = c_sys.cap[res];
+    const double *offs = wc + 3 * (int64_t)cap;
+    if (draw <= cumul_translation) {
+        if (mol >= 0) {                                           // translation.f90:21-97
+            sh.valid = 1; sh.move = MGPU_MV_TRANSLATE; sh.kind = MGPU_KIND_MOVE;
+            double tp[3];
+            for (int d = 0; d < 3; ++d) tp[d] = rng_uniform(rng);
+            for (int d = 0; d < 3; ++d) sh.com[d] = wc[d * cap + mol] + (tp[d] - 0.5) * c_sys.tstep;
+            apply_PBC(sh.com);
+            for (int e = 0; e < na * 3; ++e) sh.off[e / 3][e % 3] = offs[(int64_t)e * cap + mol];
+        }
+    } else if (draw <= cumul_rotation) {
+        if (na != 1 && mol >= 0) {                                // rotation.f90:22-60
+            sh.valid = 1; sh.move = MGPU_MV_ROTATE; sh.kind = MGPU_KIND_MOVE;
+            for (int d = 0; d < 3; ++d) sh.com[d] = wc[d * cap + mol];
+            for (int e = 0; e < na * 3; ++e) sh.off[e / 3][e % 3] = offs[(int64_t)e * cap + mol];
+            const double theta = (rng_uniform(rng) - 0.5) * c_sys.rstep;
+            const int axis = (int)(rng_uniform(rng) * 3.0) + 1;
+            rotate_offsets(axis, theta, sh.off, na);
+        }
+    } else if (draw <= cumul_swap) {
+        atomicExch(err, 3);                                       // swap moves: host-driven path only
+    } else {
+        bool create = false, widom = false, del = false;
+        if (c_sys.p_insdel > 0) { if (rng_uniform(rng) <= 0.5) create = true; else del = true; }
+        else if (c_sys.p_widom > 0) widom = true;
+        if (create || widom) {                                    // creation.f90:30-76, widom.f90:30-68
+            if (n >= cap) atomicExch(err, 2);
+            else {
+                sh.valid = 1; sh.move = widom ? MGPU_MV_WIDOM : MGPU_MV_CREATE; sh.kind = MGPU_KIND_CREATE;
+                sh.mol = n;
+                double t3[3];
+                for (int d = 0; d < 3; ++d) t3[d] = rng_uniform(rng);
+                for (int i = 0; i < 3; ++i)
+                    sh.com[i] = c_sys.lo[i] + __dadd_rn(__dadd_rn(__dmul_rn(c_sys.H[i * 3 + 0], t3[0]), __dmul_rn(c_sys.H[i * 3 + 1], t3[1])),
+                                                        __dmul_rn(c_sys.H[i * 3 + 2], t3[2]));
+                for (int e = 0; e < na * 3; ++e) sh.off[e / 3][e % 3] = offs[(int64_t)e * cap + 0];   // geometry of molecule 1
+                if (na != 1) {
+                    const double theta = rng_uniform(rng) * c_sys.twopi;
+                    const int axis = (int)(rng_uniform(rng) * 3.0) + 1;
                     rotate_offsets(axis, theta, sh.off, na);
                 }
-            } else if (draw <= cumul_swap) {
-                atomicExch(err, 3);                                       // swap moves: host-driven path only
-            } else {
-                bool create = false, widom = false, del = false;
-                if (c_sys.p_insdel > 0) { if (rng.uniform() <= 0.5) create = true; else del = true; }
-                else if (c_sys.p_widom > 0) widom = true;
-                if (create || widom) {                                    // creation.f90:30-76, widom.f90:30-68
-                    if (n >= cap) atomicExch(err, 2);
-                    else {
-                        sh.valid = 1; sh.move = widom ? MGPU_MV_WIDOM : MGPU_MV_CREATE; sh.kind = MGPU_KIND_CREATE;
-                        sh.mol = n;
-                        double t3[3];
-                        for (int d = 0; d < 3; ++d) t3[d] = rng.uniform();
-                        for (int i = 0; i < 3; ++i)
-                            sh.com[i] = c_sys.lo[i] + __dadd_rn(__dadd_rn(__dmul_rn(c_sys.H[i * 3 + 0], t3[0]), __dmul_rn(c_sys.H[i * 3 + 1], t3[1])),
-                                                                __dmul_rn(c_sys.H[i * 3 + 2], t3[2]));
-                        for (int e = 0; e < na * 3; ++e) sh.off[e / 3][e % 3] = offs[(int64_t)e * cap + 0];   // geometry of molecule 1
-                        if (na != 1) {
-                            const double theta = rng.uniform() * c_sys.twopi;
-                            const int axis = (int)(rng.uniform() * 3.0) + 1;
-                            rotate_offsets(axis, theta, sh.off, na);
-                        }
-                    }
-                } else if (del) {
-                    if (n > 0) { sh.valid = 1; sh.move = MGPU_MV_DELETE; sh.kind = MGPU_KIND_DELETE; }   // deletion.f90:29-77
-                }
             }
+        } else if (del) {
+            if (n > 0) { sh.valid = 1; sh.move = MGPU_MV_DELETE; sh.kind = MGPU_KIND_DELETE; }   // deletion.f90:29-77
         }
-        __syncthreads();
-        double e_old[6], e_new[6];
+    }
+}
+
+// lane 0: acceptance rule + counters (compute_acceptance_probability, monte_carlo_utils.f90:204-255;
+// accumulate_widom_weight, widom.f90:74-92)
+__device__ __noinline__ void decide_step(int w, GroupWS &ws, const double e_old[6], const double e_new[6])
+{
+    SweepShared &sh = ws.sh;
+    long long *cnt = ws.loc.cnt;
+    const int res = sh.res;
+    const double dU = e_new[MGPU_E_TOTAL] - e_old[MGPU_E_TOTAL];
+    const double mu = c_sys.mu[(int64_t)w * MGPU_MAX_RES + res];
+    const double lam = c_sys.lambda[res];
+    double p;
+    int acc;
+    if (sh.move == MGPU_MV_WIDOM) {
+        p = exp(-dU * c_sys.beta);
+        acc = 0;
+        cnt[10] += 1;
+        const int ok = p > MGPU_ERR_TOL;
+        if (ok) { cnt[11] += 1; c_sys.widom_w[(int64_t)w * MGPU_MAX_RES + res] += p; }
+        c_sys.widom_n[(int64_t)w * MGPU_MAX_RES + res] += 1;
+        sh.traced_accept = ok;
+    } else {
+        if (sh.move == MGPU_MV_CREATE) {
+            const double N = (double)(ws.count[res] + 1);        // count already incremented in the reference
+            p = fmin(1.0, c_sys.volume / N / (lam * lam * lam) * exp(-c_sys.beta * (dU - mu)));
+        } else if (sh.move == MGPU_MV_DELETE) {
+            const double Np1 = (double)(ws.count[res] - 1) + 1.0;
+            p = fmin(1.0, Np1 * (lam * lam * lam) / c_sys.volume * exp(-c_sys.beta * (dU + mu)));
+        } else p = fmin(1.0, exp(-c_sys.beta * dU));
+        acc = rng_uniform(ws.loc.rng) <= p;
+        const int ci = (sh.move == MGPU_MV_TRANSLATE) ? 0 : (sh.move == MGPU_MV_ROTATE) ? 1 : (sh.move == MGPU_MV_CREATE) ? 2 : 3;
+        cnt[2 * ci] += 1;
+        if (acc) { cnt[2 * ci + 1] += 1; if (ci >= 2) cnt[2 * ci] += 1; }   // creations/deletions bump both slots
+        sh.traced_accept = acc;
+    }
+    sh.prob = p;
+    sh.accept = acc;
+    for (int i = 0; i < 6; ++i) { sh.e_old[i] = e_old[i]; sh.e_new[i] = e_new[i]; }
+}
+
+template <bool TRI>
+__global__ void __launch_bounds__(MGPU_WBLOCK, 1) k_sweep(int first_walker, int n_walkers, long long n_steps, int natom_max,
+                                                      int trace_walker, mgpu_step_trace *trace, int32_t *err)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const Smem S = smem_setup(smem, natom_max, Grp<32>::id());
+    const int wl = blockIdx.x * (int)(blockDim.x >> 5) + Grp<32>::id();
+    if (wl >= n_walkers) return;
+    const int w = first_walker + wl;
+    const int lane = threadIdx.x & 31;
+    GroupWS &ws = *S.ws;
+    stage_counts<32>(S, w);
+    if (lane < 4) ws.loc.rng[lane] = c_sys.rng[(int64_t)w * 4 + lane];
+    if (lane < 12) ws.loc.cnt[lane] = 0;
+    if (lane < MGPU_MAX_RES) { ws.loc.avgN[lane] = 0.0; ws.loc.avgN2[lane] = 0.0; }
+    if (lane == 0) { ws.loc.avgE = 0.0; ws.loc.n_samples = 0; }
+    PairCount pc = { 0u, 0u, 0u };
+    __syncwarp();
+
+    for (long long step = 0; step < n_steps; ++step) {
+        if (lane == 0) propose_step(w, ws, err);
+        __syncwarp();
+        const SweepShared &sh = ws.sh;
         if (sh.valid) {
-            stage_probe(s, w, sh.kind, sh.res, sh.mol, sh.com, sh.off);
-            __syncthreads();
-            evaluate_trial<TRI>(s, w, natom_max, e_old, e_new);
-            if (tid == 0) {
-                const int res = sh.res;
-                const double dU = e_new[MGPU_E_TOTAL] - e_old[MGPU_E_TOTAL];
-                const double mu = c_sys.mu[(int64_t)w * MGPU_MAX_RES + res];
-                const double lam = c_sys.lambda[res];
-                double p;
-                int acc;
-                if (sh.move == MGPU_MV_WIDOM) {                           // widom.f90:74-92
-                    p = exp(-dU * c_sys.beta);
-                    acc = 0;
-                    cnt[10] += 1;
-                    if (p > MGPU_ERR_TOL) { cnt[11] += 1; c_sys.widom_w[(int64_t)w * MGPU_MAX_RES + res] += p; }
-                    c_sys.widom_n[(int64_t)w * MGPU_MAX_RES + res] += 1;
-                    sh.prob = p;
-                } else {
-                    // compute_acceptance_probability, monte_carlo_utils.f90:204-255
-                    if (sh.move == MGPU_MV_CREATE) {
-                        const double N = (double)(s.count[res] + 1);     // count already incremented in the reference
-                        p = fmin(1.0, c_sys.volume / N / (lam * lam * lam) * exp(-c_sys.beta * (dU - mu)));
-                    } else if (sh.move == MGPU_MV_DELETE) {
-                        const double Np1 = (double)(s.count[res] - 1) + 1.0;
-                        p = fmin(1.0, Np1 * (lam * lam * lam) / c_sys.volume * exp(-c_sys.beta * (dU + mu)));
-                    } else p = fmin(1.0, exp(-c_sys.beta * dU));
-                    acc = rng.uniform() <= p;
-                    const int ci = (sh.move == MGPU_MV_TRANSLATE) ? 0 : (sh.move == MGPU_MV_ROTATE) ? 1 : (sh.move == MGPU_MV_CREATE) ? 2 : 3;
-                    cnt[2 * ci] += 1;
-                    if (acc) { cnt[2 * ci + 1] += 1; if (ci >= 2) cnt[2 * ci] += 1; }   // creations/deletions bump both slots
-                    sh.prob = p;
-                }
-                sh.accept = acc;
-            }
-            __syncthreads();
+            stage_probe<32>(S, w, sh.kind, sh.res, sh.mol, sh.com, sh.off);
+            __syncwarp();
+            double e_old[6], e_new[6];
+            evaluate_trial<TRI, 32>(S, w, sh.move != MGPU_MV_WIDOM, e_old, e_new, pc);
+            if (lane == 0) decide_step(w, ws, e_old, e_new);
+            __syncwarp();
             if (sh.accept) {
-                commit_trial(w, sh.kind, sh.res, sh.mol, sh.com, sh.off, e_old, e_new);
-                if (tid == 0) {
-                    if (sh.kind == MGPU_KIND_CREATE) s.count[sh.res] += 1;
-                    if (sh.kind == MGPU_KIND_DELETE) s.count[sh.res] -= 1;
+                commit_trial(w, sh.kind, sh.res, sh.mol, sh.com, sh.off, sh.e_old, sh.e_new, lane, 32);
+                if (lane == 0) {
+                    if (sh.kind == MGPU_KIND_CREATE) ws.count[sh.res] += 1;
+                    if (sh.kind == MGPU_KIND_DELETE) ws.count[sh.res] -= 1;
                 }
             } else if (sh.kind == MGPU_KIND_CREATE && sh.mol == 0) {
-                write_slot(w, sh.res, 0, sh.com, sh.off);      // rejected / Widom insertion into an empty walker
+                write_slot(w, sh.res, 0, sh.com, sh.off, lane, 32);      // rejected / Widom insertion into an empty walker
             }
         }
-        if (tid == 0) {
+        __syncwarp();
+        if (lane == 0) {
             if (trace && w == trace_walker) {
                 mgpu_step_trace *t = trace + step;
-                t->move = sh.move; t->res = sh.res; t->mol = sh.mol; t->accepted = sh.accept;
+                t->move = sh.move; t->res = sh.res; t->mol = sh.mol; t->accepted = sh.traced_accept;
                 t->prob = sh.prob;
                 if (sh.valid) {
-                    t->dE = e_new[MGPU_E_TOTAL] - e_old[MGPU_E_TOTAL];
-                    for (int i = 0; i < 6; ++i) { t->e_old[i] = e_old[i]; t->e_new[i] = e_new[i]; }
+                    t->dE = sh.e_new[MGPU_E_TOTAL] - sh.e_old[MGPU_E_TOTAL];
+                    for (int i = 0; i < 6; ++i) { t->e_old[i] = sh.e_old[i]; t->e_new[i] = sh.e_new[i]; }
                 } else {
                     t->dE = 0.0;
                     for (int i = 0; i < 6; ++i) { t->e_old[i] = 0.0; t->e_new[i] = 0.0; }
@@ -934,166 +1197,112 @@ __global__ void __launch_bounds__(MGPU_BLOCK) k_sweep(int first_walker, long lon
             }
             for (int g = 0; g < c_sys.nres; ++g) {
                 if (!c_sys.active[g]) continue;
-                const double N = (double)s.count[g];
-                acc_avg[g][0] += N; acc_avg[g][1] += N * N;
+                const double N = (double)ws.count[g];
+                ws.loc.avgN[g] += N; ws.loc.avgN2[g] += N * N;
             }
-            acc_avg[0][2] += c_sys.energy[(int64_t)w * 6 + MGPU_E_TOTAL];
-            n_samples += 1;
+            ws.loc.avgE += c_sys.energy[(int64_t)w * 6 + MGPU_E_TOTAL];
+            ws.loc.n_samples += 1;
         }
-        __syncthreads();     // commit visible (coordinates, S flip, counts) before the next step
+        __threadfence_block();
+        __syncwarp();        // commit visible (coordinates, S flip, counts) to every lane before the next step
     }
-    if (tid == 0) {
-        for (int i = 0; i < 4; ++i) c_sys.rng[(int64_t)w * 4 + i] = rng.s[i];
-        for (int i = 0; i < 12; ++i) c_sys.counters[(int64_t)w * 12 + i] += cnt[i];
-        for (int g = 0; g < c_sys.nres; ++g) {
-            double *A = c_sys.avg + ((int64_t)w * MGPU_MAX_RES + g) * 4;
-            A[0] += acc_avg[g][0]; A[1] += acc_avg[g][1]; A[2] += acc_avg[0][2]; A[3] += (double)n_samples;
-        }
+    flush_pair_count(pc);
+    if (lane < 4) c_sys.rng[(int64_t)w * 4 + lane] = ws.loc.rng[lane];
+    if (lane < 12) c_sys.counters[(int64_t)w * 12 + lane] += ws.loc.cnt[lane];
+    if (lane < c_sys.nres) {
+        double *A = c_sys.avg + ((int64_t)w * MGPU_MAX_RES + lane) * 4;
+        A[0] += ws.loc.avgN[lane]; A[1] += ws.loc.avgN2[lane]; A[2] += ws.loc.avgE; A[3] += (double)ws.loc.n_samples;
     }
 }
 
 // ------------------------------------------------------------------------------------
-// K3: Widom batch.  Real space: one thread per insertion, every lane reads the same
-// target (broadcast from L1).  k space: one warp per insertion, lanes over k-vectors.
+// K3: Widom batch, one warp per insertion (persistent warps, grid-stride over ids).
 // u(id,k) = top53(mix(seed + GOLDEN*(8*id + k + 1))), k = 0..4: COM x3, angle, axis.
+// Per-warp partial sums are written in warp order and added by the host in that order,
+// so the result does not depend on scheduling.
 // ------------------------------------------------------------------------------------
-#define MGPU_WIDOM_BLOCK 128
 template <bool TRI>
-__global__ void __launch_bounds__(MGPU_WIDOM_BLOCK) k_widom_batch(int w, int res, long long first_id, long long n,
-                                                                  unsigned long long seed, double *dE_out,
-                                                                  double *block_sum_w, long long *block_n_ok, int natom_max)
+__global__ void __launch_bounds__(MGPU_WBLOCK, 1) k_widom_batch(int w, int res, long long first_id, long long n,
+                                                            unsigned long long seed, double *dE_out,
+                                                            double *warp_sum_w, long long *warp_n_ok, int natom_max)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    // layout: eps4[nt2], sig[nt2], per-warp phase table [warps][natom_max*3*KW] double2,
-    //         per-thread positions [block][natom_max][3], e_real[block]
-    const int nt2 = c_sys.ntypes * c_sys.ntypes;
-    const int KW = c_sys.kmax_max + 1;
-    double *s_eps4 = reinterpret_cast<double *>(smem);
-    double *s_sig = s_eps4 + nt2;
-    size_t o = (sizeof(double) * 2 * nt2 + 15) & ~size_t(15);
-    double2 *s_tab = reinterpret_cast<double2 *>(smem + o); o += sizeof(double2) * (MGPU_WIDOM_BLOCK / 32) * (size_t)natom_max * 3 * KW;
-    double(*s_pos)[3] = reinterpret_cast<double(*)[3]>(smem + o); o += sizeof(double) * 3 * (size_t)natom_max * MGPU_WIDOM_BLOCK;
-    double *s_e = reinterpret_cast<double *>(smem + o);
-    __shared__ double red_w[MGPU_WIDOM_BLOCK / 32];
-    __shared__ long long red_n[MGPU_WIDOM_BLOCK / 32];
-
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    for (int i = tid; i < nt2; i += blockDim.x) { s_eps4[i] = 4.0 * c_sys.eps[i]; s_sig[i] = c_sys.sig[i]; }
-    __syncthreads();
+    const Smem S = smem_setup(smem, natom_max, Grp<32>::id());
+    const int lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + Grp<32>::id();
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    GroupWS &ws = *S.ws;
+    stage_counts<32>(S, w);
+    __syncwarp();
     const int na = c_sys.natom[res];
-    const long long gid = (long long)blockIdx.x * blockDim.x + tid;
-    const bool live = gid < n;
-    const unsigned long long id = (unsigned long long)(first_id + gid);
-    double(*mypos)[3] = s_pos + (size_t)tid * natom_max;
-    double e_lj = 0.0, e_c = 0.0, e_intra = 0.0;
-    PairCount pc = { 0u, 0u, 0u };
+    const int slot = ws.count[res];                  // the test molecule would occupy slot N+1
     const double *wc = c_sys.coords + (int64_t)w * c_sys.coord_stride;
-    if (live) {
-        double u[5];
+    const int cap = c_sys.cap[res];
+    const double *offs = wc + c_sys.goff[res] + 3 * (int64_t)cap;
+    const double recip_cur = c_sys.energy[(int64_t)w * 6 + MGPU_E_RECIP];
+    double my_w = 0.0; long long my_ok = 0;
+    PairCount pc = { 0u, 0u, 0u };
+    for (long long i = gw; i < n; i += nwarps) {
+        const unsigned long long id = (unsigned long long)(first_id + i);
+        if (lane == 0) {
+            SweepShared &sh = ws.sh;
+            double u[5];
 #pragma unroll
-        for (int k = 0; k < 5; ++k) u[k] = (double)(splitmix64_mix(seed + MGPU_GOLDEN * (8ull * id + (unsigned long long)k + 1ull)) >> 11) * 0x1.0p-53;
-        double com[3];
-        for (int i = 0; i < 3; ++i)
-            com[i] = c_sys.lo[i] + __dadd_rn(__dadd_rn(__dmul_rn(c_sys.H[i * 3 + 0], u[0]), __dmul_rn(c_sys.H[i * 3 + 1], u[1])),
-                                             __dmul_rn(c_sys.H[i * 3 + 2], u[2]));
-        // geometry of molecule 1 of this residue type (insert_and_orient_molecule, :563-568)
-        const int cap = c_sys.cap[res];
-        const double *offs = wc + c_sys.goff[res] + 3 * (int64_t)cap;
-        for (int e = 0; e < na * 3; ++e) mypos[e / 3][e % 3] = offs[(int64_t)e * cap + 0];
-        if (na != 1) {
-            const double theta = u[3] * c_sys.twopi;
-            const int axis = (int)(u[4] * 3.0) + 1;
-            rotate_offsets(axis, theta, mypos, na);
-        }
-        for (int a = 0; a < na; ++a)
-            for (int d = 0; d < 3; ++d) mypos[a][d] = com[d] + mypos[a][d];
-        e_intra = intra_energy<TRI>(res, mypos);
-    }
-    // real space: all lanes walk the same target list
-    if (live) {
-        const int nt = c_sys.ntypes;
-        for (int a = 0; a < na; ++a) {
-            const double px = mypos[a][0], py = mypos[a][1], pz = mypos[a][2];
-            const double qa = c_sys.charge[res][a];
-            const bool acharged = fabs(qa) >= MGPU_ERR_TOL;
-            const int trow = c_sys.type[res][a] * nt;
-            for (int j = 0; j < c_sys.n_host; ++j) {
-                const double4 t = c_sys.host_xyzq[j];
-                const int ti = trow + __ldg(&c_sys.host_type[j]);
-                const bool charged = acharged && fabs(t.w) >= MGPU_ERR_TOL;
-                const double eps4 = s_eps4[ti];
-                if (eps4 == 0.0 && !charged) continue;
-                const double r2 = min_image_r2<TRI>(t.x - px, t.y - py, t.z - pz);
-                pair_terms(r2, eps4, s_sig[ti], qa * t.w, charged, e_lj, e_c, pc);
-            }
-            for (int g = 0; g < c_sys.nres; ++g) {
-                if (!c_sys.active[g]) continue;
-                const int capg = c_sys.cap[g], nag = c_sys.natom[g], ng = c_sys.count[(int64_t)w * MGPU_MAX_RES + g];
-                const double *comg = wc + c_sys.goff[g];
-                const double *offg = comg + 3 * (int64_t)capg;
-                for (int m = 0; m < ng; ++m)
-                    for (int b = 0; b < nag; ++b) {
-                        const double *ob = offg + (int64_t)b * 3 * capg;
-                        const double tx = comg[m] + ob[m], ty = comg[capg + m] + ob[capg + m], tz = comg[2 * capg + m] + ob[2 * capg + m];
-                        const double tq = c_sys.charge[g][b];
-                        const int ti = trow + c_sys.type[g][b];
-                        const bool charged = acharged && fabs(tq) >= MGPU_ERR_TOL;
-                        const double eps4 = s_eps4[ti];
-                        if (eps4 == 0.0 && !charged) continue;
-                        const double r2 = min_image_r2<TRI>(tx - px, ty - py, tz - pz);
-                        pair_terms(r2, eps4, s_sig[ti], qa * tq, charged, e_lj, e_c, pc);
-                    }
+            for (int k = 0; k < 5; ++k) u[k] = (double)(splitmix64_mix(seed + MGPU_GOLDEN * (8ull * id + (unsigned long long)k + 1ull)) >> 11) * 0x1.0p-53;
+            for (int d = 0; d < 3; ++d)
+                sh.com[d] = c_sys.lo[d] + __dadd_rn(__dadd_rn(__dmul_rn(c_sys.H[d * 3 + 0], u[0]), __dmul_rn(c_sys.H[d * 3 + 1], u[1])),
+                                                    __dmul_rn(c_sys.H[d * 3 + 2], u[2]));
+            // geometry of molecule 1 of this residue type (insert_and_orient_molecule, :563-568)
+            for (int e = 0; e < na * 3; ++e) sh.off[e / 3][e % 3] = offs[(int64_t)e * cap + 0];
+            if (na != 1) {
+                const double theta = u[3] * c_sys.twopi;
+                const int axis = (int)(u[4] * 3.0) + 1;
+                rotate_offsets(axis, theta, sh.off, na);
             }
         }
+        __syncwarp();
+        stage_probe<32>(S, w, MGPU_KIND_CREATE, res, slot, ws.sh.com, ws.sh.off);
+        __syncwarp();
+        double e_old[6], e_new[6];
+        evaluate_trial<TRI, 32>(S, w, false, e_old, e_new, pc);
+        if (lane == 0) {
+            const double dU = e_new[MGPU_E_TOTAL] - recip_cur;
+            if (dE_out) dE_out[i] = dU;
+            const double wgt = exp(-dU * c_sys.beta);
+            if (wgt > MGPU_ERR_TOL) { my_w += wgt; my_ok += 1; }
+        }
+        __syncwarp();
     }
     flush_pair_count(pc);
-    s_e[tid] = e_lj + e_c * c_sys.eps0_inv_real + c_sys.e_self[res] + e_intra;   // non-recip part of new%total
-    __syncthreads();
-    // k space: warp `wid` handles the 32 insertions of its own lanes, one after the other
-    const int nk = c_sys.nk;
-    const double *S_in = c_sys.S + ((int64_t)w * 2 + c_sys.cur[w]) * 2 * nk;
-    const double recip_cur = c_sys.energy[(int64_t)w * 6 + MGPU_E_RECIP];
-    double2 *tab = s_tab + (size_t)wid * natom_max * 3 * KW;
-    double my_w = 0.0; long long my_ok = 0;
-    for (int l = 0; l < 32; ++l) {
-        const long long g2 = (long long)blockIdx.x * blockDim.x + wid * 32 + l;
-        if (g2 >= n) break;                                   // uniform across the warp
-        const double(*pp)[3] = s_pos + (size_t)(wid * 32 + l) * natom_max;
-        __syncwarp();
-        fill_phase_tables(tab, pp, na, lane, 32);
-        __syncwarp();
-        double part = 0.0;
-        for (int i = lane; i < nk; i += 32) {
-            const int kx = c_sys.kx[i], ky = c_sys.ky[i], kz = c_sys.kz[i];
-            double sr = 0.0, si = 0.0;
-            for (int a = 0; a < na; ++a) {
-                const cplx p = phase_product(tab, a, kx, ky, kz);
-                const double q = c_sys.charge[res][a];
-                sr += q * p.re; si += q * p.im;
-            }
-            const double re = S_in[i] + sr, im = S_in[nk + i] + si;
-            part += c_sys.ffW[i] * (re * re + im * im);
-        }
-        part = warp_sum(part);
-        if (lane == l) {
-            const double recip_new = part * c_sys.eps0_inv_real * c_sys.twopi / c_sys.volume;
-            const double e_new_total = s_e[tid] + recip_new;     // same association as new%total up to ordering
-            const double dU = e_new_total - recip_cur;
-            if (dE_out) dE_out[gid] = dU;
-            const double wgt = exp(-dU * c_sys.beta);
-            if (wgt > MGPU_ERR_TOL) { my_w = wgt; my_ok = 1; }
+    if (lane == 0) { warp_sum_w[gw] = my_w; warp_n_ok[gw] = my_ok; }
+}
+
+// ------------------------------------------------------------------------------------
+// numerical self-test of the fast pair math against the exact forms (one launch, tiny):
+// out[0] = max relative error of rcp_fast, out[1] = max relative error of the Coulomb table
+// ------------------------------------------------------------------------------------
+__global__ void k_selftest(double s_lo, double s_hi, int n, double *out)
+{
+    double e_r = 0.0, e_g = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double s = s_lo * exp(log(s_hi / s_lo) * ((double)i + 0.5) / (double)n);
+        e_r = fmax(e_r, fabs(rcp_fast(s) * s - 1.0));
+        const int hi = __double2hiint(s);
+        const int idx = (hi >> (20 - MGPU_TAB_K)) - c_sys.tab_ibase;
+        if ((unsigned)idx < (unsigned)c_sys.tab_nint) {
+            const int chi = (hi & ~((1 << (20 - MGPU_TAB_K)) - 1)) | (1 << (19 - MGPU_TAB_K));
+            const double u = s - __hiloint2double(chi, 0);
+            const double *row = c_sys.ctab + (size_t)idx * MGPU_TAB_ROW;
+            const float uf = (float)u;
+            double p = (double)fmaf(__int_as_float(__double2hiint(row[5])), uf, __int_as_float(__double2loint(row[5])));
+            for (int k = 4; k >= 0; --k) p = fma(p, u, row[k]);
+            const double r = sqrt(s), ref = erfc(c_sys.alpha * r) / r;
+            e_g = fmax(e_g, fabs(p - ref) * r);     // error relative to the pair's Coulomb scale (g <= 1/r)
         }
     }
-    // block reduction of weights (fixed order)
-    my_w = warp_sum(my_w);
-    unsigned okmask = __ballot_sync(0xffffffffu, my_ok != 0);
-    if (lane == 0) { red_w[wid] = my_w; red_n[wid] = __popc(okmask); }
-    __syncthreads();
-    if (tid == 0) {
-        double sw = 0.0; long long sn = 0;
-        for (int i = 0; i < MGPU_WIDOM_BLOCK / 32; ++i) { sw += red_w[i]; sn += red_n[i]; }
-        block_sum_w[blockIdx.x] = sw; block_n_ok[blockIdx.x] = sn;
-    }
+    // non-negative doubles order like their bit patterns
+    atomicMax(reinterpret_cast<unsigned long long *>(out + 0), (unsigned long long)__double_as_longlong(e_r));
+    atomicMax(reinterpret_cast<unsigned long long *>(out + 1), (unsigned long long)__double_as_longlong(e_g));
 }
 
 // ------------------------------------------------------------------------------------

@@ -347,6 +347,13 @@ class Engine:
     def reset_pair_counts(self):
         self._ck(self.L.mgpu_reset_pair_counts())
 
+    def selftest_math(self):
+        """(max relative error of the fast 1/r^2, max error of the erfc(alpha r)/r table relative to
+        1/r) measured on the device against the exact forms."""
+        a, b = C.c_double(), C.c_double()
+        self._ck(self.L.mgpu_selftest_math(C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def measure_fp64_peak(self):
         tf, s = C.c_double(), C.c_double()
         self._ck(self.L.mgpu_measure_fp64_peak(C.byref(tf), C.byref(s)))

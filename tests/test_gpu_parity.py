@@ -256,11 +256,12 @@ def test_sweep_other_systems(name, steps, load, engine_cls):
         for r in s.residues:
             if r.active:
                 r.fugacity, r.chemical_potential = 50.0, 0.0
-    o = Oracle(s, capacity=128)
+    cap = 512 if name == "lj_gas" else 128
+    o = Oracle(s, capacity=cap)
     o.update_system_energy()
     o.seed(777)
     ref = o.monte_carlo_steps(steps)
-    with engine_cls(s, capacity=128) as eng:
+    with engine_cls(s, capacity=cap) as eng:
         eng.seed(777)
         tr = eng.sweep(steps, trace_walker=0)
         _compare_traces(tr, ref)
@@ -399,3 +400,12 @@ def test_host_driven_drivers_match_oracle_and_sweep(load, engine_cls):
         eng.seed(4242)
         tr2 = eng.sweep(n, trace_walker=0)
         assert (tr2["accepted"] == tr["accepted"]).all() and (tr2["move"] == tr["move"]).all()
+
+
+def test_fast_pair_math_on_device(load, engine_cls):
+    """1/r^2 from MUFU.RCP64H + Newton and the erfc(alpha r)/r table, measured on the GPU against
+    the exact double-precision forms over the whole tabulated range."""
+    with engine_cls(load("zif8_h2o_gcmc")) as eng:
+        e_rcp, e_tab = eng.selftest_math()
+        assert e_rcp < 4e-16, e_rcp
+        assert e_tab < 2e-14, e_tab

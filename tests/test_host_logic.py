@@ -141,3 +141,17 @@ def test_snapshot_roundtrip(tmp_path, load):
         np.testing.assert_array_equal(a.com, b.com)
         np.testing.assert_array_equal(a.offset, b.offset)
         assert a.mass == b.mass and a.active == b.active
+
+
+@pytest.mark.parametrize("alpha,r_hi", [(0.16215694, 30.5), (0.16215694, 43.0), (0.23463702, 21.8), (0.25430534, 27.5), (0.25396482, 27.5)])
+def test_coulomb_table_accuracy(alpha, r_hi):
+    """The piecewise-polynomial table that replaces erfc(alpha r)/r on the device (host-side
+    builder, evaluated with the device's integer indexing and Horner order) against long-double
+    erfc: error relative to the pair's Coulomb scale 1/r below 4e-15 over the whole range."""
+    import ctypes as C
+    from maniac_b200 import capi
+    L = capi.lib()
+    er, ea = C.c_double(), C.c_double()
+    n = L.mgpu_coulomb_table_check(alpha, 1.0, r_hi, 300000, C.byref(er), C.byref(ea))
+    assert n == 300000           # every sample falls inside the tabulated range
+    assert ea.value < 4e-15
