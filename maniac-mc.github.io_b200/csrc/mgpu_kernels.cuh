@@ -172,19 +172,21 @@ __device__ __forceinline__ double rcp_fast(double s)
 // The reference's pair formulas evaluated literally (pairwise_lj_energy :95-138,
 // pairwise_coulomb_energy :143-179); used off the hot path (host-host, intramolecular,
 // pairs outside the table range).  A = 4 eps sigma^12, B = 4 eps sigma^6.
-__device__ __noinline__ void pair_exact(double s, double A, double B, double qq, bool doC, double &e_lj, double &e_c)
+__device__ __noinline__ double2 pair_exact(double s, double A, double B, double qq, bool doC)
 {
+    double e_lj = 0.0, e_c = 0.0;
     const double r = sqrt(s);
     if (r < MGPU_ERR_TOL) {
-        if (r < c_sys.rc) e_lj += c_sys.overlap;
-        if (doC) e_c += c_sys.overlap;
-        return;
+        if (r < c_sys.rc) e_lj = c_sys.overlap;
+        if (doC) e_c = c_sys.overlap;
+        return make_double2(e_lj, e_c);
     }
     if (r < c_sys.rc) {
         const double y = 1.0 / s, y3 = y * y * y;
-        e_lj += (A * y3 - B) * y3;
+        e_lj = (A * y3 - B) * y3;
     }
-    if (doC) e_c += qq * erfc(c_sys.alpha * r) / r;
+    if (doC) e_c = qq * erfc(c_sys.alpha * r) / r;
+    return make_double2(e_lj, e_c);
 }
 
 // One atom pair on the hot path.  tab = this lane's replica of the Coulomb table in shared
@@ -199,7 +201,8 @@ __device__ __forceinline__ void pair_terms(double s, double2 AB, double qq, cons
     const int idx = (hi >> (20 - MGPU_TAB_K)) - c_sys.tab_ibase;
     if ((unsigned)idx >= (unsigned)c_sys.tab_nint) {           // r < table start (incl. overlap) or beyond its end: rare
         if (s >= c_sys.s_zero && s >= c_sys.rc2) { pc.coul += doC; return; }    // erfc(alpha r)/r < 1e-24: below the sum's rounding
-        pair_exact(s, AB.x, AB.y, qq, doC, e_lj, e_c);
+        const double2 e = pair_exact(s, AB.x, AB.y, qq, doC);
+        e_lj += e.x; e_c += e.y;
         pc.lj += (doL && s < c_sys.rc2); pc.coul += doC;
         return;
     }
@@ -271,6 +274,13 @@ struct GroupWS {
     WalkerLocal loc;
 };
 
+// The dynamic shared memory of every kernel here starts with the replicated Coulomb table,
+// followed by the LJ {A,B} pairs.  Going through this accessor (not through a pointer stored
+// in a struct) keeps the address space visible to the compiler: LDS.128, not generic LD.
+extern __shared__ __align__(16) unsigned char mgpu_smem[];
+__device__ __forceinline__ const double2 *smem_ctab() { return reinterpret_cast<const double2 *>(mgpu_smem) + (threadIdx.x & (MGPU_TAB_REP - 1)); }
+__device__ __forceinline__ const double2 *smem_ljAB() { return reinterpret_cast<const double2 *>(mgpu_smem) + (size_t)c_sys.tab_nint * 3 * MGPU_TAB_REP; }
+
 // Shared-memory image of a CTA: replicated Coulomb table, LJ {A,B} pairs, then `groups` workspaces.
 struct Smem {
     const double2 *ctab;        // this lane's replica: row i chunk c at ctab[(i*3 + c) * MGPU_TAB_REP]
@@ -337,18 +347,26 @@ struct HostPass {
         }
     }
 
+    template <int UU> struct Atoms { double2 xy[UU], zq[UU]; int tt[UU]; };
+
     template <int UU>
-    __device__ __forceinline__ void block(const Smem &S, int j, int stride, double &e_lj, double &e_c, PairCount &pc) const
+    __device__ __forceinline__ void fetch(Atoms<UU> &A, int j, int stride) const
     {
         const double2 *__restrict__ hxy = c_sys.host_xy;
         const double2 *__restrict__ hzq = c_sys.host_zq;
         const int32_t *__restrict__ ht = c_sys.host_type;
-        double2 txy[UU], tzq[UU]; int tt[UU];
 #pragma unroll
         for (int u = 0; u < UU; ++u) {
-            txy[u] = __ldg(hxy + j + u * stride); tzq[u] = __ldg(hzq + j + u * stride);
-            tt[u] = (MODE & 1) ? __ldg(ht + j + u * stride) : 0;
+            A.xy[u] = __ldg(hxy + j + u * stride); A.zq[u] = __ldg(hzq + j + u * stride);
+            A.tt[u] = (MODE & 1) ? __ldg(ht + j + u * stride) : 0;
         }
+    }
+
+    template <int UU>
+    __device__ __forceinline__ void block(const Atoms<UU> &A, double &e_lj, double &e_c, PairCount &pc) const
+    {
+        const double2 (&txy)[UU] = A.xy; const double2 (&tzq)[UU] = A.zq; const int (&tt)[UU] = A.tt;
+        const double2 *ctab = smem_ctab(), *ljAB = smem_ljAB();
         unsigned bad = 0u;
         double sv[UU][N];
 #pragma unroll
@@ -363,7 +381,7 @@ struct HostPass {
                 const bool out = (unsigned)idx >= (unsigned)c_sys.tab_nint;
                 if (out) bad |= 1u << (u * N + i);
                 if (MODE & 1) {
-                    const double2 AB = S.ljAB[trow[i] + tt[u]];
+                    const double2 AB = ljAB[trow[i] + tt[u]];
                     const double y = rcp_fast(out ? 1.0 : s), y3 = y * y * y;
                     const double e = (AB.x * y3 - AB.y) * y3;
                     const bool in = (s < c_sys.rc2) && !out;
@@ -373,7 +391,7 @@ struct HostPass {
                 if (MODE & 2) {
                     const int chi = (hi & ~((1 << (20 - MGPU_TAB_K)) - 1)) | (1 << (19 - MGPU_TAB_K));
                     const double uu = s - __hiloint2double(chi, 0);         // exact: same binade
-                    const double2 *t = S.ctab + (out ? 0 : idx) * (3 * MGPU_TAB_REP);
+                    const double2 *t = ctab + (out ? 0 : idx) * (3 * MGPU_TAB_REP);
                     const double2 c01 = t[0], c23 = t[MGPU_TAB_REP], c45 = t[2 * MGPU_TAB_REP];
                     const float uf = (float)uu;
                     const float pf = fmaf(__int_as_float(__double2hiint(c45.y)), uf, __int_as_float(__double2loint(c45.y)));
@@ -397,20 +415,39 @@ struct HostPass {
                         const double s = sv[u][i];
                         if (s >= c_sys.s_zero && s >= c_sys.rc2) continue;   // erfc(alpha r)/r < 1e-24: below the sum's rounding
                         double2 AB = make_double2(0.0, 0.0);
-                        if (MODE & 1) AB = S.ljAB[trow[i] + tt[u]];
+                        if (MODE & 1) AB = ljAB[trow[i] + tt[u]];
                         const double qq = (MODE & 2) ? q[i] * tzq[u].y : 0.0;
-                        pair_exact(s, AB.x, AB.y, qq, qq != 0.0, e_lj, e_c);
+                        const double2 e = pair_exact(s, AB.x, AB.y, qq, qq != 0.0);
+                        e_lj += e.x; e_c += e.y;
                         if (MODE & 1) pc.lj += ((AB.x != 0.0 || AB.y != 0.0) && s < c_sys.rc2);
                     }
         }
     }
 
-    __device__ __forceinline__ void run(const Smem &S, int t0, int stride, double &e_lj, double &e_c, PairCount &pc) const
+    // software-pipelined: the next block's atoms are in flight (L2 latency) while this one is evaluated.
+    // Accumulators are taken and returned by value so they stay in registers.
+    __device__ __forceinline__ void run(int t0, int stride, double &e_lj_io, double &e_c_io, PairCount &pc_io) const
     {
+        double e_lj = e_lj_io, e_c = e_c_io;
+        PairCount pc = pc_io;
         const int n = c_sys.n_host;
         int j = t0;
-        for (; j + (U - 1) * stride < n; j += U * stride) block<U>(S, j, stride, e_lj, e_c, pc);
-        for (; j < n; j += stride) block<1>(S, j, stride, e_lj, e_c, pc);
+        if (U > 1) {                        // U atoms in flight per thread already: no explicit prefetch
+            for (; j + (U - 1) * stride < n; j += U * stride) { Atoms<U> a; fetch<U>(a, j, stride); block<U>(a, e_lj, e_c, pc); }
+        } else if (j < n) {
+            Atoms<U> cur;
+            fetch<U>(cur, j, stride);
+            for (;;) {
+                const int jn = j + stride;
+                Atoms<U> nxt;
+                fetch<U>(nxt, jn < n ? jn : j, stride);          // unconditional (the last one reloads j): plain register rotation
+                block<U>(cur, e_lj, e_c, pc);
+                if (jn >= n) { j = jn; break; }
+                cur = nxt; j = jn;
+            }
+        }
+        for (; j < n; j += stride) { Atoms<1> a1; fetch<1>(a1, j, stride); block<1>(a1, e_lj, e_c, pc); }
+        e_lj_io = e_lj; e_c_io = e_c; pc_io = pc;
     }
 };
 
@@ -418,12 +455,12 @@ template <bool TRI, int MODE>
 __device__ __forceinline__ void host_list(const Smem &S, const Probe &P, const double (*pos)[3], const int8_t *list, int n,
                                           int t0, int stride, double &e_lj, double &e_c, PairCount &pc)
 {
-    for (int base = 0; base < n; base += 4) {
-        const int m = min(4, n - base);
-        if (m == 4) { HostPass<TRI, MODE, 4, 1> hp; hp.load(P, pos, list + base); hp.run(S, t0, stride, e_lj, e_c, pc); }
-        else if (m == 3) { HostPass<TRI, MODE, 3, 1> hp; hp.load(P, pos, list + base); hp.run(S, t0, stride, e_lj, e_c, pc); }
-        else if (m == 2) { HostPass<TRI, MODE, 2, 2> hp; hp.load(P, pos, list + base); hp.run(S, t0, stride, e_lj, e_c, pc); }
-        else { HostPass<TRI, MODE, 1, 4> hp; hp.load(P, pos, list + base); hp.run(S, t0, stride, e_lj, e_c, pc); }
+    // chunks of at most 3 probe atoms: ~3 independent pair chains per thread fit the 128-register budget
+    for (int base = 0; base < n; base += 3) {
+        const int m = min(3, n - base);
+        if (m == 3) { HostPass<TRI, MODE, 3, 1> hp; hp.load(P, pos, list + base); hp.run(t0, stride, e_lj, e_c, pc); }
+        else if (m == 2) { HostPass<TRI, MODE, 2, 1> hp; hp.load(P, pos, list + base); hp.run(t0, stride, e_lj, e_c, pc); }
+        else { HostPass<TRI, MODE, 1, 3> hp; hp.load(P, pos, list + base); hp.run(t0, stride, e_lj, e_c, pc); }
     }
 }
 
@@ -436,8 +473,8 @@ __device__ __forceinline__ void probe_vs_guest_atom(const Probe &P, const double
     const int nt = c_sys.ntypes;
     const int na = P.na;
     for (int a = 0; a < na; ++a) {
-        const double2 AB = S.ljAB[P.type[a] * nt + ttype];
-        pair_terms(min_image_r2<TRI>(tx - pos[a][0], ty - pos[a][1], tz - pos[a][2]), AB, P.q[a] * tq, S.ctab, e_lj, e_c, pc);
+        const double2 AB = smem_ljAB()[P.type[a] * nt + ttype];
+        pair_terms(min_image_r2<TRI>(tx - pos[a][0], ty - pos[a][1], tz - pos[a][2]), AB, P.q[a] * tq, smem_ctab(), e_lj, e_c, pc);
     }
 }
 
@@ -490,7 +527,9 @@ __device__ __noinline__ void pair_sums(const Smem &S, int w, double (&out)[4], P
     const int stride = both ? NT / 2 : NT;
     const int t0 = both ? (gt & (NT / 2 - 1)) : gt;
     double e_lj = 0.0, e_c = 0.0;
-    pair_loops<TRI>(P, new_set ? P.pn : P.po, S, w, t0, stride, e_lj, e_c, pc);
+    PairCount pcl = pc;                      // by value: keeps the counters in registers inside the loops
+    pair_loops<TRI>(P, new_set ? P.pn : P.po, S, w, t0, stride, e_lj, e_c, pcl);
+    pc = pcl;
     double acc[4];
     acc[0] = new_set ? 0.0 : e_lj; acc[1] = new_set ? 0.0 : e_c;
     acc[2] = new_set ? e_lj : 0.0; acc[3] = new_set ? e_c : 0.0;
@@ -767,8 +806,7 @@ struct TaskArrays {
 template <bool TRI, int NT>
 __global__ void __launch_bounds__(NT == 32 ? MGPU_WBLOCK : MGPU_BLOCK, 1) k_trial(TaskArrays T, int n_tasks, int natom_max)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const Smem S = smem_setup(smem, natom_max, Grp<NT>::id());
+    const Smem S = smem_setup(mgpu_smem, natom_max, Grp<NT>::id());
     const int t = blockIdx.x * (NT == 32 ? (int)(blockDim.x >> 5) : 1) + Grp<NT>::id();
     if (t >= n_tasks) return;                       // whole groups leave together (no later CTA barrier for NT = 32)
     const int4 meta = T.meta[t];
@@ -812,8 +850,7 @@ __global__ void __launch_bounds__(MGPU_BLOCK) k_pair_molecule(int w, int res, in
                                                               const double *geom /* com[3] + off[na][3] or NULL */,
                                                               double *out2, int natom_max)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const Smem S = smem_setup(smem, natom_max, 0);
+    const Smem S = smem_setup(mgpu_smem, natom_max, 0);
     stage_counts<MGPU_BLOCK>(S, w);
     Probe &P = S.ws->probe;
     const int na = c_sys.natom[res];
@@ -857,8 +894,7 @@ __global__ void k_intra(int w, int res, int mol, const double *geom, double *out
 #define MGPU_STILE MGPU_MAX_SITES
 __global__ void __launch_bounds__(MGPU_BLOCK) k_build_S(int mode, double *S_host_out, int first_walker)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
-    double2 *tab = reinterpret_cast<double2 *>(smem);
+    double2 *tab = reinterpret_cast<double2 *>(mgpu_smem);
     __shared__ double pos[MGPU_STILE][3];
     __shared__ double qs[MGPU_STILE];
     const int nk = c_sys.nk;
@@ -928,7 +964,8 @@ __global__ void __launch_bounds__(MGPU_BLOCK) k_host_host(const int32_t *host_mo
             const int ti = ta * nt + c_sys.host_type[j];
             const double qq = a.w * b.w;
             const double r2 = min_image_r2<TRI>(b.x - a.x, b.y - a.y, b.z - a.z);
-            pair_exact(r2, c_sys.ljA[ti], c_sys.ljB[ti], qq, qq != 0.0, acc[0], acc[1]);
+            const double2 e = pair_exact(r2, c_sys.ljA[ti], c_sys.ljB[ti], qq, qq != 0.0);
+            acc[0] += e.x; acc[1] += e.y;
         }
     }
     Grp<MGPU_BLOCK>::sum<2>(acc, red);
@@ -942,8 +979,7 @@ __global__ void __launch_bounds__(MGPU_BLOCK) k_host_host(const int32_t *host_mo
 template <bool TRI>
 __global__ void __launch_bounds__(MGPU_BLOCK) k_total_energy(int first_walker, int natom_max)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const Smem S = smem_setup(smem, natom_max, 0);
+    const Smem S = smem_setup(mgpu_smem, natom_max, 0);
     const int w = first_walker + blockIdx.x;
     stage_counts<MGPU_BLOCK>(S, w);
     __syncthreads();
@@ -1145,8 +1181,7 @@ template <bool TRI>
 __global__ void __launch_bounds__(MGPU_WBLOCK, 1) k_sweep(int first_walker, int n_walkers, long long n_steps, int natom_max,
                                                       int trace_walker, mgpu_step_trace *trace, int32_t *err)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const Smem S = smem_setup(smem, natom_max, Grp<32>::id());
+    const Smem S = smem_setup(mgpu_smem, natom_max, Grp<32>::id());
     const int wl = blockIdx.x * (int)(blockDim.x >> 5) + Grp<32>::id();
     if (wl >= n_walkers) return;
     const int w = first_walker + wl;
@@ -1226,8 +1261,7 @@ __global__ void __launch_bounds__(MGPU_WBLOCK, 1) k_widom_batch(int w, int res, 
                                                             unsigned long long seed, double *dE_out,
                                                             double *warp_sum_w, long long *warp_n_ok, int natom_max)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const Smem S = smem_setup(smem, natom_max, Grp<32>::id());
+    const Smem S = smem_setup(mgpu_smem, natom_max, Grp<32>::id());
     const int lane = threadIdx.x & 31;
     const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + Grp<32>::id();
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
