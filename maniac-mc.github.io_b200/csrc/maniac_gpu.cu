@@ -448,10 +448,10 @@ int mgpu_init(const mgpu_system *sys)
     g.dirty.assign(W, 0);
 
     // ---- shared-memory budgets ----
-    g.smem1 = smem_bytes(h.ntypes, h.tab_nint, h.kmax_max, g.natom_max, 1);
+    g.smem1 = smem_bytes(h.ntypes, h.tab_nint, h.kmax_max, g.natom_max, 1, 1);
     g.wgroups = MGPU_WGROUPS;
-    while (g.wgroups > 1 && smem_bytes(h.ntypes, h.tab_nint, h.kmax_max, g.natom_max, g.wgroups) > 227 * 1024) --g.wgroups;
-    g.smem8 = smem_bytes(h.ntypes, h.tab_nint, h.kmax_max, g.natom_max, g.wgroups);
+    while (g.wgroups > 1 && smem_bytes(h.ntypes, h.tab_nint, h.kmax_max, g.natom_max, g.wgroups, MGPU_TAB_REP) > 227 * 1024) --g.wgroups;
+    g.smem8 = smem_bytes(h.ntypes, h.tab_nint, h.kmax_max, g.natom_max, g.wgroups, MGPU_TAB_REP);
     g.smem_buildS = sizeof(double2) * (size_t)MGPU_STILE * 3 * (h.kmax_max + 1);
     const size_t smem_max = std::max(g.smem8, g.smem_buildS);
     if (smem_max > 227 * 1024) return fail("mgpu_init: kmax / ntypes / molecule size need more than 227 KB of shared memory per CTA");
@@ -722,10 +722,14 @@ int mgpu_trial_batch(int32_t n, const int32_t *walker, const int32_t *res, const
     TaskArrays T{ reinterpret_cast<const int4 *>(g.d_task_i), g.d_task_com, g.d_task_off, g.d_task_out };
     Timer tm("trial");
     // large batches: one warp per task (8 tasks per CTA); small ones: one CTA per task for latency
-    if (n >= g.sm_count * g.wgroups / 2) {
-        const int nb = (n + g.wgroups - 1) / g.wgroups;
-        if (g.h.triclinic) k_trial<true, 32><<<nb, 32 * g.wgroups, g.smem8, g.stream>>>(T, n, g.natom_max);
-        else k_trial<false, 32><<<nb, 32 * g.wgroups, g.smem8, g.stream>>>(T, n, g.natom_max);
+    if (n >= g.sm_count) {
+        // spread the tasks over every SM: ceil(n / SMs) warps per CTA, at most wgroups
+        int grp = (n + g.sm_count - 1) / g.sm_count;
+        if (grp > g.wgroups) grp = g.wgroups;
+        const int nb = (n + grp - 1) / grp;
+        const size_t sm = smem_bytes(g.h.ntypes, g.h.tab_nint, g.h.kmax_max, g.natom_max, grp, MGPU_TAB_REP);
+        if (g.h.triclinic) k_trial<true, 32><<<nb, 32 * grp, sm, g.stream>>>(T, n, g.natom_max);
+        else k_trial<false, 32><<<nb, 32 * grp, sm, g.stream>>>(T, n, g.natom_max);
     } else {
         if (g.h.triclinic) k_trial<true, MGPU_BLOCK><<<n, MGPU_BLOCK, g.smem1, g.stream>>>(T, n, g.natom_max);
         else k_trial<false, MGPU_BLOCK><<<n, MGPU_BLOCK, g.smem1, g.stream>>>(T, n, g.natom_max);

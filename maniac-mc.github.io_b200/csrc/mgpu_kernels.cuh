@@ -192,6 +192,7 @@ __device__ __noinline__ double2 pair_exact(double s, double A, double B, double 
 // One atom pair on the hot path.  tab = this lane's replica of the Coulomb table in shared
 // memory (double2 units, see mgpu_internal.h).  qq = q_i q_j with either factor already zeroed
 // when |q| < 1e-10 (:157).  AB = {4 eps sigma^12, 4 eps sigma^6}.
+template <int REP>
 __device__ __forceinline__ void pair_terms(double s, double2 AB, double qq, const double2 *__restrict__ tab,
                                            double &e_lj, double &e_c, PairCount &pc)
 {
@@ -216,8 +217,8 @@ __device__ __forceinline__ void pair_terms(double s, double2 AB, double qq, cons
     if (doC) {
         const int chi = (hi & ~((1 << (20 - MGPU_TAB_K)) - 1)) | (1 << (19 - MGPU_TAB_K));
         const double u = s - __hiloint2double(chi, 0);          // exact: same binade
-        const double2 *t = tab + idx * (3 * MGPU_TAB_REP);
-        const double2 c01 = t[0], c23 = t[MGPU_TAB_REP], c45 = t[2 * MGPU_TAB_REP];
+        const double2 *t = tab + idx * (3 * REP);
+        const double2 c01 = t[0], c23 = t[REP], c45 = t[2 * REP];
         const float uf = (float)u;
         const float pf = fmaf(__int_as_float(__double2hiint(c45.y)), uf, __int_as_float(__double2loint(c45.y)));
         double p = (double)pf;
@@ -278,13 +279,14 @@ struct GroupWS {
 // followed by the LJ {A,B} pairs.  Going through this accessor (not through a pointer stored
 // in a struct) keeps the address space visible to the compiler: LDS.128, not generic LD.
 extern __shared__ __align__(16) unsigned char mgpu_smem[];
-__device__ __forceinline__ const double2 *smem_ctab() { return reinterpret_cast<const double2 *>(mgpu_smem) + (threadIdx.x & (MGPU_TAB_REP - 1)); }
-__device__ __forceinline__ const double2 *smem_ljAB() { return reinterpret_cast<const double2 *>(mgpu_smem) + (size_t)c_sys.tab_nint * 3 * MGPU_TAB_REP; }
+// REP = number of replicas: MGPU_TAB_REP in the warp-per-task kernels (one CTA per SM, filled once
+// per launch), 1 in the CTA-per-task kernels (latency path: a 15 KB fill per task, not 123 KB).
+template <int NT> struct TabRep { static constexpr int v = (NT == 32) ? MGPU_TAB_REP : 1; };
+template <int REP> __device__ __forceinline__ const double2 *smem_ctab() { return reinterpret_cast<const double2 *>(mgpu_smem) + (threadIdx.x & (REP - 1)); }
+template <int REP> __device__ __forceinline__ const double2 *smem_ljAB() { return reinterpret_cast<const double2 *>(mgpu_smem) + (size_t)c_sys.tab_nint * 3 * REP; }
 
 // Shared-memory image of a CTA: replicated Coulomb table, LJ {A,B} pairs, then `groups` workspaces.
 struct Smem {
-    const double2 *ctab;        // this lane's replica: row i chunk c at ctab[(i*3 + c) * MGPU_TAB_REP]
-    const double2 *ljAB;        // [ntypes^2]
     GroupWS *ws;
     double2 *tab_old, *tab_new;
 };
@@ -294,16 +296,17 @@ __host__ __device__ inline size_t smem_group_bytes(int kmax_max, int natom_max)
     b += sizeof(double2) * 2 * (size_t)natom_max * 3 * (kmax_max + 1);
     return b;
 }
-__host__ __device__ inline size_t smem_common_bytes(int ntypes, int tab_nint)
+__host__ __device__ inline size_t smem_common_bytes(int ntypes, int tab_nint, int rep)
 {
-    return sizeof(double2) * ((size_t)tab_nint * 3 * MGPU_TAB_REP + (size_t)ntypes * ntypes);
+    return sizeof(double2) * ((size_t)tab_nint * 3 * rep + (size_t)ntypes * ntypes);
 }
-__host__ __device__ inline size_t smem_bytes(int ntypes, int tab_nint, int kmax_max, int natom_max, int groups)
+__host__ __device__ inline size_t smem_bytes(int ntypes, int tab_nint, int kmax_max, int natom_max, int groups, int rep)
 {
-    return smem_common_bytes(ntypes, tab_nint) + groups * smem_group_bytes(kmax_max, natom_max) + 16;
+    return smem_common_bytes(ntypes, tab_nint, rep) + groups * smem_group_bytes(kmax_max, natom_max) + 16;
 }
 // Carve the CTA's dynamic shared memory and (cooperatively, whole CTA) load the common part.
 // Every thread of the CTA must call this; it ends with __syncthreads().
+template <int REP>
 __device__ __forceinline__ Smem smem_setup(unsigned char *base, int natom_max, int group)
 {
     Smem s;
@@ -311,12 +314,10 @@ __device__ __forceinline__ Smem smem_setup(unsigned char *base, int natom_max, i
     const int nt2 = c_sys.ntypes * c_sys.ntypes;
     const int nchunk = c_sys.tab_nint * 3;
     const double2 *src = reinterpret_cast<const double2 *>(c_sys.ctab);
-    for (int i = threadIdx.x; i < nchunk * MGPU_TAB_REP; i += blockDim.x) d[i] = src[i / MGPU_TAB_REP];
-    double2 *lj = d + (size_t)nchunk * MGPU_TAB_REP;
+    for (int i = threadIdx.x; i < nchunk * REP; i += blockDim.x) d[i] = src[i / REP];
+    double2 *lj = d + (size_t)nchunk * REP;
     for (int i = threadIdx.x; i < nt2; i += blockDim.x) lj[i] = make_double2(c_sys.ljA[i], c_sys.ljB[i]);
-    s.ctab = d + (threadIdx.x & (MGPU_TAB_REP - 1));
-    s.ljAB = lj;
-    unsigned char *g = base + smem_common_bytes(c_sys.ntypes, c_sys.tab_nint) + (size_t)group * smem_group_bytes(c_sys.kmax_max, natom_max);
+    unsigned char *g = base + smem_common_bytes(c_sys.ntypes, c_sys.tab_nint, REP) + (size_t)group * smem_group_bytes(c_sys.kmax_max, natom_max);
     s.ws = reinterpret_cast<GroupWS *>(g);
     s.tab_old = reinterpret_cast<double2 *>(g + ((sizeof(GroupWS) + 15) & ~size_t(15)));
     s.tab_new = s.tab_old + (size_t)natom_max * 3 * (c_sys.kmax_max + 1);
@@ -331,7 +332,7 @@ __device__ __forceinline__ Smem smem_setup(unsigned char *base, int natom_max, i
 // chunks of N <= 4 atoms held in registers against U framework atoms per thread and
 // iteration; the body is branch free (N*U independent pair chains for the scheduler), pairs
 // that fall outside the Coulomb table are flagged and redone exactly afterwards.
-template <bool TRI, int MODE, int N, int U>
+template <bool TRI, int MODE, int N, int U, int REP>
 struct HostPass {
     double px[N], py[N], pz[N], q[N];
     int trow[N];
@@ -366,7 +367,7 @@ struct HostPass {
     __device__ __forceinline__ void block(const Atoms<UU> &A, double &e_lj, double &e_c, PairCount &pc) const
     {
         const double2 (&txy)[UU] = A.xy; const double2 (&tzq)[UU] = A.zq; const int (&tt)[UU] = A.tt;
-        const double2 *ctab = smem_ctab(), *ljAB = smem_ljAB();
+        const double2 *ctab = smem_ctab<REP>(), *ljAB = smem_ljAB<REP>();
         unsigned bad = 0u;
         double sv[UU][N];
 #pragma unroll
@@ -391,8 +392,8 @@ struct HostPass {
                 if (MODE & 2) {
                     const int chi = (hi & ~((1 << (20 - MGPU_TAB_K)) - 1)) | (1 << (19 - MGPU_TAB_K));
                     const double uu = s - __hiloint2double(chi, 0);         // exact: same binade
-                    const double2 *t = ctab + (out ? 0 : idx) * (3 * MGPU_TAB_REP);
-                    const double2 c01 = t[0], c23 = t[MGPU_TAB_REP], c45 = t[2 * MGPU_TAB_REP];
+                    const double2 *t = ctab + (out ? 0 : idx) * (3 * REP);
+                    const double2 c01 = t[0], c23 = t[REP], c45 = t[2 * REP];
                     const float uf = (float)uu;
                     const float pf = fmaf(__int_as_float(__double2hiint(c45.y)), uf, __int_as_float(__double2loint(c45.y)));
                     double p = (double)pf;
@@ -451,21 +452,21 @@ struct HostPass {
     }
 };
 
-template <bool TRI, int MODE>
+template <bool TRI, int MODE, int REP>
 __device__ __forceinline__ void host_list(const Smem &S, const Probe &P, const double (*pos)[3], const int8_t *list, int n,
                                           int t0, int stride, double &e_lj, double &e_c, PairCount &pc)
 {
     // chunks of at most 3 probe atoms: ~3 independent pair chains per thread fit the 128-register budget
     for (int base = 0; base < n; base += 3) {
         const int m = min(3, n - base);
-        if (m == 3) { HostPass<TRI, MODE, 3, 1> hp; hp.load(P, pos, list + base); hp.run(t0, stride, e_lj, e_c, pc); }
-        else if (m == 2) { HostPass<TRI, MODE, 2, 1> hp; hp.load(P, pos, list + base); hp.run(t0, stride, e_lj, e_c, pc); }
-        else { HostPass<TRI, MODE, 1, 3> hp; hp.load(P, pos, list + base); hp.run(t0, stride, e_lj, e_c, pc); }
+        if (m == 3) { HostPass<TRI, MODE, 3, 1, REP> hp; hp.load(P, pos, list + base); hp.run(t0, stride, e_lj, e_c, pc); }
+        else if (m == 2) { HostPass<TRI, MODE, 2, 1, REP> hp; hp.load(P, pos, list + base); hp.run(t0, stride, e_lj, e_c, pc); }
+        else { HostPass<TRI, MODE, 1, 3, REP> hp; hp.load(P, pos, list + base); hp.run(t0, stride, e_lj, e_c, pc); }
     }
 }
 
 // One target atom of a guest molecule against every probe atom (tq already zeroed if tiny).
-template <bool TRI>
+template <bool TRI, int REP>
 __device__ __forceinline__ void probe_vs_guest_atom(const Probe &P, const double (*pos)[3], const Smem &S,
                                                     double tx, double ty, double tz, double tq, int ttype,
                                                     double &e_lj, double &e_c, PairCount &pc)
@@ -473,23 +474,23 @@ __device__ __forceinline__ void probe_vs_guest_atom(const Probe &P, const double
     const int nt = c_sys.ntypes;
     const int na = P.na;
     for (int a = 0; a < na; ++a) {
-        const double2 AB = smem_ljAB()[P.type[a] * nt + ttype];
-        pair_terms(min_image_r2<TRI>(tx - pos[a][0], ty - pos[a][1], tz - pos[a][2]), AB, P.q[a] * tq, smem_ctab(), e_lj, e_c, pc);
+        const double2 AB = smem_ljAB<REP>()[P.type[a] * nt + ttype];
+        pair_terms<REP>(min_image_r2<TRI>(tx - pos[a][0], ty - pos[a][1], tz - pos[a][2]), AB, P.q[a] * tq, smem_ctab<REP>(), e_lj, e_c, pc);
     }
 }
 
 // The two target loops for ONE geometry of the probe: host framework (passes above) and the
 // walker's guests (one thread per molecule).  Threads t0, t0 + stride, ... of the group take part.
-template <bool TRI>
+template <bool TRI, int REP>
 __device__ __forceinline__ void pair_loops(const Probe &P, const double (*pos)[3], const Smem &S, int w, int t0, int stride,
                                            double &e_lj, double &e_c, PairCount &pc)
 {
     if (c_sys.n_host > 0) {
         const int r = P.res;
-        host_list<TRI, 1>(S, P, pos, c_sys.hl_list[r][1], c_sys.hl_n[r][1], t0, stride, e_lj, e_c, pc);
-        host_list<TRI, 2>(S, P, pos, c_sys.hl_list[r][2], c_sys.hl_n[r][2], t0, stride, e_lj, e_c, pc);
-        host_list<TRI, 3>(S, P, pos, c_sys.hl_list[r][3], c_sys.hl_n[r][3], t0, stride, e_lj, e_c, pc);
-        host_list<TRI, 0>(S, P, pos, c_sys.hl_list[r][0], c_sys.hl_n[r][0], t0, stride, e_lj, e_c, pc);
+        host_list<TRI, 1, REP>(S, P, pos, c_sys.hl_list[r][1], c_sys.hl_n[r][1], t0, stride, e_lj, e_c, pc);
+        host_list<TRI, 2, REP>(S, P, pos, c_sys.hl_list[r][2], c_sys.hl_n[r][2], t0, stride, e_lj, e_c, pc);
+        host_list<TRI, 3, REP>(S, P, pos, c_sys.hl_list[r][3], c_sys.hl_n[r][3], t0, stride, e_lj, e_c, pc);
+        host_list<TRI, 0, REP>(S, P, pos, c_sys.hl_list[r][0], c_sys.hl_n[r][0], t0, stride, e_lj, e_c, pc);
     }
     const double *wc = c_sys.coords + (int64_t)w * c_sys.coord_stride;
     for (int g = 0; g < c_sys.nres; ++g) {
@@ -506,7 +507,7 @@ __device__ __forceinline__ void pair_loops(const Probe &P, const double (*pos)[3
                 const double tx = cx + ob[m], ty = cy + ob[cap + m], tz = cz + ob[2 * cap + m];
                 double tq = c_sys.charge[g][b];
                 if (fabs(tq) < MGPU_ERR_TOL) tq = 0.0;
-                probe_vs_guest_atom<TRI>(P, pos, S, tx, ty, tz, tq, c_sys.type[g][b], e_lj, e_c, pc);
+                probe_vs_guest_atom<TRI, REP>(P, pos, S, tx, ty, tz, tq, c_sys.type[g][b], e_lj, e_c, pc);
             }
         }
     }
@@ -528,7 +529,7 @@ __device__ __noinline__ void pair_sums(const Smem &S, int w, double (&out)[4], P
     const int t0 = both ? (gt & (NT / 2 - 1)) : gt;
     double e_lj = 0.0, e_c = 0.0;
     PairCount pcl = pc;                      // by value: keeps the counters in registers inside the loops
-    pair_loops<TRI>(P, new_set ? P.pn : P.po, S, w, t0, stride, e_lj, e_c, pcl);
+    pair_loops<TRI, TabRep<NT>::v>(P, new_set ? P.pn : P.po, S, w, t0, stride, e_lj, e_c, pcl);
     pc = pcl;
     double acc[4];
     acc[0] = new_set ? 0.0 : e_lj; acc[1] = new_set ? 0.0 : e_c;
@@ -806,7 +807,7 @@ struct TaskArrays {
 template <bool TRI, int NT>
 __global__ void __launch_bounds__(NT == 32 ? MGPU_WBLOCK : MGPU_BLOCK, 1) k_trial(TaskArrays T, int n_tasks, int natom_max)
 {
-    const Smem S = smem_setup(mgpu_smem, natom_max, Grp<NT>::id());
+    const Smem S = smem_setup<TabRep<NT>::v>(mgpu_smem, natom_max, Grp<NT>::id());
     const int t = blockIdx.x * (NT == 32 ? (int)(blockDim.x >> 5) : 1) + Grp<NT>::id();
     if (t >= n_tasks) return;                       // whole groups leave together (no later CTA barrier for NT = 32)
     const int4 meta = T.meta[t];
@@ -850,7 +851,7 @@ __global__ void __launch_bounds__(MGPU_BLOCK) k_pair_molecule(int w, int res, in
                                                               const double *geom /* com[3] + off[na][3] or NULL */,
                                                               double *out2, int natom_max)
 {
-    const Smem S = smem_setup(mgpu_smem, natom_max, 0);
+    const Smem S = smem_setup<1>(mgpu_smem, natom_max, 0);
     stage_counts<MGPU_BLOCK>(S, w);
     Probe &P = S.ws->probe;
     const int na = c_sys.natom[res];
@@ -979,7 +980,7 @@ __global__ void __launch_bounds__(MGPU_BLOCK) k_host_host(const int32_t *host_mo
 template <bool TRI>
 __global__ void __launch_bounds__(MGPU_BLOCK) k_total_energy(int first_walker, int natom_max)
 {
-    const Smem S = smem_setup(mgpu_smem, natom_max, 0);
+    const Smem S = smem_setup<1>(mgpu_smem, natom_max, 0);
     const int w = first_walker + blockIdx.x;
     stage_counts<MGPU_BLOCK>(S, w);
     __syncthreads();
@@ -1181,7 +1182,7 @@ template <bool TRI>
 __global__ void __launch_bounds__(MGPU_WBLOCK, 1) k_sweep(int first_walker, int n_walkers, long long n_steps, int natom_max,
                                                       int trace_walker, mgpu_step_trace *trace, int32_t *err)
 {
-    const Smem S = smem_setup(mgpu_smem, natom_max, Grp<32>::id());
+    const Smem S = smem_setup<MGPU_TAB_REP>(mgpu_smem, natom_max, Grp<32>::id());
     const int wl = blockIdx.x * (int)(blockDim.x >> 5) + Grp<32>::id();
     if (wl >= n_walkers) return;
     const int w = first_walker + wl;
@@ -1261,7 +1262,7 @@ __global__ void __launch_bounds__(MGPU_WBLOCK, 1) k_widom_batch(int w, int res, 
                                                             unsigned long long seed, double *dE_out,
                                                             double *warp_sum_w, long long *warp_n_ok, int natom_max)
 {
-    const Smem S = smem_setup(mgpu_smem, natom_max, Grp<32>::id());
+    const Smem S = smem_setup<MGPU_TAB_REP>(mgpu_smem, natom_max, Grp<32>::id());
     const int lane = threadIdx.x & 31;
     const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + Grp<32>::id();
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
