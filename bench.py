@@ -35,7 +35,8 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-INNER_DEFAULT = 32
+INNER_DEFAULT = 256
+CAPACITY = 1024          # molecules per walker (NB_MAX_MOLECULE analogue): room for the pore-filling points of the fugacity grid
 FLOP_GEOM, FLOP_LJ, FLOP_COUL, FLOP_SINCOS = 29.0, 8.0, 69.0, 64.0      # SURVEY.md 8d, convention C1
 
 
@@ -45,7 +46,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--walkers", type=int, default=4096, help="walkers per GPU (weak scaling)")
+    ap.add_argument("--walkers", type=int, default=4736, help="walkers per GPU (weak scaling); 4736 = 2 x 148 SMs x 16 warps")
     ap.add_argument("--inner", type=int, default=INNER_DEFAULT, help="MC steps per walker per launch")
     ap.add_argument("--loading", type=int, default=64, help="initial waters per walker")
     ap.add_argument("--e2e-walkers", type=int, default=1024)
@@ -74,11 +75,18 @@ class ClockSampler:
 
     def __init__(self, gpu_index):
         self.rows, self.proc, self.idx = [], None, gpu_index
+        self.t_begin = self.t_end = None      # perf_counter bounds of the timed region (mark_begin / mark_end)
+
+    def mark_begin(self):
+        self.t_begin = time.perf_counter()
+
+    def mark_end(self):
+        self.t_end = time.perf_counter()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -86,7 +94,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
     def stop(self):
         if not self.proc:
@@ -97,7 +105,11 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        rows = self.rows
+        if self.t_begin is not None and self.t_end is not None:
+            inside = [r for r in rows if self.t_begin <= r[0] <= self.t_end + 0.05]
+            rows = inside if inside else rows
+        for _, r in rows:
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -203,7 +215,7 @@ def main():
         torch.cuda.synchronize()
 
     W = a.walkers
-    eng = Engine(s, n_walkers=W, capacity=256, device=local)
+    eng = Engine(s, n_walkers=W, capacity=CAPACITY, device=local)
     fug = isotherm_fugacities(64)
     for w in range(W):
         eng.set_fugacity(0, float(fug[(rank * W + w) % 64]), walker=w)
@@ -212,20 +224,22 @@ def main():
     ew = eng.ewald()
     na = 4
 
+    sampler = ClockSampler(local)
+    sampler.start()                                    # nvidia-smi needs ~0.5 s before its first row: start before the warm-up
     for _ in range(a.warmup):
         eng.sweep(a.inner)
     c0 = np.array([eng.counters(w) for w in range(0, W, max(1, W // 256))]).sum(axis=0)   # sampled walkers
     n_sampled = len(range(0, W, max(1, W // 256)))
     eng.reset_pair_counts()
     eng.timing_reset()
-    sampler = ClockSampler(local)
-    sampler.start()
     barrier()
+    sampler.mark_begin()
     t0 = time.perf_counter()
     for _ in range(a.steps):
         eng.sweep(a.inner)
     barrier()
     wall = time.perf_counter() - t0
+    sampler.mark_end()
     clocks = sampler.stop()
     ms_total, launches = eng.timing("sweep")
     pc = eng.pair_counts()
@@ -259,6 +273,30 @@ def main():
                 "hbm": {"achieved": bytes_alg / t_dev / 1e9 / world, "peak": hbm_peak, "unit": "GB/s",
                         "frac": bytes_alg / t_dev / 1e9 / world / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"}}
+
+    # ---- the same sweep with the per-molecule framework-energy cache off (framework swept for the old
+    #      AND the new geometry of every move, the reference's operation count) --------------------
+    from maniac_b200.engine import OPT_HOST_CACHE
+    eng.set_option(OPT_HOST_CACHE, 0)
+    eng.sweep(a.inner)
+    eng.timing_reset()
+    eng.reset_pair_counts()
+    barrier()
+    for _ in range(2):
+        eng.sweep(a.inner)
+    barrier()
+    ms_nc, l_nc = eng.timing("sweep")
+    pc_nc = eng.pair_counts()
+    t_nc = ms_nc * 1e-3
+    if world > 1:
+        t = torch.tensor([t_nc], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_nc = float(t[0])
+    fl_nc = FLOP_GEOM * pc_nc["pairs"] + FLOP_LJ * pc_nc["lj"] + FLOP_COUL * pc_nc["coulomb"] + kspace_flops(dcount, na, ew["kmax"], ew["nk"]) * 2 / a.steps
+    no_cache = {"moves_per_s": float(W) * a.inner * 2 * world / t_nc, "launches": int(l_nc),
+                "roofline_frac_c1": fl_nc / (ms_nc * 1e-3) / 1e12 / peak_tf if peak_tf else None,
+                "note": "mgpu_set_option(MGPU_OPT_HOST_CACHE, 0): old-geometry framework sums recomputed every trial"}
+    eng.set_option(OPT_HOST_CACHE, 1)
 
     # ---- Widom batch (configs[2]) ------------------------------------------------------------
     widom = None
@@ -295,7 +333,7 @@ def main():
 
     # ---- e2e: host-driven path through the C ABI with host buffers ---------------------------
     We = min(a.e2e_walkers, W)
-    enge = Engine(s, n_walkers=We, capacity=256, device=local)
+    enge = Engine(s, n_walkers=We, capacity=CAPACITY, device=local)
     for w in range(We):
         enge.set_fugacity(0, float(fug[(rank * We + w) % 64]), walker=w)
     hm = HostMonteCarlo(enge, seed=999 + rank)
@@ -339,7 +377,7 @@ def main():
     line = {"metric": "mc_trial_moves_per_s", "value": value, "unit": "moves/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": 1e3 * t_dev / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "clocks": clocks,
-            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "widom": widom,
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "widom": widom, "no_host_cache": no_cache,
             "wall_s_timed_region": wall, "mean_waters_per_walker": nmean, "fp64_peak_tflops_measured": peak_tf}
     print(json.dumps(line))
 

@@ -124,6 +124,15 @@ int mgpu_get_Ak(int32_t walker, double *re_im);
 /* running totals `energy` of a walker */
 int mgpu_get_energy(int32_t walker, double out[6]);
 
+/* Engine options.  MGPU_OPT_HOST_CACHE (default 1): the framework is static, so a guest
+ * molecule's LJ + erfc-Coulomb sum against it only changes when that molecule moves; the
+ * engine keeps it per molecule (written at every commit and every full recompute) and the
+ * OLD geometry of a move / deletion reads it instead of sweeping the framework again.
+ * 0 = recompute it every trial, like pairwise_energy_for_molecule on the old geometry
+ * (src/monte_carlo_utils.f90:367-423) does.  Same energies to rounding either way. */
+enum { MGPU_OPT_HOST_CACHE = 1 };
+int mgpu_set_option(int32_t option, int32_t value);
+
 /* ---- energy routines (single walker, drop-in) -------------------------------------- */
 /* update_system_energy, src/energy_utils.f90:22-39: full recompute of the 5 components,
  * rebuilds S(k) (compute_total_reciprocal_energy, src/ewald_energy.f90:20-58) */

@@ -63,6 +63,7 @@ SIGNATURES = {
     "mgpu_set_fugacity": (C.c_int, [I, I, D]),
     "mgpu_get_Ak": (C.c_int, [I, _pd]),
     "mgpu_get_energy": (C.c_int, [I, _pd]),
+    "mgpu_set_option": (C.c_int, [I, I]),
     "mgpu_total_energy": (C.c_int, [I, _pd]),
     "mgpu_pairwise_energy_for_molecule": (C.c_int, [I, I, I, I, _pd, _pd, _pd, _pd]),
     "mgpu_ewald_self_energy_single_mol": (C.c_int, [I, _pd]),

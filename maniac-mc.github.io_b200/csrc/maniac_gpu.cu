@@ -300,7 +300,7 @@ int mgpu_init(const mgpu_system *sys)
             if (R.natom > g.natom_max) g.natom_max = R.natom;
             for (int a = 0; a < R.natom; ++a) { h.charge[r][a] = R.charges[a]; h.type[r][a] = R.types[a]; }
             h.goff[r] = stride;
-            stride += (int64_t)(3 + 3 * R.natom) * R.capacity;
+            stride += (int64_t)(3 + 3 * R.natom + 2) * R.capacity;      // com, offsets, framework-energy cache rows
             // prepare_monte_carlo, prepare_utils.f90:231-259
             const double mass = R.mass * G_TO_KG / NA();
             double lam = H_PLANCK / std::sqrt(TWOPI * mass * KB * sys->temperature);
@@ -318,6 +318,7 @@ int mgpu_init(const mgpu_system *sys)
     h.p_trans = sys->p_translation; h.p_rot = sys->p_rotation; h.p_swap = sys->p_swap;
     h.p_insdel = sys->p_insertion_deletion; h.p_widom = sys->p_widom;
     h.tstep = sys->translation_step; h.rstep = sys->rotation_step_angle;
+    h.use_hcache = 1;
 
     // ---- static arrays ----
     std::vector<double4> hx(n_host ? n_host : 1); std::vector<int32_t> ht(n_host ? n_host : 1), hm(n_host ? n_host : 1); std::vector<double> hq(n_host ? n_host : 1);
@@ -368,6 +369,33 @@ int mgpu_init(const mgpu_system *sys)
                 h.hl_list[r][mode][h.hl_n[r][mode]++] = (int8_t)a;
             }
         }
+    }
+    {
+        // classes of a probe residue's atoms against atom b of guest residue g (guest passes of K1)
+        const size_t nl = (size_t)MGPU_MAX_RES * MGPU_MAX_RES * MGPU_MAX_SITES * 4;
+        std::vector<int8_t> gn(nl, 0), gl(nl * MGPU_MAX_SITES, 0);
+        for (int ri = 0; ri < sys->nres; ++ri) {
+            const mgpu_residue &Ri = sys->residues[ri];
+            if (!Ri.is_active) continue;
+            for (int gg = 0; gg < sys->nres; ++gg) {
+                const mgpu_residue &Rg = sys->residues[gg];
+                if (!Rg.is_active) continue;
+                for (int b = 0; b < Rg.natom; ++b)
+                    for (int a = 0; a < Ri.natom; ++a) {
+                        const size_t ti = (size_t)Ri.types[a] * sys->ntypes + Rg.types[b];
+                        const bool lj = sys->epsilon[ti] != 0.0 && sys->sigma[ti] != 0.0;
+                        const bool co = std::fabs(Ri.charges[a]) >= MGPU_ERR_TOL && std::fabs(Rg.charges[b]) >= MGPU_ERR_TOL;
+                        const int mode = (lj ? 1 : 0) | (co ? 2 : 0);
+                        const size_t gi = (((size_t)ri * MGPU_MAX_RES + gg) * MGPU_MAX_SITES + b) * 4 + mode;
+                        gl[gi * MGPU_MAX_SITES + gn[gi]++] = (int8_t)a;
+                    }
+            }
+        }
+        int8_t *d_gn, *d_gl;
+        if (dalloc(&d_gn, gn.size()) || dalloc(&d_gl, gl.size())) return 1;
+        CK(cudaMemcpy(d_gn, gn.data(), gn.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_gl, gl.data(), gl.size(), cudaMemcpyHostToDevice));
+        h.gl_n = d_gn; h.gl_list = d_gl;
     }
     {
         // pairwise_lj_energy (pairwise_energy_utils.f90:131-136): 4 eps ((sigma/r)^12 - (sigma/r)^6) = A / s^6 - B / s^3
@@ -630,6 +658,18 @@ int mgpu_get_energy(int32_t w, double out[6])
     if (check_walker(w) || ensure_clean(w)) return 1;
     CK(cudaMemcpy(out, g.h.energy + (int64_t)w * 6, sizeof(double) * 6, cudaMemcpyDeviceToHost));
     return 0;
+}
+
+int mgpu_set_option(int32_t option, int32_t value)
+{
+    NEED_READY();
+    if (option == MGPU_OPT_HOST_CACHE) {
+        g.h.use_hcache = value ? 1 : 0;
+        if (upload_sys()) return 1;
+        CK(cudaStreamSynchronize(g.stream));
+        return 0;
+    }
+    return fail("mgpu_set_option: unknown option");
 }
 
 // ---- energies -------------------------------------------------------------------------

@@ -6,7 +6,9 @@
 //     piecewise-polynomial table of erfc(alpha r)/r in r^2, the k-vector list
 //     {kx,ky,kz} + ffW(k), S_host(k);
 //   * per walker: guest coordinates as SoA with the molecule index fastest
-//     (com[3][cap], offset[natom][3][cap] per guest residue type), two S(k) buffers
+//     (com[3][cap], offset[natom][3][cap], hcache[2][cap] per guest residue type; hcache =
+//     the molecule's LJ / erfc-Coulomb sum against the static framework, refreshed on every
+//     commit, so the OLD geometry of a move or deletion needs no framework pass), two S(k) buffers
 //     (committed / trial, flipped on accept), running energies, counts, RNG state,
 //     counters and accumulators, one pending-trial record.
 #pragma once
@@ -40,6 +42,7 @@ struct MgpuTrial {
     double  com[3];
     double  off[MGPU_MAX_SITES][3];
     double  e_old[6], e_new[6];
+    double  hc_new[2];            // framework part {lj, coulomb (e^2/A)} of the trial geometry (-> per-molecule cache on commit)
 };
 
 // Constant-memory image of everything the kernels need.  Pointers are device pointers.
@@ -61,6 +64,7 @@ struct DevSys {
     int32_t active_list[MGPU_MAX_RES];
     int32_t host_count[MGPU_MAX_RES];         // molecule count of inactive residues (static)
     int64_t goff[MGPU_MAX_RES];               // offset (doubles) of the residue block inside a walker's coordinates
+    int32_t use_hcache;                       // 1: old-geometry framework sums come from the per-molecule cache
     double  charge[MGPU_MAX_RES][MGPU_MAX_SITES];
     int32_t type[MGPU_MAX_RES][MGPU_MAX_SITES];
     double  e_self[MGPU_MAX_RES];             // ewald_self_energy_single_mol(res)
@@ -76,6 +80,9 @@ struct DevSys {
     // guest atoms of each residue type by what they feel from the framework: 0 nothing, 1 LJ, 2 Coulomb, 3 both
     int32_t hl_n[MGPU_MAX_RES][4];
     int8_t  hl_list[MGPU_MAX_RES][4][MGPU_MAX_SITES];
+    // the same classification of a probe residue's atoms against atom b of guest residue g:
+    // gl_n[((ri*MAX_RES + g)*MAX_SITES + b)*4 + mode], gl_list[that index][MAX_SITES]   (global memory, warp-uniform reads)
+    const int8_t *gl_n, *gl_list;
     const double *ljA, *ljB;                  // [ntypes*ntypes] 4 eps sigma^12, 4 eps sigma^6
     const int32_t *kx, *ky, *kz; const double *ffW;
     const double *S_host;                     // [2][nk] re, im

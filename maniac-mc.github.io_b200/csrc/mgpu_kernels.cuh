@@ -240,7 +240,7 @@ struct Probe {
     int32_t has_old, has_new;
     int32_t excl_res, excl_mol;              // target slot to skip (the molecule itself)
     int32_t order_res, order_mol;            // >= 0: only targets with (res,mol) > this (ordering check)
-    int32_t pad[2];
+    int32_t host_old, host_new;              // which geometries need a framework pass (old: 0 when the cache serves it)
     double q[MGPU_MAX_SITES];                // 0 when |q| < 1e-10
     int32_t type[MGPU_MAX_SITES];
     double po[MGPU_MAX_SITES][3];            // old atom positions (com + offset)
@@ -269,7 +269,7 @@ struct WalkerLocal {
 // Fixed part of a group's workspace; the two phase tables follow it.
 struct GroupWS {
     Probe probe;
-    double red[4 * MGPU_WARPS];
+    double red[8 * MGPU_WARPS];
     int32_t count[MGPU_MAX_RES];
     SweepShared sh;
     WalkerLocal loc;
@@ -363,8 +363,10 @@ struct HostPass {
         }
     }
 
+    // vmask: bit u set = target u is real (guest passes mask the tail / the excluded molecule;
+    // framework passes hand in a constant all-ones mask and the tests fold away)
     template <int UU>
-    __device__ __forceinline__ void block(const Atoms<UU> &A, double &e_lj, double &e_c, PairCount &pc) const
+    __device__ __forceinline__ void block(const Atoms<UU> &A, const unsigned vmask, double &e_lj, double &e_c, PairCount &pc) const
     {
         const double2 (&txy)[UU] = A.xy; const double2 (&tzq)[UU] = A.zq; const int (&tt)[UU] = A.tt;
         const double2 *ctab = smem_ctab<REP>(), *ljAB = smem_ljAB<REP>();
@@ -372,15 +374,16 @@ struct HostPass {
         double sv[UU][N];
 #pragma unroll
         for (int u = 0; u < UU; ++u) {
-            if (MODE & 2) pc.coul += (tzq[u].y != 0.0) ? N : 0;
+            const bool val = (vmask >> u) & 1u;
+            if (MODE & 2) pc.coul += (val && tzq[u].y != 0.0) ? N : 0;
 #pragma unroll
             for (int i = 0; i < N; ++i) {
                 const double s = min_image_r2<TRI>(txy[u].x - px[i], txy[u].y - py[i], tzq[u].x - pz[i]);
                 sv[u][i] = s;
                 const int hi = __double2hiint(s);
                 const int idx = (hi >> (20 - MGPU_TAB_K)) - c_sys.tab_ibase;
-                const bool out = (unsigned)idx >= (unsigned)c_sys.tab_nint;
-                if (out) bad |= 1u << (u * N + i);
+                const bool out = ((unsigned)idx >= (unsigned)c_sys.tab_nint) || !val;
+                if (out && val) bad |= 1u << (u * N + i);
                 if (MODE & 1) {
                     const double2 AB = ljAB[trow[i] + tt[u]];
                     const double y = rcp_fast(out ? 1.0 : s), y3 = y * y * y;
@@ -406,7 +409,7 @@ struct HostPass {
                 }
             }
         }
-        pc.geom += UU * N;
+        pc.geom += __popc(vmask) * N;
         if (bad) {                                                  // rare: r < 1 A (incl. overlap) or beyond the table
 #pragma unroll
             for (int u = 0; u < UU; ++u)
@@ -434,7 +437,7 @@ struct HostPass {
         const int n = c_sys.n_host;
         int j = t0;
         if (U > 1) {                        // U atoms in flight per thread already: no explicit prefetch
-            for (; j + (U - 1) * stride < n; j += U * stride) { Atoms<U> a; fetch<U>(a, j, stride); block<U>(a, e_lj, e_c, pc); }
+            for (; j + (U - 1) * stride < n; j += U * stride) { Atoms<U> a; fetch<U>(a, j, stride); block<U>(a, (1u << U) - 1u, e_lj, e_c, pc); }
         } else if (j < n) {
             Atoms<U> cur;
             fetch<U>(cur, j, stride);
@@ -442,12 +445,41 @@ struct HostPass {
                 const int jn = j + stride;
                 Atoms<U> nxt;
                 fetch<U>(nxt, jn < n ? jn : j, stride);          // unconditional (the last one reloads j): plain register rotation
-                block<U>(cur, e_lj, e_c, pc);
+                block<U>(cur, (1u << U) - 1u, e_lj, e_c, pc);
                 if (jn >= n) { j = jn; break; }
                 cur = nxt; j = jn;
             }
         }
-        for (; j < n; j += stride) { Atoms<1> a1; fetch<1>(a1, j, stride); block<1>(a1, e_lj, e_c, pc); }
+        for (; j < n; j += stride) { Atoms<1> a1; fetch<1>(a1, j, stride); block<1>(a1, 1u, e_lj, e_c, pc); }
+        e_lj_io = e_lj; e_c_io = e_c; pc_io = pc;
+    }
+
+    // The same body against ONE atom (index b) of every molecule of a guest residue type of the
+    // walker: targets are com[m] + off_b[m], m = t0, t0 + stride, ... < n (molecule index fastest
+    // in memory, so the lanes' loads coalesce); tq / ttype are the target atom's charge (0 if tiny)
+    // and type.  Molecule m_skip is left out (the probe itself), and so is every m <= m_order
+    // (ordering check of pairwise_energy_for_molecule, :60-62; -1 = none).
+    __device__ __forceinline__ void run_guest(const double *__restrict__ com, const double *__restrict__ offb, int cap, int n,
+                                              int t0, int stride, int m_skip, int m_order, double tq, int ttype,
+                                              double &e_lj_io, double &e_c_io, PairCount &pc_io) const
+    {
+        double e_lj = e_lj_io, e_c = e_c_io;
+        PairCount pc = pc_io;
+        for (int m = t0; m < n; m += U * stride) {
+            Atoms<U> A;
+            unsigned vm = 0u;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int mm = m + u * stride;
+                const bool ok = (mm < n) && (mm != m_skip) && (mm > m_order);
+                const int mc = (mm < n) ? mm : m;
+                A.xy[u] = make_double2(com[mc] + offb[mc], com[cap + mc] + offb[cap + mc]);
+                A.zq[u] = make_double2(com[2 * cap + mc] + offb[2 * cap + mc], tq);
+                A.tt[u] = ttype;
+                vm |= ok ? (1u << u) : 0u;
+            }
+            block<U>(A, vm, e_lj, e_c, pc);
+        }
         e_lj_io = e_lj; e_c_io = e_c; pc_io = pc;
     }
 };
@@ -482,7 +514,7 @@ __device__ __forceinline__ void probe_vs_guest_atom(const Probe &P, const double
 // The two target loops for ONE geometry of the probe: host framework (passes above) and the
 // walker's guests (one thread per molecule).  Threads t0, t0 + stride, ... of the group take part.
 template <bool TRI, int REP>
-__device__ __forceinline__ void pair_loops(const Probe &P, const double (*pos)[3], const Smem &S, int w, int t0, int stride,
+__device__ __forceinline__ void host_loops(const Probe &P, const double (*pos)[3], const Smem &S, int t0, int stride,
                                            double &e_lj, double &e_c, PairCount &pc)
 {
     if (c_sys.n_host > 0) {
@@ -492,51 +524,106 @@ __device__ __forceinline__ void pair_loops(const Probe &P, const double (*pos)[3
         host_list<TRI, 3, REP>(S, P, pos, c_sys.hl_list[r][3], c_sys.hl_n[r][3], t0, stride, e_lj, e_c, pc);
         host_list<TRI, 0, REP>(S, P, pos, c_sys.hl_list[r][0], c_sys.hl_n[r][0], t0, stride, e_lj, e_c, pc);
     }
+}
+// index of the probe-atom list of (probe residue ri) x (target residue g, target atom b) x mode
+__device__ __forceinline__ int gl_index(int ri, int g, int b, int mode) { return ((ri * MGPU_MAX_RES + g) * MGPU_MAX_SITES + b) * 4 + mode; }
+
+template <bool TRI, int MODE, int REP>
+__device__ __forceinline__ void guest_list(const Probe &P, const double (*pos)[3], const int8_t *list, int nl,
+                                           const double *com, const double *offb, int cap, int n, int t0, int stride,
+                                           int m_skip, int m_order, double tq, int ttype, double &e_lj, double &e_c, PairCount &pc)
+{
+    for (int base = 0; base < nl; base += 3) {
+        const int k = min(3, nl - base);
+        if (k == 3) { HostPass<TRI, MODE, 3, 1, REP> hp; hp.load(P, pos, list + base); hp.run_guest(com, offb, cap, n, t0, stride, m_skip, m_order, tq, ttype, e_lj, e_c, pc); }
+        else if (k == 2) { HostPass<TRI, MODE, 2, 1, REP> hp; hp.load(P, pos, list + base); hp.run_guest(com, offb, cap, n, t0, stride, m_skip, m_order, tq, ttype, e_lj, e_c, pc); }
+        else { HostPass<TRI, MODE, 1, 3, REP> hp; hp.load(P, pos, list + base); hp.run_guest(com, offb, cap, n, t0, stride, m_skip, m_order, tq, ttype, e_lj, e_c, pc); }
+    }
+}
+
+// The walker's guests: for every (target residue g, target atom b) the probe's atoms were sorted at
+// init by what they exchange with that target atom (nothing / LJ / Coulomb / both: it only depends on
+// the two atom types and charges), and each list is swept with the branch-free body of the
+// framework passes, lanes over the molecules of g.
+template <bool TRI, int REP>
+__device__ __forceinline__ void guest_loops(const Probe &P, const double (*pos)[3], const Smem &S, int w, int t0, int stride,
+                                            double &e_lj, double &e_c, PairCount &pc)
+{
     const double *wc = c_sys.coords + (int64_t)w * c_sys.coord_stride;
     for (int g = 0; g < c_sys.nres; ++g) {
         if (!c_sys.active[g]) continue;
-        const int cap = c_sys.cap[g], na_g = c_sys.natom[g], n = S.ws->count[g];
+        const int n = S.ws->count[g];
+        if (n == 0) continue;
+        const int cap = c_sys.cap[g], na_g = c_sys.natom[g];
         const double *com = wc + c_sys.goff[g];
         const double *off = com + 3 * (int64_t)cap;
-        for (int m = t0; m < n; m += stride) {
-            if (g == P.excl_res && m == P.excl_mol) continue;
-            if (P.order_res >= 0 && (g < P.order_res || (g == P.order_res && m <= P.order_mol))) continue;
-            const double cx = com[m], cy = com[cap + m], cz = com[2 * cap + m];
-            for (int b = 0; b < na_g; ++b) {
-                const double *ob = off + (int64_t)b * 3 * cap;
-                const double tx = cx + ob[m], ty = cy + ob[cap + m], tz = cz + ob[2 * cap + m];
-                double tq = c_sys.charge[g][b];
-                if (fabs(tq) < MGPU_ERR_TOL) tq = 0.0;
-                probe_vs_guest_atom<TRI, REP>(P, pos, S, tx, ty, tz, tq, c_sys.type[g][b], e_lj, e_c, pc);
-            }
+        const int m_skip = (g == P.excl_res) ? P.excl_mol : -1;
+        int m_order = -1;                                        // molecules m <= m_order are skipped
+        if (P.order_res >= 0) m_order = (g < P.order_res) ? n : (g == P.order_res ? P.order_mol : -1);
+        if (m_order >= n - 1 || (n == 1 && m_skip == 0)) continue;
+        for (int b = 0; b < na_g; ++b) {
+            const double *offb = off + (int64_t)b * 3 * cap;
+            double tq = c_sys.charge[g][b];
+            if (fabs(tq) < MGPU_ERR_TOL) tq = 0.0;
+            const int ttype = c_sys.type[g][b];
+            const int gi = gl_index(P.res, g, b, 0);
+            const int8_t *L = c_sys.gl_list + (int64_t)gi * MGPU_MAX_SITES;
+            const int8_t *N = c_sys.gl_n + gi;
+            guest_list<TRI, 1, REP>(P, pos, L + 1 * MGPU_MAX_SITES, N[1], com, offb, cap, n, t0, stride, m_skip, m_order, tq, ttype, e_lj, e_c, pc);
+            guest_list<TRI, 2, REP>(P, pos, L + 2 * MGPU_MAX_SITES, N[2], com, offb, cap, n, t0, stride, m_skip, m_order, tq, ttype, e_lj, e_c, pc);
+            guest_list<TRI, 3, REP>(P, pos, L + 3 * MGPU_MAX_SITES, N[3], com, offb, cap, n, t0, stride, m_skip, m_order, tq, ttype, e_lj, e_c, pc);
+            guest_list<TRI, 0, REP>(P, pos, L + 0 * MGPU_MAX_SITES, N[0], com, offb, cap, n, t0, stride, m_skip, m_order, tq, ttype, e_lj, e_c, pc);
         }
     }
 }
 
 // K1: group-cooperative pair sums of the probe against host atoms + the walker's guests.
-// A move needs the old AND the new geometry: the group splits in two halves, one per
-// geometry, so every thread works on a single geometry.  Creation / deletion / Widom use
-// the whole group on the one geometry there is.
-// Returns {lj_old, coul_old(e^2/A), lj_new, coul_new(e^2/A)} in every thread of the group.
+// When two geometries need the same kind of pass (old AND new of a move) the group splits in
+// two halves, one per geometry, so every thread works on a single geometry; otherwise the
+// whole group works on the one geometry there is (creation / deletion / Widom; and the
+// framework pass of a move whose old-geometry framework sum comes from the per-molecule cache).
+// out[0..3] = framework part {lj_old, coul_old(e^2/A), lj_new, coul_new}; out[4..7] = guest part.
+// Valid in every thread of the group.
 template <bool TRI, int NT>
-__device__ __noinline__ void pair_sums(const Smem &S, int w, double (&out)[4], PairCount &pc)
+__device__ __noinline__ void pair_sums(const Smem &S, int w, double (&out)[8], PairCount &pc)
 {
     const Probe &P = S.ws->probe;
     const int gt = Grp<NT>::tid();
-    const bool both = P.has_old && P.has_new;
-    const bool new_set = both ? (gt >= NT / 2) : (P.has_new != 0);
-    const int stride = both ? NT / 2 : NT;
-    const int t0 = both ? (gt & (NT / 2 - 1)) : gt;
-    double e_lj = 0.0, e_c = 0.0;
     PairCount pcl = pc;                      // by value: keeps the counters in registers inside the loops
-    pair_loops<TRI, TabRep<NT>::v>(P, new_set ? P.pn : P.po, S, w, t0, stride, e_lj, e_c, pcl);
-    pc = pcl;
-    double acc[4];
-    acc[0] = new_set ? 0.0 : e_lj; acc[1] = new_set ? 0.0 : e_c;
-    acc[2] = new_set ? e_lj : 0.0; acc[3] = new_set ? e_c : 0.0;
-    Grp<NT>::template sum<4>(acc, S.ws->red);
+    double acc[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) out[i] = acc[i];
+    for (int i = 0; i < 8; ++i) acc[i] = 0.0;
+    if (P.host_old || P.host_new) {
+        const bool both = P.host_old && P.host_new;
+        const bool new_set = both ? (gt >= NT / 2) : (P.host_new != 0);
+        const int stride = both ? NT / 2 : NT;
+        const int t0 = both ? (gt & (NT / 2 - 1)) : gt;
+        double e_lj = 0.0, e_c = 0.0;
+        host_loops<TRI, TabRep<NT>::v>(P, new_set ? P.pn : P.po, S, t0, stride, e_lj, e_c, pcl);
+        acc[0] = new_set ? 0.0 : e_lj; acc[1] = new_set ? 0.0 : e_c;
+        acc[2] = new_set ? e_lj : 0.0; acc[3] = new_set ? e_c : 0.0;
+    }
+    {
+        const bool both = P.has_old && P.has_new;
+        const bool new_set = both ? (gt >= NT / 2) : (P.has_new != 0);
+        const int stride = both ? NT / 2 : NT;
+        const int t0 = both ? (gt & (NT / 2 - 1)) : gt;
+        double e_lj = 0.0, e_c = 0.0;
+        guest_loops<TRI, TabRep<NT>::v>(P, new_set ? P.pn : P.po, S, w, t0, stride, e_lj, e_c, pcl);
+        acc[4] = new_set ? 0.0 : e_lj; acc[5] = new_set ? 0.0 : e_c;
+        acc[6] = new_set ? e_lj : 0.0; acc[7] = new_set ? e_c : 0.0;
+    }
+    pc = pcl;
+    Grp<NT>::template sum<8>(acc, S.ws->red);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] = acc[i];
+}
+
+// per-molecule framework-energy cache of walker w, residue res: rows {lj, coulomb (e^2/A)} x cap,
+// stored right behind the offset rows of the residue block
+__device__ __forceinline__ double *hcache_rows(int w, int res)
+{
+    return c_sys.coords + (int64_t)w * c_sys.coord_stride + c_sys.goff[res] + (int64_t)(3 + 3 * c_sys.natom[res]) * c_sys.cap[res];
 }
 
 // intra_res_real_coulomb_energy, ewald_energy.f90:212-252 (one thread, tiny)
@@ -674,6 +761,8 @@ __device__ __forceinline__ void stage_probe(const Smem &S, int w, int kind, int 
         P.has_new = (kind != MGPU_KIND_DELETE);
         P.excl_res = res; P.excl_mol = mol;
         P.order_res = -1; P.order_mol = -1;
+        P.host_old = P.has_old && !c_sys.use_hcache;
+        P.host_new = P.has_new;
     }
     if (t < na) {
         const double q = c_sys.charge[res][t];
@@ -690,12 +779,18 @@ __device__ __forceinline__ void stage_probe(const Smem &S, int w, int kind, int 
 // Evaluate one trial held in the group's probe (positions staged): fills e_old / e_new
 // (6 each, valid in every thread) and writes S_trial into the walker's non-committed buffer
 // (store_S) -- compute_old_energy / compute_new_energy, monte_carlo_utils.f90:300-423.
+// hc_new = framework part of the new geometry {lj, coulomb (e^2/A)}: the cache entry if the trial is committed.
 template <bool TRI, int NT>
-__device__ void evaluate_trial(const Smem &S, int w, bool store_S, double e_old[6], double e_new[6], PairCount &pc)
+__device__ void evaluate_trial(const Smem &S, int w, bool store_S, double e_old[6], double e_new[6], double hc_new[2], PairCount &pc)
 {
     const Probe &P = S.ws->probe;
-    double ps[4];
+    double ps[8];
     pair_sums<TRI, NT>(S, w, ps, pc);
+    if (P.has_old && !P.host_old) {          // framework sum of the committed geometry: cached at its own commit / rebuild
+        const double *hc = hcache_rows(w, P.res);
+        ps[0] = hc[P.mol]; ps[1] = hc[c_sys.cap[P.res] + P.mol];
+    }
+    hc_new[0] = ps[2]; hc_new[1] = ps[3];
     if (P.has_old) fill_phase_tables(S.tab_old, P.po, P.na, Grp<NT>::tid(), NT);
     if (P.has_new) fill_phase_tables(S.tab_new, P.pn, P.na, Grp<NT>::tid(), NT);
     Grp<NT>::sync();
@@ -709,12 +804,12 @@ __device__ void evaluate_trial(const Smem &S, int w, bool store_S, double e_old[
     e_old[MGPU_E_RECIP] = recip_cur;
     e_new[MGPU_E_RECIP] = recip_new;
     if (P.has_old) {
-        e_old[MGPU_E_NON_COULOMB] = ps[0];
-        e_old[MGPU_E_COULOMB] = ps[1] * c_sys.eps0_inv_real;
+        e_old[MGPU_E_NON_COULOMB] = ps[0] + ps[4];
+        e_old[MGPU_E_COULOMB] = (ps[1] + ps[5]) * c_sys.eps0_inv_real;
     }
     if (P.has_new) {
-        e_new[MGPU_E_NON_COULOMB] = ps[2];
-        e_new[MGPU_E_COULOMB] = ps[3] * c_sys.eps0_inv_real;
+        e_new[MGPU_E_NON_COULOMB] = ps[2] + ps[6];
+        e_new[MGPU_E_COULOMB] = (ps[3] + ps[7]) * c_sys.eps0_inv_real;
     }
     if (P.kind != MGPU_KIND_MOVE) {
         // rigid molecule: one thread evaluates the 1/2 na (na-1) intramolecular pairs, then broadcast
@@ -738,7 +833,7 @@ __device__ void evaluate_trial(const Smem &S, int w, bool store_S, double e_old[
 // accept_molecule_move / accept_creation_move / accept_deletion_move + remove_molecule +
 // update_counts (monte_carlo_utils.f90:429-442,642-672; creation.f90:82-116; deletion.f90:83-122).
 __device__ void commit_trial(int w, int kind, int res, int mol, const double *com, const double (*off)[3],
-                             const double e_old[6], const double e_new[6], int tid, int nthreads)
+                             const double e_old[6], const double e_new[6], const double hc_new[2], int tid, int nthreads)
 {
     double *wc = c_sys.coords + (int64_t)w * c_sys.coord_stride + c_sys.goff[res];
     const int cap = c_sys.cap[res], na = c_sys.natom[res];
@@ -746,13 +841,14 @@ __device__ void commit_trial(int w, int kind, int res, int mol, const double *co
     const int n = c_sys.count[(int64_t)w * MGPU_MAX_RES + res];
     if (kind == MGPU_KIND_DELETE) {
         const int last = n - 1;
-        if (mol != last) {
+        if (mol != last) {                  // the last molecule moves into the hole, with its cache rows (na*3, na*3+1)
             if (tid < 3) wc[tid * cap + mol] = wc[tid * cap + last];
-            for (int e = tid; e < na * 3; e += nthreads) offs[(int64_t)e * cap + mol] = offs[(int64_t)e * cap + last];
+            for (int e = tid; e < na * 3 + 2; e += nthreads) offs[(int64_t)e * cap + mol] = offs[(int64_t)e * cap + last];
         }
     } else {
         if (tid < 3) wc[tid * cap + mol] = com[tid];
         for (int e = tid; e < na * 3; e += nthreads) offs[(int64_t)e * cap + mol] = off[e / 3][e % 3];
+        if (tid < 2) offs[(int64_t)(na * 3 + tid) * cap + mol] = hc_new[tid];
     }
     if (tid == 0) {
         if (kind == MGPU_KIND_CREATE) c_sys.count[(int64_t)w * MGPU_MAX_RES + res] = n + 1;
@@ -818,15 +914,16 @@ __global__ void __launch_bounds__(NT == 32 ? MGPU_WBLOCK : MGPU_BLOCK, 1) k_tria
     const double(*off)[3] = reinterpret_cast<const double(*)[3]>(T.off + (int64_t)t * MGPU_MAX_SITES * 3);
     stage_probe<NT>(S, w, kind, res, mol, com, off);
     Grp<NT>::sync();
-    double e_old[6], e_new[6];
+    double e_old[6], e_new[6], hc_new[2];
     PairCount pc = { 0u, 0u, 0u };
-    evaluate_trial<TRI, NT>(S, w, true, e_old, e_new, pc);
+    evaluate_trial<TRI, NT>(S, w, true, e_old, e_new, hc_new, pc);
     flush_pair_count(pc);
     // record the pending trial
     MgpuTrial *tr = c_sys.trial + w;
     if (gt == 0) {
         tr->active = 1; tr->kind = kind; tr->res = res; tr->mol = mol;
         for (int d = 0; d < 3; ++d) tr->com[d] = (kind == MGPU_KIND_DELETE) ? 0.0 : com[d];
+        tr->hc_new[0] = hc_new[0]; tr->hc_new[1] = hc_new[1];
         for (int i = 0; i < 6; ++i) { tr->e_old[i] = e_old[i]; tr->e_new[i] = e_new[i]; T.out[(int64_t)t * 12 + i] = e_old[i]; T.out[(int64_t)t * 12 + 6 + i] = e_new[i]; }
     }
     if (kind != MGPU_KIND_DELETE)
@@ -839,7 +936,7 @@ __global__ void __launch_bounds__(128) k_commit(const int32_t *walker, const int
     const int w = walker[t];
     MgpuTrial *tr = c_sys.trial + w;
     if (!tr->active) { if (threadIdx.x == 0) atomicExch(err, 1); return; }
-    if (accept[t]) commit_trial(w, tr->kind, tr->res, tr->mol, tr->com, tr->off, tr->e_old, tr->e_new, threadIdx.x, blockDim.x);
+    if (accept[t]) commit_trial(w, tr->kind, tr->res, tr->mol, tr->com, tr->off, tr->e_old, tr->e_new, tr->hc_new, threadIdx.x, blockDim.x);
     else if (tr->kind == MGPU_KIND_CREATE && tr->mol == 0) write_slot(w, tr->res, 0, tr->com, tr->off, threadIdx.x, blockDim.x);
     __syncthreads();
     if (threadIdx.x == 0) tr->active = 0;
@@ -857,6 +954,7 @@ __global__ void __launch_bounds__(MGPU_BLOCK) k_pair_molecule(int w, int res, in
     const int na = c_sys.natom[res];
     if (threadIdx.x == 0) {
         P.kind = MGPU_KIND_DELETE; P.res = res; P.mol = mol; P.na = na; P.has_old = 1; P.has_new = 0;
+        P.host_old = 1; P.host_new = 0;
         P.excl_res = res; P.excl_mol = mol;
         P.order_res = skip_ordering ? -1 : res; P.order_mol = skip_ordering ? -1 : mol;
     }
@@ -868,10 +966,10 @@ __global__ void __launch_bounds__(MGPU_BLOCK) k_pair_molecule(int w, int res, in
         else load_positions(w, res, mol, P.po, a);
     }
     __syncthreads();
-    double ps[4];
+    double ps[8];
     PairCount pc = { 0u, 0u, 0u };
     pair_sums<TRI, MGPU_BLOCK>(S, w, ps, pc);
-    if (threadIdx.x == 0) { out2[0] = ps[0]; out2[1] = ps[1] * c_sys.eps0_inv_real; }
+    if (threadIdx.x == 0) { out2[0] = ps[0] + ps[4]; out2[1] = (ps[1] + ps[5]) * c_sys.eps0_inv_real; }
 }
 
 template <bool TRI>
@@ -994,6 +1092,7 @@ __global__ void __launch_bounds__(MGPU_BLOCK) k_total_energy(int first_walker, i
             __syncthreads();
             if (threadIdx.x == 0) {
                 P.kind = MGPU_KIND_DELETE; P.res = g; P.mol = m; P.na = na; P.has_old = 1; P.has_new = 0;
+                P.host_old = 1; P.host_new = 0;
                 P.excl_res = g; P.excl_mol = m; P.order_res = g; P.order_mol = m;
             }
             if (threadIdx.x < na) {
@@ -1002,10 +1101,14 @@ __global__ void __launch_bounds__(MGPU_BLOCK) k_total_energy(int first_walker, i
                 load_positions(w, g, m, P.po, threadIdx.x);
             }
             __syncthreads();
-            double ps[4];
+            double ps[8];
             pair_sums<TRI, MGPU_BLOCK>(S, w, ps, pc);
-            e_lj += ps[0]; e_c += ps[1];
-            if (threadIdx.x == 0) e_intra += intra_energy<TRI>(g, P.po);
+            e_lj += ps[0] + ps[4]; e_c += ps[1] + ps[5];
+            if (threadIdx.x == 0) {
+                e_intra += intra_energy<TRI>(g, P.po);
+                double *hc = hcache_rows(w, g);              // (re)fill the molecule's framework-energy cache
+                hc[m] = ps[0]; hc[c_sys.cap[g] + m] = ps[1];
+            }
         }
         e_self += c_sys.e_self[g] * n;
     }
@@ -1203,12 +1306,12 @@ __global__ void __launch_bounds__(MGPU_WBLOCK, 1) k_sweep(int first_walker, int 
         if (sh.valid) {
             stage_probe<32>(S, w, sh.kind, sh.res, sh.mol, sh.com, sh.off);
             __syncwarp();
-            double e_old[6], e_new[6];
-            evaluate_trial<TRI, 32>(S, w, sh.move != MGPU_MV_WIDOM, e_old, e_new, pc);
+            double e_old[6], e_new[6], hc_new[2];
+            evaluate_trial<TRI, 32>(S, w, sh.move != MGPU_MV_WIDOM, e_old, e_new, hc_new, pc);
             if (lane == 0) decide_step(w, ws, e_old, e_new);
             __syncwarp();
             if (sh.accept) {
-                commit_trial(w, sh.kind, sh.res, sh.mol, sh.com, sh.off, sh.e_old, sh.e_new, lane, 32);
+                commit_trial(w, sh.kind, sh.res, sh.mol, sh.com, sh.off, sh.e_old, sh.e_new, hc_new, lane, 32);
                 if (lane == 0) {
                     if (sh.kind == MGPU_KIND_CREATE) ws.count[sh.res] += 1;
                     if (sh.kind == MGPU_KIND_DELETE) ws.count[sh.res] -= 1;
@@ -1298,8 +1401,8 @@ __global__ void __launch_bounds__(MGPU_WBLOCK, 1) k_widom_batch(int w, int res, 
         __syncwarp();
         stage_probe<32>(S, w, MGPU_KIND_CREATE, res, slot, ws.sh.com, ws.sh.off);
         __syncwarp();
-        double e_old[6], e_new[6];
-        evaluate_trial<TRI, 32>(S, w, false, e_old, e_new, pc);
+        double e_old[6], e_new[6], hc_new[2];
+        evaluate_trial<TRI, 32>(S, w, false, e_old, e_new, hc_new, pc);
         if (lane == 0) {
             const double dU = e_new[MGPU_E_TOTAL] - recip_cur;
             if (dE_out) dE_out[i] = dU;

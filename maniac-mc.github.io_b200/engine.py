@@ -21,6 +21,7 @@ from .inputs import ERROR, System
 
 E_NON_COULOMB, E_COULOMB, E_RECIP, E_SELF, E_INTRA, E_TOTAL = range(6)
 KIND_MOVE, KIND_CREATE, KIND_DELETE = 0, 1, 2
+OPT_HOST_CACHE = 1
 MV_NONE, MV_TRANSLATE, MV_ROTATE, MV_CREATE, MV_DELETE, MV_SWAP, MV_WIDOM = range(7)
 
 TRACE_DTYPE = np.dtype([("move", "i4"), ("res", "i4"), ("mol", "i4"), ("accepted", "i4"),
@@ -202,6 +203,10 @@ class Engine:
         return out
 
     # -- the reference's energy routines ---------------------------------------------------------
+    def set_option(self, option, value):
+        """mgpu_set_option; OPT_HOST_CACHE = 1 (per-molecule framework-energy cache on / off)."""
+        self._ck(self.L.mgpu_set_option(int(option), int(value)))
+
     def update_system_energy(self, walker=0):
         out = np.zeros(6)
         self._ck(self.L.mgpu_total_energy(walker, _pd(out)))

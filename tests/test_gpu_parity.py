@@ -24,10 +24,20 @@ def assert_e(a, b, rel=REL_E, what=""):
     assert close_e(a, b, rel), f"{what}: gpu={np.asarray(a)!r} ref={np.asarray(b)!r} diff={np.asarray(a) - np.asarray(b)!r}"
 
 
-@pytest.fixture
-def engine_cls():
-    from maniac_b200.engine import Engine
-    return Engine
+@pytest.fixture(params=["hcache", "nocache"])
+def engine_cls(request):
+    """Every parity test runs twice: with the per-molecule framework-energy cache (default: the old
+    geometry of a move / deletion reads the molecule's cached framework sum) and without it (the
+    framework is swept for old and new geometry, like the reference does)."""
+    from maniac_b200.engine import OPT_HOST_CACHE, Engine
+    if request.param == "hcache":
+        return Engine
+
+    class EngineNoCache(Engine):
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+            self.set_option(OPT_HOST_CACHE, 0)
+    return EngineNoCache
 
 
 ALL = ["lj_gas", "zif8_h2o", "h2o_gas", "methanol", "two_atoms", "dipole", "two_dipole", "dipole_triclinic",
