@@ -298,6 +298,25 @@ def main():
                 "note": "mgpu_set_option(MGPU_OPT_HOST_CACHE, 0): old-geometry framework sums recomputed every trial"}
     eng.set_option(OPT_HOST_CACHE, 1)
 
+    # ---- the same sweep without the per-quartet phase alignment (MGPU_OPT_PHASE_SYNC) -------------
+    from maniac_b200.engine import OPT_PHASE_SYNC
+    eng.set_option(OPT_PHASE_SYNC, 0)
+    eng.sweep(a.inner)
+    eng.timing_reset()
+    barrier()
+    for _ in range(2):
+        eng.sweep(a.inner)
+    barrier()
+    ms_ns, _ = eng.timing("sweep")
+    t_ns = ms_ns * 1e-3
+    if world > 1:
+        t = torch.tensor([t_ns], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_ns = float(t[0])
+    no_sync = {"moves_per_s": float(W) * a.inner * 2 * world / t_ns,
+               "note": "mgpu_set_option(MGPU_OPT_PHASE_SYNC, 0): walkers of a CTA free-running (no per-quartet barrier)"}
+    eng.set_option(OPT_PHASE_SYNC, 1)
+
     # ---- Widom batch (configs[2]) ------------------------------------------------------------
     widom = None
     eng.close()
@@ -377,7 +396,7 @@ def main():
     line = {"metric": "mc_trial_moves_per_s", "value": value, "unit": "moves/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": 1e3 * t_dev / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "clocks": clocks,
-            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "widom": widom, "no_host_cache": no_cache,
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "widom": widom, "no_host_cache": no_cache, "no_phase_sync": no_sync,
             "wall_s_timed_region": wall, "mean_waters_per_walker": nmean, "fp64_peak_tflops_measured": peak_tf}
     print(json.dumps(line))
 

@@ -50,7 +50,11 @@ enum { MGPU_E_NON_COULOMB = 0, MGPU_E_COULOMB = 1, MGPU_E_RECIP = 2,
        MGPU_E_SELF = 3, MGPU_E_INTRA = 4, MGPU_E_TOTAL = 5 };
 
 /* is_creation / is_deletion flags of compute_old/new_energy */
-enum { MGPU_KIND_MOVE = 0, MGPU_KIND_CREATE = 1, MGPU_KIND_DELETE = 2 };
+enum { MGPU_KIND_MOVE = 0, MGPU_KIND_CREATE = 1, MGPU_KIND_DELETE = 2,
+       /* identity swap (src/swapping.f90:34-105): deletion-style old energy of (res, mol) +
+        * creation-style new energy of a molecule of another type at the same CoM.  In
+        * mgpu_trial_batch the new type rides in the upper bits: kind = MGPU_KIND_SWAP | (res_new << 8) */
+       MGPU_KIND_SWAP = 3 };
 
 /* move codes reported by mgpu_sweep traces (same numbering as the oracle) */
 enum { MGPU_MV_NONE = 0, MGPU_MV_TRANSLATE = 1, MGPU_MV_ROTATE = 2, MGPU_MV_CREATE = 3,
@@ -106,6 +110,10 @@ int  mgpu_device_info(char *name, int name_len, int *sm_count, double *mem_gb);
 int mgpu_get_ewald(double *alpha, int32_t kmax[3], int32_t *nkvec, double *rc_used);
 int mgpu_get_kvectors(int32_t *kx, int32_t *ky, int32_t *kz, double *k_squared_mag, double *form_factor_times_weight);
 int mgpu_get_box(double matrix[9], double reciprocal[9], double *volume, int32_t *is_triclinic);
+/* triclinic cells: number of extra lattice vectors min_image examines per pair after rounding the
+ * fractional coordinates (0 for orthorhombic cells); -1 = the literal 27-image search of
+ * src/geometry_utils.f90:263-280 is used for every pair (very skewed cell) */
+int mgpu_get_triclinic_candidates(int32_t *n);
 int mgpu_get_thermo(int32_t res, double *beta, double *lambda, double *mu_walker0);
 
 /* ---- per-walker state --------------------------------------------------------------- */
@@ -130,7 +138,12 @@ int mgpu_get_energy(int32_t walker, double out[6]);
  * OLD geometry of a move / deletion reads it instead of sweeping the framework again.
  * 0 = recompute it every trial, like pairwise_energy_for_molecule on the old geometry
  * (src/monte_carlo_utils.f90:367-423) does.  Same energies to rounding either way. */
-enum { MGPU_OPT_HOST_CACHE = 1 };
+enum { MGPU_OPT_HOST_CACHE = 1,
+       /* MGPU_OPT_PHASE_SYNC (default 1): in mgpu_sweep the four walkers (warps) that share an SM
+        * sub-partition start every MC step together (named barrier), so they run the same loop at the
+        * same time and share its instructions in the L0 instruction cache.  Results are identical
+        * either way (walkers never exchange data). */
+       MGPU_OPT_PHASE_SYNC = 2 };
 int mgpu_set_option(int32_t option, int32_t value);
 
 /* ---- energy routines (single walker, drop-in) -------------------------------------- */
@@ -155,6 +168,13 @@ int mgpu_old_energy(int32_t walker, int32_t res, int32_t mol, int32_t kind, doub
  * host proposed; DELETE: ignored (may be NULL).  Leaves a pending trial on the walker. */
 int mgpu_new_energy(int32_t walker, int32_t res, int32_t mol, int32_t kind,
                     const double *com, const double *offset, double out[6]);
+/* attempt_swap_move, src/swapping.f90:59-88: compute_old_energy(res_old, mol_old, is_deletion) and,
+ * with that molecule removed, compute_new_energy(res_new, N(res_new)+1, is_creation) for the geometry
+ * (com, offset[natom(res_new)][3]) the host built with insert_and_orient_molecule.  Like the
+ * reference, S(k) of the trial keeps the swapped-out molecule's contribution.  Leaves a pending
+ * trial: mgpu_commit = accept_swap_move (:143-155), mgpu_rollback = reject_swap_move (:113-137). */
+int mgpu_swap_energy(int32_t walker, int32_t res_old, int32_t mol_old, int32_t res_new,
+                     const double *com, const double *offset, double e_old[6], double e_new[6]);
 /* accept_molecule_move :429-442 / accept_creation_move (creation.f90:82-116) /
  * accept_deletion_move (deletion.f90:83-122) incl. remove_molecule + update_counts */
 int mgpu_commit(int32_t walker);

@@ -54,6 +54,7 @@ SIGNATURES = {
     "mgpu_get_ewald": (C.c_int, [_pd, _pi, _pi, _pd]),
     "mgpu_get_kvectors": (C.c_int, [_pi, _pi, _pi, _pd, _pd]),
     "mgpu_get_box": (C.c_int, [_pd, _pd, _pd, _pi]),
+    "mgpu_get_triclinic_candidates": (C.c_int, [_pi]),
     "mgpu_get_thermo": (C.c_int, [I, _pd, _pd, _pd]),
     "mgpu_set_molecule": (C.c_int, [I, I, I, _pd, _pd]),
     "mgpu_get_molecule": (C.c_int, [I, I, I, _pd, _pd]),
@@ -71,6 +72,7 @@ SIGNATURES = {
     "mgpu_reciprocal_ewald_energy": (C.c_int, [I, _pd]),
     "mgpu_old_energy": (C.c_int, [I, I, I, I, _pd]),
     "mgpu_new_energy": (C.c_int, [I, I, I, I, _pd, _pd, _pd]),
+    "mgpu_swap_energy": (C.c_int, [I, I, I, I, _pd, _pd, _pd, _pd]),
     "mgpu_commit": (C.c_int, [I]),
     "mgpu_rollback": (C.c_int, [I]),
     "mgpu_trial_batch": (C.c_int, [I, _pi, _pi, _pi, _pi, _pd, _pd, _pd, _pd]),

@@ -47,6 +47,7 @@ struct Context {
     int natom_max = 1;
     size_t smem1 = 0, smem8 = 0, smem_buildS = 0;   // dynamic shared memory: 1 group (CTA) / MGPU_WARPS groups (warps) per CTA
     int sm_count = 0, ctas_per_sm = 1;
+    int phase_sync = 1;                // MGPU_OPT_PHASE_SYNC
     int wgroups = MGPU_WGROUPS;        // walkers (warps) per CTA of the warp-per-task kernels
     int tab_emin = 0, tab_noct = 0;
     std::vector<void *> allocs;
@@ -132,7 +133,6 @@ int check_err_flag(const char *where)
         cudaStreamSynchronize(g.stream);
         if (e == 1) return fail(std::string(where) + ": commit without a pending trial");
         if (e == 2) return fail(std::string(where) + ": Trying to insert a molecule beyond the walker's capacity (NB_MAX_MOLECULE analogue)");
-        if (e == 3) return fail(std::string(where) + ": swap moves are not available in the device-resident sweep");
         return fail(std::string(where) + ": device error flag");
     }
     return 0;
@@ -233,6 +233,25 @@ int mgpu_init(const mgpu_system *sys)
         for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) h.Hinv[i * 3 + j] = rcp * adj[i][j];
     }
     for (int d = 0; d < 3; ++d) { h.L[d] = M[d][d]; h.invL[d] = 1.0 / M[d][d]; }
+    h.tri_nrel = 0;
+    if (h.triclinic) {
+        // lattice vectors that can beat the fractionally rounded image (min_image_r2<true>): m is relevant iff
+        // min over f in [-1/2,1/2]^3 of |C(f+m)|^2 - |C f|^2 = m.G.m - sum_d |(G m)_d| < 0, G = C^T C (C = columns of matrix)
+        double G[3][3];
+        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { G[a][b] = 0.0; for (int i = 0; i < 3; ++i) G[a][b] += M[i][a] * M[i][b]; }
+        int n = 0;
+        for (int a = -3; a <= 3 && n >= 0; ++a) for (int b = -3; b <= 3 && n >= 0; ++b) for (int c = -3; c <= 3; ++c) {
+            if (!a && !b && !c) continue;
+            const double m[3] = { (double)a, (double)b, (double)c };
+            double Gm[3], mGm = 0.0, s1 = 0.0;
+            for (int d = 0; d < 3; ++d) { Gm[d] = G[d][0] * m[0] + G[d][1] * m[1] + G[d][2] * m[2]; mGm += m[d] * Gm[d]; s1 += std::fabs(Gm[d]); }
+            if (!(mGm < s1 * (1.0 - 1e-13))) continue;
+            if (n == MGPU_TRI_MAXREL || std::abs(a) == 3 || std::abs(b) == 3 || std::abs(c) == 3) { n = -1; break; }   // very skewed cell: literal search
+            for (int i = 0; i < 3; ++i) { h.tri_rel[n][i] = M[i][0] * m[0] + M[i][1] * m[1] + M[i][2] * m[2]; h.tri_m[n][i] = m[i]; }
+            ++n;
+        }
+        h.tri_nrel = n;
+    }
 
     // ---- Ewald: setup_ewald, prepare_utils.f90:110-226 ----
     double rc = sys->real_space_cutoff;
@@ -569,6 +588,7 @@ int mgpu_get_box(double matrix[9], double reciprocal[9], double *volume, int32_t
     if (is_triclinic) *is_triclinic = g.h.triclinic;
     return 0;
 }
+int mgpu_get_triclinic_candidates(int32_t *n) { NEED_READY(); *n = g.h.tri_nrel; return 0; }
 int mgpu_get_thermo(int32_t res, double *beta, double *lambda, double *mu_walker0)
 {
     NEED_READY();
@@ -663,6 +683,7 @@ int mgpu_get_energy(int32_t w, double out[6])
 int mgpu_set_option(int32_t option, int32_t value)
 {
     NEED_READY();
+    if (option == MGPU_OPT_PHASE_SYNC) { g.phase_sync = value ? 1 : 0; return 0; }
     if (option == MGPU_OPT_HOST_CACHE) {
         g.h.use_hcache = value ? 1 : 0;
         if (upload_sys()) return 1;
@@ -749,8 +770,13 @@ int mgpu_trial_batch(int32_t n, const int32_t *walker, const int32_t *res, const
     if (ensure_task_cap(n)) return 1;
     for (int t = 0; t < n; ++t) {
         if (check_walker(walker[t]) || check_guest(res[t])) return 1;
-        if (kind[t] < MGPU_KIND_MOVE || kind[t] > MGPU_KIND_DELETE) return fail("mgpu_trial_batch: unknown kind");
+        const int k = kind[t] & 0xff, res2 = kind[t] >> 8;
+        if (k < MGPU_KIND_MOVE || k > MGPU_KIND_SWAP || (k != MGPU_KIND_SWAP && res2 != 0)) return fail("mgpu_trial_batch: unknown kind");
         if (mol[t] < 0 || mol[t] >= g.h.cap[res[t]]) return fail("Trying to insert / move a molecule with an index beyond the walker's capacity");
+        if (k == MGPU_KIND_SWAP) {
+            if (check_guest(res2)) return 1;
+            if (res2 == res[t]) return fail("mgpu_trial_batch: swap needs two different residue types");
+        }
         if (ensure_clean(walker[t])) return 1;
         g.h_task_i[4 * t] = walker[t]; g.h_task_i[4 * t + 1] = res[t]; g.h_task_i[4 * t + 2] = mol[t]; g.h_task_i[4 * t + 3] = kind[t];
     }
@@ -827,6 +853,17 @@ int mgpu_new_energy(int32_t w, int32_t res, int32_t mol, int32_t kind, const dou
     if (com) std::memcpy(c3, com, sizeof c3);
     return mgpu_trial_batch(1, &w, &res, &mol, &kind, c3, off16, nullptr, out);
 }
+int mgpu_swap_energy(int32_t w, int32_t res_old, int32_t mol_old, int32_t res_new, const double *com, const double *offset,
+                     double e_old[6], double e_new[6])
+{
+    NEED_READY();
+    if (check_walker(w) || check_guest(res_old) || check_guest(res_new)) return 1;
+    if (!com || !offset) return fail("mgpu_swap_energy: geometry of the new molecule required");
+    double off16[MGPU_MAX_SITES * 3] = { 0 };
+    std::memcpy(off16, offset, sizeof(double) * 3 * g.h.natom[res_new]);
+    int32_t kind = MGPU_KIND_SWAP | (res_new << 8);
+    return mgpu_trial_batch(1, &w, &res_old, &mol_old, &kind, com, off16, e_old, e_new);
+}
 int mgpu_commit(int32_t w) { int32_t one = 1; return mgpu_commit_batch(1, &w, &one); }
 int mgpu_rollback(int32_t w) { int32_t zero = 0; return mgpu_commit_batch(1, &w, &zero); }
 
@@ -860,8 +897,8 @@ int mgpu_sweep(int32_t first, int32_t n, int64_t n_steps, int32_t trace_walker, 
     if (trace) CK(cudaMalloc(&d_trace, sizeof(mgpu_step_trace) * n_steps));
     Timer tm("sweep");
     const int nb_sweep = (n + g.wgroups - 1) / g.wgroups;
-    if (g.h.triclinic) k_sweep<true><<<nb_sweep, 32 * g.wgroups, g.smem8, g.stream>>>(first, n, n_steps, g.natom_max, trace_walker, d_trace, g.d_err);
-    else k_sweep<false><<<nb_sweep, 32 * g.wgroups, g.smem8, g.stream>>>(first, n, n_steps, g.natom_max, trace_walker, d_trace, g.d_err);
+    if (g.h.triclinic) k_sweep<true><<<nb_sweep, 32 * g.wgroups, g.smem8, g.stream>>>(first, n, n_steps, g.natom_max, trace_walker, d_trace, g.d_err, g.phase_sync);
+    else k_sweep<false><<<nb_sweep, 32 * g.wgroups, g.smem8, g.stream>>>(first, n, n_steps, g.natom_max, trace_walker, d_trace, g.d_err, g.phase_sync);
     tm.stop();
     cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess) { if (d_trace) cudaFree(d_trace); return fail(std::string("k_sweep: ") + cudaGetErrorString(le)); }

@@ -49,7 +49,7 @@ struct Walker {
     long long counter[6][2];
     std::vector<double> widom_w; std::vector<long long> widom_n;
 };
-struct Pending { int valid, move, kind, res, mol; double com[3]; double off[MGPU_MAX_SITES][3]; };
+struct Pending { int valid, move, kind, res, mol, res2; double com[3]; double off[MGPU_MAX_SITES][3]; };
 } // namespace
 
 struct mhost_sim {
@@ -190,8 +190,24 @@ int mhost_run(mhost_sim *S, int64_t n_steps, int32_t trace_walker, mgpu_step_tra
                     const int axis = (int)(W.rng.uniform() * 3.0) + 1;
                     rotate_offsets(axis, theta, P.off, na);
                 }
-            } else if (draw <= cumul_swap) {
-                return hfail("mhost_run: swap moves are not implemented in the host driver");
+            } else if (draw <= cumul_swap) {                              // swapping.f90:34-105
+                int res_bis = -1;
+                for (int attempt = 0; attempt < 10; ++attempt) {          // pick_different_residue_type :165-197
+                    const int nt = S->active_list[(int)(W.rng.uniform() * (double)S->active_list.size())];
+                    if (nt != res) { res_bis = nt; break; }
+                }
+                if (res_bis >= 0 && W.count[res_bis] > 0 && mol >= 0) {
+                    const int nb2 = W.count[res_bis], nab = S->res[res_bis].natom;
+                    if (nb2 >= S->res[res_bis].cap) return hfail("Trying to insert a molecule beyond the walker's capacity");
+                    P.valid = 1; P.move = MGPU_MV_SWAP; P.kind = MGPU_KIND_SWAP; P.res2 = res_bis;
+                    std::memcpy(P.com, com + 3 * mol, sizeof(double) * 3);                        // same CoM (:80)
+                    std::memcpy(P.off, W.off[res_bis].data(), sizeof(double) * 3 * nab);          // geometry of molecule 1 of the new type
+                    if (nab != 1) {
+                        const double theta = W.rng.uniform() * TWOPI_;
+                        const int axis = (int)(W.rng.uniform() * 3.0) + 1;
+                        rotate_offsets(axis, theta, P.off, nab);
+                    }
+                }
             } else {
                 bool create = false, widom = false, del = false;
                 if (S->p_insdel > 0) { if (W.rng.uniform() <= 0.5) create = true; else del = true; }
@@ -216,10 +232,12 @@ int mhost_run(mhost_sim *S, int64_t n_steps, int32_t trace_walker, mgpu_step_tra
                 }
             }
             if (P.valid) {
-                S->b_walker[nb] = w; S->b_res[nb] = P.res; S->b_mol[nb] = P.mol; S->b_kind[nb] = P.kind;
+                S->b_walker[nb] = w; S->b_res[nb] = P.res; S->b_mol[nb] = P.mol;
+                S->b_kind[nb] = (P.kind == MGPU_KIND_SWAP) ? (MGPU_KIND_SWAP | (P.res2 << 8)) : P.kind;
                 std::memcpy(&S->b_com[(size_t)3 * nb], P.com, sizeof(double) * 3);
                 std::memset(&S->b_off[(size_t)3 * MGPU_MAX_SITES * nb], 0, sizeof(double) * 3 * MGPU_MAX_SITES);
-                if (P.kind != MGPU_KIND_DELETE) std::memcpy(&S->b_off[(size_t)3 * MGPU_MAX_SITES * nb], P.off, sizeof(double) * 3 * na);
+                const int na_new = (P.kind == MGPU_KIND_SWAP) ? S->res[P.res2].natom : na;
+                if (P.kind != MGPU_KIND_DELETE) std::memcpy(&S->b_off[(size_t)3 * MGPU_MAX_SITES * nb], P.off, sizeof(double) * 3 * na_new);
                 ++nb;
             }
         }
@@ -252,22 +270,32 @@ int mhost_run(mhost_sim *S, int64_t n_steps, int32_t trace_walker, mgpu_step_tra
                 } else if (P.move == MGPU_MV_DELETE) {
                     const double Np1 = (double)(W.count[res] - 1) + 1.0;
                     p = std::fmin(1.0, Np1 * (lam * lam * lam) / S->volume * std::exp(-S->beta * (dU + mu)));
+                } else if (P.move == MGPU_MV_SWAP) {                       // swap_acceptance_probability :264-294, counts as the reference has them there
+                    const double N_old = (double)(W.count[res] - 1), Nplus1 = (double)(W.count[P.res2] + 1) + 1.0;
+                    p = std::fmin(1.0, (N_old / Nplus1) * std::exp(-S->beta * (dU + W.mu[P.res2] - mu)));
                 } else p = std::fmin(1.0, std::exp(-S->beta * dU));
                 acc = W.rng.uniform() <= p;
-                const int ci = (P.move == MGPU_MV_TRANSLATE) ? 0 : (P.move == MGPU_MV_ROTATE) ? 1 : (P.move == MGPU_MV_CREATE) ? 2 : 3;
+                const int ci = (P.move == MGPU_MV_TRANSLATE) ? 0 : (P.move == MGPU_MV_ROTATE) ? 1 : (P.move == MGPU_MV_CREATE) ? 2
+                             : (P.move == MGPU_MV_DELETE) ? 3 : 4;
                 W.counter[ci][0] += 1;
                 if (acc) { W.counter[ci][1] += 1; if (ci >= 2) W.counter[ci][0] += 1; }
             }
             S->b_accept[b] = acc;
             if (acc) {
                 double *com = W.com[res].data(), *off = W.off[res].data();
-                if (P.kind == MGPU_KIND_DELETE) {                         // remove_molecule + update_counts
+                if (P.kind == MGPU_KIND_DELETE || P.kind == MGPU_KIND_SWAP) { // remove_molecule + update_counts
                     const int last = W.count[res] - 1;
                     if (P.mol != last) {
                         std::memcpy(com + 3 * (size_t)P.mol, com + 3 * (size_t)last, sizeof(double) * 3);
                         std::memcpy(off + (size_t)3 * na * P.mol, off + (size_t)3 * na * last, sizeof(double) * 3 * na);
                     }
                     W.count[res] -= 1;
+                    if (P.kind == MGPU_KIND_SWAP) {                       // the new molecule goes to slot N+1 of its type
+                        const int r2 = P.res2, n2 = W.count[r2], na2 = S->res[r2].natom;
+                        std::memcpy(W.com[r2].data() + 3 * (size_t)n2, P.com, sizeof(double) * 3);
+                        std::memcpy(W.off[r2].data() + (size_t)3 * na2 * n2, P.off, sizeof(double) * 3 * na2);
+                        W.count[r2] += 1;
+                    }
                 } else {
                     std::memcpy(com + 3 * (size_t)P.mol, P.com, sizeof(double) * 3);
                     std::memcpy(off + (size_t)3 * na * P.mol, P.off, sizeof(double) * 3 * na);

@@ -30,6 +30,7 @@
 // to the pair's Coulomb scale 1/r is < 4e-15 (tests/test_host_logic.py::
 // test_coulomb_table_accuracy); pairs outside the tabulated range take the exact erfc path,
 // and g = 0 beyond alpha r > MGPU_TAB_XCUT where erfc(x)/r < 1e-24.
+#define MGPU_TRI_MAXREL 14
 #define MGPU_TAB_K 5
 #define MGPU_TAB_ROW 6            // doubles per row
 #define MGPU_TAB_REP 8            // shared-memory replicas
@@ -39,6 +40,7 @@
 struct MgpuTrial {
     int32_t active;               // 1 while a trial is pending on the walker
     int32_t kind, res, mol;
+    int32_t res2, pad_;           // res2: the new residue type of a swap trial
     double  com[3];
     double  off[MGPU_MAX_SITES][3];
     double  e_old[6], e_new[6];
@@ -50,6 +52,11 @@ struct DevSys {
     // box (type_cell, src/simulation_state.f90:103-112)
     double H[9], Hinv[9], lo[3], L[3], invL[3], volume;
     int32_t triclinic;
+    // triclinic minimum image without the 27-image loop (see min_image_r2<true>): lattice vectors
+    // C m (tri_rel) that can beat the fractionally rounded image, and their integer coefficients m
+    // (tri_m); tri_nrel < 0 = too many of them, keep the reference's 27-image search.
+    int32_t tri_nrel;
+    double tri_rel[MGPU_TRI_MAXREL][3], tri_m[MGPU_TRI_MAXREL][3];
     // ewald / constants
     double rc, rc2, alpha, eps0_inv_real, twopi, beta, overlap;
     int32_t kmax[3], kmax_max, nk;

@@ -121,6 +121,26 @@ __device__ __forceinline__ void apply_PBC(double pos[3])
 // minimum image (geometry_utils.f90:210-284) -> squared distance
 // ------------------------------------------------------------------------------------
 #define MGPU_RINT_MAGIC 6755399441055744.0     // 1.5 * 2^52: (x + M) - M = rint(x) for |x| < 2^51
+// The reference's triclinic branch, literally: minimum over the 27 shifts i c1 + j c2 + k c3 of the RAW
+// difference vector, c = COLUMNS of matrix (geometry_utils.f90:263-280).
+__device__ __noinline__ double min_image_27(double dx, double dy, double dz)
+{
+    double best = 1.7976931348623157e308;
+#pragma unroll 1
+    for (int sx = -1; sx <= 1; ++sx)
+#pragma unroll 1
+        for (int sy = -1; sy <= 1; ++sy)
+#pragma unroll
+            for (int sz = -1; sz <= 1; ++sz) {
+                double tx = dx + sx * c_sys.H[0] + sy * c_sys.H[1] + sz * c_sys.H[2];
+                double ty = dy + sx * c_sys.H[3] + sy * c_sys.H[4] + sz * c_sys.H[5];
+                double tz = dz + sx * c_sys.H[6] + sy * c_sys.H[7] + sz * c_sys.H[8];
+                double d2 = tx * tx + ty * ty + tz * tz;
+                best = fmin(best, d2);
+            }
+    return best;
+}
+
 template <bool TRI>
 __device__ __forceinline__ double min_image_r2(double dx, double dy, double dz)
 {
@@ -135,20 +155,32 @@ __device__ __forceinline__ double min_image_r2(double dx, double dy, double dz)
         dz = fma(-c_sys.L[2], nz, dz);
         return fma(dx, dx, fma(dy, dy, dz * dz));
     } else {
-        // 27-image search with the COLUMNS of matrix as cell vectors, exactly like the reference
-        double best = 1.7976931348623157e308;
-#pragma unroll
-        for (int sx = -1; sx <= 1; ++sx)
-#pragma unroll
-            for (int sy = -1; sy <= 1; ++sy)
-#pragma unroll
-                for (int sz = -1; sz <= 1; ++sz) {
-                    double tx = dx + sx * c_sys.H[0] + sy * c_sys.H[1] + sz * c_sys.H[2];
-                    double ty = dy + sx * c_sys.H[3] + sy * c_sys.H[4] + sz * c_sys.H[5];
-                    double tz = dz + sx * c_sys.H[6] + sy * c_sys.H[7] + sz * c_sys.H[8];
-                    double d2 = tx * tx + ty * ty + tz * tz;
-                    best = fmin(best, d2);
-                }
+        // Same minimum as the 27-image search, found in 1 + tri_nrel candidates: round the fractional
+        // coordinates (image n), then try the few lattice vectors C m that can shorten ANY vector with
+        // fractional coordinates in [-1/2, 1/2]^3 (m G m < sum_d |(G m)_d|, G = C^T C; listed at init).
+        // That is the global minimum over the lattice; it is the reference's answer whenever its shift
+        // n - m lies in {-1,0,1}^3, which is checked -- otherwise (atoms far outside the cell, extreme
+        // skew) the literal 27-image search decides.
+        if (c_sys.tri_nrel < 0) return min_image_27(dx, dy, dz);
+        const double f0 = fma(c_sys.Hinv[0], dx, fma(c_sys.Hinv[1], dy, c_sys.Hinv[2] * dz));
+        const double f1 = fma(c_sys.Hinv[3], dx, fma(c_sys.Hinv[4], dy, c_sys.Hinv[5] * dz));
+        const double f2 = fma(c_sys.Hinv[6], dx, fma(c_sys.Hinv[7], dy, c_sys.Hinv[8] * dz));
+        const double n0 = (f0 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC, n1 = (f1 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC,
+                     n2 = (f2 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC;
+        const double tx = dx - fma(c_sys.H[0], n0, fma(c_sys.H[1], n1, c_sys.H[2] * n2));
+        const double ty = dy - fma(c_sys.H[3], n0, fma(c_sys.H[4], n1, c_sys.H[5] * n2));
+        const double tz = dz - fma(c_sys.H[6], n0, fma(c_sys.H[7], n1, c_sys.H[8] * n2));
+        double best = fma(tx, tx, fma(ty, ty, tz * tz));
+        int bk = -1;
+        const int nrel = c_sys.tri_nrel;
+        for (int k = 0; k < nrel; ++k) {
+            const double cx = tx + c_sys.tri_rel[k][0], cy = ty + c_sys.tri_rel[k][1], cz = tz + c_sys.tri_rel[k][2];
+            const double d2 = fma(cx, cx, fma(cy, cy, cz * cz));
+            if (d2 < best) { best = d2; bk = k; }
+        }
+        double o0 = n0, o1 = n1, o2 = n2;                // shift of the winner in the reference's convention: -(n - m)
+        if (bk >= 0) { o0 -= c_sys.tri_m[bk][0]; o1 -= c_sys.tri_m[bk][1]; o2 -= c_sys.tri_m[bk][2]; }
+        if (fmax(fabs(o0), fmax(fabs(o1), fabs(o2))) > 1.0) return min_image_27(dx, dy, dz);
         return best;
     }
 }
@@ -249,7 +281,7 @@ struct Probe {
 
 // Proposal / decision record of the device-resident drivers (one per group)
 struct SweepShared {
-    int32_t valid, move, kind, res, mol, accept, traced_accept, pad;
+    int32_t valid, move, kind, res, mol, accept, traced_accept, res2;   // res2: the new residue type of a swap
     double com[3];
     double off[MGPU_MAX_SITES][3];
     double prob;
@@ -748,9 +780,11 @@ __device__ __forceinline__ void load_positions(int w, int res, int mol, double (
 }
 
 // Stage the probe for a trial of `kind` on (res, mol) with new geometry (com, off).
+// (xres, xmol) >= 0: the target slot to leave out instead of (res, mol) -- the creation half of a
+// swap, whose new molecule of type `res` must not see the molecule it replaces.
 template <int NT>
 __device__ __forceinline__ void stage_probe(const Smem &S, int w, int kind, int res, int mol,
-                                            const double *com, const double (*off)[3])
+                                            const double *com, const double (*off)[3], int xres = -1, int xmol = -1)
 {
     Probe &P = S.ws->probe;
     const int na = c_sys.natom[res];
@@ -759,7 +793,7 @@ __device__ __forceinline__ void stage_probe(const Smem &S, int w, int kind, int 
         P.kind = kind; P.res = res; P.mol = mol; P.na = na;
         P.has_old = (kind != MGPU_KIND_CREATE);
         P.has_new = (kind != MGPU_KIND_DELETE);
-        P.excl_res = res; P.excl_mol = mol;
+        P.excl_res = (xres >= 0) ? xres : res; P.excl_mol = (xres >= 0) ? xmol : mol;
         P.order_res = -1; P.order_mol = -1;
         P.host_old = P.has_old && !c_sys.use_hcache;
         P.host_new = P.has_new;
@@ -781,7 +815,8 @@ __device__ __forceinline__ void stage_probe(const Smem &S, int w, int kind, int 
 // (store_S) -- compute_old_energy / compute_new_energy, monte_carlo_utils.f90:300-423.
 // hc_new = framework part of the new geometry {lj, coulomb (e^2/A)}: the cache entry if the trial is committed.
 template <bool TRI, int NT>
-__device__ void evaluate_trial(const Smem &S, int w, bool store_S, double e_old[6], double e_new[6], double hc_new[2], PairCount &pc)
+__device__ void evaluate_trial(const Smem &S, int w, bool store_S, double e_old[6], double e_new[6], double hc_new[2], PairCount &pc,
+                               bool do_kspace = true)
 {
     const Probe &P = S.ws->probe;
     double ps[8];
@@ -791,14 +826,17 @@ __device__ void evaluate_trial(const Smem &S, int w, bool store_S, double e_old[
         ps[0] = hc[P.mol]; ps[1] = hc[c_sys.cap[P.res] + P.mol];
     }
     hc_new[0] = ps[2]; hc_new[1] = ps[3];
-    if (P.has_old) fill_phase_tables(S.tab_old, P.po, P.na, Grp<NT>::tid(), NT);
-    if (P.has_new) fill_phase_tables(S.tab_new, P.pn, P.na, Grp<NT>::tid(), NT);
-    Grp<NT>::sync();
-    const int cur = c_sys.cur[w];
-    const double *S_in = c_sys.S + ((int64_t)w * 2 + cur) * 2 * c_sys.nk;
-    double *S_out = store_S ? c_sys.S + ((int64_t)w * 2 + (cur ^ 1)) * 2 * c_sys.nk : nullptr;
-    const double recip_new = kspace<NT>(S, S_in, S_out);
     const double recip_cur = c_sys.energy[(int64_t)w * 6 + MGPU_E_RECIP];
+    double recip_new = recip_cur;
+    if (do_kspace) {
+        if (P.has_old) fill_phase_tables(S.tab_old, P.po, P.na, Grp<NT>::tid(), NT);
+        if (P.has_new) fill_phase_tables(S.tab_new, P.pn, P.na, Grp<NT>::tid(), NT);
+        Grp<NT>::sync();
+        const int cur = c_sys.cur[w];
+        const double *S_in = c_sys.S + ((int64_t)w * 2 + cur) * 2 * c_sys.nk;
+        double *S_out = store_S ? c_sys.S + ((int64_t)w * 2 + (cur ^ 1)) * 2 * c_sys.nk : nullptr;
+        recip_new = kspace<NT>(S, S_in, S_out);
+    }
 #pragma unroll
     for (int i = 0; i < 6; ++i) { e_old[i] = 0.0; e_new[i] = 0.0; }
     e_old[MGPU_E_RECIP] = recip_cur;
@@ -866,6 +904,66 @@ __device__ void commit_trial(int w, int kind, int res, int mol, const double *co
     }
 }
 
+// attempt_swap_move, swapping.f90:34-105: old = deletion-style energies of molecule (resA, molA)
+// (compute_old_energy(..., is_deletion), :62); new = creation-style energies of a molecule of type
+// resB with geometry (com, off) in slot count(resB), evaluated with (resA, molA) gone from the
+// coordinates (:69-88) but on top of an S(k) that STILL contains it -- the reference never applies
+// the deletion dS of the swapped-out molecule; S_trial = S + dS(B).
+// The probe is left staged for the creation half.  count[] = the walker's counts before the swap.
+template <bool TRI, int NT>
+__device__ void evaluate_swap(const Smem &S, int w, bool store_S, int resA, int molA, int resB, int molB,
+                              const double *com, const double (*off)[3],
+                              double e_old[6], double e_new[6], double hc_new[2], PairCount &pc)
+{
+    double e_tmp[6], hc_tmp[2];
+    stage_probe<NT>(S, w, MGPU_KIND_DELETE, resA, molA, nullptr, nullptr);
+    Grp<NT>::sync();
+    evaluate_trial<TRI, NT>(S, w, false, e_old, e_tmp, hc_tmp, pc, false);
+    Grp<NT>::sync();
+    stage_probe<NT>(S, w, MGPU_KIND_CREATE, resB, molB, com, off, resA, molA);
+    Grp<NT>::sync();
+    evaluate_trial<TRI, NT>(S, w, store_S, e_tmp, e_new, hc_new, pc, true);
+}
+
+// accept_swap_move (swapping.f90:143-155) + the coordinate / count changes the reference made
+// before the accept test (:66-81): (resA, molA) removed by swap-with-last, the new molecule of type
+// resB appended, S flipped, all five components updated.
+__device__ void commit_swap(int w, int resA, int molA, int resB, const double *com, const double (*off)[3],
+                            const double e_old[6], const double e_new[6], const double hc_new[2], int tid, int nthreads)
+{
+    {
+        double *wc = c_sys.coords + (int64_t)w * c_sys.coord_stride + c_sys.goff[resA];
+        const int cap = c_sys.cap[resA], na = c_sys.natom[resA];
+        double *offs = wc + 3 * (int64_t)cap;
+        const int last = c_sys.count[(int64_t)w * MGPU_MAX_RES + resA] - 1;
+        if (molA != last) {
+            if (tid < 3) wc[tid * cap + molA] = wc[tid * cap + last];
+            for (int e = tid; e < na * 3 + 2; e += nthreads) offs[(int64_t)e * cap + molA] = offs[(int64_t)e * cap + last];
+        }
+    }
+    const int nB = c_sys.count[(int64_t)w * MGPU_MAX_RES + resB];
+    {
+        double *wc = c_sys.coords + (int64_t)w * c_sys.coord_stride + c_sys.goff[resB];
+        const int cap = c_sys.cap[resB], na = c_sys.natom[resB];
+        double *offs = wc + 3 * (int64_t)cap;
+        if (tid < 3) wc[tid * cap + nB] = com[tid];
+        for (int e = tid; e < na * 3; e += nthreads) offs[(int64_t)e * cap + nB] = off[e / 3][e % 3];
+        if (tid < 2) offs[(int64_t)(na * 3 + tid) * cap + nB] = hc_new[tid];
+    }
+    if (tid == 0) {
+        c_sys.count[(int64_t)w * MGPU_MAX_RES + resA] -= 1;
+        c_sys.count[(int64_t)w * MGPU_MAX_RES + resB] = nB + 1;
+        c_sys.cur[w] ^= 1;
+        double *E = c_sys.energy + (int64_t)w * 6;
+        E[MGPU_E_RECIP] = e_new[MGPU_E_RECIP];
+        E[MGPU_E_NON_COULOMB] = E[MGPU_E_NON_COULOMB] + e_new[MGPU_E_NON_COULOMB] - e_old[MGPU_E_NON_COULOMB];
+        E[MGPU_E_COULOMB] = E[MGPU_E_COULOMB] + e_new[MGPU_E_COULOMB] - e_old[MGPU_E_COULOMB];
+        E[MGPU_E_SELF] = E[MGPU_E_SELF] + e_new[MGPU_E_SELF] - e_old[MGPU_E_SELF];
+        E[MGPU_E_INTRA] = E[MGPU_E_INTRA] + e_new[MGPU_E_INTRA] - e_old[MGPU_E_INTRA];
+        E[MGPU_E_TOTAL] = E[MGPU_E_TOTAL] + e_new[MGPU_E_TOTAL] - e_old[MGPU_E_TOTAL];
+    }
+}
+
 // Coordinates of a slot only (no counts / energies / S).  The reference writes a created
 // molecule into slot N+1 before the accept test and does not undo it on reject
 // (reject_creation_move, monte_carlo_utils.f90:579-591); that is observable when N = 0,
@@ -907,27 +1005,34 @@ __global__ void __launch_bounds__(NT == 32 ? MGPU_WBLOCK : MGPU_BLOCK, 1) k_tria
     const int t = blockIdx.x * (NT == 32 ? (int)(blockDim.x >> 5) : 1) + Grp<NT>::id();
     if (t >= n_tasks) return;                       // whole groups leave together (no later CTA barrier for NT = 32)
     const int4 meta = T.meta[t];
-    const int w = meta.x, res = meta.y, mol = meta.z, kind = meta.w;
+    const int w = meta.x, res = meta.y, mol = meta.z, kind = meta.w & 0xff, res2 = meta.w >> 8;   // res2: new type of a swap
     const int gt = Grp<NT>::tid();
     stage_counts<NT>(S, w);
     const double *com = T.com + (int64_t)t * 3;
     const double(*off)[3] = reinterpret_cast<const double(*)[3]>(T.off + (int64_t)t * MGPU_MAX_SITES * 3);
-    stage_probe<NT>(S, w, kind, res, mol, com, off);
-    Grp<NT>::sync();
     double e_old[6], e_new[6], hc_new[2];
     PairCount pc = { 0u, 0u, 0u };
-    evaluate_trial<TRI, NT>(S, w, true, e_old, e_new, hc_new, pc);
+    if (kind == MGPU_KIND_SWAP) {
+        Grp<NT>::sync();
+        evaluate_swap<TRI, NT>(S, w, true, res, mol, res2, S.ws->count[res2], com, off, e_old, e_new, hc_new, pc);
+    } else {
+        stage_probe<NT>(S, w, kind, res, mol, com, off);
+        Grp<NT>::sync();
+        evaluate_trial<TRI, NT>(S, w, true, e_old, e_new, hc_new, pc);
+    }
     flush_pair_count(pc);
     // record the pending trial
     MgpuTrial *tr = c_sys.trial + w;
     if (gt == 0) {
-        tr->active = 1; tr->kind = kind; tr->res = res; tr->mol = mol;
+        tr->active = 1; tr->kind = kind; tr->res = res; tr->mol = mol; tr->res2 = res2;
         for (int d = 0; d < 3; ++d) tr->com[d] = (kind == MGPU_KIND_DELETE) ? 0.0 : com[d];
         tr->hc_new[0] = hc_new[0]; tr->hc_new[1] = hc_new[1];
         for (int i = 0; i < 6; ++i) { tr->e_old[i] = e_old[i]; tr->e_new[i] = e_new[i]; T.out[(int64_t)t * 12 + i] = e_old[i]; T.out[(int64_t)t * 12 + 6 + i] = e_new[i]; }
     }
-    if (kind != MGPU_KIND_DELETE)
-        for (int e = gt; e < c_sys.natom[res] * 3; e += NT) tr->off[e / 3][e % 3] = off[e / 3][e % 3];
+    if (kind != MGPU_KIND_DELETE) {
+        const int na_new = c_sys.natom[kind == MGPU_KIND_SWAP ? res2 : res];
+        for (int e = gt; e < na_new * 3; e += NT) tr->off[e / 3][e % 3] = off[e / 3][e % 3];
+    }
 }
 
 __global__ void __launch_bounds__(128) k_commit(const int32_t *walker, const int32_t *accept, int32_t *err)
@@ -936,8 +1041,10 @@ __global__ void __launch_bounds__(128) k_commit(const int32_t *walker, const int
     const int w = walker[t];
     MgpuTrial *tr = c_sys.trial + w;
     if (!tr->active) { if (threadIdx.x == 0) atomicExch(err, 1); return; }
-    if (accept[t]) commit_trial(w, tr->kind, tr->res, tr->mol, tr->com, tr->off, tr->e_old, tr->e_new, tr->hc_new, threadIdx.x, blockDim.x);
-    else if (tr->kind == MGPU_KIND_CREATE && tr->mol == 0) write_slot(w, tr->res, 0, tr->com, tr->off, threadIdx.x, blockDim.x);
+    if (accept[t]) {
+        if (tr->kind == MGPU_KIND_SWAP) commit_swap(w, tr->res, tr->mol, tr->res2, tr->com, tr->off, tr->e_old, tr->e_new, tr->hc_new, threadIdx.x, blockDim.x);
+        else commit_trial(w, tr->kind, tr->res, tr->mol, tr->com, tr->off, tr->e_old, tr->e_new, tr->hc_new, threadIdx.x, blockDim.x);
+    } else if (tr->kind == MGPU_KIND_CREATE && tr->mol == 0) write_slot(w, tr->res, 0, tr->com, tr->off, threadIdx.x, blockDim.x);
     __syncthreads();
     if (threadIdx.x == 0) tr->active = 0;
 }
@@ -1213,8 +1320,28 @@ __device__ __noinline__ void propose_step(int w, GroupWS &ws, int32_t *err)
             const int axis = (int)(rng_uniform(rng) * 3.0) + 1;
             rotate_offsets(axis, theta, sh.off, na);
         }
-    } else if (draw <= cumul_swap) {
-        atomicExch(err, 3);                                       // swap moves: host-driven path only
+    } else if (draw <= cumul_swap) {                              // swapping.f90:34-105
+        int res_bis = -1;                                         // pick_different_residue_type :165-197
+        for (int attempt = 0; attempt < 10; ++attempt) {
+            const int nt = c_sys.active_list[(int)(rng_uniform(rng) * c_sys.nactive)];
+            if (nt != res) { res_bis = nt; break; }
+        }
+        // no molecule of the old type: the reference indexes molecule 0 (undefined); like the oracle, nothing is tried
+        if (res_bis >= 0 && ws.count[res_bis] > 0 && mol >= 0) {
+            const int nb = ws.count[res_bis], capb = c_sys.cap[res_bis], nab = c_sys.natom[res_bis];
+            if (nb >= capb) atomicExch(err, 2);
+            else {
+                sh.valid = 1; sh.move = MGPU_MV_SWAP; sh.kind = MGPU_KIND_SWAP; sh.res2 = res_bis;
+                for (int d = 0; d < 3; ++d) sh.com[d] = wc[d * cap + mol];            // CoM of the swapped-out molecule (:80)
+                const double *offb = c_sys.coords + (int64_t)w * c_sys.coord_stride + c_sys.goff[res_bis] + 3 * (int64_t)capb;
+                for (int e = 0; e < nab * 3; ++e) sh.off[e / 3][e % 3] = offb[(int64_t)e * capb + 0];   // geometry of molecule 1 of the new type
+                if (nab != 1) {
+                    const double theta = rng_uniform(rng) * c_sys.twopi;
+                    const int axis = (int)(rng_uniform(rng) * 3.0) + 1;
+                    rotate_offsets(axis, theta, sh.off, nab);
+                }
+            }
+        }
     } else {
         bool create = false, widom = false, del = false;
         if (c_sys.p_insdel > 0) { if (rng_uniform(rng) <= 0.5) create = true; else del = true; }
@@ -1269,11 +1396,18 @@ __device__ __noinline__ void decide_step(int w, GroupWS &ws, const double e_old[
         } else if (sh.move == MGPU_MV_DELETE) {
             const double Np1 = (double)(ws.count[res] - 1) + 1.0;
             p = fmin(1.0, Np1 * (lam * lam * lam) / c_sys.volume * exp(-c_sys.beta * (dU + mu)));
+        } else if (sh.move == MGPU_MV_SWAP) {
+            // swap_acceptance_probability, monte_carlo_utils.f90:264-294, with the counts the reference has at
+            // that point: old type already decremented, new type already incremented (swapping.f90:73-77)
+            const double N_old = (double)(ws.count[res] - 1), Nplus1 = (double)(ws.count[sh.res2] + 1) + 1.0;
+            const double mu_new = c_sys.mu[(int64_t)w * MGPU_MAX_RES + sh.res2];
+            p = fmin(1.0, (N_old / Nplus1) * exp(-c_sys.beta * (dU + mu_new - mu)));
         } else p = fmin(1.0, exp(-c_sys.beta * dU));
         acc = rng_uniform(ws.loc.rng) <= p;
-        const int ci = (sh.move == MGPU_MV_TRANSLATE) ? 0 : (sh.move == MGPU_MV_ROTATE) ? 1 : (sh.move == MGPU_MV_CREATE) ? 2 : 3;
+        const int ci = (sh.move == MGPU_MV_TRANSLATE) ? 0 : (sh.move == MGPU_MV_ROTATE) ? 1 : (sh.move == MGPU_MV_CREATE) ? 2
+                     : (sh.move == MGPU_MV_DELETE) ? 3 : 4;
         cnt[2 * ci] += 1;
-        if (acc) { cnt[2 * ci + 1] += 1; if (ci >= 2) cnt[2 * ci] += 1; }   // creations/deletions bump both slots
+        if (acc) { cnt[2 * ci + 1] += 1; if (ci >= 2) cnt[2 * ci] += 1; }   // creations/deletions/swaps bump both slots
         sh.traced_accept = acc;
     }
     sh.prob = p;
@@ -1281,40 +1415,68 @@ __device__ __noinline__ void decide_step(int w, GroupWS &ws, const double e_old[
     for (int i = 0; i < 6; ++i) { sh.e_old[i] = e_old[i]; sh.e_new[i] = e_new[i]; }
 }
 
+// Phase alignment.  The four warps with the same (warp id mod 4) share an SM sub-partition, i.e. its
+// issue port and its ~6 KB L0 instruction cache.  Left alone, the walkers of a CTA drift apart in the
+// MC step (the r01k profile: 46 % of all stall samples were "no instruction", in every loop), because
+// four warps in four different loops evict each other's code.  A named barrier per quartet at the top
+// of every MC step (and again before the energy evaluation) keeps those four warps in the same loop at
+// the same time; quartets stay independent of each other, and a walker's serial section (lane 0:
+// RNG, proposal, Metropolis) still only idles its own quartet for as long as the quartet's slowest
+// proposal.
+__device__ __forceinline__ void quartet_sync(int nthreads_in_quartet)
+{
+    asm volatile("bar.sync %0, %1;" :: "r"(1 + (int)((threadIdx.x >> 5) & 3)), "r"(nthreads_in_quartet) : "memory");
+}
+
 template <bool TRI>
 __global__ void __launch_bounds__(MGPU_WBLOCK, 1) k_sweep(int first_walker, int n_walkers, long long n_steps, int natom_max,
-                                                      int trace_walker, mgpu_step_trace *trace, int32_t *err)
+                                                      int trace_walker, mgpu_step_trace *trace, int32_t *err, int phase_sync)
 {
     const Smem S = smem_setup<MGPU_TAB_REP>(mgpu_smem, natom_max, Grp<32>::id());
     const int wl = blockIdx.x * (int)(blockDim.x >> 5) + Grp<32>::id();
-    if (wl >= n_walkers) return;
-    const int w = first_walker + wl;
+    const bool live = wl < n_walkers;
+    if (!live && !phase_sync) return;
+    const int nwarps = (int)(blockDim.x >> 5);
+    const int qthreads = 32 * ((nwarps - (int)((threadIdx.x >> 5) & 3) + 3) / 4);
+    const int w = first_walker + (live ? wl : 0);
     const int lane = threadIdx.x & 31;
     GroupWS &ws = *S.ws;
-    stage_counts<32>(S, w);
-    if (lane < 4) ws.loc.rng[lane] = c_sys.rng[(int64_t)w * 4 + lane];
-    if (lane < 12) ws.loc.cnt[lane] = 0;
-    if (lane < MGPU_MAX_RES) { ws.loc.avgN[lane] = 0.0; ws.loc.avgN2[lane] = 0.0; }
-    if (lane == 0) { ws.loc.avgE = 0.0; ws.loc.n_samples = 0; }
+    if (live) {
+        stage_counts<32>(S, w);
+        if (lane < 4) ws.loc.rng[lane] = c_sys.rng[(int64_t)w * 4 + lane];
+        if (lane < 12) ws.loc.cnt[lane] = 0;
+        if (lane < MGPU_MAX_RES) { ws.loc.avgN[lane] = 0.0; ws.loc.avgN2[lane] = 0.0; }
+        if (lane == 0) { ws.loc.avgE = 0.0; ws.loc.n_samples = 0; }
+    }
+    if (lane == 0) ws.sh.valid = 0;
     PairCount pc = { 0u, 0u, 0u };
     __syncwarp();
 
     for (long long step = 0; step < n_steps; ++step) {
+        if (phase_sync) quartet_sync(qthreads);
+        if (!live) { if (phase_sync) quartet_sync(qthreads); continue; }
         if (lane == 0) propose_step(w, ws, err);
         __syncwarp();
+        if (phase_sync) quartet_sync(qthreads);
         const SweepShared &sh = ws.sh;
         if (sh.valid) {
-            stage_probe<32>(S, w, sh.kind, sh.res, sh.mol, sh.com, sh.off);
-            __syncwarp();
             double e_old[6], e_new[6], hc_new[2];
-            evaluate_trial<TRI, 32>(S, w, sh.move != MGPU_MV_WIDOM, e_old, e_new, hc_new, pc);
+            if (sh.kind == MGPU_KIND_SWAP) {
+                evaluate_swap<TRI, 32>(S, w, true, sh.res, sh.mol, sh.res2, ws.count[sh.res2], sh.com, sh.off, e_old, e_new, hc_new, pc);
+            } else {
+                stage_probe<32>(S, w, sh.kind, sh.res, sh.mol, sh.com, sh.off);
+                __syncwarp();
+                evaluate_trial<TRI, 32>(S, w, sh.move != MGPU_MV_WIDOM, e_old, e_new, hc_new, pc);
+            }
             if (lane == 0) decide_step(w, ws, e_old, e_new);
             __syncwarp();
             if (sh.accept) {
-                commit_trial(w, sh.kind, sh.res, sh.mol, sh.com, sh.off, sh.e_old, sh.e_new, hc_new, lane, 32);
+                if (sh.kind == MGPU_KIND_SWAP) commit_swap(w, sh.res, sh.mol, sh.res2, sh.com, sh.off, sh.e_old, sh.e_new, hc_new, lane, 32);
+                else commit_trial(w, sh.kind, sh.res, sh.mol, sh.com, sh.off, sh.e_old, sh.e_new, hc_new, lane, 32);
                 if (lane == 0) {
                     if (sh.kind == MGPU_KIND_CREATE) ws.count[sh.res] += 1;
                     if (sh.kind == MGPU_KIND_DELETE) ws.count[sh.res] -= 1;
+                    if (sh.kind == MGPU_KIND_SWAP) { ws.count[sh.res] -= 1; ws.count[sh.res2] += 1; }
                 }
             } else if (sh.kind == MGPU_KIND_CREATE && sh.mol == 0) {
                 write_slot(w, sh.res, 0, sh.com, sh.off, lane, 32);      // rejected / Widom insertion into an empty walker
@@ -1345,6 +1507,7 @@ __global__ void __launch_bounds__(MGPU_WBLOCK, 1) k_sweep(int first_walker, int 
         __threadfence_block();
         __syncwarp();        // commit visible (coordinates, S flip, counts) to every lane before the next step
     }
+    if (!live) return;
     flush_pair_count(pc);
     if (lane < 4) c_sys.rng[(int64_t)w * 4 + lane] = ws.loc.rng[lane];
     if (lane < 12) c_sys.counters[(int64_t)w * 12 + lane] += ws.loc.cnt[lane];

@@ -20,8 +20,8 @@ from . import capi
 from .inputs import ERROR, System
 
 E_NON_COULOMB, E_COULOMB, E_RECIP, E_SELF, E_INTRA, E_TOTAL = range(6)
-KIND_MOVE, KIND_CREATE, KIND_DELETE = 0, 1, 2
-OPT_HOST_CACHE = 1
+KIND_MOVE, KIND_CREATE, KIND_DELETE, KIND_SWAP = 0, 1, 2, 3
+OPT_HOST_CACHE, OPT_PHASE_SYNC = 1, 2
 MV_NONE, MV_TRANSLATE, MV_ROTATE, MV_CREATE, MV_DELETE, MV_SWAP, MV_WIDOM = range(7)
 
 TRACE_DTYPE = np.dtype([("move", "i4"), ("res", "i4"), ("mol", "i4"), ("accepted", "i4"),
@@ -155,6 +155,11 @@ class Engine:
         self._ck(self.L.mgpu_get_box(_pd(m), _pd(r), C.byref(v), C.byref(t)))
         return dict(matrix=m, reciprocal=r, volume=v.value, triclinic=bool(t.value))
 
+    def triclinic_candidates(self):
+        n = C.c_int32(0)
+        self._ck(self.L.mgpu_get_triclinic_candidates(C.byref(n)))
+        return n.value
+
     def thermo(self, res):
         b, l, m = C.c_double(), C.c_double(), C.c_double()
         self._ck(self.L.mgpu_get_thermo(res, C.byref(b), C.byref(l), C.byref(m)))
@@ -257,6 +262,16 @@ class Engine:
             pc, po = _pd(com), _pd(offset)
         self._ck(self.L.mgpu_new_energy(walker, res, mol, kind, pc, po, _pd(out)))
         return out
+
+    def swap_energy(self, res_old, mol_old, res_new, com, offset, walker=0):
+        """attempt_swap_move's two energy calls (src/swapping.f90:62,88): deletion-style ``old`` of
+        (res_old, mol_old), creation-style ``new`` of a res_new molecule with geometry (com, offset)."""
+        com = np.ascontiguousarray(com, dtype=np.float64)
+        offset = np.ascontiguousarray(offset, dtype=np.float64)
+        e_old, e_new = np.zeros(6), np.zeros(6)
+        self._ck(self.L.mgpu_swap_energy(walker, res_old, mol_old, res_new, _pd(com), _pd(offset),
+                                         _pd(e_old), _pd(e_new)))
+        return e_old, e_new
 
     def commit(self, walker=0):
         self._ck(self.L.mgpu_commit(walker))

@@ -419,3 +419,138 @@ def test_fast_pair_math_on_device(load, engine_cls):
         e_rcp, e_tab = eng.selftest_math()
         assert e_rcp < 4e-16, e_rcp
         assert e_tab < 2e-14, e_tab
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE configs[4]: binary CO2 / N2 mixture with identity swaps in a triclinic supercell
+# ---------------------------------------------------------------------------------------------
+def _mixture(load, reps=(1, 1, 1), tilt=2.5, n_co2=6, n_n2=6):
+    from maniac_b200.workloads import mixture_supercell
+    return mixture_supercell(load("zif8_co2_widom"), reps=reps, tilt_xy=tilt, n_co2=n_co2, n_n2=n_n2)
+
+
+def test_mixture_triclinic_energy_and_fast_min_image(load, engine_cls):
+    """Mildly tilted cell: min_image takes the rounded image + a few lattice candidates instead of the
+    27-image loop and must still give the reference's minimum (total energy, S(k), every molecule's pair energy)."""
+    s = _mixture(load)
+    o = Oracle(s, capacity=64)
+    e_ref = o.update_system_energy()
+    with engine_cls(s, capacity=64) as eng:
+        assert 0 < eng.triclinic_candidates() <= 8
+        assert_e(eng.update_system_energy(), e_ref, what="mixture total energy")
+        np.testing.assert_allclose(eng.Ak(), o.Ak(), rtol=0, atol=1e-9)
+        for res in (1, 2):
+            for m in range(o.count(res)):
+                assert_e(eng.pairwise_energy_for_molecule(res, m), o.pairwise_energy_for_molecule(res, m), what=f"pair {res},{m}")
+
+
+def test_very_skewed_cell_keeps_27_image_search(load, engine_cls):
+    s = load("dipole_triclinic")
+    with engine_cls(s) as eng:
+        n = eng.triclinic_candidates()
+        assert n == -1 or n > 0
+        o = Oracle(s)
+        assert_e(eng.update_system_energy(), o.update_system_energy())
+
+
+def test_swap_energy_commit_rollback(load, engine_cls):
+    """attempt_swap_move through the single-trial C ABI: mgpu_swap_energy + mgpu_commit / mgpu_rollback
+    against the oracle's driver (forced accept and forced reject)."""
+    s = _mixture(load)
+    s.p_translation, s.p_rotation, s.p_swap, s.p_insertion_deletion = 0.0, 0.0, 1.0, 0.0
+    o = Oracle(s, capacity=64)
+    o.update_system_energy()
+    o.seed(99)
+    with engine_cls(s, capacity=64) as eng:
+        eng.update_system_energy()
+        done = 0
+        for step in range(60):
+            n1, n2 = o.count(1), o.count(2)
+            tr = o.monte_carlo_steps(1)
+            if tr["move"][0] != 5:
+                continue
+            ra, ma = int(tr["res"][0]), int(tr["mol"][0])
+            rb = 3 - ra
+            nb_before = n2 if rb == 2 else n1
+            if tr["accepted"][0]:
+                com, off = o.get_molecule(rb, nb_before)       # the new molecule sits in slot N+1 of its type
+            else:
+                continue                                        # rejected: the oracle restored everything; geometry not observable
+            e_old, e_new = eng.swap_energy(ra, ma, rb, com, off)
+            assert_e(e_old, tr["e_old"][0], rel=REL_DE, what="swap old")
+            assert_e(e_new, tr["e_new"][0], rel=REL_DE, what="swap new")
+            d_ref = tr["e_new"][0][5] - tr["e_old"][0][5]
+            assert abs((e_new[5] - e_old[5]) - d_ref) <= REL_DE * max(1.0, abs(d_ref))
+            # a rollback first (state must be untouched), then the same trial again and commit
+            eng.rollback()
+            assert eng.count(1) == n1 and eng.count(2) == n2
+            eng.swap_energy(ra, ma, rb, com, off)
+            eng.commit()
+            assert eng.count(1) == o.count(1) and eng.count(2) == o.count(2)
+            assert_e(eng.energy(), o.energy(), rel=1e-9, what="running energy after swap")
+            np.testing.assert_allclose(eng.Ak(), o.Ak(), rtol=0, atol=1e-9)     # incl. the reference's un-removed dS of the old molecule
+            done += 1
+        assert done >= 3
+
+
+@pytest.mark.parametrize("steps", [1500])
+def test_sweep_mixture_with_swaps(steps, load, engine_cls):
+    """Device-resident drivers incl. swapping.f90 on the triclinic mixture: same move / accept sequence,
+    per-move energies within 1e-9, same final state as the oracle."""
+    s = _mixture(load)
+    o = Oracle(s, capacity=64)
+    o.update_system_energy()
+    o.seed(31337)
+    ref = o.monte_carlo_steps(steps)
+    assert (ref["move"] == 5).sum() > 50 and ((ref["move"] == 5) & (ref["accepted"] == 1)).sum() > 5
+    with engine_cls(s, n_walkers=2, capacity=64) as eng:
+        eng.seed(31337)
+        tr = eng.sweep(steps, trace_walker=0)
+        _compare_traces(tr, ref)
+        for res in (1, 2):
+            assert eng.count(res) == o.count(res)
+        assert_e(eng.energy(), o.energy(), rel=1e-9)
+        np.testing.assert_array_equal(eng.counters(0), o.counters())
+        assert eng.rng_state(0) == o.rng_state()
+        np.testing.assert_allclose(eng.Ak(), o.Ak(), rtol=0, atol=1e-8)
+
+
+def test_host_driven_mixture_with_swaps(load, engine_cls):
+    from maniac_b200.hostmc import HostMonteCarlo
+    s = _mixture(load)
+    n = 600
+    o = Oracle(s, capacity=64)
+    o.update_system_energy()
+    o.seed(2718)
+    ref = o.monte_carlo_steps(n)
+    with engine_cls(s, n_walkers=3, capacity=64) as eng:
+        hm = HostMonteCarlo(eng, seed=2718)
+        tr = hm.run(n, trace_walker=0)
+        _compare_traces(tr, ref)
+        for res in (1, 2):
+            assert hm.count(res) == o.count(res) == eng.count(res)
+        assert_e(eng.energy(0), o.energy(), rel=1e-9)
+        np.testing.assert_array_equal(hm.counters(), o.counters())
+        hm.close()
+
+
+def test_large_triclinic_supercell(load, engine_cls):
+    """configs[4] at full size: 2x2x2 blocks = 17 664 framework atoms, dense k set; total energy and a short
+    trajectory against the oracle, then a longer device run audited by a full recompute (drift gate)."""
+    s = _mixture(load, reps=(2, 2, 2), tilt=3.0, n_co2=24, n_n2=24)
+    o = Oracle(s, capacity=128)
+    e_ref = o.update_system_energy()
+    o.seed(5)
+    ref = o.monte_carlo_steps(40)
+    with engine_cls(s, n_walkers=8, capacity=128) as eng:
+        assert eng.ewald()["nk"] == o.ewald()["nk"] > 2000
+        assert_e(eng.update_system_energy(), e_ref, what="17.7k-atom triclinic total energy")
+        eng.seed(5)
+        tr = eng.sweep(40, trace_walker=0)
+        _compare_traces(tr, ref)
+        eng.sweep(400)
+        for w in (0, 7):
+            inc = eng.energy(w)
+            full = eng.update_system_energy(w)
+            # swaps leave the old molecule's dS in S(k) (reference behaviour), so only the real-space parts can be audited
+            assert_e(inc[[0, 1, 3, 4]], full[[0, 1, 3, 4]], rel=1e-8, what=f"drift walker {w}")

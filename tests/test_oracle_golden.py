@@ -174,3 +174,37 @@ def test_rng_contract():
     st = (__import__("ctypes").c_uint64 * 4)()
     o.L.orc_get_rng_state(o.h, st)
     assert st[0] == 0xE220A8397B1DCDAF
+
+
+def test_swap_moves_bookkeeping(load):
+    """attempt_swap_move (src/swapping.f90:34-105) in the oracle: counts change by -1 / +1, the real-space,
+    self and intramolecular running totals stay equal to a full recompute, and the reciprocal running total
+    does NOT (the reference never removes the swapped-out molecule's dS from Ak) -- the quirk
+    every implementation here has to reproduce."""
+    from maniac_b200.workloads import mixture_supercell
+    s = mixture_supercell(load("zif8_co2_widom"), reps=(1, 1, 1), tilt_xy=2.5, n_co2=6, n_n2=6)
+    s.p_translation, s.p_rotation, s.p_swap, s.p_insertion_deletion = 0.0, 0.0, 1.0, 0.0
+    o = Oracle(s, capacity=64)
+    o.update_system_energy()
+    o.seed(99)
+    n_tot = o.count(1) + o.count(2)
+    tr = o.monte_carlo_steps(200)
+    acc = int(((tr["move"] == 5) & (tr["accepted"] == 1)).sum())
+    assert acc >= 3
+    assert o.count(1) + o.count(2) == n_tot
+    c = o.counters()
+    assert c[4][1] == acc and c[4][0] == int((tr["move"] == 5).sum()) + acc       # "counter%swaps = counter%swaps + 1" bumps both slots
+    inc = np.array(o.energy())
+    full = np.array(o.update_system_energy())
+    np.testing.assert_allclose(inc[[0, 1, 3, 4]], full[[0, 1, 3, 4]], rtol=0, atol=1e-8)
+    assert abs(inc[2] - full[2]) > 1e-3
+
+
+def test_mixture_supercell_builder(load):
+    from maniac_b200.workloads import mixture_supercell
+    s = mixture_supercell(load("zif8_co2_widom"), reps=(2, 1, 1), tilt_xy=3.0, n_co2=4, n_n2=5)
+    assert s.residues[0].natom == 2 * 2208 and s.residues[1].nmol == 4 and s.residues[2].nmol == 5
+    assert s.matrix[1, 0] == 3.0 and s.matrix[0, 1] == 0.0
+    o = Oracle(s, capacity=16)
+    assert o.box()["shape"] == 2          # TRICLINIC (geometry_utils.f90:341-361)
+    assert np.isfinite(o.update_system_energy()).all()

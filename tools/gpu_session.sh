@@ -5,7 +5,7 @@ set -u
 mkdir -p gpurun_out
 TAG=${1:-r01}; shift
 BENCH_ARGS=${BENCH_ARGS:-"--steps 8 --warmup 3"}
-BENCH_SMALL="python bench.py --steps 2 --warmup 1 --walkers 2368 --inner 8 --widom 200000 --e2e-walkers 256 --e2e-steps 3 --no-cpu"
+BENCH_SMALL="python bench.py --steps 2 --warmup 1 --walkers 2368 --inner ${PROF_INNER:-64} --widom 200000 --e2e-walkers 256 --e2e-steps 3 --no-cpu"
 for what in "$@"; do
 case $what in
 test)
