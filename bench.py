@@ -11,9 +11,11 @@ prints ONE JSON line on rank 0.
             spread over a 64-point fugacity grid (the isotherm sweep of configs[3])
   value     trial moves / s over all ranks, state resident in HBM, device-timed (CUDA events on
             the launching stream), max over ranks
-  e2e       the same metric through the host-driven C-ABI path (mgpu_trial_batch +
-            mgpu_commit_batch from HOST buffers, the role of the Fortran drivers): proposals
-            are copied host->device and energies device->host every MC step, wall clock
+  e2e       the same metric through the block-level C-ABI call with HOST buffers (mgpu_block):
+            every step the walkers' whole state travels pinned host -> device, the MC steps run,
+            and the updated state travels back; wall clock
+  host_driven  the Fortran drivers' role: host RNG / proposal / Metropolis, one mgpu_trial_batch +
+            mgpu_commit_batch per MC step (proposals H2D, energies D2H)
   roofline  the sweep kernel against the FP64-pipe peak measured on this GPU by a DFMA loop
             (the binding roof of K1; SURVEY.md 8d convention C1 for the algorithmic FLOPs)
   cpu_baseline  the CPU oracle (a C restatement of the reference's serial algorithm) on the
@@ -52,6 +54,8 @@ def parse():
     ap.add_argument("--e2e-walkers", type=int, default=1024)
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--widom", type=int, default=1_000_000, help="insertions in the Widom batch (0 = skip)")
+    ap.add_argument("--mixture-walkers", type=int, default=2368, help="walkers of the configs[4] leg (0 = skip)")
+    ap.add_argument("--mixture-steps", type=int, default=32)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -217,8 +221,14 @@ def main():
     W = a.walkers
     eng = Engine(s, n_walkers=W, capacity=CAPACITY, device=local)
     fug = isotherm_fugacities(64)
+
+    def point(w):
+        # replica -> isotherm point: the four walkers (warps) of a CTA that share an SM sub-partition
+        # (w, w+4, w+8, w+12) are replicas of the SAME fugacity point, so their loadings -- hence the
+        # lengths of their MC steps -- are statistically alike and the per-quartet phase barrier waits little
+        return ((rank * W + w) // 16 * 4 + w % 4) % 64
     for w in range(W):
-        eng.set_fugacity(0, float(fug[(rank * W + w) % 64]), walker=w)
+        eng.set_fugacity(0, float(fug[point(w)]), walker=w)
     eng.seed(12345 + 7919 * rank)
     peak_tf, _ = eng.measure_fp64_peak()
     ew = eng.ewald()
@@ -273,6 +283,25 @@ def main():
                 "hbm": {"achieved": bytes_alg / t_dev / 1e9 / world, "peak": hbm_peak, "unit": "GB/s",
                         "frac": bytes_alg / t_dev / 1e9 / world / hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"}}
+
+    # ---- the one exchange of the path: per-point sums over ranks, once, after the sampling -----
+    from maniac_b200.isotherm import IsothermPlan, reduce_sums, summarize
+    plan = IsothermPlan(n_points=64, walkers_per_rank=W, world_size=world, rank=rank)
+    assert all(plan.point_of(rank * W + w) == point(w) for w in range(0, W, 97))
+    per_walker = np.zeros((W, 6))
+    per_walker[:, :4] = eng.all_averages(0)
+    local = plan.accumulate(per_walker)
+    if world > 1:
+        eng.nccl_init_from_torch()
+    total = reduce_sums(local, engine=eng)
+    if world > 1:
+        eng.nccl_finalize()
+    summ = summarize(total, eng.thermo(0)["beta"])
+    isotherm = {"points": 64, "replicas_per_point": float(W * world) / 64.0,
+                "reduction": "mgpu_reduce_averages (one ncclAllReduce of 384 doubles)" if world > 1 else "single rank: none",
+                "fugacity": [float(fug[i]) for i in range(0, 64, 9)],
+                "mean_waters": [float(summ["mean_N"][i]) for i in range(0, 64, 9)],
+                "note": "block averages since the start of the run (not equilibrated: a throughput benchmark)"}
 
     # ---- the same sweep with the per-molecule framework-energy cache off (framework swept for the old
     #      AND the new geometry of every move, the reference's operation count) --------------------
@@ -350,7 +379,82 @@ def main():
                               "frac": fl / (ms_w * 1e-3) / 1e12 / peak_tf if peak_tf else None, "kernel": "k_widom_batch<false>"}}
         engw.close()
 
-    # ---- e2e: host-driven path through the C ABI with host buffers ---------------------------
+    # ---- configs[4]: CO2 / N2 mixture with swaps in the 17 664-atom triclinic supercell ---------------
+    mixture = None
+    if a.mixture_walkers > 0:
+        from maniac_b200.snapshot import load_snapshot
+        from maniac_b200.workloads import mixture_supercell
+        sm = mixture_supercell(load_snapshot(ROOT / "tests" / "golden" / "zif8_co2_widom.npz"), reps=(2, 2, 2), tilt_xy=3.0,
+                               n_co2=48, n_n2=48)
+        Wm = a.mixture_walkers
+        engm = Engine(sm, n_walkers=Wm, capacity=256, device=local)
+        engm.seed(777 + rank)
+        engm.sweep(8)
+        engm.timing_reset()
+        engm.reset_pair_counts()
+        cm0 = np.array([engm.counters(w) for w in range(0, Wm, max(1, Wm // 64))]).sum(axis=0)
+        barrier()
+        engm.sweep(a.mixture_steps)
+        barrier()
+        ms_m, _ = engm.timing("sweep")
+        cm1 = np.array([engm.counters(w) for w in range(0, Wm, max(1, Wm // 64))]).sum(axis=0)
+        pcm = engm.pair_counts()
+        t_m = ms_m * 1e-3
+        if world > 1:
+            t = torch.tensor([t_m], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_m = float(t[0])
+        ewm = engm.ewald()
+        fl_m = FLOP_GEOM * pcm["pairs"] + FLOP_LJ * pcm["lj"] + FLOP_COUL * pcm["coulomb"]      # geometry counted at the orthorhombic 29 / pair
+        dcm = (cm1 - cm0).reshape(6, 2)
+        mixture = {"workload": "CO2/N2 mixture GCMC with identity swaps (0.3/0.3/0.2/0.2 translate/rotate/swap/insert-delete), ZIF-8 4x4x4 "
+                               "unit cells = 17 664 framework atoms, triclinic (xy tilt 3 A), BASELINE configs[4]",
+                   "walkers_per_gpu": Wm, "mc_steps_per_launch": a.mixture_steps, "nkvec": ewm["nk"], "kmax": ewm["kmax"],
+                   "moves_per_s": float(Wm) * a.mixture_steps * world / t_m, "ms": ms_m,
+                   "triclinic_candidates": engm.triclinic_candidates(),
+                   "swap_trials_sampled": int(dcm[4, 0] - dcm[4, 1]), "swap_accepted_sampled": int(dcm[4, 1]),
+                   "roofline_frac_c1_realspace": fl_m / (ms_m * 1e-3) / 1e12 / peak_tf if peak_tf else None}
+        engm.close()
+
+    # ---- e2e: the block-level C-ABI entry with HOST buffers (mgpu_block) ------------------------
+    # every step = one block of the MC loop: the walkers' records (coordinates, S(k), energies, RNG,
+    # counters) are copied from pinned host memory to the device, `inner` MC steps run, the updated records
+    # are copied back -- the same moves as `value`, plus the host<->device traffic of the whole state.
+    enge = Engine(s, n_walkers=W, capacity=CAPACITY, device=local)
+    for w in range(W):
+        enge.set_fugacity(0, float(fug[point(w)]), walker=w)
+    enge.seed(4321 + 7919 * rank)
+    for _ in range(2):
+        enge.sweep(a.inner)                          # move towards the steady-state loading before records are sized
+    rec_max = enge.record_doubles_max()
+    nmax = max(enge.count(0, walker=w) for w in range(0, W, max(1, W // 128)))
+    per_walker = 64 + 2 * ew["nk"] + int(1.5 * nmax + 64) * (3 + 3 * na + 2)
+    blob = [enge.host_buffer(min(rec_max, per_walker) * W) for _ in range(2)]
+    off = enge.save_walkers(blob[0])
+    for i in range(max(1, a.warmup)):
+        off = enge.block(a.inner, blob[i % 2], off, blob[(i + 1) % 2])
+        cur = (i + 1) % 2
+    enge.traffic(reset=True)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(a.steps):
+        off = enge.block(a.inner, blob[cur], off, blob[cur ^ 1])
+        cur ^= 1
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    tr1 = enge.traffic()
+    if world > 1:
+        t = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t[0])
+    e2e = {"value": float(W) * a.inner * a.steps * world / t_e2e, "unit": "moves/s",
+           "h2d_bytes_per_step": tr1["h2d_bytes"] / a.steps, "d2h_bytes_per_step": tr1["d2h_bytes"] / a.steps,
+           "walkers_per_gpu": W, "mc_steps_per_call": a.inner, "ms_per_step": 1e3 * t_e2e / a.steps,
+           "path": "mgpu_block: walker records (guest%com / guest%offset, ewald%Ak, energy, RNG, counters) H2D from pinned host "
+                   "memory -> k_unpack -> k_sweep -> k_pack -> records D2H, every step; wall clock, max over ranks"}
+    enge.close()
+
+    # ---- the Fortran drivers' role: host-driven trials (host RNG / proposal / Metropolis per MC step) ----
     We = min(a.e2e_walkers, W)
     enge = Engine(s, n_walkers=We, capacity=CAPACITY, device=local)
     for w in range(We):
@@ -365,19 +469,18 @@ def main():
     t0 = time.perf_counter()
     hm.run(a.e2e_steps)
     barrier()
-    t_e2e = time.perf_counter() - t0
+    t_hd = time.perf_counter() - t0
     tr1 = hm.traffic()
     if world > 1:
-        t = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
+        t = torch.tensor([t_hd], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_e2e = float(t[0])
-    e2e_moves = (tr1["trials"] - tr0["trials"]) * world
-    e2e = {"value": e2e_moves / t_e2e, "unit": "moves/s",
-           "h2d_bytes_per_step": (tr1["h2d_bytes"] - tr0["h2d_bytes"]) / a.e2e_steps,
-           "d2h_bytes_per_step": (tr1["d2h_bytes"] - tr0["d2h_bytes"]) / a.e2e_steps,
-           "walkers_per_gpu": We, "mc_steps": a.e2e_steps,
-           "path": "mhost_run -> mgpu_trial_batch + mgpu_commit_batch (host RNG/proposal/Metropolis, pinned staging, "
-                   "H2D proposals + D2H energies every MC step), wall clock"}
+        t_hd = float(t[0])
+    host_driven = {"value": (tr1["trials"] - tr0["trials"]) * world / t_hd, "unit": "moves/s",
+                   "h2d_bytes_per_mc_step": (tr1["h2d_bytes"] - tr0["h2d_bytes"]) / a.e2e_steps,
+                   "d2h_bytes_per_mc_step": (tr1["d2h_bytes"] - tr0["d2h_bytes"]) / a.e2e_steps,
+                   "walkers_per_gpu": We, "mc_steps": a.e2e_steps,
+                   "path": "mhost_run -> mgpu_trial_batch + mgpu_commit_batch (host RNG/proposal/Metropolis, pinned staging, "
+                           "H2D proposals + D2H energies every MC step), wall clock"}
     hm.close()
     enge.close()
 
@@ -396,7 +499,7 @@ def main():
     line = {"metric": "mc_trial_moves_per_s", "value": value, "unit": "moves/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": 1e3 * t_dev / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "clocks": clocks,
-            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "widom": widom, "no_host_cache": no_cache, "no_phase_sync": no_sync,
+            "e2e": e2e, "host_driven": host_driven, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "widom": widom, "no_host_cache": no_cache, "no_phase_sync": no_sync, "mixture": mixture, "isotherm": isotherm,
             "wall_s_timed_region": wall, "mean_waters_per_walker": nmean, "fp64_peak_tflops_measured": peak_tf}
     print(json.dumps(line))
 

@@ -37,6 +37,7 @@
 #define MANIAC_GPU_H
 
 #include <stdint.h>
+#include <stddef.h>
 
 #ifdef __cplusplus
 extern "C" {
@@ -205,6 +206,30 @@ int mgpu_get_rng_state(int32_t walker, uint64_t st[4]);
  * trace (optional) receives the steps of walker `trace_walker` only ([n_steps]). */
 int mgpu_sweep(int32_t first_walker, int32_t n_walkers, int64_t n_steps,
                int32_t trace_walker, mgpu_step_trace *trace);
+/* ---- block-level entry: HOST state in, HOST state out -------------------------------------
+ * One block of monte_carlo_loop (src/monte_carlo.f90:40-118: nb_step MC steps, then the per-block
+ * outputs energy.dat / number_*.dat / moves.dat / trajectory, src/write_utils.f90:16-34) for the
+ * walkers [first, first+n), from and to flat HOST arrays.  A walker's record (doubles) is
+ *   [0] record length | [1..8] primary%num%residues | [9..14] energy (energy_type order) |
+ *   [15..18] RNG state (raw bits) | [19..30] counters%... (trials, successes) x 6 | [31] 0 |
+ *   [32..63] block averages [res][sum N, sum N^2, sum E, samples] | [64..64+2 nk) ewald%Ak (re[nk], im[nk]) |
+ *   then for every active residue type, for mol = 1..count: guest%com(:,res,mol), guest%offset(:,res,mol,1:natom),
+ *   and the molecule's cached framework energy {lj, coulomb (e^2/A)}.
+ * Record i starts at blob[offsets[i]]; offsets[n] is the total length.  mgpu_save_walkers fills
+ * blob and offsets (capacity in doubles; mgpu_record_doubles_max() bounds one record);
+ * mgpu_load_walkers restores walkers from records (no recompute: the record is the full state);
+ * mgpu_block = load (if blob_in) + mgpu_sweep(n_steps) + save (if blob_out).  Buffers from
+ * mgpu_host_alloc are page-locked, so the copies run at full PCIe rate; any host pointer works. */
+void *mgpu_host_alloc(size_t bytes);
+void  mgpu_host_free(void *p);
+int64_t mgpu_record_doubles_max(void);
+int mgpu_save_walkers(int32_t first_walker, int32_t n_walkers, double *blob, int64_t capacity, int64_t *offsets);
+int mgpu_load_walkers(int32_t first_walker, int32_t n_walkers, const double *blob, const int64_t *offsets);
+int mgpu_block(int32_t first_walker, int32_t n_walkers, int64_t n_steps,
+               const double *blob_in, const int64_t *offsets_in,
+               double *blob_out, int64_t capacity_out, int64_t *offsets_out);
+/* bytes moved host->device / device->host by the three calls above since the last reset */
+int mgpu_get_traffic(int64_t *h2d_bytes, int64_t *d2h_bytes, int32_t reset);
 /* counters%{translations,rotations,creations,deletions,swaps,widom}(1:2) of a walker */
 int mgpu_get_counters(int32_t walker, int64_t out[12]);
 /* statistic%weight / statistic%sample (src/widom.f90:74-92) accumulated by mgpu_sweep */

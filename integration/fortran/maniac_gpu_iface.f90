@@ -101,6 +101,24 @@ module maniac_gpu_iface
             real(c_double), intent(in) :: com(3), offset(*)
             real(c_double), intent(out) :: out(6)
         end function
+        ! attempt_swap_move (src/swapping.f90:59-88): both energy calls of the swap in one
+        integer(c_int) function mgpu_swap_energy(walker, res_old, mol_old, res_new, com, offset, e_old, e_new) &
+                bind(C, name="mgpu_swap_energy")
+            import :: c_int, c_int32_t, c_double
+            integer(c_int32_t), value :: walker, res_old, mol_old, res_new
+            real(c_double), intent(in) :: com(3), offset(*)
+            real(c_double), intent(out) :: e_old(6), e_new(6)
+        end function
+        ! one block of monte_carlo_loop for many walkers, host records in / out (src/monte_carlo.f90:40-118)
+        integer(c_int) function mgpu_block(first_walker, n_walkers, n_steps, blob_in, offsets_in, &
+                blob_out, capacity_out, offsets_out) bind(C, name="mgpu_block")
+            import :: c_int, c_int32_t, c_int64_t, c_double, c_ptr
+            integer(c_int32_t), value :: first_walker, n_walkers
+            integer(c_int64_t), value :: n_steps, capacity_out
+            type(c_ptr), value :: blob_in, offsets_in       ! c_null_ptr = continue from the device-resident state
+            real(c_double), intent(out) :: blob_out(*)
+            integer(c_int64_t), intent(out) :: offsets_out(*)
+        end function
         integer(c_int) function mgpu_commit(walker) bind(C, name="mgpu_commit")
             import :: c_int, c_int32_t
             integer(c_int32_t), value :: walker

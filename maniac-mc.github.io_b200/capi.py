@@ -80,6 +80,13 @@ SIGNATURES = {
     "mgpu_seed": (C.c_int, [U64]),
     "mgpu_get_rng_state": (C.c_int, [I, _pu]),
     "mgpu_sweep": (C.c_int, [I, I, L64, I, C.c_void_p]),
+    "mgpu_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "mgpu_host_free": (None, [C.c_void_p]),
+    "mgpu_record_doubles_max": (L64, []),
+    "mgpu_save_walkers": (C.c_int, [I, I, C.c_void_p, L64, C.c_void_p]),
+    "mgpu_load_walkers": (C.c_int, [I, I, C.c_void_p, C.c_void_p]),
+    "mgpu_block": (C.c_int, [I, I, L64, C.c_void_p, C.c_void_p, C.c_void_p, L64, C.c_void_p]),
+    "mgpu_get_traffic": (C.c_int, [_pl, _pl, I]),
     "mgpu_get_counters": (C.c_int, [I, _pl]),
     "mgpu_get_widom": (C.c_int, [I, I, _pd, _pl]),
     "mgpu_get_averages": (C.c_int, [I, I, _pd]),

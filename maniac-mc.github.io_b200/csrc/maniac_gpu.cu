@@ -12,6 +12,7 @@
 #include <map>
 
 #include "mgpu_kernels.cuh"
+#include "mgpu_records.cuh"
 #include "mgpu_table.h"
 
 // ---- constants (src/constants.f90:8-21, src/parameters.f90:31-37) --------------------
@@ -66,6 +67,10 @@ struct Context {
     double *d_geom = nullptr;         // com + off of one molecule
     std::map<std::string, TimingSlot> timing;
     std::vector<char> dirty;          // per walker: coordinates changed outside commit
+    // walker records (mgpu_save_walkers / mgpu_load_walkers / mgpu_block)
+    double *d_blob = nullptr; size_t blob_cap = 0;
+    long long *d_rec_off = nullptr; size_t rec_cap = 0;
+    long long h2d_bytes = 0, d2h_bytes = 0;
 };
 Context g;
 std::string g_err;
@@ -132,6 +137,7 @@ int check_err_flag(const char *where)
         cudaMemcpyAsync(g.d_err, &z, sizeof z, cudaMemcpyHostToDevice, g.stream);
         cudaStreamSynchronize(g.stream);
         if (e == 1) return fail(std::string(where) + ": commit without a pending trial");
+        if (e == 4) return fail(std::string(where) + ": malformed walker record (length / counts / capacity)");
         if (e == 2) return fail(std::string(where) + ": Trying to insert a molecule beyond the walker's capacity (NB_MAX_MOLECULE analogue)");
         return fail(std::string(where) + ": device error flag");
     }
@@ -161,6 +167,8 @@ const char *mgpu_last_error(void) { return g_err.c_str(); }
 
 void mgpu_finalize(void)
 {
+    if (g.d_blob) { cudaFree(g.d_blob); g.d_blob = nullptr; g.blob_cap = 0; }
+    if (g.d_rec_off) { cudaFree(g.d_rec_off); g.d_rec_off = nullptr; g.rec_cap = 0; }
     if (g.stream) cudaStreamSynchronize(g.stream);
     for (void *p : g.allocs) cudaFree(p);
     g.allocs.clear();
@@ -242,12 +250,14 @@ int mgpu_init(const mgpu_system *sys)
         int n = 0;
         for (int a = -3; a <= 3 && n >= 0; ++a) for (int b = -3; b <= 3 && n >= 0; ++b) for (int c = -3; c <= 3; ++c) {
             if (!a && !b && !c) continue;
+            if (a < 0 || (a == 0 && (b < 0 || (b == 0 && c < 0)))) continue;       // one of every +-m pair
             const double m[3] = { (double)a, (double)b, (double)c };
             double Gm[3], mGm = 0.0, s1 = 0.0;
             for (int d = 0; d < 3; ++d) { Gm[d] = G[d][0] * m[0] + G[d][1] * m[1] + G[d][2] * m[2]; mGm += m[d] * Gm[d]; s1 += std::fabs(Gm[d]); }
             if (!(mGm < s1 * (1.0 - 1e-13))) continue;
             if (n == MGPU_TRI_MAXREL || std::abs(a) == 3 || std::abs(b) == 3 || std::abs(c) == 3) { n = -1; break; }   // very skewed cell: literal search
             for (int i = 0; i < 3; ++i) { h.tri_rel[n][i] = M[i][0] * m[0] + M[i][1] * m[1] + M[i][2] * m[2]; h.tri_m[n][i] = m[i]; }
+            h.tri_len2[n] = h.tri_rel[n][0] * h.tri_rel[n][0] + h.tri_rel[n][1] * h.tri_rel[n][1] + h.tri_rel[n][2] * h.tri_rel[n][2];
             ++n;
         }
         h.tri_nrel = n;
@@ -908,6 +918,93 @@ int mgpu_sweep(int32_t first, int32_t n, int64_t n_steps, int32_t trace_walker, 
         cudaFree(d_trace);
     }
     return check_err_flag("mgpu_sweep");
+}
+// ---- walker records: host state <-> device state ----------------------------------------------
+static int ensure_rec_cap(size_t n_walkers, size_t n_doubles)
+{
+    if (n_walkers + 1 > g.rec_cap) {
+        if (g.d_rec_off) cudaFree(g.d_rec_off);
+        g.rec_cap = n_walkers + 1;
+        CK(cudaMalloc(&g.d_rec_off, sizeof(long long) * g.rec_cap));
+    }
+    if (n_doubles > g.blob_cap) {
+        if (g.d_blob) cudaFree(g.d_blob);
+        g.blob_cap = n_doubles + n_doubles / 8;
+        CK(cudaMalloc(&g.d_blob, sizeof(double) * g.blob_cap));
+    }
+    return 0;
+}
+void *mgpu_host_alloc(size_t bytes) { void *p = nullptr; return cudaMallocHost(&p, bytes ? bytes : 1) == cudaSuccess ? p : nullptr; }
+void mgpu_host_free(void *p) { if (p) cudaFreeHost(p); }
+int64_t mgpu_record_doubles_max(void)
+{
+    if (!g.ready) return 0;
+    int64_t L = MGPU_REC_HDR + 2 * (int64_t)g.h.nk;
+    for (int r = 0; r < g.h.nres; ++r) if (g.h.active[r]) L += (int64_t)g.h.cap[r] * (3 + 3 * g.h.natom[r] + 2);
+    return L;
+}
+int mgpu_save_walkers(int32_t first, int32_t n, double *blob, int64_t capacity, int64_t *offsets)
+{
+    NEED_READY();
+    if (n <= 0) return 0;
+    if (!blob || !offsets) return fail("mgpu_save_walkers: null buffer");
+    if (check_walker(first) || check_walker(first + n - 1)) return 1;
+    for (int w = first; w < first + n; ++w) if (ensure_clean(w)) return 1;
+    if (ensure_rec_cap(n, 0)) return 1;
+    k_record_len<<<(n + 255) / 256, 256, 0, g.stream>>>(first, n, g.d_rec_off);
+    std::vector<long long> len(n);
+    CK(cudaMemcpyAsync(len.data(), g.d_rec_off, sizeof(long long) * n, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    offsets[0] = 0;
+    for (int i = 0; i < n; ++i) offsets[i + 1] = offsets[i] + len[i];
+    if (offsets[n] > capacity) return fail("mgpu_save_walkers: buffer too small, need " + std::to_string((long long)offsets[n]) + " doubles");
+    if (ensure_rec_cap(n, (size_t)offsets[n])) return 1;
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64");
+    CK(cudaMemcpyAsync(g.d_rec_off, offsets, sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, g.stream));
+    Timer tm("pack");
+    k_pack<<<(n + 7) / 8, 256, 0, g.stream>>>(first, n, g.d_rec_off, g.d_blob);
+    tm.stop();
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(blob, g.d_blob, sizeof(double) * offsets[n], cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    g.d2h_bytes += (long long)sizeof(double) * offsets[n] + (long long)sizeof(long long) * n;
+    g.h2d_bytes += (long long)sizeof(long long) * (n + 1);
+    return 0;
+}
+int mgpu_load_walkers(int32_t first, int32_t n, const double *blob, const int64_t *offsets)
+{
+    NEED_READY();
+    if (n <= 0) return 0;
+    if (!blob || !offsets) return fail("mgpu_load_walkers: null buffer");
+    if (check_walker(first) || check_walker(first + n - 1)) return 1;
+    if (offsets[0] != 0) return fail("mgpu_load_walkers: offsets[0] must be 0");
+    for (int i = 0; i < n; ++i) if (offsets[i + 1] <= offsets[i]) return fail("mgpu_load_walkers: offsets must increase");
+    if (ensure_rec_cap(n, (size_t)offsets[n])) return 1;
+    CK(cudaMemcpyAsync(g.d_rec_off, offsets, sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(g.d_blob, blob, sizeof(double) * offsets[n], cudaMemcpyHostToDevice, g.stream));
+    Timer tm("unpack");
+    k_unpack<<<(n + 7) / 8, 256, 0, g.stream>>>(first, n, g.d_rec_off, g.d_blob, g.d_err);
+    tm.stop();
+    CK(cudaGetLastError());
+    g.h2d_bytes += (long long)sizeof(double) * offsets[n] + (long long)sizeof(long long) * (n + 1);
+    if (check_err_flag("mgpu_load_walkers")) return 1;
+    for (int w = first; w < first + n; ++w) g.dirty[w] = 0;     // the record carries S(k), energies and the cache rows
+    return 0;
+}
+int mgpu_block(int32_t first, int32_t n, int64_t n_steps, const double *blob_in, const int64_t *offsets_in,
+               double *blob_out, int64_t capacity_out, int64_t *offsets_out)
+{
+    if (blob_in && mgpu_load_walkers(first, n, blob_in, offsets_in)) return 1;
+    if (mgpu_sweep(first, n, n_steps, -1, nullptr)) return 1;
+    if (blob_out && mgpu_save_walkers(first, n, blob_out, capacity_out, offsets_out)) return 1;
+    return 0;
+}
+int mgpu_get_traffic(int64_t *h2d_bytes, int64_t *d2h_bytes, int32_t reset)
+{
+    if (h2d_bytes) *h2d_bytes = g.h2d_bytes;
+    if (d2h_bytes) *d2h_bytes = g.d2h_bytes;
+    if (reset) { g.h2d_bytes = 0; g.d2h_bytes = 0; }
+    return 0;
 }
 int mgpu_get_counters(int32_t w, int64_t out[12])
 {

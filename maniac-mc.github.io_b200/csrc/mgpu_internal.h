@@ -56,7 +56,7 @@ struct DevSys {
     // C m (tri_rel) that can beat the fractionally rounded image, and their integer coefficients m
     // (tri_m); tri_nrel < 0 = too many of them, keep the reference's 27-image search.
     int32_t tri_nrel;
-    double tri_rel[MGPU_TRI_MAXREL][3], tri_m[MGPU_TRI_MAXREL][3];
+    double tri_rel[MGPU_TRI_MAXREL][3], tri_m[MGPU_TRI_MAXREL][3], tri_len2[MGPU_TRI_MAXREL];   // one of every +-m pair
     // ewald / constants
     double rc, rc2, alpha, eps0_inv_real, twopi, beta, overlap;
     int32_t kmax[3], kmax_max, nk;

@@ -156,32 +156,38 @@ __device__ __forceinline__ double min_image_r2(double dx, double dy, double dz)
         return fma(dx, dx, fma(dy, dy, dz * dz));
     } else {
         // Same minimum as the 27-image search, found in 1 + tri_nrel candidates: round the fractional
-        // coordinates (image n), then try the few lattice vectors C m that can shorten ANY vector with
+        // coordinates (image n), then try the few lattice vectors +-C m that can shorten ANY vector with
         // fractional coordinates in [-1/2, 1/2]^3 (m G m < sum_d |(G m)_d|, G = C^T C; listed at init).
         // That is the global minimum over the lattice; it is the reference's answer whenever its shift
         // n - m lies in {-1,0,1}^3, which is checked -- otherwise (atoms far outside the cell, extreme
         // skew) the literal 27-image search decides.
         if (c_sys.tri_nrel < 0) return min_image_27(dx, dy, dz);
-        const double f0 = fma(c_sys.Hinv[0], dx, fma(c_sys.Hinv[1], dy, c_sys.Hinv[2] * dz));
-        const double f1 = fma(c_sys.Hinv[3], dx, fma(c_sys.Hinv[4], dy, c_sys.Hinv[5] * dz));
-        const double f2 = fma(c_sys.Hinv[6], dx, fma(c_sys.Hinv[7], dy, c_sys.Hinv[8] * dz));
+        // fractional coordinates: c_sys.Hinv holds the reference's "reciprocal" = TRANSPOSE of inverse(matrix)
+        const double f0 = fma(c_sys.Hinv[0], dx, fma(c_sys.Hinv[3], dy, c_sys.Hinv[6] * dz));
+        const double f1 = fma(c_sys.Hinv[1], dx, fma(c_sys.Hinv[4], dy, c_sys.Hinv[7] * dz));
+        const double f2 = fma(c_sys.Hinv[2], dx, fma(c_sys.Hinv[5], dy, c_sys.Hinv[8] * dz));
         const double n0 = (f0 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC, n1 = (f1 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC,
                      n2 = (f2 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC;
         const double tx = dx - fma(c_sys.H[0], n0, fma(c_sys.H[1], n1, c_sys.H[2] * n2));
         const double ty = dy - fma(c_sys.H[3], n0, fma(c_sys.H[4], n1, c_sys.H[5] * n2));
         const double tz = dz - fma(c_sys.H[6], n0, fma(c_sys.H[7], n1, c_sys.H[8] * n2));
-        double best = fma(tx, tx, fma(ty, ty, tz * tz));
+        // the list holds one vector of every +-m pair; of the two, only the one pointing against t can
+        // shorten it: |t -+ C m|^2 - |t|^2 = |C m|^2 - 2 |t . C m|
+        double gain = 0.0, bsign = 0.0;
         int bk = -1;
         const int nrel = c_sys.tri_nrel;
         for (int k = 0; k < nrel; ++k) {
-            const double cx = tx + c_sys.tri_rel[k][0], cy = ty + c_sys.tri_rel[k][1], cz = tz + c_sys.tri_rel[k][2];
-            const double d2 = fma(cx, cx, fma(cy, cy, cz * cz));
-            if (d2 < best) { best = d2; bk = k; }
+            const double dot = fma(tx, c_sys.tri_rel[k][0], fma(ty, c_sys.tri_rel[k][1], tz * c_sys.tri_rel[k][2]));
+            const double gk = fma(-2.0, fabs(dot), c_sys.tri_len2[k]);
+            if (gk < gain) { gain = gk; bk = k; bsign = dot > 0.0 ? -1.0 : 1.0; }
         }
-        double o0 = n0, o1 = n1, o2 = n2;                // shift of the winner in the reference's convention: -(n - m)
-        if (bk >= 0) { o0 -= c_sys.tri_m[bk][0]; o1 -= c_sys.tri_m[bk][1]; o2 -= c_sys.tri_m[bk][2]; }
+        double cx = tx, cy = ty, cz = tz, o0 = n0, o1 = n1, o2 = n2;   // o = shift of the winner in the reference's convention, -(n - s m)
+        if (bk >= 0) {
+            cx = fma(bsign, c_sys.tri_rel[bk][0], tx); cy = fma(bsign, c_sys.tri_rel[bk][1], ty); cz = fma(bsign, c_sys.tri_rel[bk][2], tz);
+            o0 = fma(-bsign, c_sys.tri_m[bk][0], n0); o1 = fma(-bsign, c_sys.tri_m[bk][1], n1); o2 = fma(-bsign, c_sys.tri_m[bk][2], n2);
+        }
         if (fmax(fabs(o0), fmax(fabs(o1), fabs(o2))) > 1.0) return min_image_27(dx, dy, dz);
-        return best;
+        return fma(cx, cx, fma(cy, cy, cz * cz));
     }
 }
 
@@ -460,26 +466,28 @@ struct HostPass {
         }
     }
 
-    // software-pipelined: the next block's atoms are in flight (L2 latency) while this one is evaluated.
-    // Accumulators are taken and returned by value so they stay in registers.
+    // software-pipelined: the next block's atoms are in flight (L1 / L2 latency) while this one is evaluated
+    // (plain register rotation; the last fetch reloads the current block).  Accumulators are taken and
+    // returned by value so they stay in registers.
     __device__ __forceinline__ void run(int t0, int stride, double &e_lj_io, double &e_c_io, PairCount &pc_io) const
     {
         double e_lj = e_lj_io, e_c = e_c_io;
         PairCount pc = pc_io;
         const int n = c_sys.n_host;
+        const int step = U * stride, reach = (U - 1) * stride;
         int j = t0;
-        if (U > 1) {                        // U atoms in flight per thread already: no explicit prefetch
-            for (; j + (U - 1) * stride < n; j += U * stride) { Atoms<U> a; fetch<U>(a, j, stride); block<U>(a, (1u << U) - 1u, e_lj, e_c, pc); }
-        } else if (j < n) {
+        if (j + reach < n) {
             Atoms<U> cur;
             fetch<U>(cur, j, stride);
             for (;;) {
-                const int jn = j + stride;
+                const int jn = j + step;
+                const bool more = jn + reach < n;
                 Atoms<U> nxt;
-                fetch<U>(nxt, jn < n ? jn : j, stride);          // unconditional (the last one reloads j): plain register rotation
+                fetch<U>(nxt, more ? jn : j, stride);
                 block<U>(cur, (1u << U) - 1u, e_lj, e_c, pc);
-                if (jn >= n) { j = jn; break; }
-                cur = nxt; j = jn;
+                j = jn;
+                if (!more) break;
+                cur = nxt;
             }
         }
         for (; j < n; j += stride) { Atoms<1> a1; fetch<1>(a1, j, stride); block<1>(a1, 1u, e_lj, e_c, pc); }
@@ -491,26 +499,48 @@ struct HostPass {
     // in memory, so the lanes' loads coalesce); tq / ttype are the target atom's charge (0 if tiny)
     // and type.  Molecule m_skip is left out (the probe itself), and so is every m <= m_order
     // (ordering check of pairwise_energy_for_molecule, :60-62; -1 = none).
+    template <int UU> struct GRaw { double c[UU][3], o[UU][3]; };
+    template <int UU>
+    __device__ __forceinline__ void fetch_guest(GRaw<UU> &R, const double *__restrict__ com, const double *__restrict__ offb,
+                                                int cap, int n, int m, int stride) const
+    {
+#pragma unroll
+        for (int u = 0; u < UU; ++u) {
+            const int mm = m + u * stride;
+            const int mc = (mm < n) ? mm : m;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) { R.c[u][d] = com[d * cap + mc]; R.o[u][d] = offb[d * cap + mc]; }
+        }
+    }
     __device__ __forceinline__ void run_guest(const double *__restrict__ com, const double *__restrict__ offb, int cap, int n,
                                               int t0, int stride, int m_skip, int m_order, double tq, int ttype,
                                               double &e_lj_io, double &e_c_io, PairCount &pc_io) const
     {
+        if (t0 >= n) return;
         double e_lj = e_lj_io, e_c = e_c_io;
         PairCount pc = pc_io;
-        for (int m = t0; m < n; m += U * stride) {
+        int m = t0;
+        GRaw<U> cur;
+        fetch_guest<U>(cur, com, offb, cap, n, m, stride);
+        for (;;) {                                   // next chunk's coordinates in flight while this one is evaluated
+            const int mn = m + U * stride;
+            const bool more = mn < n;
+            GRaw<U> nxt;
+            fetch_guest<U>(nxt, com, offb, cap, n, more ? mn : m, stride);
             Atoms<U> A;
             unsigned vm = 0u;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int mm = m + u * stride;
                 const bool ok = (mm < n) && (mm != m_skip) && (mm > m_order);
-                const int mc = (mm < n) ? mm : m;
-                A.xy[u] = make_double2(com[mc] + offb[mc], com[cap + mc] + offb[cap + mc]);
-                A.zq[u] = make_double2(com[2 * cap + mc] + offb[2 * cap + mc], tq);
+                A.xy[u] = make_double2(cur.c[u][0] + cur.o[u][0], cur.c[u][1] + cur.o[u][1]);
+                A.zq[u] = make_double2(cur.c[u][2] + cur.o[u][2], tq);
                 A.tt[u] = ttype;
                 vm |= ok ? (1u << u) : 0u;
             }
             block<U>(A, vm, e_lj, e_c, pc);
+            if (!more) break;
+            cur = nxt; m = mn;
         }
         e_lj_io = e_lj; e_c_io = e_c; pc_io = pc;
     }
@@ -731,17 +761,25 @@ __device__ double kspace(const Smem &S, const double *S_in, double *S_out)
     const int nk = c_sys.nk;
     double part[1] = { 0.0 };
     const int kind = P.kind, na = P.na;
-    for (int i = Grp<NT>::tid(); i < nk; i += NT) {
-        const int kx = c_sys.kx[i], ky = c_sys.ky[i], kz = c_sys.kz[i];
+    // the next k-vector's index triple, weight and S(k) are in flight while this one is evaluated
+    int i = Grp<NT>::tid();
+    int kx = 0, ky = 0, kz = 0;
+    double w = 0.0, s_re = 0.0, s_im = 0.0;
+    if (i < nk) { kx = __ldg(c_sys.kx + i); ky = __ldg(c_sys.ky + i); kz = __ldg(c_sys.kz + i); w = __ldg(c_sys.ffW + i); s_re = S_in[i]; s_im = S_in[nk + i]; }
+    while (i < nk) {
+        const int in = i + NT, ip = in < nk ? in : i;
+        const int nkx = __ldg(c_sys.kx + ip), nky = __ldg(c_sys.ky + ip), nkz = __ldg(c_sys.kz + ip);
+        const double nw = __ldg(c_sys.ffW + ip), n_re = S_in[ip], n_im = S_in[nk + ip];
         double sr = 0.0, si = 0.0;
         for (int a = 0; a < na; ++a) {
             const double q = c_sys.charge[P.res][a];
             if (kind != MGPU_KIND_DELETE) { const cplx pn = phase_product(S.tab_new, a, kx, ky, kz); sr += q * pn.re; si += q * pn.im; }
             if (kind != MGPU_KIND_CREATE) { const cplx po = phase_product(S.tab_old, a, kx, ky, kz); sr -= q * po.re; si -= q * po.im; }
         }
-        const double re = S_in[i] + sr, im = S_in[nk + i] + si;
+        const double re = s_re + sr, im = s_im + si;
         if (S_out) { S_out[i] = re; S_out[nk + i] = im; }
-        part[0] += c_sys.ffW[i] * (re * re + im * im);
+        part[0] += w * (re * re + im * im);
+        i = in; kx = nkx; ky = nky; kz = nkz; w = nw; s_re = n_re; s_im = n_im;
     }
     Grp<NT>::template sum<1>(part, S.ws->red);
     return part[0] * c_sys.eps0_inv_real * c_sys.twopi / c_sys.volume;

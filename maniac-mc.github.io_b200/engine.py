@@ -115,6 +115,7 @@ class Engine:
         s.device = device
         self._sys_struct = s
         self._keep.append(res_arr)
+        self._pinned = []
         self._ck(self.L.mgpu_init(C.byref(s)))
         self._open = True
 
@@ -125,6 +126,9 @@ class Engine:
 
     def close(self):
         if getattr(self, "_open", False):
+            for p in self._pinned:
+                self.L.mgpu_host_free(C.c_void_p(p))
+            self._pinned = []
             self.L.mgpu_finalize()
             self._open = False
 
@@ -324,6 +328,97 @@ class Engine:
             tw = trace_walker
         self._ck(self.L.mgpu_sweep(first_walker, n, n_steps, tw, ptr))
         return tr
+
+    # ---- walker records / block-level entry (host state in, host state out) ------------------
+    def host_buffer(self, n_doubles):
+        """Page-locked host array of ``n_doubles`` float64 (mgpu_host_alloc); freed by close()."""
+        p = self.L.mgpu_host_alloc(C.c_size_t(int(n_doubles) * 8))
+        if not p:
+            raise ManiacAbort("mgpu_host_alloc failed")
+        self._pinned.append(p)
+        return np.ctypeslib.as_array((C.c_double * int(n_doubles)).from_address(p))
+
+    def record_doubles_max(self):
+        return int(self.L.mgpu_record_doubles_max())
+
+    def save_walkers(self, blob, first_walker=0, n_walkers=None):
+        n = self.n_walkers - first_walker if n_walkers is None else n_walkers
+        off = np.zeros(n + 1, dtype=np.int64)
+        self._ck(self.L.mgpu_save_walkers(first_walker, n, blob.ctypes.data, blob.size, off.ctypes.data))
+        return off
+
+    def load_walkers(self, blob, offsets, first_walker=0):
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self._ck(self.L.mgpu_load_walkers(first_walker, len(offsets) - 1, blob.ctypes.data, offsets.ctypes.data))
+
+    def block(self, n_steps, blob_in, offsets_in, blob_out, first_walker=0, n_walkers=None):
+        """One block of the MC loop from host records to host records (mgpu_block)."""
+        n = self.n_walkers - first_walker if n_walkers is None else n_walkers
+        off_out = np.zeros(n + 1, dtype=np.int64)
+        pin = pof = None
+        if blob_in is not None:
+            offsets_in = np.ascontiguousarray(offsets_in, dtype=np.int64)
+            pin, pof = blob_in.ctypes.data, offsets_in.ctypes.data
+        self._ck(self.L.mgpu_block(first_walker, n, n_steps, pin, pof, blob_out.ctypes.data, blob_out.size, off_out.ctypes.data))
+        return off_out
+
+    def traffic(self, reset=False):
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._ck(self.L.mgpu_get_traffic(C.byref(a), C.byref(b), 1 if reset else 0))
+        return dict(h2d_bytes=a.value, d2h_bytes=b.value)
+
+    @staticmethod
+    def parse_record(rec, nk, residues):
+        """Decode one walker record (see include/maniac_gpu.h) into a dict; ``residues`` = [(active, natom)]."""
+        out = dict(length=int(rec[0]), count=rec[1:9].astype(int), energy=rec[9:15].copy(),
+                   rng=rec[15:19].view(np.uint64).copy(), counters=rec[19:31].astype(np.int64).reshape(6, 2),
+                   averages=rec[32:64].reshape(8, 4).copy(), Ak=rec[64:64 + 2 * nk].copy(), molecules={})
+        p = 64 + 2 * nk
+        for r, (active, na) in enumerate(residues):
+            if not active:
+                continue
+            ms, cnt = 3 + 3 * na + 2, int(rec[1 + r])
+            m = rec[p:p + cnt * ms].reshape(cnt, ms)
+            out["molecules"][r] = dict(com=m[:, :3].copy(), offset=m[:, 3:3 + 3 * na].reshape(cnt, na, 3).copy(), cache=m[:, -2:].copy())
+            p += cnt * ms
+        return out
+
+    # ---- multi-GPU: the one exchange of the path (SURVEY 8e) -----------------------------------
+    def nccl_init_from_torch(self):
+        """Bootstrap the library's own NCCL communicator: rank 0 makes the id, torch.distributed carries it."""
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(), dist.get_rank()
+        ident = C.create_string_buffer(128)
+        if rank == 0:
+            self._ck_nccl(self.L.mgpu_nccl_unique_id(ident))
+        box = [ident.raw]
+        dist.broadcast_object_list(box, src=0)
+        ident = C.create_string_buffer(box[0], 128)
+        self._ck_nccl(self.L.mgpu_nccl_init(ident, world, rank))
+        self.nccl_ready = True
+
+    def _ck_nccl(self, rc):
+        if rc:
+            raise ManiacAbort(self.L.mgpu_nccl_last_error().decode())
+
+    def reduce_averages(self, buf):
+        """In-place sum over ranks of a float64 host array (mgpu_reduce_averages, one ncclAllReduce)."""
+        assert buf.dtype == np.float64 and buf.flags.c_contiguous
+        self._ck_nccl(self.L.mgpu_reduce_averages(_pd(buf), buf.size))
+
+    def nccl_finalize(self):
+        if getattr(self, "nccl_ready", False):
+            self.L.mgpu_nccl_finalize()
+            self.nccl_ready = False
+
+    def all_averages(self, res):
+        """[n_walkers, 4] block accumulators (sum N, sum N^2, sum E, samples) of residue ``res``."""
+        out = np.zeros((self.n_walkers, 4))
+        tmp = np.zeros(4)
+        for w in range(self.n_walkers):
+            self._ck(self.L.mgpu_get_averages(w, res, _pd(tmp)))
+            out[w] = tmp
+        return out
 
     def counters(self, walker=0):
         out = (C.c_int64 * 12)()

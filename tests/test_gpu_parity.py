@@ -554,3 +554,76 @@ def test_large_triclinic_supercell(load, engine_cls):
             full = eng.update_system_energy(w)
             # swaps leave the old molecule's dS in S(k) (reference behaviour), so only the real-space parts can be audited
             assert_e(inc[[0, 1, 3, 4]], full[[0, 1, 3, 4]], rel=1e-8, what=f"drift walker {w}")
+
+
+# ---------------------------------------------------------------------------------------------
+# walker records and the block-level entry (host state in, host state out)
+# ---------------------------------------------------------------------------------------------
+def test_walker_records_roundtrip_and_block(load, engine_cls):
+    """mgpu_save_walkers / mgpu_load_walkers / mgpu_block: the record is the whole state, so
+    (a) save -> load into another walker reproduces that walker exactly, (b) a trajectory cut into
+    blocks that travel through host memory equals the uninterrupted device-resident one and the
+    oracle's, (c) malformed records are refused."""
+    from maniac_b200.engine import Engine, ManiacAbort
+    s = load("zif8_h2o_gcmc")
+    nW, cap = 6, 96
+    o = Oracle(s, capacity=cap)
+    o.update_system_energy()
+    o.seed(2025)
+    ref = o.monte_carlo_steps(900)
+    with engine_cls(s, n_walkers=nW, capacity=cap) as eng:
+        eng.seed(2025)
+        blob_a = eng.host_buffer(nW * eng.record_doubles_max())
+        blob_b = eng.host_buffer(nW * eng.record_doubles_max())
+        tr1 = eng.sweep(300, trace_walker=0)
+        off = eng.save_walkers(blob_a)
+        nk = eng.ewald()["nk"]
+        resinfo = [(r.active, r.natom) for r in s.residues]
+        rec0 = Engine.parse_record(blob_a[off[0]:off[1]], nk, resinfo)
+        assert rec0["length"] == off[1] - off[0]
+        assert rec0["count"][0] == eng.count(0, walker=0) == len(rec0["molecules"][0]["com"])
+        np.testing.assert_array_equal(rec0["energy"], eng.energy(0))
+        np.testing.assert_array_equal(rec0["counters"], eng.counters(0))
+        assert tuple(int(x) for x in rec0["rng"]) == tuple(eng.rng_state(0))
+        com, offs = eng.get_molecule(0, 2, walker=0)
+        np.testing.assert_array_equal(rec0["molecules"][0]["com"][2], com)
+        np.testing.assert_array_equal(rec0["molecules"][0]["offset"][2], offs)
+        ak = eng.Ak(0)
+        np.testing.assert_array_equal(rec0["Ak"][:nk], np.asarray(ak).real)
+        np.testing.assert_array_equal(rec0["Ak"][nk:], np.asarray(ak).imag)
+        # (a) walker 0's record loaded into walker 3: identical state, identical continuation
+        eng.load_walkers(blob_a[off[0]:off[1]], np.array([0, off[1] - off[0]]), first_walker=3)
+        assert eng.count(0, walker=3) == eng.count(0, walker=0)
+        np.testing.assert_array_equal(eng.energy(3), eng.energy(0))
+        # (b) two more blocks through host memory: records in, records out
+        off2 = eng.block(300, blob_a, off, blob_b)
+        off3 = eng.block(300, blob_b, off2, blob_a)
+        rec_end = Engine.parse_record(blob_a[off3[0]:off3[1]], nk, resinfo)
+        rec_end3 = Engine.parse_record(blob_a[off3[3]:off3[4]], nk, resinfo)
+        assert rec_end["count"][0] == o.count(0)
+        assert_e(rec_end["energy"], o.energy(), rel=1e-9, what="energy after 3 blocks through host records")
+        np.testing.assert_array_equal(rec_end["counters"], o.counters())
+        assert tuple(int(x) for x in rec_end["rng"]) == tuple(o.rng_state())
+        # walker 3 was a clone of walker 0 after block 1 (same RNG state): it must have followed the same path
+        np.testing.assert_array_equal(rec_end3["energy"], rec_end["energy"])
+        np.testing.assert_array_equal(rec_end3["molecules"][0]["com"], rec_end["molecules"][0]["com"])
+        # the uninterrupted run of a fresh engine state gives the same trajectory as the oracle (sanity of ref)
+        assert (tr1["accepted"] == ref["accepted"][:300]).all()
+        # drift audit on the restored state
+        inc = eng.energy(0)
+        full = eng.update_system_energy(0)
+        assert_e(inc, full, rel=1e-9, what="restored state vs full recompute")
+        t = eng.traffic()
+        assert t["h2d_bytes"] > 8 * off[-1] and t["d2h_bytes"] > 8 * off[-1]
+        # (c) malformed: wrong length word, count beyond capacity
+        bad = blob_b[off2[0]:off2[1]].copy()
+        bad[0] += 1
+        with pytest.raises(ManiacAbort):
+            eng.load_walkers(bad, np.array([0, len(bad)]), first_walker=1)
+        bad = blob_b[off2[0]:off2[1]].copy()
+        bad[1] = cap + 5
+        with pytest.raises(ManiacAbort):
+            eng.load_walkers(bad, np.array([0, len(bad)]), first_walker=1)
+        small = eng.host_buffer(100)
+        with pytest.raises(ManiacAbort):
+            eng.save_walkers(small)

@@ -5,11 +5,11 @@ set -u
 mkdir -p gpurun_out
 TAG=${1:-r01}; shift
 BENCH_ARGS=${BENCH_ARGS:-"--steps 8 --warmup 3"}
-BENCH_SMALL="python bench.py --steps 2 --warmup 1 --walkers 2368 --inner ${PROF_INNER:-64} --widom 200000 --e2e-walkers 256 --e2e-steps 3 --no-cpu"
+BENCH_SMALL="python bench.py --steps 2 --warmup 1 --walkers 2368 --inner ${PROF_INNER:-64} --widom 200000 --e2e-walkers 256 --e2e-steps 3 --no-cpu --mixture-walkers 0"
 for what in "$@"; do
 case $what in
 test)
-  timeout 1500 python -m pytest tests -m gpu -q --timeout 900 --tb=short ${PYTEST_ARGS:-} > gpurun_out/pytest_$TAG.log 2>&1
+  timeout 1500 python -m pytest tests -m gpu -q --timeout 900 --tb=short ${PYTEST_K:+-k "$PYTEST_K"} > gpurun_out/pytest_$TAG.log 2>&1
   tail -40 gpurun_out/pytest_$TAG.log ;;
 bench)
   timeout 900 python bench.py $BENCH_ARGS > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
