@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--mixture-steps", type=int, default=32)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="kernel-variant experiments: the timed sweep only, prints a short line")
     return ap.parse_args()
 
 
@@ -263,6 +264,12 @@ def main():
     moves = float(W) * a.inner * a.steps * world
     value = moves / t_dev
 
+    if a.quick:
+        if rank == 0:
+            print(json.dumps({"quick": True, "lib": os.environ.get("MANIAC_GPU_LIB", "default"), "moves_per_s": value,
+                              "ms_per_step": 1e3 * t_dev / a.steps, "clocks": clocks}))
+        eng.close()
+        return
     flops = FLOP_GEOM * pc["pairs"] + FLOP_LJ * pc["lj"] + FLOP_COUL * pc["coulomb"] + kspace_flops(dcount, na, ew["kmax"], ew["nk"])
     ach_tf = flops / (ms_total * 1e-3) / 1e12
     nmean = float(np.mean([eng.count(0, walker=w) for w in range(0, W, max(1, W // 64))]))
@@ -290,10 +297,10 @@ def main():
     assert all(plan.point_of(rank * W + w) == point(w) for w in range(0, W, 97))
     per_walker = np.zeros((W, 6))
     per_walker[:, :4] = eng.all_averages(0)
-    local = plan.accumulate(per_walker)
+    local_sums = plan.accumulate(per_walker)
     if world > 1:
         eng.nccl_init_from_torch()
-    total = reduce_sums(local, engine=eng)
+    total = reduce_sums(local_sums, engine=eng)
     if world > 1:
         eng.nccl_finalize()
     summ = summarize(total, eng.thermo(0)["beta"])
@@ -428,7 +435,7 @@ def main():
         enge.sweep(a.inner)                          # move towards the steady-state loading before records are sized
     rec_max = enge.record_doubles_max()
     nmax = max(enge.count(0, walker=w) for w in range(0, W, max(1, W // 128)))
-    per_walker = 64 + 2 * ew["nk"] + int(1.5 * nmax + 64) * (3 + 3 * na + 2)
+    per_walker = 72 + 2 * ew["nk"] + int(1.5 * nmax + 64) * (3 + 3 * na + 2)
     blob = [enge.host_buffer(min(rec_max, per_walker) * W) for _ in range(2)]
     off = enge.save_walkers(blob[0])
     for i in range(max(1, a.warmup)):

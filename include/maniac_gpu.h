@@ -212,7 +212,8 @@ int mgpu_sweep(int32_t first_walker, int32_t n_walkers, int64_t n_steps,
  * walkers [first, first+n), from and to flat HOST arrays.  A walker's record (doubles) is
  *   [0] record length | [1..8] primary%num%residues | [9..14] energy (energy_type order) |
  *   [15..18] RNG state (raw bits) | [19..30] counters%... (trials, successes) x 6 | [31] 0 |
- *   [32..63] block averages [res][sum N, sum N^2, sum E, samples] | [64..64+2 nk) ewald%Ak (re[nk], im[nk]) |
+ *   [32..63] block averages [res][sum N, sum N^2, sum E, samples] | [64] translation_step [65] rotation_step_angle
+ *   [66..71] 0 | [72..72+2 nk) ewald%Ak (re[nk], im[nk]) |
  *   then for every active residue type, for mol = 1..count: guest%com(:,res,mol), guest%offset(:,res,mol,1:natom),
  *   and the molecule's cached framework energy {lj, coulomb (e^2/A)}.
  * Record i starts at blob[offsets[i]]; offsets[n] is the total length.  mgpu_save_walkers fills
@@ -230,6 +231,12 @@ int mgpu_block(int32_t first_walker, int32_t n_walkers, int64_t n_steps,
                double *blob_out, int64_t capacity_out, int64_t *offsets_out);
 /* bytes moved host->device / device->host by the three calls above since the last reset */
 int mgpu_get_traffic(int64_t *h2d_bytes, int64_t *d2h_bytes, int32_t reset);
+/* adjust_move_step_sizes, src/monte_carlo_utils.f90:98-134: Robbins-Monro update of mc_input%translation_step /
+ * rotation_step_angle from the cumulative counters, called at the end of a block when recalibrate_moves is set.
+ * Every walker carries its own pair of step sizes (each starts from the input values). */
+int mgpu_adjust_move_step_sizes(int32_t first_walker, int32_t n_walkers);
+int mgpu_get_step_sizes(int32_t walker, double out[2]);
+int mgpu_set_step_sizes(int32_t walker, double translation_step, double rotation_step_angle);
 /* counters%{translations,rotations,creations,deletions,swaps,widom}(1:2) of a walker */
 int mgpu_get_counters(int32_t walker, int64_t out[12]);
 /* statistic%weight / statistic%sample (src/widom.f90:74-92) accumulated by mgpu_sweep */

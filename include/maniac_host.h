@@ -37,6 +37,9 @@ const char *mhost_last_error(void);
  * `trace_walker`.  Returns 0 or an error (message in mhost_last_error). */
 int mhost_run(mhost_sim *sim, int64_t n_steps, int32_t trace_walker, mgpu_step_trace *trace);
 
+/* adjust_move_step_sizes (src/monte_carlo_utils.f90:98-134) for every walker, from its own counters */
+int mhost_adjust_move_step_sizes(mhost_sim *sim);
+int mhost_get_step_sizes(const mhost_sim *sim, int32_t walker, double out[2]);
 /* thermo%chemical_potential(res) of one walker (isotherm points) */
 int mhost_set_chemical_potential(mhost_sim *sim, int32_t walker, int32_t res, double mu);
 int mhost_get_count(const mhost_sim *sim, int32_t walker, int32_t res);

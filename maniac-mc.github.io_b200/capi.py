@@ -12,7 +12,9 @@ MAX_RES = 8
 MAX_SITES = 16
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "libmaniac_gpu.so"
+import os as _os
+# MANIAC_GPU_LIB: another build of the SAME library (kernel-variant experiments); still CUDA, still no CPU path
+LIB_PATH = Path(_os.environ["MANIAC_GPU_LIB"]) if _os.environ.get("MANIAC_GPU_LIB") else _HERE / "libmaniac_gpu.so"
 _LIB = None
 
 
@@ -87,6 +89,9 @@ SIGNATURES = {
     "mgpu_load_walkers": (C.c_int, [I, I, C.c_void_p, C.c_void_p]),
     "mgpu_block": (C.c_int, [I, I, L64, C.c_void_p, C.c_void_p, C.c_void_p, L64, C.c_void_p]),
     "mgpu_get_traffic": (C.c_int, [_pl, _pl, I]),
+    "mgpu_adjust_move_step_sizes": (C.c_int, [I, I]),
+    "mgpu_get_step_sizes": (C.c_int, [I, _pd]),
+    "mgpu_set_step_sizes": (C.c_int, [I, D, D]),
     "mgpu_get_counters": (C.c_int, [I, _pl]),
     "mgpu_get_widom": (C.c_int, [I, I, _pd, _pl]),
     "mgpu_get_averages": (C.c_int, [I, I, _pd]),

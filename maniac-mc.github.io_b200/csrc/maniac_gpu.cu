@@ -463,7 +463,7 @@ int mgpu_init(const mgpu_system *sys)
     // ---- per-walker arrays ----
     const size_t W = sys->n_walkers;
     if (dalloc(&h.coords, W * (size_t)stride) || dalloc(&h.count, W * MGPU_MAX_RES) || dalloc(&h.S, W * 4 * nk1) || dalloc(&h.cur, W) ||
-        dalloc(&h.energy, W * 6) || dalloc(&h.mu, W * MGPU_MAX_RES) || dalloc(&h.rng, W * 4) || dalloc(&h.counters, W * 12) ||
+        dalloc(&h.energy, W * 6) || dalloc(&h.mu, W * MGPU_MAX_RES) || dalloc(&h.rng, W * 4) || dalloc(&h.step, W * 2) || dalloc(&h.counters, W * 12) ||
         dalloc(&h.widom_w, W * MGPU_MAX_RES) || dalloc(&h.widom_n, W * MGPU_MAX_RES) || dalloc(&h.avg, W * MGPU_MAX_RES * 4) ||
         dalloc(&h.trial, W) || dalloc(&h.pair_count, 4) || dalloc(&g.d_err, 1) || dalloc(&g.d_scratch, 64) || dalloc(&g.d_geom, 3 + 3 * MGPU_MAX_SITES)) return 1;
     CK(cudaMallocHost(&g.h_scratch, sizeof(double) * 64));
@@ -501,6 +501,11 @@ int mgpu_init(const mgpu_system *sys)
         if (stride) CK(cudaMemcpy(h.coords, all.data(), sizeof(double) * W * stride, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(h.count, allc.data(), sizeof(int32_t) * allc.size(), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(h.mu, allmu.data(), sizeof(double) * allmu.size(), cudaMemcpyHostToDevice));
+    }
+    {
+        std::vector<double> st(W * 2);
+        for (size_t w = 0; w < W; ++w) { st[2 * w] = sys->translation_step; st[2 * w + 1] = sys->rotation_step_angle; }
+        CK(cudaMemcpy(h.step, st.data(), sizeof(double) * st.size(), cudaMemcpyHostToDevice));
     }
     g.dirty.assign(W, 0);
 
@@ -1004,6 +1009,31 @@ int mgpu_get_traffic(int64_t *h2d_bytes, int64_t *d2h_bytes, int32_t reset)
     if (h2d_bytes) *h2d_bytes = g.h2d_bytes;
     if (d2h_bytes) *d2h_bytes = g.d2h_bytes;
     if (reset) { g.h2d_bytes = 0; g.d2h_bytes = 0; }
+    return 0;
+}
+int mgpu_adjust_move_step_sizes(int32_t first, int32_t n)
+{
+    NEED_READY();
+    if (n <= 0) return 0;
+    if (check_walker(first) || check_walker(first + n - 1)) return 1;
+    k_adjust_steps<<<(n + 127) / 128, 128, 0, g.stream>>>(first, n);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+int mgpu_get_step_sizes(int32_t w, double out[2])
+{
+    NEED_READY();
+    if (check_walker(w)) return 1;
+    CK(cudaMemcpy(out, g.h.step + (int64_t)w * 2, sizeof(double) * 2, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int mgpu_set_step_sizes(int32_t w, double translation_step, double rotation_step_angle)
+{
+    NEED_READY();
+    if (check_walker(w)) return 1;
+    const double v[2] = { translation_step, rotation_step_angle };
+    CK(cudaMemcpy(g.h.step + (int64_t)w * 2, v, sizeof v, cudaMemcpyHostToDevice));
     return 0;
 }
 int mgpu_get_counters(int32_t w, int64_t out[12])

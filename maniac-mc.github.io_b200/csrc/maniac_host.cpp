@@ -48,6 +48,7 @@ struct Walker {
     Rng rng;
     long long counter[6][2];
     std::vector<double> widom_w; std::vector<long long> widom_n;
+    double tstep = 0.0, rstep = 0.0;              // mc_input%translation_step / rotation_step_angle (adjust_move_step_sizes)
 };
 struct Pending { int valid, move, kind, res, mol, res2; double com[3]; double off[MGPU_MAX_SITES][3]; };
 } // namespace
@@ -145,6 +146,7 @@ mhost_sim *mhost_create(const mgpu_system *sys, uint64_t seed)
         }
         if (mgpu_get_energy(w, W.energy)) { h_err = mgpu_last_error(); delete S; return nullptr; }
         W.rng.seed(seed + 104729ull * (uint64_t)w);
+        W.tstep = S->tstep; W.rstep = S->rstep;
     }
     return S;
 }
@@ -177,7 +179,7 @@ int mhost_run(mhost_sim *S, int64_t n_steps, int32_t trace_walker, mgpu_step_tra
                     P.valid = 1; P.move = MGPU_MV_TRANSLATE; P.kind = MGPU_KIND_MOVE;
                     double tp[3];
                     for (int d = 0; d < 3; ++d) tp[d] = W.rng.uniform();
-                    for (int d = 0; d < 3; ++d) P.com[d] = com[3 * mol + d] + (tp[d] - 0.5) * S->tstep;
+                    for (int d = 0; d < 3; ++d) P.com[d] = com[3 * mol + d] + (tp[d] - 0.5) * W.tstep;
                     apply_PBC(S, P.com);
                     std::memcpy(P.off, off + (size_t)3 * na * mol, sizeof(double) * 3 * na);
                 }
@@ -186,7 +188,7 @@ int mhost_run(mhost_sim *S, int64_t n_steps, int32_t trace_walker, mgpu_step_tra
                     P.valid = 1; P.move = MGPU_MV_ROTATE; P.kind = MGPU_KIND_MOVE;
                     std::memcpy(P.com, com + 3 * mol, sizeof(double) * 3);
                     std::memcpy(P.off, off + (size_t)3 * na * mol, sizeof(double) * 3 * na);
-                    const double theta = (W.rng.uniform() - 0.5) * S->rstep;
+                    const double theta = (W.rng.uniform() - 0.5) * W.rstep;
                     const int axis = (int)(W.rng.uniform() * 3.0) + 1;
                     rotate_offsets(axis, theta, P.off, na);
                 }
@@ -330,6 +332,23 @@ int mhost_run(mhost_sim *S, int64_t n_steps, int32_t trace_walker, mgpu_step_tra
     return 0;
 }
 
+// adjust_move_step_sizes, monte_carlo_utils.f90:98-134 (host side, the walker's own counters)
+int mhost_adjust_move_step_sizes(mhost_sim *S)
+{
+    const double gamma = 0.10, TARGET_ACCEPTANCE = 0.40;
+    for (Walker &W : S->w) {
+        if (W.counter[0][0] > 500) {
+            const double acc = (double)W.counter[0][1] / (double)W.counter[0][0];
+            W.tstep = std::fmax(1.0e-3, std::fmin(W.tstep * std::exp(gamma * (acc - TARGET_ACCEPTANCE)), 3.0));
+        }
+        if (W.counter[1][0] > 500) {
+            const double acc = (double)W.counter[1][1] / (double)W.counter[1][0];
+            W.rstep = std::fmax(1.0e-3, std::fmin(W.rstep * std::exp(gamma * (acc - TARGET_ACCEPTANCE)), 0.78));
+        }
+    }
+    return 0;
+}
+int mhost_get_step_sizes(const mhost_sim *S, int32_t w, double out[2]) { out[0] = S->w[w].tstep; out[1] = S->w[w].rstep; return 0; }
 int mhost_set_chemical_potential(mhost_sim *S, int32_t w, int32_t res, double mu)
 {
     if (w < 0 || w >= S->nw || res < 0 || res >= S->nres) return hfail("mhost_set_chemical_potential: index out of range");

@@ -30,9 +30,23 @@
 
 __constant__ DevSys c_sys;
 
+// software prefetch (register rotation) switches: framework pass with U > 1 targets per thread, guest pass, k-space loop.
+// Measured on B200 (4736 walkers x 256 steps): none 18.22, k-space only 19.10, guest only 18.56, framework-U only 18.86,
+// all three 18.36 M moves/s -- at 128 registers per thread the rotations compete for registers, so only k-space is on.
+#ifndef MGPU_PF_HOSTU
+#define MGPU_PF_HOSTU 0
+#endif
+#ifndef MGPU_PF_GUEST
+#define MGPU_PF_GUEST 0
+#endif
+#ifndef MGPU_PF_KSPACE
+#define MGPU_PF_KSPACE 1
+#endif
 #define MGPU_BLOCK 256                    // CTA-per-task kernels (NT = MGPU_BLOCK)
 #define MGPU_WARPS (MGPU_BLOCK / 32)
+#ifndef MGPU_WBLOCK
 #define MGPU_WBLOCK 512                   // warp-per-task kernels (NT = 32): one CTA per SM
+#endif
 #define MGPU_WGROUPS (MGPU_WBLOCK / 32)
 
 // ------------------------------------------------------------------------------------
@@ -476,7 +490,9 @@ struct HostPass {
         const int n = c_sys.n_host;
         const int step = U * stride, reach = (U - 1) * stride;
         int j = t0;
-        if (j + reach < n) {
+        if (!MGPU_PF_HOSTU && U > 1) {
+            for (; j + reach < n; j += step) { Atoms<U> a; fetch<U>(a, j, stride); block<U>(a, (1u << U) - 1u, e_lj, e_c, pc); }
+        } else if (j + reach < n) {
             Atoms<U> cur;
             fetch<U>(cur, j, stride);
             for (;;) {
@@ -526,7 +542,7 @@ struct HostPass {
             const int mn = m + U * stride;
             const bool more = mn < n;
             GRaw<U> nxt;
-            fetch_guest<U>(nxt, com, offb, cap, n, more ? mn : m, stride);
+            if (MGPU_PF_GUEST) fetch_guest<U>(nxt, com, offb, cap, n, more ? mn : m, stride);
             Atoms<U> A;
             unsigned vm = 0u;
 #pragma unroll
@@ -540,7 +556,8 @@ struct HostPass {
             }
             block<U>(A, vm, e_lj, e_c, pc);
             if (!more) break;
-            cur = nxt; m = mn;
+            if (MGPU_PF_GUEST) cur = nxt; else fetch_guest<U>(cur, com, offb, cap, n, mn, stride);
+            m = mn;
         }
         e_lj_io = e_lj; e_c_io = e_c; pc_io = pc;
     }
@@ -768,8 +785,9 @@ __device__ double kspace(const Smem &S, const double *S_in, double *S_out)
     if (i < nk) { kx = __ldg(c_sys.kx + i); ky = __ldg(c_sys.ky + i); kz = __ldg(c_sys.kz + i); w = __ldg(c_sys.ffW + i); s_re = S_in[i]; s_im = S_in[nk + i]; }
     while (i < nk) {
         const int in = i + NT, ip = in < nk ? in : i;
-        const int nkx = __ldg(c_sys.kx + ip), nky = __ldg(c_sys.ky + ip), nkz = __ldg(c_sys.kz + ip);
-        const double nw = __ldg(c_sys.ffW + ip), n_re = S_in[ip], n_im = S_in[nk + ip];
+        int nkx = 0, nky = 0, nkz = 0;
+        double nw = 0.0, n_re = 0.0, n_im = 0.0;
+        if (MGPU_PF_KSPACE) { nkx = __ldg(c_sys.kx + ip); nky = __ldg(c_sys.ky + ip); nkz = __ldg(c_sys.kz + ip); nw = __ldg(c_sys.ffW + ip); n_re = S_in[ip]; n_im = S_in[nk + ip]; }
         double sr = 0.0, si = 0.0;
         for (int a = 0; a < na; ++a) {
             const double q = c_sys.charge[P.res][a];
@@ -779,6 +797,7 @@ __device__ double kspace(const Smem &S, const double *S_in, double *S_out)
         const double re = s_re + sr, im = s_im + si;
         if (S_out) { S_out[i] = re; S_out[nk + i] = im; }
         part[0] += w * (re * re + im * im);
+        if (!MGPU_PF_KSPACE && in < nk) { nkx = __ldg(c_sys.kx + in); nky = __ldg(c_sys.ky + in); nkz = __ldg(c_sys.kz + in); nw = __ldg(c_sys.ffW + in); n_re = S_in[in]; n_im = S_in[nk + in]; }
         i = in; kx = nkx; ky = nky; kz = nkz; w = nw; s_re = n_re; s_im = n_im;
     }
     Grp<NT>::template sum<1>(part, S.ws->red);
@@ -1345,7 +1364,7 @@ __device__ __noinline__ void propose_step(int w, GroupWS &ws, int32_t *err)
             sh.valid = 1; sh.move = MGPU_MV_TRANSLATE; sh.kind = MGPU_KIND_MOVE;
             double tp[3];
             for (int d = 0; d < 3; ++d) tp[d] = rng_uniform(rng);
-            for (int d = 0; d < 3; ++d) sh.com[d] = wc[d * cap + mol] + (tp[d] - 0.5) * c_sys.tstep;
+            for (int d = 0; d < 3; ++d) sh.com[d] = wc[d * cap + mol] + (tp[d] - 0.5) * c_sys.step[(int64_t)w * 2];
             apply_PBC(sh.com);
             for (int e = 0; e < na * 3; ++e) sh.off[e / 3][e % 3] = offs[(int64_t)e * cap + mol];
         }
@@ -1354,7 +1373,7 @@ __device__ __noinline__ void propose_step(int w, GroupWS &ws, int32_t *err)
             sh.valid = 1; sh.move = MGPU_MV_ROTATE; sh.kind = MGPU_KIND_MOVE;
             for (int d = 0; d < 3; ++d) sh.com[d] = wc[d * cap + mol];
             for (int e = 0; e < na * 3; ++e) sh.off[e / 3][e % 3] = offs[(int64_t)e * cap + mol];
-            const double theta = (rng_uniform(rng) - 0.5) * c_sys.rstep;
+            const double theta = (rng_uniform(rng) - 0.5) * c_sys.step[(int64_t)w * 2 + 1];
             const int axis = (int)(rng_uniform(rng) * 3.0) + 1;
             rotate_offsets(axis, theta, sh.off, na);
         }
@@ -1552,6 +1571,28 @@ __global__ void __launch_bounds__(MGPU_WBLOCK, 1) k_sweep(int first_walker, int 
     if (lane < c_sys.nres) {
         double *A = c_sys.avg + ((int64_t)w * MGPU_MAX_RES + lane) * 4;
         A[0] += ws.loc.avgN[lane]; A[1] += ws.loc.avgN2[lane]; A[2] += ws.loc.avgE; A[3] += (double)ws.loc.n_samples;
+    }
+}
+
+// adjust_move_step_sizes (monte_carlo_utils.f90:98-134): Robbins-Monro update of every walker's
+// translation / rotation step from its own cumulative counters, at the end of a block
+__global__ void k_adjust_steps(int first, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int w = first + i;
+    const double gamma = 0.10, TARGET_ACCEPTANCE = 0.40;
+    const long long *c = c_sys.counters + (int64_t)w * 12;
+    double *st = c_sys.step + (int64_t)w * 2;
+    if (c[0] > 500) {                                           // MIN_TRIALS_FOR_RECALIBRATION, parameters.f90:24
+        const double acc = (double)c[1] / (double)c[0];
+        double v = st[0] * exp(gamma * (acc - TARGET_ACCEPTANCE));
+        st[0] = fmax(1.0e-3, fmin(v, 3.0));                      // MIN/MAX_TRANSLATION_STEP
+    }
+    if (c[2] > 500) {
+        const double acc = (double)c[3] / (double)c[2];
+        double v = st[1] * exp(gamma * (acc - TARGET_ACCEPTANCE));
+        st[1] = fmax(1.0e-3, fmin(v, 0.78));                     // MIN/MAX_ROTATION_ANGLE
     }
 }
 

@@ -10,13 +10,14 @@
 //   [15 .. 18]     xoshiro256** state
 //   [19 .. 30]     counters (translations, rotations, creations, deletions, swaps, widom) x (trials, successes)
 //   [32 .. 63]     block averages [res][sum N, sum N^2, sum E, samples]
-//   [64 .. 64+2nk) S(k) = ewald%Ak: re[nk], im[nk]
+//   [64], [65]     mc_input%translation_step, mc_input%rotation_step_angle of the walker;  [66 .. 71] reserved (0)
+//   [72 .. 72+2nk) S(k) = ewald%Ak: re[nk], im[nk]
 //   then, for every ACTIVE residue type in index order, count(res) molecules of
 //   { com[3], offset[natom][3], framework-energy cache {lj, coulomb} }   (guest%com(:,res,mol), guest%offset(:,res,mol,1:natom))
 #pragma once
 #include "mgpu_kernels.cuh"
 
-#define MGPU_REC_HDR 64
+#define MGPU_REC_HDR 72
 
 __device__ __forceinline__ int rec_molsize(int res) { return 3 + 3 * c_sys.natom[res] + 2; }
 
@@ -46,6 +47,7 @@ __global__ void __launch_bounds__(256) k_pack(int first, int n, const long long 
     if (lane < 12) rec[19 + lane] = (double)c_sys.counters[(int64_t)w * 12 + lane];
     if (lane == 0) rec[31] = 0.0;
     rec[32 + lane] = c_sys.avg[(int64_t)w * MGPU_MAX_RES * 4 + lane];
+    if (lane < 8) rec[64 + lane] = lane < 2 ? c_sys.step[(int64_t)w * 2 + lane] : 0.0;
     const double *Sk = c_sys.S + ((int64_t)w * 2 + c_sys.cur[w]) * 2 * nk;
     for (int k = lane; k < 2 * nk; k += 32) rec[MGPU_REC_HDR + k] = Sk[k];
     double *p = rec + MGPU_REC_HDR + 2 * nk;
@@ -83,6 +85,7 @@ __global__ void __launch_bounds__(256) k_unpack(int first, int n, const long lon
     if (lane < 4) c_sys.rng[(int64_t)w * 4 + lane] = (uint64_t)__double_as_longlong(rec[15 + lane]);
     if (lane < 12) c_sys.counters[(int64_t)w * 12 + lane] = (long long)rec[19 + lane];
     c_sys.avg[(int64_t)w * MGPU_MAX_RES * 4 + lane] = rec[32 + lane];
+    if (lane < 2) c_sys.step[(int64_t)w * 2 + lane] = rec[64 + lane];
     if (lane == 0) { c_sys.cur[w] = 0; c_sys.trial[w].active = 0; }
     double *Sk = c_sys.S + ((int64_t)w * 2 + 0) * 2 * nk;
     for (int k = lane; k < 2 * nk; k += 32) Sk[k] = rec[MGPU_REC_HDR + k];

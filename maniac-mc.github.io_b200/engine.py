@@ -372,8 +372,9 @@ class Engine:
         """Decode one walker record (see include/maniac_gpu.h) into a dict; ``residues`` = [(active, natom)]."""
         out = dict(length=int(rec[0]), count=rec[1:9].astype(int), energy=rec[9:15].copy(),
                    rng=rec[15:19].view(np.uint64).copy(), counters=rec[19:31].astype(np.int64).reshape(6, 2),
-                   averages=rec[32:64].reshape(8, 4).copy(), Ak=rec[64:64 + 2 * nk].copy(), molecules={})
-        p = 64 + 2 * nk
+                   averages=rec[32:64].reshape(8, 4).copy(), step_sizes=(float(rec[64]), float(rec[65])),
+                   Ak=rec[72:72 + 2 * nk].copy(), molecules={})
+        p = 72 + 2 * nk
         for r, (active, na) in enumerate(residues):
             if not active:
                 continue
@@ -419,6 +420,18 @@ class Engine:
             self._ck(self.L.mgpu_get_averages(w, res, _pd(tmp)))
             out[w] = tmp
         return out
+
+    def adjust_move_step_sizes(self, first_walker=0, n_walkers=None):
+        n = self.n_walkers - first_walker if n_walkers is None else n_walkers
+        self._ck(self.L.mgpu_adjust_move_step_sizes(first_walker, n))
+
+    def step_sizes(self, walker=0):
+        out = np.zeros(2)
+        self._ck(self.L.mgpu_get_step_sizes(walker, _pd(out)))
+        return float(out[0]), float(out[1])
+
+    def set_step_sizes(self, translation_step, rotation_step_angle, walker=0):
+        self._ck(self.L.mgpu_set_step_sizes(walker, translation_step, rotation_step_angle))
 
     def counters(self, walker=0):
         out = (C.c_int64 * 12)()

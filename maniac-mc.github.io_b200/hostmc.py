@@ -21,6 +21,8 @@ _SIGS = {
     "mhost_get_energy": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_double)]),
     "mhost_get_counters": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_int64)]),
     "mhost_get_molecule": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "mhost_adjust_move_step_sizes": (C.c_int, [C.c_void_p]),
+    "mhost_get_step_sizes": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_double)]),
     "mhost_get_traffic": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
 }
 
@@ -69,6 +71,14 @@ class HostMonteCarlo:
         out = np.zeros(6)
         self.L.mhost_get_energy(self.h, walker, out.ctypes.data_as(C.POINTER(C.c_double)))
         return out
+
+    def adjust_move_step_sizes(self):
+        self.L.mhost_adjust_move_step_sizes(self.h)
+
+    def step_sizes(self, walker=0):
+        out = (C.c_double * 2)()
+        self.L.mhost_get_step_sizes(self.h, walker, out)
+        return float(out[0]), float(out[1])
 
     def counters(self, walker=0):
         out = (C.c_int64 * 12)()

@@ -556,6 +556,26 @@ int orc_set_mc_input(orc_system *s, double tstep, double rstep, double pt, doubl
     s->p_translation = pt; s->p_rotation = pr; s->p_swap = ps; s->p_insdel = pid; s->p_widom = pw;
     return 0;
 }
+/* adjust_move_step_sizes, monte_carlo_utils.f90:98-134 (Robbins-Monro, called at the end of a block when
+ * mc_input%recalibrate_moves is set; constants of parameters.f90:17-24) */
+int orc_adjust_move_step_sizes(orc_system *s)
+{
+    const double gamma = 0.10, TARGET_ACCEPTANCE = 0.40;
+    const double MIN_TRANSLATION_STEP = 1.0e-3, MAX_TRANSLATION_STEP = 3.0, MIN_ROTATION_ANGLE = 1.0e-3, MAX_ROTATION_ANGLE = 0.78;
+    const int64_t MIN_TRIALS_FOR_RECALIBRATION = 500;
+    if (s->counter[0][0] > MIN_TRIALS_FOR_RECALIBRATION) {
+        double acc_trans = (double)s->counter[0][1] / (double)s->counter[0][0];
+        s->translation_step = s->translation_step * exp(gamma * (acc_trans - TARGET_ACCEPTANCE));
+        s->translation_step = fmax(MIN_TRANSLATION_STEP, fmin(s->translation_step, MAX_TRANSLATION_STEP));
+    }
+    if (s->counter[1][0] > MIN_TRIALS_FOR_RECALIBRATION) {
+        double acc_rot = (double)s->counter[1][1] / (double)s->counter[1][0];
+        s->rotation_step_angle = s->rotation_step_angle * exp(gamma * (acc_rot - TARGET_ACCEPTANCE));
+        s->rotation_step_angle = fmax(MIN_ROTATION_ANGLE, fmin(s->rotation_step_angle, MAX_ROTATION_ANGLE));
+    }
+    return 0;
+}
+int orc_get_step_sizes(const orc_system *s, double out[2]) { out[0] = s->translation_step; out[1] = s->rotation_step_angle; return 0; }
 double orc_get_beta(const orc_system *s) { return s->beta; }
 double orc_get_lambda(const orc_system *s, int res) { return s->res[res].lambda; }
 double orc_get_mu(const orc_system *s, int res) { return s->res[res].mu; }

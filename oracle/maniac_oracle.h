@@ -136,6 +136,8 @@ int orc_widom_trial(orc_system *s, int res, int mol, orc_step_trace *t);
 /* n iterations of the body of monte_carlo_loop (monte_carlo.f90:50-120), no
  * block bookkeeping / step-size recalibration / file output */
 int orc_monte_carlo_steps(orc_system *s, int64_t nsteps, orc_step_trace *trace /* nsteps or NULL */);
+int orc_adjust_move_step_sizes(orc_system *s);           /* monte_carlo_utils.f90:98-134 */
+int orc_get_step_sizes(const orc_system *s, double out[2]);
 int orc_get_counters(const orc_system *s, int64_t out[12]); /* trans,rot,create,delete,swap,widom x (trial,success) */
 int orc_get_widom(const orc_system *s, int res, double *sum_weight, int64_t *samples);
 int orc_reset_widom(orc_system *s);

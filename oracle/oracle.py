@@ -87,6 +87,8 @@ def lib():
         "orc_widom_trial": (I, [P, I, I, C.POINTER(StepTrace)]),
         "orc_monte_carlo_steps": (I, [P, L64, C.c_void_p]),
         "orc_get_counters": (I, [P, C.POINTER(L64)]),
+        "orc_adjust_move_step_sizes": (I, [P]),
+        "orc_get_step_sizes": (I, [P, C.POINTER(D)]),
         "orc_get_widom": (I, [P, I, pd, C.POINTER(L64)]), "orc_reset_widom": (I, [P]),
         "orc_widom_batch": (I, [P, I, L64, L64, U64, pd, pd, C.POINTER(L64)]),
     }
@@ -303,6 +305,14 @@ class Oracle:
 
     def widom_trial(self, res, mol):
         return self._move(self.L.orc_widom_trial, res, mol)
+
+    def adjust_move_step_sizes(self):
+        self._ck(self.L.orc_adjust_move_step_sizes(self.h))
+
+    def step_sizes(self):
+        out = (C.c_double * 2)()
+        self.L.orc_get_step_sizes(self.h, out)
+        return float(out[0]), float(out[1])
 
     def counters(self):
         out = (C.c_int64 * 12)()

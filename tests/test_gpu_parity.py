@@ -595,6 +595,7 @@ def test_walker_records_roundtrip_and_block(load, engine_cls):
         eng.load_walkers(blob_a[off[0]:off[1]], np.array([0, off[1] - off[0]]), first_walker=3)
         assert eng.count(0, walker=3) == eng.count(0, walker=0)
         np.testing.assert_array_equal(eng.energy(3), eng.energy(0))
+        off = eng.save_walkers(blob_a)                       # records again, walker 3 now being the clone
         # (b) two more blocks through host memory: records in, records out
         off2 = eng.block(300, blob_a, off, blob_b)
         off3 = eng.block(300, blob_b, off2, blob_a)
@@ -627,3 +628,43 @@ def test_walker_records_roundtrip_and_block(load, engine_cls):
         small = eng.host_buffer(100)
         with pytest.raises(ManiacAbort):
             eng.save_walkers(small)
+
+
+def test_step_size_adaptation_per_block(load, engine_cls):
+    """adjust_move_step_sizes (src/monte_carlo_utils.f90:98-134) at the end of every block, on the device, per walker:
+    same step sizes and same trajectory as the oracle doing the same."""
+    s = load("zif8_h2o_gcmc")
+    o = Oracle(s, capacity=96)
+    o.update_system_energy()
+    o.seed(808)
+    with engine_cls(s, n_walkers=2, capacity=96) as eng:
+        eng.seed(808)
+        assert eng.step_sizes(0) == o.step_sizes()
+        for blk in range(4):
+            ref = o.monte_carlo_steps(700)
+            tr = eng.sweep(700, trace_walker=0)
+            _compare_traces(tr, ref)
+            o.adjust_move_step_sizes()
+            eng.adjust_move_step_sizes()
+            t_ref, r_ref = o.step_sizes()
+            t_gpu, r_gpu = eng.step_sizes(0)
+            assert abs(t_gpu - t_ref) <= 1e-14 * t_ref and abs(r_gpu - r_ref) <= 1e-14 * r_ref
+        assert eng.step_sizes(0) != (s.translation_step, s.rotation_step_angle)       # it did adapt
+        assert eng.step_sizes(1) != eng.step_sizes(0)                                  # every walker its own
+        eng.set_step_sizes(0.5, 0.3, walker=1)
+        assert eng.step_sizes(1) == (0.5, 0.3)
+    # the host-driven drivers adapt the same way
+    from maniac_b200.hostmc import HostMonteCarlo
+    o = Oracle(s, capacity=96)
+    o.update_system_energy()
+    o.seed(909)
+    with engine_cls(s, n_walkers=2, capacity=96) as eng:
+        hm = HostMonteCarlo(eng, seed=909)
+        for blk in range(3):
+            ref = o.monte_carlo_steps(700)
+            tr = hm.run(700, trace_walker=0)
+            _compare_traces(tr, ref)
+            o.adjust_move_step_sizes()
+            hm.adjust_move_step_sizes()
+            assert np.allclose(hm.step_sizes(0), o.step_sizes(), rtol=1e-14, atol=0)
+        hm.close()
