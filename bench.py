@@ -267,7 +267,7 @@ def main():
     if a.quick:
         if rank == 0:
             print(json.dumps({"quick": True, "lib": os.environ.get("MANIAC_GPU_LIB", "default"), "moves_per_s": value,
-                              "ms_per_step": 1e3 * t_dev / a.steps, "clocks": clocks}))
+                              "ms_per_step": 1e3 * t_dev / a.steps, "launch": eng.launch_info(), "clocks": clocks}))
         eng.close()
         return
     flops = FLOP_GEOM * pc["pairs"] + FLOP_LJ * pc["lj"] + FLOP_COUL * pc["coulomb"] + kspace_flops(dcount, na, ew["kmax"], ew["nk"])

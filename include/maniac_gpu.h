@@ -111,6 +111,8 @@ int  mgpu_device_info(char *name, int name_len, int *sm_count, double *mem_gb);
 int mgpu_get_ewald(double *alpha, int32_t kmax[3], int32_t *nkvec, double *rc_used);
 int mgpu_get_kvectors(int32_t *kx, int32_t *ky, int32_t *kz, double *k_squared_mag, double *form_factor_times_weight);
 int mgpu_get_box(double matrix[9], double reciprocal[9], double *volume, int32_t *is_triclinic);
+/* launch shape of the warp-per-walker kernels: walkers (warps) per CTA, dynamic shared memory per CTA, SMs */
+int mgpu_get_launch_info(int32_t *walkers_per_cta, int64_t *smem_bytes_per_cta, int32_t *sm_count);
 /* triclinic cells: number of extra lattice vectors min_image examines per pair after rounding the
  * fractional coordinates (0 for orthorhombic cells); -1 = the literal 27-image search of
  * src/geometry_utils.f90:263-280 is used for every pair (very skewed cell) */

@@ -362,13 +362,14 @@ int mgpu_init(const mgpu_system *sys)
                     const double q = R.charges[a];
                     hx[k] = make_double4(c[0] + o[0], c[1] + o[1], c[2] + o[2], std::fabs(q) < MGPU_ERR_TOL ? 0.0 : q);   // geometry_utils.f90:235-241; :157
                     hq[k] = q; ht[k] = R.types[a]; hm[k] = molid;
+                    if (std::fabs(q) >= MGPU_ERR_TOL) ++h.n_host_charged;
                 }
         }
     }
     double4 *d_hx; int32_t *d_ht, *d_hm; double *d_eps, *d_sig, *d_ffW, *d_Shost, *d_hq, *d_ctab; int32_t *d_kx, *d_ky, *d_kz;
     const size_t nk1 = h.nk ? h.nk : 1, nt2 = (size_t)sys->ntypes * sys->ntypes;
     if (dalloc(&d_hx, hx.size()) || dalloc(&d_ht, ht.size()) || dalloc(&d_hm, hm.size()) || dalloc(&d_eps, nt2) || dalloc(&d_sig, nt2) ||
-        dalloc(&d_hq, hq.size()) || dalloc(&d_ctab, (size_t)MGPU_TAB_MAXOCT * (1 << MGPU_TAB_K) * MGPU_TAB_ROW) ||
+        dalloc(&d_hq, hq.size()) || dalloc(&d_ctab, ((size_t)MGPU_TAB_MAXOCT * (1 << MGPU_TAB_K) + 1) * MGPU_TAB_ROW) ||
         dalloc(&d_ffW, nk1) || dalloc(&d_kx, nk1) || dalloc(&d_ky, nk1) || dalloc(&d_kz, nk1) || dalloc(&d_Shost, 2 * nk1)) return 1;
     CK(cudaMemcpy(d_hx, hx.data(), sizeof(double4) * hx.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_ht, ht.data(), sizeof(int32_t) * ht.size(), cudaMemcpyHostToDevice));
@@ -447,9 +448,15 @@ int mgpu_init(const mgpu_system *sys)
         if (r_hi > r_zero) r_hi = r_zero;
         std::vector<double> tab;
         mgpu_build_coulomb_table(alpha, 1.0, r_hi, &g.tab_emin, &g.tab_noct, tab);
+        // the hot loops send everything beyond the last interval to an all-zero row, so the table has to reach
+        // the largest distance that still matters (the box limit or alpha r = 7, whichever is smaller)
+        if (std::ldexp(1.0, g.tab_emin + g.tab_noct) < r_hi * r_hi)
+            return fail("mgpu_init: real-space Coulomb table would need more than MGPU_TAB_MAXOCT octaves (very small alpha / huge cutoff)");
+        tab.resize(tab.size() + MGPU_TAB_ROW, 0.0);           // the all-zero closing row
         CK(cudaMemcpy(d_ctab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice));
         h.tab_ibase = (1023 + g.tab_emin) << MGPU_TAB_K;
         h.tab_nint = g.tab_noct << MGPU_TAB_K;
+        h.tab_hi_lo = (1023 + g.tab_emin) << 20;
         h.ctab = d_ctab;
     }
     if (h.nk) {
@@ -528,6 +535,20 @@ int mgpu_init(const mgpu_system *sys)
     SET_SMEM(k_build_S, g.smem_buildS);
 #undef SET_SMEM
     {
+        // shared-memory carve-out of the warp-per-walker kernels: the smallest supported configuration that holds one
+        // CTA (dynamic + 1 KB reserved), so that the rest of the 256 KB stays L1 for the framework atoms.
+        // MGPU_CARVEOUT (percent of the maximum) overrides it for experiments.
+        int pct = (int)((g.smem8 + 1024 + 2048) * 100 / (228 * 1024)) + 1;
+        if (pct > 100) pct = 100;
+        if (const char *e = std::getenv("MGPU_CARVEOUT")) pct = std::atoi(e);
+        cudaFuncSetAttribute(k_sweep<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(k_sweep<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(k_widom_batch<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(k_widom_batch<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute((k_trial<false, 32>), cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute((k_trial<true, 32>), cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
+    {
         int nb = 1;
         if (h.triclinic) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_widom_batch<true>, 32 * g.wgroups, g.smem8));
         else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_widom_batch<false>, 32 * g.wgroups, g.smem8));
@@ -601,6 +622,14 @@ int mgpu_get_box(double matrix[9], double reciprocal[9], double *volume, int32_t
     if (reciprocal) std::memcpy(reciprocal, g.h.Hinv, sizeof g.h.Hinv);
     if (volume) *volume = g.h.volume;
     if (is_triclinic) *is_triclinic = g.h.triclinic;
+    return 0;
+}
+int mgpu_get_launch_info(int32_t *walkers_per_cta, int64_t *smem_bytes_per_cta, int32_t *sm_count)
+{
+    NEED_READY();
+    if (walkers_per_cta) *walkers_per_cta = g.wgroups;
+    if (smem_bytes_per_cta) *smem_bytes_per_cta = (int64_t)g.smem8;
+    if (sm_count) *sm_count = g.sm_count;
     return 0;
 }
 int mgpu_get_triclinic_candidates(int32_t *n) { NEED_READY(); *n = g.h.tri_nrel; return 0; }

@@ -34,7 +34,7 @@
 #define MGPU_TAB_K 5
 #define MGPU_TAB_ROW 6            // doubles per row
 #define MGPU_TAB_REP 8            // shared-memory replicas
-#define MGPU_TAB_MAXOCT 11
+#define MGPU_TAB_MAXOCT 14
 #define MGPU_TAB_XCUT 7.0
 
 struct MgpuTrial {
@@ -62,7 +62,9 @@ struct DevSys {
     int32_t kmax[3], kmax_max, nk;
     // Coulomb table
     int32_t tab_ibase;            // (1023 + emin) << MGPU_TAB_K
-    int32_t tab_nint;             // number of intervals (octaves << MGPU_TAB_K)
+    int32_t tab_nint;             // number of intervals (octaves << MGPU_TAB_K); row tab_nint is all zeros
+    int32_t tab_hi_lo;            // high word of the table's first s: pairs below it (r < 1 A) take the exact path
+    int32_t n_host_charged;       // framework atoms with |q| >= 1e-10 (work counters)
     const double *ctab;           // [tab_nint][MGPU_TAB_ROW]
     double s_zero;                // g == 0 for s >= s_zero (alpha r > MGPU_TAB_XCUT)
     // residues

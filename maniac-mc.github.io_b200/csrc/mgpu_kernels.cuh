@@ -24,6 +24,7 @@
 // 1/r, see mgpu_internal.h); 1/r^2 for the LJ term comes from MUFU.RCP64H + two Newton steps.
 // Out-of-range pairs use the exact forms.
 #pragma once
+#include <cstddef>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include "mgpu_internal.h"
@@ -38,6 +39,12 @@ __constant__ DevSys c_sys;
 #endif
 #ifndef MGPU_PF_GUEST
 #define MGPU_PF_GUEST 0
+#endif
+#ifndef MGPU_ACC_PER_ATOM
+#define MGPU_ACC_PER_ATOM 0
+#endif
+#ifndef MGPU_PINGPONG
+#define MGPU_PINGPONG 0
 #endif
 #ifndef MGPU_PF_KSPACE
 #define MGPU_PF_KSPACE 1
@@ -318,14 +325,21 @@ struct WalkerLocal {
     unsigned long long pc[3];
 };
 
-// Fixed part of a group's workspace; the two phase tables follow it.
+// Fixed part of a group's workspace; the two phase tables follow it.  `red` (cross-warp reduction
+// scratch) is only needed when the group is a whole CTA: warp groups end their workspace before it, which
+// keeps the 16-walker CTA under 196 KB of shared memory, i.e. one carve-out step lower and 32 KB more L1
+// for the framework atoms every quartet streams.
 struct GroupWS {
     Probe probe;
-    double red[8 * MGPU_WARPS];
     int32_t count[MGPU_MAX_RES];
     SweepShared sh;
     WalkerLocal loc;
+    double red[8 * MGPU_WARPS];
 };
+__host__ __device__ inline size_t smem_ws_bytes(bool warp_group)
+{
+    return ((warp_group ? offsetof(GroupWS, red) : sizeof(GroupWS)) + 15) & ~size_t(15);
+}
 
 // The dynamic shared memory of every kernel here starts with the replicated Coulomb table,
 // followed by the LJ {A,B} pairs.  Going through this accessor (not through a pointer stored
@@ -335,26 +349,26 @@ extern __shared__ __align__(16) unsigned char mgpu_smem[];
 // per launch), 1 in the CTA-per-task kernels (latency path: a 15 KB fill per task, not 123 KB).
 template <int NT> struct TabRep { static constexpr int v = (NT == 32) ? MGPU_TAB_REP : 1; };
 template <int REP> __device__ __forceinline__ const double2 *smem_ctab() { return reinterpret_cast<const double2 *>(mgpu_smem) + (threadIdx.x & (REP - 1)); }
-template <int REP> __device__ __forceinline__ const double2 *smem_ljAB() { return reinterpret_cast<const double2 *>(mgpu_smem) + (size_t)c_sys.tab_nint * 3 * REP; }
+template <int REP> __device__ __forceinline__ const double2 *smem_ljAB() { return reinterpret_cast<const double2 *>(mgpu_smem) + (size_t)(c_sys.tab_nint + 1) * 3 * REP; }
 
 // Shared-memory image of a CTA: replicated Coulomb table, LJ {A,B} pairs, then `groups` workspaces.
 struct Smem {
     GroupWS *ws;
     double2 *tab_old, *tab_new;
 };
-__host__ __device__ inline size_t smem_group_bytes(int kmax_max, int natom_max)
+__host__ __device__ inline size_t smem_group_bytes(int kmax_max, int natom_max, int rep)
 {
-    size_t b = (sizeof(GroupWS) + 15) & ~size_t(15);
+    size_t b = smem_ws_bytes(rep > 1);
     b += sizeof(double2) * 2 * (size_t)natom_max * 3 * (kmax_max + 1);
     return b;
 }
 __host__ __device__ inline size_t smem_common_bytes(int ntypes, int tab_nint, int rep)
 {
-    return sizeof(double2) * ((size_t)tab_nint * 3 * rep + (size_t)ntypes * ntypes);
+    return sizeof(double2) * ((size_t)(tab_nint + 1) * 3 * rep + (size_t)ntypes * ntypes);      // + the all-zero row that closes the table
 }
 __host__ __device__ inline size_t smem_bytes(int ntypes, int tab_nint, int kmax_max, int natom_max, int groups, int rep)
 {
-    return smem_common_bytes(ntypes, tab_nint, rep) + groups * smem_group_bytes(kmax_max, natom_max) + 16;
+    return smem_common_bytes(ntypes, tab_nint, rep) + groups * smem_group_bytes(kmax_max, natom_max, rep) + 16;
 }
 // Carve the CTA's dynamic shared memory and (cooperatively, whole CTA) load the common part.
 // Every thread of the CTA must call this; it ends with __syncthreads().
@@ -364,14 +378,14 @@ __device__ __forceinline__ Smem smem_setup(unsigned char *base, int natom_max, i
     Smem s;
     double2 *d = reinterpret_cast<double2 *>(base);
     const int nt2 = c_sys.ntypes * c_sys.ntypes;
-    const int nchunk = c_sys.tab_nint * 3;
+    const int nchunk = (c_sys.tab_nint + 1) * 3;              // ctab holds tab_nint rows + one all-zero row
     const double2 *src = reinterpret_cast<const double2 *>(c_sys.ctab);
     for (int i = threadIdx.x; i < nchunk * REP; i += blockDim.x) d[i] = src[i / REP];
     double2 *lj = d + (size_t)nchunk * REP;
     for (int i = threadIdx.x; i < nt2; i += blockDim.x) lj[i] = make_double2(c_sys.ljA[i], c_sys.ljB[i]);
-    unsigned char *g = base + smem_common_bytes(c_sys.ntypes, c_sys.tab_nint, REP) + (size_t)group * smem_group_bytes(c_sys.kmax_max, natom_max);
+    unsigned char *g = base + smem_common_bytes(c_sys.ntypes, c_sys.tab_nint, REP) + (size_t)group * smem_group_bytes(c_sys.kmax_max, natom_max, REP);
     s.ws = reinterpret_cast<GroupWS *>(g);
-    s.tab_old = reinterpret_cast<double2 *>(g + ((sizeof(GroupWS) + 15) & ~size_t(15)));
+    s.tab_old = reinterpret_cast<double2 *>(g + smem_ws_bytes(REP > 1));
     s.tab_new = s.tab_old + (size_t)natom_max * 3 * (c_sys.kmax_max + 1);
     __syncthreads();
     return s;
@@ -416,38 +430,42 @@ struct HostPass {
     }
 
     // vmask: bit u set = target u is real (guest passes mask the tail / the excluded molecule;
-    // framework passes hand in a constant all-ones mask and the tests fold away)
+    // framework passes hand in a constant all-ones mask and the tests fold away).
+    // Coulomb sums are kept per probe atom WITHOUT its charge (acc[i] += q_j g(s)); the caller multiplies by
+    // q_i once per pass.  Pairs below the table start (r < 1 A, incl. the overlap sentinel) read the all-zero
+    // row that closes the table (the unsigned clamp sends both ends there), are left out of the LJ sum, and
+    // are redone with the exact formulas when the block's smallest r^2 says there was one (e_x: their sum).
     template <int UU>
-    __device__ __forceinline__ void block(const Atoms<UU> &A, const unsigned vmask, double &e_lj, double &e_c, PairCount &pc) const
+    __device__ __forceinline__ void block(const Atoms<UU> &A, const unsigned vmask, double &e_lj, double (&acc)[N], double2 &e_x, PairCount &pc) const
     {
         const double2 (&txy)[UU] = A.xy; const double2 (&tzq)[UU] = A.zq; const int (&tt)[UU] = A.tt;
         const double2 *ctab = smem_ctab<REP>(), *ljAB = smem_ljAB<REP>();
-        unsigned bad = 0u;
+        const bool all = (vmask == (1u << UU) - 1u);
+        int hmin = 0x7fffffff;
         double sv[UU][N];
 #pragma unroll
         for (int u = 0; u < UU; ++u) {
             const bool val = (vmask >> u) & 1u;
-            if (MODE & 2) pc.coul += (val && tzq[u].y != 0.0) ? N : 0;
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                const double s = min_image_r2<TRI>(txy[u].x - px[i], txy[u].y - py[i], tzq[u].x - pz[i]);
+                double s = min_image_r2<TRI>(txy[u].x - px[i], txy[u].y - py[i], tzq[u].x - pz[i]);
+                if (!all) s = val ? s : 1.0e30;                                 // not a target: beyond every range (and (float)(s - centre) stays finite)
                 sv[u][i] = s;
                 const int hi = __double2hiint(s);
-                const int idx = (hi >> (20 - MGPU_TAB_K)) - c_sys.tab_ibase;
-                const bool out = ((unsigned)idx >= (unsigned)c_sys.tab_nint) || !val;
-                if (out && val) bad |= 1u << (u * N + i);
+                hmin = min(hmin, hi);
                 if (MODE & 1) {
                     const double2 AB = ljAB[trow[i] + tt[u]];
-                    const double y = rcp_fast(out ? 1.0 : s), y3 = y * y * y;
+                    const double y = rcp_fast(s), y3 = y * y * y;
                     const double e = (AB.x * y3 - AB.y) * y3;
-                    const bool in = (s < c_sys.rc2) && !out;
+                    const bool in = (s < c_sys.rc2) && (hi >= c_sys.tab_hi_lo);
                     e_lj += in ? e : 0.0;
                     pc.lj += (in && (AB.x != 0.0 || AB.y != 0.0));
                 }
                 if (MODE & 2) {
+                    const unsigned idx = min((unsigned)((hi >> (20 - MGPU_TAB_K)) - c_sys.tab_ibase), (unsigned)c_sys.tab_nint);
                     const int chi = (hi & ~((1 << (20 - MGPU_TAB_K)) - 1)) | (1 << (19 - MGPU_TAB_K));
                     const double uu = s - __hiloint2double(chi, 0);         // exact: same binade
-                    const double2 *t = ctab + (out ? 0 : idx) * (3 * REP);
+                    const double2 *t = ctab + idx * (3 * REP);
                     const double2 c01 = t[0], c23 = t[REP], c45 = t[2 * REP];
                     const float uf = (float)uu;
                     const float pf = fmaf(__int_as_float(__double2hiint(c45.y)), uf, __int_as_float(__double2loint(c45.y)));
@@ -457,24 +475,23 @@ struct HostPass {
                     p = fma(p, uu, c23.x);
                     p = fma(p, uu, c01.y);
                     p = fma(p, uu, c01.x);
-                    e_c = fma(out ? 0.0 : q[i] * tzq[u].y, p, e_c);
+                    if (MGPU_ACC_PER_ATOM) acc[i] = fma(tzq[u].y, p, acc[i]);
+                    else acc[0] = fma(q[i] * tzq[u].y, p, acc[0]);
                 }
             }
         }
-        pc.geom += __popc(vmask) * N;
-        if (bad) {                                                  // rare: r < 1 A (incl. overlap) or beyond the table
+        if (hmin < c_sys.tab_hi_lo) {                               // rare: some r < 1 A (incl. overlap)
 #pragma unroll
             for (int u = 0; u < UU; ++u)
 #pragma unroll
                 for (int i = 0; i < N; ++i)
-                    if (bad & (1u << (u * N + i))) {
+                    if (__double2hiint(sv[u][i]) < c_sys.tab_hi_lo) {
                         const double s = sv[u][i];
-                        if (s >= c_sys.s_zero && s >= c_sys.rc2) continue;   // erfc(alpha r)/r < 1e-24: below the sum's rounding
                         double2 AB = make_double2(0.0, 0.0);
                         if (MODE & 1) AB = ljAB[trow[i] + tt[u]];
                         const double qq = (MODE & 2) ? q[i] * tzq[u].y : 0.0;
                         const double2 e = pair_exact(s, AB.x, AB.y, qq, qq != 0.0);
-                        e_lj += e.x; e_c += e.y;
+                        e_x.x += e.x; e_x.y += e.y;
                         if (MODE & 1) pc.lj += ((AB.x != 0.0 || AB.y != 0.0) && s < c_sys.rc2);
                     }
         }
@@ -485,13 +502,35 @@ struct HostPass {
     // returned by value so they stay in registers.
     __device__ __forceinline__ void run(int t0, int stride, double &e_lj_io, double &e_c_io, PairCount &pc_io) const
     {
-        double e_lj = e_lj_io, e_c = e_c_io;
+        double e_lj = e_lj_io;
+        double acc[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) acc[i] = 0.0;
+        double2 e_x = make_double2(0.0, 0.0);
         PairCount pc = pc_io;
         const int n = c_sys.n_host;
         const int step = U * stride, reach = (U - 1) * stride;
         int j = t0;
         if (!MGPU_PF_HOSTU && U > 1) {
-            for (; j + reach < n; j += step) { Atoms<U> a; fetch<U>(a, j, stride); block<U>(a, (1u << U) - 1u, e_lj, e_c, pc); }
+            for (; j + reach < n; j += step) { Atoms<U> a; fetch<U>(a, j, stride); block<U>(a, (1u << U) - 1u, e_lj, acc, e_x, pc); }
+        } else if (MGPU_PINGPONG && j + reach < n) {
+            // two register sets used in turn, so the rotation costs no moves
+            Atoms<U> A, B;
+            fetch<U>(A, j, stride);
+            for (;;) {
+                int jn = j + step;
+                bool more = jn + reach < n;
+                fetch<U>(B, more ? jn : j, stride);
+                block<U>(A, (1u << U) - 1u, e_lj, acc, e_x, pc);
+                j = jn;
+                if (!more) break;
+                jn = j + step;
+                more = jn + reach < n;
+                fetch<U>(A, more ? jn : j, stride);
+                block<U>(B, (1u << U) - 1u, e_lj, acc, e_x, pc);
+                j = jn;
+                if (!more) break;
+            }
         } else if (j + reach < n) {
             Atoms<U> cur;
             fetch<U>(cur, j, stride);
@@ -500,14 +539,23 @@ struct HostPass {
                 const bool more = jn + reach < n;
                 Atoms<U> nxt;
                 fetch<U>(nxt, more ? jn : j, stride);
-                block<U>(cur, (1u << U) - 1u, e_lj, e_c, pc);
+                block<U>(cur, (1u << U) - 1u, e_lj, acc, e_x, pc);
                 j = jn;
                 if (!more) break;
                 cur = nxt;
             }
         }
-        for (; j < n; j += stride) { Atoms<1> a1; fetch<1>(a1, j, stride); block<1>(a1, 1u, e_lj, e_c, pc); }
-        e_lj_io = e_lj; e_c_io = e_c; pc_io = pc;
+        for (; j < n; j += stride) { Atoms<1> a1; fetch<1>(a1, j, stride); block<1>(a1, 1u, e_lj, acc, e_x, pc); }
+        double e_c = e_x.y;
+        if (MGPU_ACC_PER_ATOM) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) e_c = fma(q[i], acc[i], e_c);
+        } else e_c += acc[0];
+        if (t0 == 0) {                                           // work counters of the whole pass, once (SURVEY 8d accounting)
+            pc.geom += (unsigned)(N * n);
+            if (MODE & 2) pc.coul += (unsigned)(N * c_sys.n_host_charged);
+        }
+        e_lj_io = e_lj + e_x.x; e_c_io = e_c_io + e_c; pc_io = pc;
     }
 
     // The same body against ONE atom (index b) of every molecule of a guest residue type of the
@@ -533,12 +581,16 @@ struct HostPass {
                                               double &e_lj_io, double &e_c_io, PairCount &pc_io) const
     {
         if (t0 >= n) return;
-        double e_lj = e_lj_io, e_c = e_c_io;
+        double e_lj = e_lj_io;
+        double acc[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) acc[i] = 0.0;
+        double2 e_x = make_double2(0.0, 0.0);
         PairCount pc = pc_io;
         int m = t0;
         GRaw<U> cur;
         fetch_guest<U>(cur, com, offb, cap, n, m, stride);
-        for (;;) {                                   // next chunk's coordinates in flight while this one is evaluated
+        for (;;) {                                   // (MGPU_PF_GUEST) next chunk's coordinates in flight while this one is evaluated
             const int mn = m + U * stride;
             const bool more = mn < n;
             GRaw<U> nxt;
@@ -554,12 +606,23 @@ struct HostPass {
                 A.tt[u] = ttype;
                 vm |= ok ? (1u << u) : 0u;
             }
-            block<U>(A, vm, e_lj, e_c, pc);
+            block<U>(A, vm, e_lj, acc, e_x, pc);
             if (!more) break;
             if (MGPU_PF_GUEST) cur = nxt; else fetch_guest<U>(cur, com, offb, cap, n, mn, stride);
             m = mn;
         }
-        e_lj_io = e_lj; e_c_io = e_c; pc_io = pc;
+        double e_c = e_x.y;
+        if (MGPU_ACC_PER_ATOM) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) e_c = fma(q[i], acc[i], e_c);
+        } else e_c += acc[0];
+        if (t0 == 0) {                                           // work counters of the whole list, once
+            const int first = m_order + 1;                       // molecules first .. n-1 except m_skip
+            const int nv = (n - first) - ((m_skip >= first && m_skip < n) ? 1 : 0);
+            pc.geom += (unsigned)(N * nv);
+            if ((MODE & 2) && tq != 0.0) pc.coul += (unsigned)(N * nv);
+        }
+        e_lj_io = e_lj + e_x.x; e_c_io = e_c_io + e_c; pc_io = pc;
     }
 };
 

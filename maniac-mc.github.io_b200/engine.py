@@ -159,6 +159,11 @@ class Engine:
         self._ck(self.L.mgpu_get_box(_pd(m), _pd(r), C.byref(v), C.byref(t)))
         return dict(matrix=m, reciprocal=r, volume=v.value, triclinic=bool(t.value))
 
+    def launch_info(self):
+        w, s, n = C.c_int32(0), C.c_int64(0), C.c_int32(0)
+        self._ck(self.L.mgpu_get_launch_info(C.byref(w), C.byref(s), C.byref(n)))
+        return dict(walkers_per_cta=w.value, smem_bytes_per_cta=s.value, sm_count=n.value)
+
     def triclinic_candidates(self):
         n = C.c_int32(0)
         self._ck(self.L.mgpu_get_triclinic_candidates(C.byref(n)))
