@@ -267,7 +267,7 @@ def main():
     if a.quick:
         if rank == 0:
             print(json.dumps({"quick": True, "lib": os.environ.get("MANIAC_GPU_LIB", "default"), "moves_per_s": value,
-                              "ms_per_step": 1e3 * t_dev / a.steps, "launch": eng.launch_info(), "clocks": clocks}))
+                              "ms_per_step": 1e3 * t_dev / a.steps, "clocks": clocks}))
         eng.close()
         return
     flops = FLOP_GEOM * pc["pairs"] + FLOP_LJ * pc["lj"] + FLOP_COUL * pc["coulomb"] + kspace_flops(dcount, na, ew["kmax"], ew["nk"])
@@ -280,8 +280,16 @@ def main():
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic, traffic_note = None, "no ncu capture committed"
+    try:
+        tj = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())["k_sweep"]
+        traffic = tj["dram_bytes_per_move"] * float(W) * a.inner
+        traffic_note = (f"dram__bytes_read.sum + dram__bytes_write.sum of {tj['capture']} ({tj['walkers']} walkers x {tj['steps']} MC steps, "
+                        f"{tj['dram_bytes']:.4g} B) scaled per move to this launch")
+    except Exception:
+        pass
     roofline = {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf if peak_tf else None,
-                "traffic": None, "kernel": "k_sweep<false>",
+                "traffic": traffic, "traffic_note": traffic_note, "kernel": "k_sweep<false>",
                 "note": "K1/K2 are FP64-pipe bound, not HBM/tensor bound (SURVEY 8d): peak = DFMA loop measured on this GPU in this "
                         "run (mgpu_measure_fp64_peak, 2 FLOP per FMA); achieved = convention-C1 algorithmic FLOPs "
                         "(29/pair geometry, 8/LJ term, 69/erfc-Coulomb term, k-space per SURVEY 8d) / event-timed kernel time",

@@ -580,36 +580,52 @@ struct HostPass {
                                               int t0, int stride, int m_skip, int m_order, double tq, int ttype,
                                               double &e_lj_io, double &e_c_io, PairCount &pc_io) const
     {
-        if (t0 >= n) return;
         double e_lj = e_lj_io;
         double acc[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) acc[i] = 0.0;
         double2 e_x = make_double2(0.0, 0.0);
         PairCount pc = pc_io;
-        int m = t0;
-        GRaw<U> cur;
-        fetch_guest<U>(cur, com, offb, cap, n, m, stride);
-        for (;;) {                                   // (MGPU_PF_GUEST) next chunk's coordinates in flight while this one is evaluated
-            const int mn = m + U * stride;
-            const bool more = mn < n;
-            GRaw<U> nxt;
-            if (MGPU_PF_GUEST) fetch_guest<U>(nxt, com, offb, cap, n, more ? mn : m, stride);
-            Atoms<U> A;
-            unsigned vm = 0u;
+        if (!MGPU_PF_GUEST) {
+            for (int m = t0; m < n; m += U * stride) {
+                Atoms<U> A;
+                unsigned vm = 0u;
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int mm = m + u * stride;
-                const bool ok = (mm < n) && (mm != m_skip) && (mm > m_order);
-                A.xy[u] = make_double2(cur.c[u][0] + cur.o[u][0], cur.c[u][1] + cur.o[u][1]);
-                A.zq[u] = make_double2(cur.c[u][2] + cur.o[u][2], tq);
-                A.tt[u] = ttype;
-                vm |= ok ? (1u << u) : 0u;
+                for (int u = 0; u < U; ++u) {
+                    const int mm = m + u * stride;
+                    const bool ok = (mm < n) && (mm != m_skip) && (mm > m_order);
+                    const int mc = (mm < n) ? mm : m;
+                    A.xy[u] = make_double2(com[mc] + offb[mc], com[cap + mc] + offb[cap + mc]);
+                    A.zq[u] = make_double2(com[2 * cap + mc] + offb[2 * cap + mc], tq);
+                    A.tt[u] = ttype;
+                    vm |= ok ? (1u << u) : 0u;
+                }
+                block<U>(A, vm, e_lj, acc, e_x, pc);
             }
-            block<U>(A, vm, e_lj, acc, e_x, pc);
-            if (!more) break;
-            if (MGPU_PF_GUEST) cur = nxt; else fetch_guest<U>(cur, com, offb, cap, n, mn, stride);
-            m = mn;
+        } else {
+            int m = t0;
+            GRaw<U> cur;
+            fetch_guest<U>(cur, com, offb, cap, n, m, stride);
+            for (;;) {                                   // next chunk's coordinates in flight while this one is evaluated
+                const int mn = m + U * stride;
+                const bool more = mn < n;
+                GRaw<U> nxt;
+                fetch_guest<U>(nxt, com, offb, cap, n, more ? mn : m, stride);
+                Atoms<U> A;
+                unsigned vm = 0u;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int mm = m + u * stride;
+                    const bool ok = (mm < n) && (mm != m_skip) && (mm > m_order);
+                    A.xy[u] = make_double2(cur.c[u][0] + cur.o[u][0], cur.c[u][1] + cur.o[u][1]);
+                    A.zq[u] = make_double2(cur.c[u][2] + cur.o[u][2], tq);
+                    A.tt[u] = ttype;
+                    vm |= ok ? (1u << u) : 0u;
+                }
+                block<U>(A, vm, e_lj, acc, e_x, pc);
+                if (!more) break;
+                cur = nxt; m = mn;
+            }
         }
         double e_c = e_x.y;
         if (MGPU_ACC_PER_ATOM) {

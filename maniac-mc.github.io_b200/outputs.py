@@ -1,0 +1,122 @@
+"""Per-block output files in the reference's formats, written from walker records.
+
+The reference appends one line per block to ``energy.dat``, ``number_<res>.dat``, ``moves.dat`` and
+``widom_<res>.dat`` (``src/write_utils.f90:153-403``).  With thousands of walkers per GPU the same
+lines are produced per walker (or per isotherm point) from the record ``mgpu_save_walkers`` /
+``mgpu_block`` return -- the host stays in charge of I/O, the device never formats text.  The
+strings below reproduce the Fortran edit descriptors (``I10``, ``F16.6``, ``A10`` truncation of
+longer literals, ``trim``) character by character.  Host logic only: no GPU, no oracle.
+"""
+from __future__ import annotations
+
+import math
+from pathlib import Path
+from typing import Dict, Iterable, Sequence
+
+import numpy as np
+
+KB_KCALMOL = 1.9872171591124124e-3      # KB * NA * J_to_kcal with the reference's literals
+
+
+def _a(text: str, width: int) -> str:
+    """Fortran ``Aw`` output editing: right-justified, truncated on the right if longer."""
+    return text[:width].rjust(width)
+
+
+# ---- energy.dat (write_dat_energy, src/write_utils.f90:153-186) --------------------------------------
+ENERGY_HEADER = ("#    block        total        recipCoulomb"
+                 "     non-coulomb      coulomb     ewald_self    intramolecular-coulomb")
+
+
+def energy_line(block: int, energy: Sequence[float]) -> str:
+    """``energy`` in energy_type order (non_coulomb, coulomb, recip, self, intra, total)."""
+    nc, c, rec, self_, intra, tot = (float(x) for x in energy)
+    return f"{block:10d} {tot:16.6f} {rec:16.6f} {nc:16.6f} {c:16.6f} {self_:16.6f} {intra:16.6f}".rstrip()
+
+
+# ---- number_<res>.dat (write_dat_number :247-285) --------------------------------------------------
+NUMBER_HEADER = (_a("# Block", 10) + " " + _a("Active_Molecules", 10)).rstrip()
+
+
+def number_line(block: int, count: int) -> str:
+    return f"{block:10d} {count:10d}"
+
+
+# ---- moves.dat (write_dat_mcmove :291-403) ---------------------------------------------------------
+def _enabled(p: Dict[str, float]):
+    return [k for k in ("translation", "rotation", "insertion_deletion", "swap", "widom") if p.get(k, 0.0) > 0]
+
+
+def moves_header(proba: Dict[str, float]) -> str:
+    cols = []
+    names = {"translation": ("Trans_Acc", "Trans_Trial"), "rotation": ("Rot_Acc", "Rot_Trial"),
+             "insertion_deletion": ("Create_Acc", "Create_Trial", "Delete_Acc", "Delete_Trial"),
+             "swap": ("Swap_Acc", "Swap_Trial"), "widom": ("Widom_Trial",)}
+    for k in _enabled(proba):
+        cols += names[k]
+    return (_a("Block", 12).strip() + "".join(" " + _a(c, 12) for c in cols)).rstrip()
+
+
+def moves_line(block: int, counters, proba: Dict[str, float]) -> str:
+    """``counters`` = [6][2] (translations, rotations, creations, deletions, swaps, widom) x (trials, successes)."""
+    c = np.asarray(counters).reshape(6, 2)
+    out = f"{block:12d}"
+    idx = {"translation": [0], "rotation": [1], "insertion_deletion": [2, 3], "swap": [4], "widom": [5]}
+    for k in _enabled(proba):
+        for i in idx[k]:
+            out += f" {int(c[i, 1]):12d} {int(c[i, 0]):12d}"
+    return out.rstrip()
+
+
+# ---- widom_<res>.dat (write_dat_widom :191-241, calculate_excess_mu monte_carlo_utils.f90:598-636) ----
+WIDOM_HEADER = (_a("# Block", 10) + " " + _a("Excess_Mu_kcalmol", 16) + " " + _a("Total_Mu_kcalmol", 16) + " "
+                + _a("Widom_Samples", 16)).rstrip()
+
+
+def excess_mu(sum_weight: float, samples: int, temperature: float, n_molecules: int, volume: float, lam: float):
+    """(mu_ex, mu_tot) in kcal/mol; mu_tot = mu_ideal + mu_ex with mu_ideal = kT ln(rho Lambda^3)."""
+    avg = sum_weight / float(samples)
+    mu_ex = -KB_KCALMOL * temperature * math.log(avg)
+    rho = float(n_molecules) / volume
+    mu_ideal = KB_KCALMOL * temperature * math.log(rho * lam ** 3) if rho > 0 else -math.inf
+    return mu_ex, mu_ideal + mu_ex
+
+
+def widom_line(block: int, mu_ex: float, mu_tot: float, samples: int) -> str:
+    return f"{block:10d} {mu_ex:16.6f} {mu_tot:16.6f} {samples:12d}".rstrip()
+
+
+# ---- one directory per walker / isotherm point -------------------------------------------------------
+class BlockWriter:
+    """Appends the reference's per-block lines for one walker.  ``names`` = residue names of the active types."""
+
+    def __init__(self, out_dir, names: Dict[int, str], proba: Dict[str, float]):
+        self.dir = Path(out_dir)
+        self.dir.mkdir(parents=True, exist_ok=True)
+        self.names, self.proba = names, proba
+
+    def _append(self, name: str, header: str, line: str, first: bool):
+        with open(self.dir / name, "w" if first else "a") as f:
+            if first:
+                f.write(header + "\n")
+            f.write(line + "\n")
+
+    def write(self, block: int, record: dict, widom: Dict[int, tuple] | None = None):
+        """``record`` = Engine.parse_record(...) of this walker; ``widom`` = {res: (mu_ex, mu_tot, samples)}."""
+        first = block == 0
+        self._append("energy.dat", ENERGY_HEADER, energy_line(block, record["energy"]), first)
+        for r, nm in self.names.items():
+            self._append(f"number_{nm}.dat", NUMBER_HEADER, number_line(block, int(record["count"][r])), first)
+        self._append("moves.dat", moves_header(self.proba), moves_line(block, record["counters"], self.proba), first)
+        if self.proba.get("widom", 0.0) > 0 and widom:
+            for r, (mu_ex, mu_tot, ns) in widom.items():
+                self._append(f"widom_{self.names[r]}.dat", WIDOM_HEADER, widom_line(block, mu_ex, mu_tot, ns), first)
+
+
+def write_isotherm(path, fugacity: Iterable[float], summary: dict):
+    """Isotherm table (new: the reference runs one point per process): fugacity, <N>, sqrt(var N), <E>, samples."""
+    with open(path, "w") as f:
+        f.write("#       fugacity           mean_N            std_N           mean_E      samples\n")
+        for i, fu in enumerate(fugacity):
+            f.write(f"{fu:16.6e} {summary['mean_N'][i]:16.6f} {math.sqrt(max(summary['var_N'][i], 0.0)):16.6f} "
+                    f"{summary['mean_E'][i]:16.6f} {int(summary['samples'][i]):12d}\n")

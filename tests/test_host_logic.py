@@ -155,3 +155,33 @@ def test_coulomb_table_accuracy(alpha, r_hi):
     n = L.mgpu_coulomb_table_check(alpha, 1.0, r_hi, 300000, C.byref(er), C.byref(ea))
     assert n == 300000           # every sample falls inside the tabulated range
     assert ea.value < 4e-15
+
+
+def test_output_lines_follow_the_fortran_formats(tmp_path):
+    """energy.dat / number_*.dat / moves.dat / widom_*.dat lines, character by character as the edit descriptors of
+    src/write_utils.f90:153-403 produce them (I10, F16.6, A10 truncation, trim)."""
+    from maniac_b200 import outputs as out
+    e = [-3.5031658, 133.29021, 3.90647708, -10181.6689, 147.525509, -10050.673]   # energy_type order
+    line = out.energy_line(7, e)
+    assert line == "         7    -10050.673000         3.906477        -3.503166       133.290210    -10181.668900       147.525509"
+    assert len(line) == 10 + 6 * 17
+    assert out.ENERGY_HEADER.startswith("#    block        total        recipCoulomb")
+    assert out.NUMBER_HEADER == "   # Block Active_Mol"               # A10 truncates the 16-character literal
+    assert out.number_line(3, 114) == "         3        114"
+    p = dict(translation=0.4, rotation=0.4, insertion_deletion=0.2, swap=0.0, widom=0.0)
+    assert out.moves_header(p) == "Block" + "".join(f" {c:>12}" for c in
+                                                   ["Trans_Acc", "Trans_Trial", "Rot_Acc", "Rot_Trial", "Create_Acc", "Create_Trial", "Delete_Acc", "Delete_Trial"])
+    c = [[100, 40], [90, 80], [30, 5], [25, 3], [0, 0], [0, 0]]
+    assert out.moves_line(2, c, p) == f"{2:12d} {40:12d} {100:12d} {80:12d} {90:12d} {5:12d} {30:12d} {3:12d} {25:12d}"
+    assert out.WIDOM_HEADER == "   # Block Excess_Mu_kcalmo Total_Mu_kcalmol    Widom_Samples"
+    mu_ex, mu_tot = out.excess_mu(sum_weight=250.0, samples=1000, temperature=300.0, n_molecules=10, volume=39400.0, lam=0.5)
+    assert abs(mu_ex - (-out.KB_KCALMOL * 300.0 * np.log(0.25))) < 1e-15
+    assert abs(mu_tot - mu_ex - out.KB_KCALMOL * 300.0 * np.log(10 / 39400.0 * 0.125)) < 1e-12
+    assert out.widom_line(1, mu_ex, mu_tot, 1000) == f"{1:10d} {mu_ex:16.6f} {mu_tot:16.6f} {1000:12d}"
+    w = out.BlockWriter(tmp_path / "w0", {0: "wat"}, p)
+    rec = dict(energy=e, count=np.array([114, 0, 0, 0, 0, 0, 0, 0]), counters=np.array(c))
+    w.write(0, rec)
+    w.write(1, rec)
+    assert (tmp_path / "w0" / "energy.dat").read_text().splitlines() == [out.ENERGY_HEADER, out.energy_line(0, e), out.energy_line(1, e)]
+    assert (tmp_path / "w0" / "number_wat.dat").read_text().splitlines()[1:] == [out.number_line(0, 114), out.number_line(1, 114)]
+    assert len((tmp_path / "w0" / "moves.dat").read_text().splitlines()) == 3
