@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--mixture-steps", type=int, default=32)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--phase-sync", type=int, default=-1, help="experiment: MGPU_OPT_PHASE_SYNC value (2 = top-of-step barrier only, 3 = both)")
     ap.add_argument("--quick", action="store_true", help="kernel-variant experiments: the timed sweep only, prints a short line")
     return ap.parse_args()
 
@@ -231,6 +232,9 @@ def main():
     for w in range(W):
         eng.set_fugacity(0, float(fug[point(w)]), walker=w)
     eng.seed(12345 + 7919 * rank)
+    if a.phase_sync >= 0:
+        from maniac_b200.engine import OPT_PHASE_SYNC as _OPS
+        eng.set_option(_OPS, a.phase_sync)
     peak_tf, _ = eng.measure_fp64_peak()
     ew = eng.ewald()
     na = 4
@@ -499,6 +503,22 @@ def main():
     hm.close()
     enge.close()
 
+    # ---- the literal drop-in: ONE walker, one trial per call (what a single unchanged Fortran process does) ----
+    eng1 = Engine(s, n_walkers=1, capacity=CAPACITY, device=local)
+    hm1 = HostMonteCarlo(eng1, seed=5 + rank)
+    hm1.run(200)
+    eng1.timing_reset()
+    t0 = time.perf_counter()
+    n1 = 1500
+    hm1.run(n1)
+    t_1 = time.perf_counter() - t0
+    ms_k1, l_k1 = eng1.timing("trial")
+    single = {"moves_per_s": n1 / t_1, "us_per_move_wall": 1e6 * t_1 / n1, "us_per_trial_kernel": 1e3 * ms_k1 / max(1, l_k1),
+              "path": "mhost_run with 1 walker -> mgpu_trial_batch(n=1) (one 256-thread CTA per trial) + mgpu_commit_batch, synchronous; "
+                      "the latency a single unchanged Fortran process sees per move"}
+    hm1.close()
+    eng1.close()
+
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
@@ -514,7 +534,7 @@ def main():
     line = {"metric": "mc_trial_moves_per_s", "value": value, "unit": "moves/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": 1e3 * t_dev / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "clocks": clocks,
-            "e2e": e2e, "host_driven": host_driven, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "widom": widom, "no_host_cache": no_cache, "no_phase_sync": no_sync, "mixture": mixture, "isotherm": isotherm,
+            "e2e": e2e, "host_driven": host_driven, "single_walker_dropin": single, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "widom": widom, "no_host_cache": no_cache, "no_phase_sync": no_sync, "mixture": mixture, "isotherm": isotherm,
             "wall_s_timed_region": wall, "mean_waters_per_walker": nmean, "fp64_peak_tflops_measured": peak_tf}
     print(json.dumps(line))
 

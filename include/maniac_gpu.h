@@ -114,8 +114,10 @@ int mgpu_get_box(double matrix[9], double reciprocal[9], double *volume, int32_t
 /* launch shape of the warp-per-walker kernels: walkers (warps) per CTA, dynamic shared memory per CTA, SMs */
 int mgpu_get_launch_info(int32_t *walkers_per_cta, int64_t *smem_bytes_per_cta, int32_t *sm_count);
 /* triclinic cells: number of extra lattice vectors min_image examines per pair after rounding the
- * fractional coordinates (0 for orthorhombic cells); -1 = the literal 27-image search of
- * src/geometry_utils.f90:263-280 is used for every pair (very skewed cell) */
+ * fractional coordinates (0 for orthorhombic cells, and for large triclinic cells where a candidate could only
+ * matter beyond the LJ cutoff at distances whose erfc-Coulomb terms sum to < 1e-12 kcal/mol per trial -- bound
+ * evaluated in mgpu_init); -1 = the literal 27-image search of src/geometry_utils.f90:263-280 is used for every
+ * pair (very skewed cell) */
 int mgpu_get_triclinic_candidates(int32_t *n);
 int mgpu_get_thermo(int32_t res, double *beta, double *lambda, double *mu_walker0);
 

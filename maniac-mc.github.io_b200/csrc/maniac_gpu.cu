@@ -48,7 +48,8 @@ struct Context {
     int natom_max = 1;
     size_t smem1 = 0, smem8 = 0, smem_buildS = 0;   // dynamic shared memory: 1 group (CTA) / MGPU_WARPS groups (warps) per CTA
     int sm_count = 0, ctas_per_sm = 1;
-    int phase_sync = 1;                // MGPU_OPT_PHASE_SYNC
+    int phase_sync = 3;                // MGPU_OPT_PHASE_SYNC: bit 0 = barrier at the top of the MC step, bit 1 = before the energy evaluation
+    int tri_listed = 0;                // triclinic: candidates listed but provably irrelevant (see mgpu_init)
     int wgroups = MGPU_WGROUPS;        // walkers (warps) per CTA of the warp-per-task kernels
     int tab_emin = 0, tab_noct = 0;
     std::vector<void *> allocs;
@@ -67,6 +68,11 @@ struct Context {
     double *d_geom = nullptr;         // com + off of one molecule
     std::map<std::string, TimingSlot> timing;
     std::vector<char> dirty;          // per walker: coordinates changed outside commit
+    std::vector<char> pending;        // per walker: a trial is pending (host mirror of MgpuTrial::active)
+    // latency path (few trials per call, e.g. one unchanged Fortran process): the kernels read the task and write
+    // the energies straight from / to page-locked host memory (UVA), so a call is one launch + one synchronisation
+    int32_t *hc_walker = nullptr, *hc_accept = nullptr;    // pinned, commit arguments
+    bool commit_inflight = false;
     // walker records (mgpu_save_walkers / mgpu_load_walkers / mgpu_block)
     double *d_blob = nullptr; size_t blob_cap = 0;
     long long *d_rec_off = nullptr; size_t rec_cap = 0;
@@ -77,7 +83,10 @@ std::string g_err;
 
 int fail(const std::string &m) { g_err = m; return 1; }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
-#define NEED_READY() do { if (!g.ready) return fail("mgpu: engine not initialised (mgpu_init)"); } while (0)
+// every export starts here; a commit queued by the latency path (no synchronisation of its own) is waited for first,
+// because the getters copy on the legacy stream, which does not order against the engine's non-blocking stream
+#define NEED_READY_NOSYNC() do { if (!g.ready) return fail("mgpu: engine not initialised (mgpu_init)"); } while (0)
+#define NEED_READY() do { NEED_READY_NOSYNC(); if (g.commit_inflight) { cudaStreamSynchronize(g.stream); g.commit_inflight = false; } } while (0)
 
 template <typename T> int dalloc(T **p, size_t n)
 {
@@ -117,12 +126,14 @@ int ensure_task_cap(int n)
     if (dalloc(&g.d_task_off, (size_t)3 * MGPU_MAX_SITES * cap)) return 1;
     if (dalloc(&g.d_task_out, (size_t)12 * cap)) return 1;
     if (dalloc(&g.d_accept, (size_t)cap)) return 1;
-    if (g.h_task_i) { cudaFreeHost(g.h_task_i); cudaFreeHost(g.h_task_com); cudaFreeHost(g.h_task_off); cudaFreeHost(g.h_task_out); cudaFreeHost(g.h_accept); }
+    if (g.h_task_i) { cudaStreamSynchronize(g.stream); cudaFreeHost(g.h_task_i); cudaFreeHost(g.h_task_com); cudaFreeHost(g.h_task_off); cudaFreeHost(g.h_task_out); cudaFreeHost(g.h_accept); cudaFreeHost(g.hc_walker); cudaFreeHost(g.hc_accept); }
     CK(cudaMallocHost(&g.h_task_i, sizeof(int32_t) * 4 * cap));
     CK(cudaMallocHost(&g.h_task_com, sizeof(double) * 3 * cap));
     CK(cudaMallocHost(&g.h_task_off, sizeof(double) * 3 * MGPU_MAX_SITES * cap));
     CK(cudaMallocHost(&g.h_task_out, sizeof(double) * 12 * cap));
     CK(cudaMallocHost(&g.h_accept, sizeof(int32_t) * cap));
+    CK(cudaMallocHost(&g.hc_walker, sizeof(int32_t) * cap));
+    CK(cudaMallocHost(&g.hc_accept, sizeof(int32_t) * cap));
     g.task_cap = cap;
     return 0;
 }
@@ -172,7 +183,7 @@ void mgpu_finalize(void)
     if (g.stream) cudaStreamSynchronize(g.stream);
     for (void *p : g.allocs) cudaFree(p);
     g.allocs.clear();
-    if (g.h_task_i) { cudaFreeHost(g.h_task_i); cudaFreeHost(g.h_task_com); cudaFreeHost(g.h_task_off); cudaFreeHost(g.h_task_out); cudaFreeHost(g.h_accept); }
+    if (g.h_task_i) { cudaStreamSynchronize(g.stream); cudaFreeHost(g.h_task_i); cudaFreeHost(g.h_task_com); cudaFreeHost(g.h_task_off); cudaFreeHost(g.h_task_out); cudaFreeHost(g.h_accept); cudaFreeHost(g.hc_walker); cudaFreeHost(g.hc_accept); }
     if (g.h_scratch) cudaFreeHost(g.h_scratch);
     if (g.ev0) cudaEventDestroy(g.ev0);
     if (g.ev1) cudaEventDestroy(g.ev1);
@@ -241,7 +252,7 @@ int mgpu_init(const mgpu_system *sys)
         for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) h.Hinv[i * 3 + j] = rcp * adj[i][j];
     }
     for (int d = 0; d < 3; ++d) { h.L[d] = M[d][d]; h.invL[d] = 1.0 / M[d][d]; }
-    h.tri_nrel = 0;
+    h.tri_nrel = 0; g.tri_listed = 0;
     if (h.triclinic) {
         // lattice vectors that can beat the fractionally rounded image (min_image_r2<true>): m is relevant iff
         // min over f in [-1/2,1/2]^3 of |C(f+m)|^2 - |C f|^2 = m.G.m - sum_d |(G m)_d| < 0, G = C^T C (C = columns of matrix)
@@ -272,6 +283,22 @@ int mgpu_init(const mgpu_system *sys)
     const double t2 = 2.0 * screen * alpha;
     const double fprec = std::sqrt(-std::log(tol * rc * (t2 * t2)));
     h.rc = rc; h.rc2 = rc * rc; h.alpha = alpha;
+    if (h.triclinic && h.tri_nrel > 0) {
+        // A listed lattice vector C m can only shorten a rounded vector t when |t| > |C m| / 2.  If every pair that far
+        // apart is beyond the LJ cutoff and its erfc-Coulomb term is so small that ALL such pairs of a trial together
+        // stay below 1e-12 kcal/mol (bound: targets x max|q|^2 x erfc(alpha r)/r at r = min|C m|/2), the candidates
+        // cannot change any energy at the 1e-9 parity tolerance and are not evaluated at all: the rounded image is used.
+        double r_safe = 1e300;
+        for (int k = 0; k < h.tri_nrel; ++k) r_safe = std::fmin(r_safe, 0.5 * std::sqrt(h.tri_len2[k]));
+        double qmax = 0.0; long long targets = 0;
+        for (int r = 0; r < sys->nres; ++r) {
+            const mgpu_residue &R = sys->residues[r];
+            for (int a = 0; a < R.natom; ++a) qmax = std::fmax(qmax, std::fabs(R.charges[a]));
+            targets += (long long)R.natom * (R.is_active ? R.capacity : R.nmol);
+        }
+        const double bound = (double)targets * MGPU_MAX_SITES * qmax * qmax * std::erfc(alpha * r_safe) / r_safe * EPS0_INV_real();
+        if (rc <= r_safe && bound < 1.0e-12) { g.tri_listed = h.tri_nrel; h.tri_nrel = 0; }
+    }
     for (int d = 0; d < 3; ++d) h.kmax[d] = f_nint(0.25 + metrics[d] * alpha * fprec / PI);
     h.kmax_max = std::max(h.kmax[0], std::max(h.kmax[1], h.kmax[2]));
     h.eps0_inv_real = EPS0_INV_real(); h.twopi = TWOPI; h.overlap = OVERLAP();
@@ -515,6 +542,8 @@ int mgpu_init(const mgpu_system *sys)
         CK(cudaMemcpy(h.step, st.data(), sizeof(double) * st.size(), cudaMemcpyHostToDevice));
     }
     g.dirty.assign(W, 0);
+    g.pending.assign(W, 0);
+    g.commit_inflight = false;
 
     // ---- shared-memory budgets ----
     g.smem1 = smem_bytes(h.ntypes, h.tab_nint, h.kmax_max, g.natom_max, 1, 1);
@@ -727,7 +756,7 @@ int mgpu_get_energy(int32_t w, double out[6])
 int mgpu_set_option(int32_t option, int32_t value)
 {
     NEED_READY();
-    if (option == MGPU_OPT_PHASE_SYNC) { g.phase_sync = value ? 1 : 0; return 0; }
+    if (option == MGPU_OPT_PHASE_SYNC) { g.phase_sync = (value == 1) ? 3 : (value & 3); return 0; }
     if (option == MGPU_OPT_HOST_CACHE) {
         g.h.use_hcache = value ? 1 : 0;
         if (upload_sys()) return 1;
@@ -809,7 +838,7 @@ int mgpu_reciprocal_ewald_energy(int32_t w, double *e)
 int mgpu_trial_batch(int32_t n, const int32_t *walker, const int32_t *res, const int32_t *mol, const int32_t *kind,
                      const double *com, const double *offset, double *e_old, double *e_new)
 {
-    NEED_READY();
+    NEED_READY_NOSYNC();
     if (n <= 0) return 0;
     if (ensure_task_cap(n)) return 1;
     for (int t = 0; t < n; ++t) {
@@ -826,29 +855,37 @@ int mgpu_trial_batch(int32_t n, const int32_t *walker, const int32_t *res, const
     }
     if (com) std::memcpy(g.h_task_com, com, sizeof(double) * 3 * n); else std::memset(g.h_task_com, 0, sizeof(double) * 3 * n);
     if (offset) std::memcpy(g.h_task_off, offset, sizeof(double) * 3 * MGPU_MAX_SITES * n); else std::memset(g.h_task_off, 0, sizeof(double) * 3 * MGPU_MAX_SITES * n);
-    CK(cudaMemcpyAsync(g.d_task_i, g.h_task_i, sizeof(int32_t) * 4 * n, cudaMemcpyHostToDevice, g.stream));
-    CK(cudaMemcpyAsync(g.d_task_com, g.h_task_com, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, g.stream));
-    CK(cudaMemcpyAsync(g.d_task_off, g.h_task_off, sizeof(double) * 3 * MGPU_MAX_SITES * n, cudaMemcpyHostToDevice, g.stream));
-    TaskArrays T{ reinterpret_cast<const int4 *>(g.d_task_i), g.d_task_com, g.d_task_off, g.d_task_out };
-    Timer tm("trial");
-    // large batches: one warp per task (8 tasks per CTA); small ones: one CTA per task for latency
-    if (n >= g.sm_count) {
-        // spread the tasks over every SM: ceil(n / SMs) warps per CTA, at most wgroups
+    const bool latency = n < g.sm_count;
+    if (latency) {
+        // few trials: no staging copies at all -- the kernel dereferences the page-locked host buffers (zero copy)
+        TaskArrays T{ reinterpret_cast<const int4 *>(g.h_task_i), g.h_task_com, g.h_task_off, g.h_task_out };
+        Timer tm("trial");
+        if (g.h.triclinic) k_trial<true, MGPU_BLOCK><<<n, MGPU_BLOCK, g.smem1, g.stream>>>(T, n, g.natom_max);
+        else k_trial<false, MGPU_BLOCK><<<n, MGPU_BLOCK, g.smem1, g.stream>>>(T, n, g.natom_max);
+        tm.stop();                                   // synchronises on the kernel's end (and on any commit queued before it)
+        g.commit_inflight = false;
+        CK(cudaGetLastError());
+    } else {
+        CK(cudaMemcpyAsync(g.d_task_i, g.h_task_i, sizeof(int32_t) * 4 * n, cudaMemcpyHostToDevice, g.stream));
+        CK(cudaMemcpyAsync(g.d_task_com, g.h_task_com, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, g.stream));
+        CK(cudaMemcpyAsync(g.d_task_off, g.h_task_off, sizeof(double) * 3 * MGPU_MAX_SITES * n, cudaMemcpyHostToDevice, g.stream));
+        TaskArrays T{ reinterpret_cast<const int4 *>(g.d_task_i), g.d_task_com, g.d_task_off, g.d_task_out };
+        Timer tm("trial");
+        // one warp per task, spread over every SM: ceil(n / SMs) warps per CTA, at most wgroups
         int grp = (n + g.sm_count - 1) / g.sm_count;
         if (grp > g.wgroups) grp = g.wgroups;
         const int nb = (n + grp - 1) / grp;
         const size_t sm = smem_bytes(g.h.ntypes, g.h.tab_nint, g.h.kmax_max, g.natom_max, grp, MGPU_TAB_REP);
         if (g.h.triclinic) k_trial<true, 32><<<nb, 32 * grp, sm, g.stream>>>(T, n, g.natom_max);
         else k_trial<false, 32><<<nb, 32 * grp, sm, g.stream>>>(T, n, g.natom_max);
-    } else {
-        if (g.h.triclinic) k_trial<true, MGPU_BLOCK><<<n, MGPU_BLOCK, g.smem1, g.stream>>>(T, n, g.natom_max);
-        else k_trial<false, MGPU_BLOCK><<<n, MGPU_BLOCK, g.smem1, g.stream>>>(T, n, g.natom_max);
+        tm.stop();
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(g.h_task_out, g.d_task_out, sizeof(double) * 12 * n, cudaMemcpyDeviceToHost, g.stream));
+        CK(cudaStreamSynchronize(g.stream));
+        g.commit_inflight = false;
     }
-    tm.stop();
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(g.h_task_out, g.d_task_out, sizeof(double) * 12 * n, cudaMemcpyDeviceToHost, g.stream));
-    CK(cudaStreamSynchronize(g.stream));
     for (int t = 0; t < n; ++t) {
+        g.pending[walker[t]] = 1;
         if (e_old) std::memcpy(e_old + 6 * (size_t)t, g.h_task_out + 12 * (size_t)t, sizeof(double) * 6);
         if (e_new) std::memcpy(e_new + 6 * (size_t)t, g.h_task_out + 12 * (size_t)t + 6, sizeof(double) * 6);
     }
@@ -857,12 +894,25 @@ int mgpu_trial_batch(int32_t n, const int32_t *walker, const int32_t *res, const
 
 int mgpu_commit_batch(int32_t n, const int32_t *walker, const int32_t *accept)
 {
-    NEED_READY();
+    NEED_READY_NOSYNC();
     if (n <= 0) return 0;
     if (ensure_task_cap(n)) return 1;
-    for (int t = 0; t < n; ++t) { if (check_walker(walker[t])) return 1; g.h_task_i[t] = walker[t]; g.h_accept[t] = accept[t] ? 1 : 0; }
-    CK(cudaMemcpyAsync(g.d_task_i, g.h_task_i, sizeof(int32_t) * n, cudaMemcpyHostToDevice, g.stream));
-    CK(cudaMemcpyAsync(g.d_accept, g.h_accept, sizeof(int32_t) * n, cudaMemcpyHostToDevice, g.stream));
+    for (int t = 0; t < n; ++t) {
+        if (check_walker(walker[t])) return 1;
+        if (!g.pending[walker[t]]) return fail("mgpu_commit: commit without a pending trial");
+    }
+    if (g.commit_inflight) { CK(cudaStreamSynchronize(g.stream)); g.commit_inflight = false; }   // the argument buffers are being read
+    for (int t = 0; t < n; ++t) { g.hc_walker[t] = walker[t]; g.hc_accept[t] = accept[t] ? 1 : 0; g.pending[walker[t]] = 0; }
+    if (n < g.sm_count) {
+        // latency path: arguments read from page-locked host memory, no synchronisation -- the next energy call (or any
+        // getter, all of which synchronise the stream) orders after it
+        k_commit<<<n, 128, 0, g.stream>>>(g.hc_walker, g.hc_accept, g.d_err);
+        CK(cudaGetLastError());
+        g.commit_inflight = true;
+        return 0;
+    }
+    CK(cudaMemcpyAsync(g.d_task_i, g.hc_walker, sizeof(int32_t) * n, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(g.d_accept, g.hc_accept, sizeof(int32_t) * n, cudaMemcpyHostToDevice, g.stream));
     k_commit<<<n, 128, 0, g.stream>>>(g.d_task_i, g.d_accept, g.d_err);
     CK(cudaGetLastError());
     return check_err_flag("mgpu_commit");
@@ -1022,7 +1072,7 @@ int mgpu_load_walkers(int32_t first, int32_t n, const double *blob, const int64_
     CK(cudaGetLastError());
     g.h2d_bytes += (long long)sizeof(double) * offsets[n] + (long long)sizeof(long long) * (n + 1);
     if (check_err_flag("mgpu_load_walkers")) return 1;
-    for (int w = first; w < first + n; ++w) g.dirty[w] = 0;     // the record carries S(k), energies and the cache rows
+    for (int w = first; w < first + n; ++w) { g.dirty[w] = 0; g.pending[w] = 0; }   // the record carries S(k), energies and the cache rows
     return 0;
 }
 int mgpu_block(int32_t first, int32_t n, int64_t n_steps, const double *blob_in, const int64_t *offsets_in,

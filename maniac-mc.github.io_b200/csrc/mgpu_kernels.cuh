@@ -1589,11 +1589,11 @@ __global__ void __launch_bounds__(MGPU_WBLOCK, 1) k_sweep(int first_walker, int 
     __syncwarp();
 
     for (long long step = 0; step < n_steps; ++step) {
-        if (phase_sync) quartet_sync(qthreads);
-        if (!live) { if (phase_sync) quartet_sync(qthreads); continue; }
+        if (phase_sync & 1) quartet_sync(qthreads);
+        if (!live) { if (phase_sync & 2) quartet_sync(qthreads); continue; }
         if (lane == 0) propose_step(w, ws, err);
         __syncwarp();
-        if (phase_sync) quartet_sync(qthreads);
+        if (phase_sync & 2) quartet_sync(qthreads);
         const SweepShared &sh = ws.sh;
         if (sh.valid) {
             double e_old[6], e_new[6], hc_new[2];

@@ -544,6 +544,7 @@ def test_large_triclinic_supercell(load, engine_cls):
     ref = o.monte_carlo_steps(40)
     with engine_cls(s, n_walkers=8, capacity=128) as eng:
         assert eng.ewald()["nk"] == o.ewald()["nk"] > 2000
+        assert eng.triclinic_candidates() == 6        # (in cells > ~82 A the list is provably irrelevant and dropped, see mgpu_init)
         assert_e(eng.update_system_energy(), e_ref, what="17.7k-atom triclinic total energy")
         eng.seed(5)
         tr = eng.sweep(40, trace_walker=0)
