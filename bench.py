@@ -295,9 +295,11 @@ def main():
     roofline = {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf if peak_tf else None,
                 "traffic": traffic, "traffic_note": traffic_note, "kernel": "k_sweep<false>",
                 "note": "K1/K2 are FP64-pipe bound, not HBM/tensor bound (SURVEY 8d): peak = DFMA loop measured on this GPU in this "
-                        "run (mgpu_measure_fp64_peak, 2 FLOP per FMA); achieved = convention-C1 algorithmic FLOPs "
-                        "(29/pair geometry, 8/LJ term, 69/erfc-Coulomb term, k-space per SURVEY 8d) / event-timed kernel time",
-                "pairs_per_launch": pc["pairs"] / max(1, launches), "lj_terms_per_launch": pc["lj"] / max(1, launches),
+                        "run (mgpu_measure_fp64_peak, 2 FLOP per FMA); achieved = convention-C1 FLOPs (29/pair geometry, 8/LJ term, "
+                        "69/erfc-Coulomb term, k-space per SURVEY 8d) of the pairs this launch EVALUATED / event-timed kernel time; "
+                        "the framework-energy cache and the per-molecule screen skip pairs the reference evaluates, "
+                        "frac_reference_ops credits the reference's full operation count per move (measured by the no_host_cache leg)",
+                "pairs_per_launch": pc["pairs"] / max(1, launches), "screened_pairs_per_launch": pc.get("screened", 0) / max(1, launches), "lj_terms_per_launch": pc["lj"] / max(1, launches),
                 "coulomb_terms_per_launch": pc["coulomb"] / max(1, launches),
                 "hbm": {"achieved": bytes_alg / t_dev / 1e9 / world, "peak": hbm_peak, "unit": "GB/s",
                         "frac": bytes_alg / t_dev / 1e9 / world / hbm_peak,
@@ -340,11 +342,17 @@ def main():
         t = torch.tensor([t_nc], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_nc = float(t[0])
-    fl_nc = FLOP_GEOM * pc_nc["pairs"] + FLOP_LJ * pc_nc["lj"] + FLOP_COUL * pc_nc["coulomb"] + kspace_flops(dcount, na, ew["kmax"], ew["nk"]) * 2 / a.steps
+    fl_nc = FLOP_GEOM * (pc_nc["pairs"] + pc_nc.get("screened", 0)) + FLOP_LJ * pc_nc["lj"] + FLOP_COUL * pc_nc["coulomb"] + kspace_flops(dcount, na, ew["kmax"], ew["nk"]) * 2 / a.steps
     no_cache = {"moves_per_s": float(W) * a.inner * 2 * world / t_nc, "launches": int(l_nc),
                 "roofline_frac_c1": fl_nc / (ms_nc * 1e-3) / 1e12 / peak_tf if peak_tf else None,
                 "note": "mgpu_set_option(MGPU_OPT_HOST_CACHE, 0): old-geometry framework sums recomputed every trial"}
     eng.set_option(OPT_HOST_CACHE, 1)
+    # the reference's own operation count per move on this workload state (no cache: every pair the Fortran loops visit),
+    # credited to the cached run: "how fast would the FP64 pipe have to be to do the reference's arithmetic at this rate"
+    ref_flops_per_move = fl_nc / (float(W) * a.inner * 2)
+    roofline["reference_ops_per_move_c1"] = ref_flops_per_move
+    roofline["achieved_reference_ops"] = ref_flops_per_move * value / world / 1e12
+    roofline["frac_reference_ops"] = roofline["achieved_reference_ops"] / peak_tf if peak_tf else None
 
     # ---- the same sweep without the per-quartet phase alignment (MGPU_OPT_PHASE_SYNC) -------------
     from maniac_b200.engine import OPT_PHASE_SYNC

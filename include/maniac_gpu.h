@@ -277,6 +277,9 @@ int mgpu_timing_get(const char *kernel, double *total_ms, int64_t *launches);
  * LJ terms inside the cutoff, erfc-Coulomb terms (the algorithmic-work figures of the
  * roofline) */
 int mgpu_get_pair_counts(int64_t out[3]);
+/* atom pairs with neither LJ nor Coulomb interaction (only the r < 1e-10 overlap sentinel could make them count) that the
+ * per-molecule screen settled without evaluating them; the reference visits them (they belong to its operation count) */
+int mgpu_get_screened_pairs(int64_t *n);
 int mgpu_reset_pair_counts(void);
 /* achieved FP64 FMA throughput of a register-resident DFMA loop (TFLOP/s) and the SM
  * clock it ran at: the roofline denominator for the FP64-bound kernels */

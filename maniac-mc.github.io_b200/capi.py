@@ -106,6 +106,7 @@ SIGNATURES = {
     "mgpu_timing_reset": (C.c_int, []),
     "mgpu_timing_get": (C.c_int, [C.c_char_p, _pd, _pl]),
     "mgpu_get_pair_counts": (C.c_int, [_pl]),
+    "mgpu_get_screened_pairs": (C.c_int, [_pl]),
     "mgpu_reset_pair_counts": (C.c_int, []),
     "mgpu_measure_fp64_peak": (C.c_int, [_pd, _pd]),
     "mgpu_selftest_math": (C.c_int, [_pd, _pd]),

@@ -68,6 +68,7 @@ struct Context {
     double *d_geom = nullptr;         // com + off of one molecule
     std::map<std::string, TimingSlot> timing;
     std::vector<char> dirty;          // per walker: coordinates changed outside commit
+    std::vector<double> rmax2;        // host mirror of DevSys::rmax2 (grown by mgpu_set_molecule)
     std::vector<char> pending;        // per walker: a trial is pending (host mirror of MgpuTrial::active)
     // latency path (few trials per call, e.g. one unchanged Fortran process): the kernels read the task and write
     // the energies straight from / to page-locked host memory (UVA), so a call is one launch + one synchronisation
@@ -497,7 +498,7 @@ int mgpu_init(const mgpu_system *sys)
     // ---- per-walker arrays ----
     const size_t W = sys->n_walkers;
     if (dalloc(&h.coords, W * (size_t)stride) || dalloc(&h.count, W * MGPU_MAX_RES) || dalloc(&h.S, W * 4 * nk1) || dalloc(&h.cur, W) ||
-        dalloc(&h.energy, W * 6) || dalloc(&h.mu, W * MGPU_MAX_RES) || dalloc(&h.rng, W * 4) || dalloc(&h.step, W * 2) || dalloc(&h.counters, W * 12) ||
+        dalloc(&h.energy, W * 6) || dalloc(&h.mu, W * MGPU_MAX_RES) || dalloc(&h.rng, W * 4) || dalloc(&h.step, W * 2) || dalloc(&h.rmax2, MGPU_MAX_RES) || dalloc(&h.counters, W * 12) ||
         dalloc(&h.widom_w, W * MGPU_MAX_RES) || dalloc(&h.widom_n, W * MGPU_MAX_RES) || dalloc(&h.avg, W * MGPU_MAX_RES * 4) ||
         dalloc(&h.trial, W) || dalloc(&h.pair_count, 4) || dalloc(&g.d_err, 1) || dalloc(&g.d_scratch, 64) || dalloc(&g.d_geom, 3 + 3 * MGPU_MAX_SITES)) return 1;
     CK(cudaMallocHost(&g.h_scratch, sizeof(double) * 64));
@@ -540,6 +541,20 @@ int mgpu_init(const mgpu_system *sys)
         std::vector<double> st(W * 2);
         for (size_t w = 0; w < W; ++w) { st[2 * w] = sys->translation_step; st[2 * w + 1] = sys->rotation_step_angle; }
         CK(cudaMemcpy(h.step, st.data(), sizeof(double) * st.size(), cudaMemcpyHostToDevice));
+    }
+    {
+        // bound of |offset|^2 per residue type (screen of the "nothing" lists, guest_loops)
+        g.rmax2.assign(MGPU_MAX_RES, 0.0);
+        for (int r = 0; r < sys->nres; ++r) {
+            const mgpu_residue &R = sys->residues[r];
+            if (!R.is_active) continue;
+            for (int m = 0; m < R.nmol; ++m)
+                for (int a = 0; a < R.natom; ++a) {
+                    const double *o = R.offset + ((size_t)m * R.natom + a) * 3;
+                    g.rmax2[r] = std::fmax(g.rmax2[r], o[0] * o[0] + o[1] * o[1] + o[2] * o[2]);
+                }
+        }
+        CK(cudaMemcpy(h.rmax2, g.rmax2.data(), sizeof(double) * MGPU_MAX_RES, cudaMemcpyHostToDevice));
     }
     g.dirty.assign(W, 0);
     g.pending.assign(W, 0);
@@ -686,6 +701,12 @@ int mgpu_set_molecule(int32_t w, int32_t res, int32_t mol, const double com[3], 
     for (int e = 0; e < 3 * na; ++e) tmp[3 + e] = offset[e];
     CK(cudaMemcpy2DAsync(base + mol, sizeof(double) * cap, tmp.data(), sizeof(double), sizeof(double), 3 + 3 * na, cudaMemcpyHostToDevice, g.stream));
     CK(cudaStreamSynchronize(g.stream));
+    double r2 = 0.0;
+    for (int a = 0; a < na; ++a) r2 = std::fmax(r2, offset[3 * a] * offset[3 * a] + offset[3 * a + 1] * offset[3 * a + 1] + offset[3 * a + 2] * offset[3 * a + 2]);
+    if (r2 > g.rmax2[res]) {                                 // keep the |offset|^2 bound of the residue type valid
+        CK(cudaMemcpy(g.rmax2.data(), g.h.rmax2, sizeof(double) * MGPU_MAX_RES, cudaMemcpyDeviceToHost));   // device side may have grown too
+        if (r2 > g.rmax2[res]) { g.rmax2[res] = r2; CK(cudaMemcpy(g.h.rmax2 + res, &r2, sizeof(double), cudaMemcpyHostToDevice)); }
+    }
     g.dirty[w] = 1;
     return 0;
 }
@@ -1188,6 +1209,12 @@ int mgpu_get_pair_counts(int64_t out[3])
 {
     NEED_READY();
     CK(cudaMemcpy(out, g.h.pair_count, sizeof(int64_t) * 3, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int mgpu_get_screened_pairs(int64_t *n)
+{
+    NEED_READY();
+    CK(cudaMemcpy(n, g.h.pair_count + 3, sizeof(int64_t), cudaMemcpyDeviceToHost));
     return 0;
 }
 int mgpu_reset_pair_counts(void)

@@ -105,6 +105,7 @@ struct DevSys {
     double  *energy;                          // [W][6]
     double  *mu;                              // [W][MGPU_MAX_RES]
     uint64_t *rng;                            // [W][4]
+    double  *rmax2;                           // [MGPU_MAX_RES] upper bound of |offset|^2 over every molecule of the residue type, all walkers
     double  *step;                            // [W][2] translation_step, rotation_step_angle of the walker (adjust_move_step_sizes)
     long long *counters;                      // [W][12]
     double  *widom_w; long long *widom_n;     // [W][MGPU_MAX_RES]

@@ -40,6 +40,9 @@ __constant__ DevSys c_sys;
 #ifndef MGPU_PF_GUEST
 #define MGPU_PF_GUEST 0
 #endif
+#ifndef MGPU_SCREEN_NOTHING
+#define MGPU_SCREEN_NOTHING 1
+#endif
 #ifndef MGPU_ACC_PER_ATOM
 #define MGPU_ACC_PER_ATOM 0
 #endif
@@ -49,7 +52,9 @@ __constant__ DevSys c_sys;
 #ifndef MGPU_PF_KSPACE
 #define MGPU_PF_KSPACE 1
 #endif
+#ifndef MGPU_BLOCK
 #define MGPU_BLOCK 256                    // CTA-per-task kernels (NT = MGPU_BLOCK)
+#endif
 #define MGPU_WARPS (MGPU_BLOCK / 32)
 #ifndef MGPU_WBLOCK
 #define MGPU_WBLOCK 512                   // warp-per-task kernels (NT = 32): one CTA per SM
@@ -214,7 +219,7 @@ __device__ __forceinline__ double min_image_r2(double dx, double dy, double dz)
 
 // Work counters for the roofline accounting: pairs evaluated, LJ terms inside the
 // cutoff, erfc-Coulomb terms.  Integer adds on the otherwise idle ALU pipe.
-struct PairCount { unsigned geom, lj, coul; };
+struct PairCount { unsigned geom, lj, coul, scr; };      // scr: pairs of "nothing" lists settled by the per-molecule screen
 
 // 1/s: MUFU.RCP64H seed + two Newton steps (s is a normal positive double here)
 __device__ __forceinline__ double rcp_fast(double s)
@@ -708,6 +713,22 @@ __device__ __forceinline__ void guest_loops(const Probe &P, const double (*pos)[
                                             double &e_lj, double &e_c, PairCount &pc)
 {
     const double *wc = c_sys.coords + (int64_t)w * c_sys.coord_stride;
+    // Screen for the "nothing" lists (atom pairs with neither LJ nor Coulomb, e.g. TIP4P O x M/H: 6 of the 16 pairs of two
+    // waters).  Their only possible contribution is the reference's overlap sentinel at r < 1e-10 (pairwise_lj_energy :116-119),
+    // which needs two atoms on top of each other -- impossible for a molecule whose centre is farther from the probe's
+    // centre than the two molecular radii.  Each thread checks that once per molecule it is responsible for (one
+    // minimum image per molecule instead of one per atom pair) and only sweeps the "nothing" lists when it fails.
+    double pcx = 0.0, pcy = 0.0, pcz = 0.0, prad2 = 0.0;
+    if (MGPU_SCREEN_NOTHING) {
+        const int na = P.na;
+        for (int a = 0; a < na; ++a) { pcx += pos[a][0]; pcy += pos[a][1]; pcz += pos[a][2]; }
+        const double inv = 1.0 / (double)na;
+        pcx *= inv; pcy *= inv; pcz *= inv;
+        for (int a = 0; a < na; ++a) {
+            const double ax = pos[a][0] - pcx, ay = pos[a][1] - pcy, az = pos[a][2] - pcz;
+            prad2 = fmax(prad2, ax * ax + ay * ay + az * az);
+        }
+    }
     for (int g = 0; g < c_sys.nres; ++g) {
         if (!c_sys.active[g]) continue;
         const int n = S.ws->count[g];
@@ -719,6 +740,16 @@ __device__ __forceinline__ void guest_loops(const Probe &P, const double (*pos)[
         int m_order = -1;                                        // molecules m <= m_order are skipped
         if (P.order_res >= 0) m_order = (g < P.order_res) ? n : (g == P.order_res ? P.order_mol : -1);
         if (m_order >= n - 1 || (n == 1 && m_skip == 0)) continue;
+        bool nothing_lists = true;
+        if (MGPU_SCREEN_NOTHING) {
+            const double rr = sqrt(prad2) + sqrt(c_sys.rmax2[g] * (1.0 + 1.0e-6)) + 1.0e-9;
+            const double thr2 = rr * rr;
+            nothing_lists = false;
+            for (int m = t0; m < n; m += stride) {
+                const double s = min_image_r2<TRI>(com[m] - pcx, com[cap + m] - pcy, com[2 * cap + m] - pcz);
+                nothing_lists |= (s < thr2) && (m != m_skip);
+            }
+        }
         for (int b = 0; b < na_g; ++b) {
             const double *offb = off + (int64_t)b * 3 * cap;
             double tq = c_sys.charge[g][b];
@@ -730,7 +761,12 @@ __device__ __forceinline__ void guest_loops(const Probe &P, const double (*pos)[
             guest_list<TRI, 1, REP>(P, pos, L + 1 * MGPU_MAX_SITES, N[1], com, offb, cap, n, t0, stride, m_skip, m_order, tq, ttype, e_lj, e_c, pc);
             guest_list<TRI, 2, REP>(P, pos, L + 2 * MGPU_MAX_SITES, N[2], com, offb, cap, n, t0, stride, m_skip, m_order, tq, ttype, e_lj, e_c, pc);
             guest_list<TRI, 3, REP>(P, pos, L + 3 * MGPU_MAX_SITES, N[3], com, offb, cap, n, t0, stride, m_skip, m_order, tq, ttype, e_lj, e_c, pc);
-            guest_list<TRI, 0, REP>(P, pos, L + 0 * MGPU_MAX_SITES, N[0], com, offb, cap, n, t0, stride, m_skip, m_order, tq, ttype, e_lj, e_c, pc);
+            if (nothing_lists)
+                guest_list<TRI, 0, REP>(P, pos, L + 0 * MGPU_MAX_SITES, N[0], com, offb, cap, n, t0, stride, m_skip, m_order, tq, ttype, e_lj, e_c, pc);
+            else if (t0 == 0) {                                  // this thread's share is not known per list; credit the whole list once
+                const int first = m_order + 1;
+                pc.scr += (unsigned)(N[0] * ((n - first) - ((m_skip >= first && m_skip < n) ? 1 : 0)));
+            }
         }
     }
 }
@@ -1003,6 +1039,17 @@ __device__ void evaluate_trial(const Smem &S, int w, bool store_S, double e_old[
     e_new[MGPU_E_TOTAL] = e_new[0] + e_new[1] + e_new[2] + e_new[3] + e_new[4];
 }
 
+// A molecule whose geometry came from the host (mgpu_new_energy / mgpu_trial_batch) may be larger than anything seen so
+// far: keep the per-residue bound of |offset|^2 (screen of the "nothing" lists) valid.  Device-generated geometries are
+// rotations of stored ones and never grow it beyond its 1e-6 margin.
+__device__ __forceinline__ void grow_rmax2(int res, const double (*off)[3], int na, int tid, int nthreads)
+{
+    for (int a = tid; a < na; a += nthreads) {
+        const double r2 = off[a][0] * off[a][0] + off[a][1] * off[a][1] + off[a][2] * off[a][2];
+        if (r2 > c_sys.rmax2[res]) atomicMax(reinterpret_cast<unsigned long long *>(c_sys.rmax2 + res), (unsigned long long)__double_as_longlong(r2));
+    }
+}
+
 // Apply an accepted trial to the walker (group-cooperative).
 // accept_molecule_move / accept_creation_move / accept_deletion_move + remove_molecule +
 // update_counts (monte_carlo_utils.f90:429-442,642-672; creation.f90:82-116; deletion.f90:83-122).
@@ -1023,6 +1070,7 @@ __device__ void commit_trial(int w, int kind, int res, int mol, const double *co
         if (tid < 3) wc[tid * cap + mol] = com[tid];
         for (int e = tid; e < na * 3; e += nthreads) offs[(int64_t)e * cap + mol] = off[e / 3][e % 3];
         if (tid < 2) offs[(int64_t)(na * 3 + tid) * cap + mol] = hc_new[tid];
+        grow_rmax2(res, off, na, tid, nthreads);
     }
     if (tid == 0) {
         if (kind == MGPU_KIND_CREATE) c_sys.count[(int64_t)w * MGPU_MAX_RES + res] = n + 1;
@@ -1085,6 +1133,7 @@ __device__ void commit_swap(int w, int resA, int molA, int resB, const double *c
         if (tid < 3) wc[tid * cap + nB] = com[tid];
         for (int e = tid; e < na * 3; e += nthreads) offs[(int64_t)e * cap + nB] = off[e / 3][e % 3];
         if (tid < 2) offs[(int64_t)(na * 3 + tid) * cap + nB] = hc_new[tid];
+        grow_rmax2(resB, off, na, tid, nthreads);
     }
     if (tid == 0) {
         c_sys.count[(int64_t)w * MGPU_MAX_RES + resA] -= 1;
@@ -1111,16 +1160,18 @@ __device__ __forceinline__ void write_slot(int w, int res, int mol, const double
     double *offs = wc + 3 * (int64_t)cap;
     if (tid < 3) wc[tid * cap + mol] = com[tid];
     for (int e = tid; e < na * 3; e += nthreads) offs[(int64_t)e * cap + mol] = off[e / 3][e % 3];
+    grow_rmax2(res, off, na, tid, nthreads);
 }
 
 __device__ __forceinline__ void flush_pair_count(const PairCount &pc)
 {
     const unsigned g = __reduce_add_sync(0xffffffffu, pc.geom), l = __reduce_add_sync(0xffffffffu, pc.lj),
-                   c = __reduce_add_sync(0xffffffffu, pc.coul);
+                   c = __reduce_add_sync(0xffffffffu, pc.coul), x = __reduce_add_sync(0xffffffffu, pc.scr);
     if ((threadIdx.x & 31) == 0) {
         atomicAdd(c_sys.pair_count + 0, (unsigned long long)g);
         atomicAdd(c_sys.pair_count + 1, (unsigned long long)l);
         atomicAdd(c_sys.pair_count + 2, (unsigned long long)c);
+        atomicAdd(c_sys.pair_count + 3, (unsigned long long)x);
     }
 }
 
@@ -1147,7 +1198,7 @@ __global__ void __launch_bounds__(NT == 32 ? MGPU_WBLOCK : MGPU_BLOCK, 1) k_tria
     const double *com = T.com + (int64_t)t * 3;
     const double(*off)[3] = reinterpret_cast<const double(*)[3]>(T.off + (int64_t)t * MGPU_MAX_SITES * 3);
     double e_old[6], e_new[6], hc_new[2];
-    PairCount pc = { 0u, 0u, 0u };
+    PairCount pc = { 0u, 0u, 0u, 0u };
     if (kind == MGPU_KIND_SWAP) {
         Grp<NT>::sync();
         evaluate_swap<TRI, NT>(S, w, true, res, mol, res2, S.ws->count[res2], com, off, e_old, e_new, hc_new, pc);
@@ -1210,7 +1261,7 @@ __global__ void __launch_bounds__(MGPU_BLOCK) k_pair_molecule(int w, int res, in
     }
     __syncthreads();
     double ps[8];
-    PairCount pc = { 0u, 0u, 0u };
+    PairCount pc = { 0u, 0u, 0u, 0u };
     pair_sums<TRI, MGPU_BLOCK>(S, w, ps, pc);
     if (threadIdx.x == 0) { out2[0] = ps[0] + ps[4]; out2[1] = (ps[1] + ps[5]) * c_sys.eps0_inv_real; }
 }
@@ -1327,7 +1378,7 @@ __global__ void __launch_bounds__(MGPU_BLOCK) k_total_energy(int first_walker, i
     __syncthreads();
     Probe &P = S.ws->probe;
     double e_lj = c_sys.hh_lj, e_c = 0.0, e_intra = 0.0, e_self = c_sys.self_host_total;
-    PairCount pc = { 0u, 0u, 0u };
+    PairCount pc = { 0u, 0u, 0u, 0u };
     for (int g = 0; g < c_sys.nres; ++g) {
         if (!c_sys.active[g]) continue;
         const int n = S.ws->count[g], na = c_sys.natom[g];
@@ -1585,7 +1636,7 @@ __global__ void __launch_bounds__(MGPU_WBLOCK, 1) k_sweep(int first_walker, int 
         if (lane == 0) { ws.loc.avgE = 0.0; ws.loc.n_samples = 0; }
     }
     if (lane == 0) ws.sh.valid = 0;
-    PairCount pc = { 0u, 0u, 0u };
+    PairCount pc = { 0u, 0u, 0u, 0u };
     __syncwarp();
 
     for (long long step = 0; step < n_steps; ++step) {
@@ -1700,7 +1751,7 @@ __global__ void __launch_bounds__(MGPU_WBLOCK, 1) k_widom_batch(int w, int res, 
     const double *offs = wc + c_sys.goff[res] + 3 * (int64_t)cap;
     const double recip_cur = c_sys.energy[(int64_t)w * 6 + MGPU_E_RECIP];
     double my_w = 0.0; long long my_ok = 0;
-    PairCount pc = { 0u, 0u, 0u };
+    PairCount pc = { 0u, 0u, 0u, 0u };
     for (long long i = gw; i < n; i += nwarps) {
         const unsigned long long id = (unsigned long long)(first_id + i);
         if (lane == 0) {

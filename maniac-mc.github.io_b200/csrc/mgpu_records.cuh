@@ -99,6 +99,18 @@ __global__ void __launch_bounds__(256) k_unpack(int first, int n, const long lon
             const int m = t / ms, e = t - m * ms;
             dst[(int64_t)e * cap + m] = p[t];
         }
+        // keep the bound on |offset|^2 of this residue type valid for whatever the record brings in
+        double r2 = 0.0;
+        const int na = c_sys.natom[r];
+        for (int t = lane; t < cnt * na; t += 32) {
+            const int m = t / na, a = t - m * na;
+            const double *o = p + (long long)m * ms + 3 + 3 * a;
+            r2 = fmax(r2, o[0] * o[0] + o[1] * o[1] + o[2] * o[2]);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r2 = fmax(r2, __shfl_xor_sync(0xffffffffu, r2, o));
+        if (lane == 0 && r2 > c_sys.rmax2[r])
+            atomicMax(reinterpret_cast<unsigned long long *>(c_sys.rmax2 + r), (unsigned long long)__double_as_longlong(r2));
         p += (long long)cnt * ms;
     }
 }

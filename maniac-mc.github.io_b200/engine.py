@@ -475,7 +475,10 @@ class Engine:
     def pair_counts(self):
         out = (C.c_int64 * 3)()
         self._ck(self.L.mgpu_get_pair_counts(out))
-        return dict(pairs=out[0], lj=out[1], coulomb=out[2])
+        scr = C.c_int64(0)
+        if hasattr(self.L, "mgpu_get_screened_pairs"):
+            self._ck(self.L.mgpu_get_screened_pairs(C.byref(scr)))
+        return dict(pairs=out[0], lj=out[1], coulomb=out[2], screened=scr.value)
 
     def reset_pair_counts(self):
         self._ck(self.L.mgpu_reset_pair_counts())

@@ -669,3 +669,42 @@ def test_step_size_adaptation_per_block(load, engine_cls):
             hm.adjust_move_step_sizes()
             assert np.allclose(hm.step_sizes(0), o.step_sizes(), rtol=1e-14, atol=0)
         hm.close()
+
+
+def test_overlap_sentinel_of_pairs_with_no_interaction(load, engine_cls):
+    """pairwise_lj_energy returns 1e20 for r < 1e-10 whatever epsilon is (src/pairwise_energy_utils.f90:116-119), so even an
+    atom pair with neither LJ nor Coulomb (TIP4P O on top of another water's M or H) must show up.  The engine screens
+    those pair lists per molecule (centre distance vs molecular radii); the screen must let exactly these cases through."""
+    s = load("zif8_h2o_gcmc")
+    o = Oracle(s, capacity=16)
+    o.update_system_energy()
+    com0, off0 = o.get_molecule(0, 0)
+    com1, off1 = o.get_molecule(0, 1)
+    with engine_cls(s, capacity=16) as eng:
+        eng.update_system_energy()
+        for tgt_atom in (1, 2):                      # O of molecule 1 exactly on M, then on H, of molecule 0
+            new_com = (com0 + off0[tgt_atom]) - off1[0]
+            o.save_fourier(0, 1)
+            old_ref = o.compute_old_energy(0, 1, KIND_MOVE)
+            o.set_molecule(0, 1, new_com, off1)
+            new_ref = o.compute_new_energy(0, 1, KIND_MOVE)
+            o.set_molecule(0, 1, com1, off1)
+            o.update_system_energy()
+            assert new_ref[0] > 1e19                  # the sentinel is in the non-Coulomb component
+            new_gpu = eng.compute_new_energy(0, 1, KIND_MOVE, new_com, off1)
+            eng.rollback()
+            assert new_gpu[0] > 1e19 and abs(new_gpu[0] - new_ref[0]) <= 1e-9 * abs(new_ref[0])
+        # a molecule larger than any seen before, handed in through the API, must still be screened correctly
+        big = off1 * 3.0
+        eng.set_molecule(0, 2, com1 + np.array([9.0, 0.0, 0.0]), big)
+        eng.update_system_energy()
+        o.set_molecule(0, 2, com1 + np.array([9.0, 0.0, 0.0]), big)
+        o.update_system_energy()
+        cb, ob = o.get_molecule(0, 2)
+        new_com = (cb + ob[2]) - off1[0]              # O of molecule 1 on the far-out H of the enlarged molecule
+        o.save_fourier(0, 1)
+        o.compute_old_energy(0, 1, KIND_MOVE)
+        o.set_molecule(0, 1, new_com, off1)
+        new_ref = o.compute_new_energy(0, 1, KIND_MOVE)
+        new_gpu = eng.compute_new_energy(0, 1, KIND_MOVE, new_com, off1)
+        assert new_ref[0] > 1e19 and new_gpu[0] > 1e19
