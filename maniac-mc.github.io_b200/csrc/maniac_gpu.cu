@@ -475,7 +475,7 @@ int mgpu_init(const mgpu_system *sys)
         h.s_zero = r_zero * r_zero;
         if (r_hi > r_zero) r_hi = r_zero;
         std::vector<double> tab;
-        mgpu_build_coulomb_table(alpha, 1.0, r_hi, &g.tab_emin, &g.tab_noct, tab);
+        mgpu_build_coulomb_table(alpha, MGPU_TAB_RLO, r_hi, &g.tab_emin, &g.tab_noct, tab);
         // the hot loops send everything beyond the last interval to an all-zero row, so the table has to reach
         // the largest distance that still matters (the box limit or alpha r = 7, whichever is smaller)
         if (std::ldexp(1.0, g.tab_emin + g.tab_noct) < r_hi * r_hi)

@@ -307,8 +307,8 @@ struct Probe {
     int32_t host_old, host_new;              // which geometries need a framework pass (old: 0 when the cache serves it)
     double q[MGPU_MAX_SITES];                // 0 when |q| < 1e-10
     int32_t type[MGPU_MAX_SITES];
-    double po[MGPU_MAX_SITES][3];            // old atom positions (com + offset)
-    double pn[MGPU_MAX_SITES][3];            // new atom positions
+    double (*po)[3];                         // old atom positions (com + offset), [natom_max][3] behind the workspace
+    double (*pn)[3];                         // new atom positions
 };
 
 // Proposal / decision record of the device-resident drivers (one per group)
@@ -364,6 +364,7 @@ struct Smem {
 __host__ __device__ inline size_t smem_group_bytes(int kmax_max, int natom_max, int rep)
 {
     size_t b = smem_ws_bytes(rep > 1);
+    b += (sizeof(double) * 2 * 3 * (size_t)natom_max + 15) & ~size_t(15);          // probe positions, old and new
     b += sizeof(double2) * 2 * (size_t)natom_max * 3 * (kmax_max + 1);
     return b;
 }
@@ -390,7 +391,9 @@ __device__ __forceinline__ Smem smem_setup(unsigned char *base, int natom_max, i
     for (int i = threadIdx.x; i < nt2; i += blockDim.x) lj[i] = make_double2(c_sys.ljA[i], c_sys.ljB[i]);
     unsigned char *g = base + smem_common_bytes(c_sys.ntypes, c_sys.tab_nint, REP) + (size_t)group * smem_group_bytes(c_sys.kmax_max, natom_max, REP);
     s.ws = reinterpret_cast<GroupWS *>(g);
-    s.tab_old = reinterpret_cast<double2 *>(g + smem_ws_bytes(REP > 1));
+    double (*ppos)[3] = reinterpret_cast<double (*)[3]>(g + smem_ws_bytes(REP > 1));
+    if ((REP > 1) ? ((threadIdx.x & 31) == 0) : (threadIdx.x == 0)) { s.ws->probe.po = ppos; s.ws->probe.pn = ppos + natom_max; }
+    s.tab_old = reinterpret_cast<double2 *>(g + smem_ws_bytes(REP > 1) + ((sizeof(double) * 2 * 3 * (size_t)natom_max + 15) & ~size_t(15)));
     s.tab_new = s.tab_old + (size_t)natom_max * 3 * (c_sys.kmax_max + 1);
     __syncthreads();
     return s;
