@@ -3,6 +3,7 @@
 // (src/prepare_utils.f90:110-259, src/ewald_kvectors.f90:24-175, src/constants.f90) so the
 // Fortran host and the engine agree on alpha / kmax / the k-vector list bit for bit.
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -273,6 +274,8 @@ int mgpu_init(const mgpu_system *sys)
             ++n;
         }
         h.tri_nrel = n;
+        h.tri_safe2 = 1e300;
+        for (int k = 0; k < n; ++k) h.tri_safe2 = std::fmin(h.tri_safe2, 0.25 * h.tri_len2[k]);
     }
 
     // ---- Ewald: setup_ewald, prepare_utils.f90:110-226 ----
@@ -393,6 +396,28 @@ int mgpu_init(const mgpu_system *sys)
                     if (std::fabs(q) >= MGPU_ERR_TOL) ++h.n_host_charged;
                 }
         }
+    }
+    if (n_host > 64) {
+        // Static framework atoms in Morton (Z-curve) order of their fractional coordinates: the 32 consecutive atoms a warp
+        // takes per iteration then sit in one small region, so "beyond the LJ cutoff" / "no lattice candidate can help"
+        // become warp-uniform facts that whole iterations can act on (triclinic passes).  Sums are order-independent
+        // up to rounding; the host-host constant and S_host use the same permuted arrays.
+        std::vector<std::pair<uint32_t, int>> key(n_host);
+        auto spread = [](uint32_t v) { v &= 1023u; v = (v | (v << 16)) & 0x030000FFu; v = (v | (v << 8)) & 0x0300F00Fu; v = (v | (v << 4)) & 0x030C30C3u; v = (v | (v << 2)) & 0x09249249u; return v; };
+        for (int k = 0; k < n_host; ++k) {
+            const double r[3] = { hx[k].x - h.lo[0], hx[k].y - h.lo[1], hx[k].z - h.lo[2] };
+            uint32_t q[3];
+            for (int d = 0; d < 3; ++d) {
+                double f = h.Hinv[0 * 3 + d] * r[0] + h.Hinv[1 * 3 + d] * r[1] + h.Hinv[2 * 3 + d] * r[2];   // Hinv = transposed inverse
+                f -= std::floor(f);
+                q[d] = (uint32_t)std::fmin(1023.0, f * 1024.0);
+            }
+            key[k] = { spread(q[0]) | (spread(q[1]) << 1) | (spread(q[2]) << 2), k };
+        }
+        std::stable_sort(key.begin(), key.end());
+        std::vector<double4> hx2(n_host); std::vector<int32_t> ht2(n_host), hm2(n_host); std::vector<double> hq2(n_host);
+        for (int k = 0; k < n_host; ++k) { const int o = key[k].second; hx2[k] = hx[o]; ht2[k] = ht[o]; hm2[k] = hm[o]; hq2[k] = hq[o]; }
+        hx.swap(hx2); ht.swap(ht2); hm.swap(hm2); hq.swap(hq2);
     }
     double4 *d_hx; int32_t *d_ht, *d_hm; double *d_eps, *d_sig, *d_ffW, *d_Shost, *d_hq, *d_ctab; int32_t *d_kx, *d_ky, *d_kz;
     const size_t nk1 = h.nk ? h.nk : 1, nt2 = (size_t)sys->ntypes * sys->ntypes;

@@ -62,6 +62,7 @@ struct DevSys {
     // C m (tri_rel) that can beat the fractionally rounded image, and their integer coefficients m
     // (tri_m); tri_nrel < 0 = too many of them, keep the reference's 27-image search.
     int32_t tri_nrel;
+    double tri_safe2;             // a listed vector can only shorten t when |t|^2 > tri_safe2 = min |C m|^2 / 4
     double tri_rel[MGPU_TRI_MAXREL][3], tri_m[MGPU_TRI_MAXREL][3], tri_len2[MGPU_TRI_MAXREL];   // one of every +-m pair
     // ewald / constants
     double rc, rc2, alpha, eps0_inv_real, twopi, beta, overlap;

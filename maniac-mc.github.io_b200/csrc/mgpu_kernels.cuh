@@ -208,7 +208,9 @@ __device__ __forceinline__ double min_image_r2(double dx, double dy, double dz)
         // shorten it: |t -+ C m|^2 - |t|^2 = |C m|^2 - 2 |t . C m|
         double gain = 0.0, bsign = 0.0;
         int bk = -1;
-        const int nrel = c_sys.tri_nrel;
+        // (framework atoms are Morton-sorted: the lanes of a warp look at one small region, so this is usually unanimous)
+        const double t2 = fma(tx, tx, fma(ty, ty, tz * tz));
+        const int nrel = __any_sync(__activemask(), t2 > c_sys.tri_safe2) ? c_sys.tri_nrel : 0;
         for (int k = 0; k < nrel; ++k) {
             const double dot = fma(tx, c_sys.tri_rel[k][0], fma(ty, c_sys.tri_rel[k][1], tz * c_sys.tri_rel[k][2]));
             const double gk = fma(-2.0, fabs(dot), c_sys.tri_len2[k]);
@@ -477,7 +479,7 @@ struct HostPass {
                 sv[u][i] = s;
                 const int hi = __double2hiint(s);
                 hmin = min(hmin, hi);
-                if (MODE & 1) {
+                if ((MODE & 1) && (!TRI || __any_sync(__activemask(), s < c_sys.rc2))) {     // triclinic (large cells): whole warps are beyond the cutoff
                     const double2 AB = ljAB[trow[i] + tt[u]];
                     const double y = rcp_fast(s), y3 = y * y * y;
                     const double e = (AB.x * y3 - AB.y) * y3;
