@@ -120,3 +120,55 @@ def write_isotherm(path, fugacity: Iterable[float], summary: dict):
         for i, fu in enumerate(fugacity):
             f.write(f"{fu:16.6e} {summary['mean_N'][i]:16.6f} {math.sqrt(max(summary['var_N'][i], 0.0)):16.6f} "
                     f"{summary['mean_E'][i]:16.6f} {int(summary['samples'][i]):12d}\n")
+
+
+# ---- trajectory.lammpstrj (write_dump_lammpstrj, src/write_utils.f90:38-119) ---------------------------
+def _reciprocal(matrix: np.ndarray) -> np.ndarray:
+    """box%cell%reciprocal as compute_box_determinant_and_inverse builds it (geometry_utils.f90:148-200): column j of the
+    adjugate = cross product of the other two COLUMNS of the matrix, divided by the determinant."""
+    m = np.asarray(matrix, dtype=float)
+    adj = np.column_stack([np.cross(m[:, 1], m[:, 2]), np.cross(m[:, 2], m[:, 0]), np.cross(m[:, 0], m[:, 1])])
+    det = m[:, 0] @ adj[:, 0]
+    return adj / det
+
+
+def wrap_into_box(pos, matrix) -> np.ndarray:
+    """wrap_into_box (geometry_utils.f90:105-140): into [-L/2, L/2] per axis (orthorhombic) or fractional [-1/2, 1/2)."""
+    m = np.asarray(matrix, dtype=float)
+    p = np.array(pos, dtype=float)
+    off = m - np.diag(np.diag(m))
+    if np.abs(off).max() <= 1e-10:
+        for d in range(3):
+            p[d] = p[d] - m[d, d] * np.floor(p[d] / m[d, d] + 0.5) if p[d] / m[d, d] >= 0 else p[d] - m[d, d] * np.ceil(p[d] / m[d, d] - 0.5)
+        return p
+    f = _reciprocal(m) @ p
+    f = f - np.where(f >= 0, np.floor(f + 0.5), np.ceil(f - 0.5))       # Fortran nint: halves away from zero
+    return m @ f
+
+
+def lammpstrj_frame(timestep: int, matrix, residues, record_molecules: dict) -> str:
+    """One frame.  ``residues`` = list of dict(active, types (1-based ids per site), com [nmol,3], offset [nmol,natom,3]) in
+    residue order, giving the static (inactive) residues; active residues take their molecules from ``record_molecules``
+    (Engine.parse_record(...)["molecules"]).  CoMs of active molecules are wrapped, atoms of inactive ones are wrapped,
+    exactly like the reference does."""
+    m = np.asarray(matrix, dtype=float)
+    rows = []
+    atom_id = 0
+    for r, res in enumerate(residues):
+        if res["active"]:
+            mol = record_molecules.get(r)
+            coms, offs = (mol["com"], mol["offset"]) if mol is not None else (np.zeros((0, 3)), np.zeros((0, len(res["types"]), 3)))
+        else:
+            coms, offs = np.asarray(res["com"]), np.asarray(res["offset"])
+        for k in range(len(coms)):
+            com = wrap_into_box(coms[k], m) if res["active"] else np.asarray(coms[k], dtype=float)
+            for a, t in enumerate(res["types"]):
+                atom_id += 1
+                pos = com + offs[k][a]
+                if not res["active"]:
+                    pos = wrap_into_box(pos, m)
+                rows.append(f"{atom_id:6d} {int(t):4d} {pos[0]:12.7f} {pos[1]:12.7f} {pos[2]:12.7f}")
+    head = ["ITEM: TIMESTEP", f"{timestep:10d}", "ITEM: NUMBER OF ATOMS", f"{atom_id:10d}", "ITEM: BOX BOUNDS pp pp pp"]
+    head += [f"{-m[d, d] / 2:15.8f} {m[d, d] / 2:15.8f}" for d in range(3)]
+    head.append("ITEM: ATOMS id type x y z")
+    return "\n".join(head + rows) + "\n"

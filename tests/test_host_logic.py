@@ -185,3 +185,27 @@ def test_output_lines_follow_the_fortran_formats(tmp_path):
     assert (tmp_path / "w0" / "energy.dat").read_text().splitlines() == [out.ENERGY_HEADER, out.energy_line(0, e), out.energy_line(1, e)]
     assert (tmp_path / "w0" / "number_wat.dat").read_text().splitlines()[1:] == [out.number_line(0, 114), out.number_line(1, 114)]
     assert len((tmp_path / "w0" / "moves.dat").read_text().splitlines()) == 3
+
+
+def test_lammpstrj_frame_and_wrap():
+    """write_dump_lammpstrj (src/write_utils.f90:38-119) + wrap_into_box (src/geometry_utils.f90:105-140, the values of
+    tests/units/test_wrap_into_box.f90's style: nint wrapping into [-L/2, L/2])."""
+    from maniac_b200 import outputs as out
+    m = np.diag([10.0, 20.0, 30.0])
+    np.testing.assert_allclose(out.wrap_into_box([6.0, -11.0, 44.0], m), [-4.0, 9.0, 14.0], atol=1e-12)
+    np.testing.assert_allclose(out.wrap_into_box([5.0, -10.0, 0.0], m), [-5.0, 10.0, 0.0], atol=1e-12)     # nint: halves away from zero
+    tri = np.array([[10.0, 0.0, 0.0], [2.0, 10.0, 0.0], [0.0, 0.0, 10.0]])
+    p = out.wrap_into_box([17.0, 3.0, -6.0], tri)
+    f = out._reciprocal(tri) @ p
+    assert (np.abs(f) <= 0.5 + 1e-12).all()
+    residues = [dict(active=False, types=[3, 4], com=np.array([[0.0, 0.0, 0.0]]), offset=np.array([[[1.0, 0.0, 0.0], [6.0, 0.0, 0.0]]])),
+                dict(active=True, types=[1, 2, 2])]
+    mol = {1: dict(com=np.array([[7.0, 0.0, 0.0]]), offset=np.array([[[0.0, 0.0, 0.0], [0.5, 0.0, 0.0], [-0.5, 0.0, 0.0]]]))}
+    txt = out.lammpstrj_frame(12, m, residues, mol).splitlines()
+    assert txt[0] == "ITEM: TIMESTEP" and txt[1] == "        12" and txt[3] == "         5"
+    assert txt[5] == "    -5.00000000      5.00000000"
+    assert txt[8] == "ITEM: ATOMS id type x y z"
+    assert txt[9] == "     1    3    1.0000000    0.0000000    0.0000000"
+    assert txt[10] == "     2    4   -4.0000000    0.0000000    0.0000000"          # inactive: the ATOM is wrapped
+    assert txt[11] == "     3    1   -3.0000000    0.0000000    0.0000000"          # active: the CoM is wrapped, atoms follow it
+    assert txt[12] == "     4    2   -2.5000000    0.0000000    0.0000000"
