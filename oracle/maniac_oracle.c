@@ -7,6 +7,18 @@
  * known quirks of the reference are preserved on purpose; nothing here is
  * tuned.  Build: gcc -O2 -ffp-contract=off (no FMA contraction, like the
  * reference's x86-64 gfortran build).
+ *
+ * Pinning.  PINNED on every golden value the reference's own tests hold for this
+ * path (tests/golden/kat.json, tests/test_oracle_golden.py): total energies vs
+ * LAMMPS (LJ-gas, ZIF8-H2O, H2O-gas), the three analytic cases, the methanol
+ * create / delete values, the 150-move drift gate, the minimum-image / PBC unit
+ * values -- inside the reference's own tolerances.  PARITY UNPINNED (the
+ * reference holds no test for them and cannot be built here: Fortran only, no
+ * Fortran compiler in the image): per-move dE, accept / reject sequences, swap
+ * moves, triclinic energies, step-size adaptation, Widom weights.  For those the
+ * oracle is a careful reading of the Fortran, nothing more.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's CPU legs may load this.
  */
 #include "maniac_oracle.h"
 
