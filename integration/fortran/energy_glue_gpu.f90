@@ -99,6 +99,37 @@ contains
         call unpack_energy(buf, energy)
     end subroutine update_system_energy
 
+    !> attempt_swap_move (swapping.f90:59-88): the two energy calls of a swap and what lies between them.  Called in
+    !> swapping.f90 after insert_and_orient_molecule(residue_type_bis, molecule_index_bis, ..., place_random_com=.false.)
+    !> has written the new molecule; replaces compute_old_energy(..., is_deletion) + remove_molecule + the count updates
+    !> + compute_new_energy(..., is_creation).  accept_swap_move -> gpu_accept, reject_swap_move -> gpu_reject.
+    subroutine compute_swap_energies(res_type, mol_index, res_type_bis, mol_index_bis)
+        integer, intent(in) :: res_type, mol_index, res_type_bis, mol_index_bis
+        real(c_double) :: buf_old(6), buf_new(6), com(3), off(3, MGPU_MAX_SITES)
+        integer :: n
+        n = res%atom(res_type_bis)
+        com = guest%com(:, res_type_bis, mol_index_bis)
+        off = 0.0_real64
+        off(:, 1:n) = guest%offset(:, res_type_bis, mol_index_bis, 1:n)
+        call mgpu_check(mgpu_swap_energy(WALKER0, int(res_type - 1, c_int32_t), int(mol_index - 1, c_int32_t), &
+                                         int(res_type_bis - 1, c_int32_t), com, off, buf_old, buf_new))
+        call unpack_energy(buf_old, old)
+        call unpack_energy(buf_new, new)
+    end subroutine compute_swap_energies
+
+    !> one block of monte_carlo_loop (monte_carlo.f90:40-118) for n_walkers device-resident walkers: nb_step MC steps with
+    !> the device-side drivers, then the walkers' records (counts, energies, counters, coordinates, ewald%Ak) in HOST memory
+    !> for the per-block writers (write_utils.f90:16-34), then adjust_move_step_sizes (monte_carlo_utils.f90:98-134).
+    subroutine gpu_block(n_walkers, nb_step, blob, capacity, offsets)
+        integer, intent(in) :: n_walkers, nb_step
+        integer(c_int64_t), intent(in) :: capacity
+        real(c_double), intent(out) :: blob(*)
+        integer(c_int64_t), intent(out) :: offsets(*)
+        call mgpu_check(mgpu_block(0_c_int32_t, int(n_walkers, c_int32_t), int(nb_step, c_int64_t), c_null_ptr, c_null_ptr, &
+                                   blob, capacity, offsets))
+        if (mc_input%recalibrate_moves) call mgpu_check(mgpu_adjust_move_step_sizes(0_c_int32_t, int(n_walkers, c_int32_t)))
+    end subroutine gpu_block
+
     !> widom.f90: n independent test insertions in one launch instead of n calls
     !> of widom_trial; accumulates statistic%weight / statistic%sample (:74-92).
     subroutine widom_batch(res_type, n, seed)

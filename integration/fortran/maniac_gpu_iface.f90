@@ -20,7 +20,7 @@ module maniac_gpu_iface
     implicit none
 
     integer(c_int), parameter :: MGPU_MAX_RES = 8, MGPU_MAX_SITES = 16
-    integer(c_int), parameter :: MGPU_KIND_MOVE = 0, MGPU_KIND_CREATE = 1, MGPU_KIND_DELETE = 2
+    integer(c_int), parameter :: MGPU_KIND_MOVE = 0, MGPU_KIND_CREATE = 1, MGPU_KIND_DELETE = 2, MGPU_KIND_SWAP = 3
 
     ! mgpu_residue, include/maniac_gpu.h:61-73
     type, bind(C) :: mgpu_residue
@@ -118,6 +118,10 @@ module maniac_gpu_iface
             type(c_ptr), value :: blob_in, offsets_in       ! c_null_ptr = continue from the device-resident state
             real(c_double), intent(out) :: blob_out(*)
             integer(c_int64_t), intent(out) :: offsets_out(*)
+        end function
+        integer(c_int) function mgpu_adjust_move_step_sizes(first_walker, n_walkers) bind(C, name="mgpu_adjust_move_step_sizes")
+            import :: c_int, c_int32_t
+            integer(c_int32_t), value :: first_walker, n_walkers
         end function
         integer(c_int) function mgpu_commit(walker) bind(C, name="mgpu_commit")
             import :: c_int, c_int32_t
