@@ -5,7 +5,7 @@ Contract (driver):  python bench.py --gpus N --steps K --warmup W     (N > 1 via
 prints ONE JSON line on rank 0.
 
   step      one launch of the device-resident sweep kernel: INNER Monte Carlo steps for every
-            walker of this rank (one CTA per walker, zero host round trips inside the launch)
+            walker of this rank (one warp per walker, zero host round trips inside the launch)
   workload  BASELINE.json configs[1]: ZIF-8 2x2x2 + TIP4P water GCMC, move mix 0.4/0.4/0.2
             (translate / rotate / insert-delete), 64 waters per walker initially, walkers
             spread over a 64-point fugacity grid (the isotherm sweep of configs[3])
@@ -16,8 +16,16 @@ prints ONE JSON line on rank 0.
             and the updated state travels back; wall clock
   host_driven  the Fortran drivers' role: host RNG / proposal / Metropolis, one mgpu_trial_batch +
             mgpu_commit_batch per MC step (proposals H2D, energies D2H)
+  single_walker_dropin  one walker, one trial per call: the latency one unchanged Fortran process sees
   roofline  the sweep kernel against the FP64-pipe peak measured on this GPU by a DFMA loop
-            (the binding roof of K1; SURVEY.md 8d convention C1 for the algorithmic FLOPs)
+            (the binding roof of K1; SURVEY.md 8d convention C1): frac = C1 FLOPs of the pairs
+            EVALUATED; frac_reference_ops = the reference's full operation count per move at this
+            rate (the framework-energy cache and the per-molecule screen skip pairs); traffic =
+            DRAM bytes per launch from the committed ncu capture
+  no_host_cache / no_phase_sync   the same sweep with MGPU_OPT_HOST_CACHE / MGPU_OPT_PHASE_SYNC off
+  widom     BASELINE configs[2]: 10^6 CO2 test insertions in empty ZIF-8, one launch
+  mixture   BASELINE configs[4]: CO2/N2 with identity swaps in the 17 664-atom triclinic supercell
+  isotherm  per-point averages summed over ranks by the library's NCCL reduction (the one exchange)
   cpu_baseline  the CPU oracle (a C restatement of the reference's serial algorithm) on the
             host cores, bounded sample of the same workload
   --impl reference   times that CPU path as the main line (no Fortran compiler in the image,

@@ -47,6 +47,10 @@ __constant__ DevSys c_sys;
 #define MGPU_STAGE 0
 #endif
 #define MGPU_STAGE_BYTES 2048            // per warp: 2 stages x 32 lanes x {xy, zq}
+// framework atoms per thread and iteration in the 3-probe-atom passes (1: three pair chains per thread; 2: six)
+#ifndef MGPU_HOST_U3
+#define MGPU_HOST_U3 1
+#endif
 #ifndef MGPU_SCREEN_NOTHING
 #define MGPU_SCREEN_NOTHING 1
 #endif
@@ -704,7 +708,7 @@ __device__ __forceinline__ void host_list(const Smem &S, const Probe &P, const d
     // chunks of at most 3 probe atoms: ~3 independent pair chains per thread fit the 128-register budget
     for (int base = 0; base < n; base += 3) {
         const int m = min(3, n - base);
-        if (m == 3) { HostPass<TRI, MODE, 3, 1, REP> hp; hp.load(P, pos, list + base); hp.run(t0, stride, e_lj, e_c, pc, S.stage); }
+        if (m == 3) { HostPass<TRI, MODE, 3, MGPU_HOST_U3, REP> hp; hp.load(P, pos, list + base); hp.run(t0, stride, e_lj, e_c, pc, S.stage); }
         else if (m == 2) { HostPass<TRI, MODE, 2, 1, REP> hp; hp.load(P, pos, list + base); hp.run(t0, stride, e_lj, e_c, pc, S.stage); }
         else { HostPass<TRI, MODE, 1, 3, REP> hp; hp.load(P, pos, list + base); hp.run(t0, stride, e_lj, e_c, pc); }
     }
