@@ -196,7 +196,7 @@ int mgpu_commit_batch(int32_t n, const int32_t *walker, const int32_t *accept);
 
 /* ---- device-resident Monte Carlo (new capability; drivers of src/translation.f90,
  * rotation.f90, creation.f90, deletion.f90, widom.f90 and the loop body of
- * src/monte_carlo.f90:50-99 run on the GPU, one CTA per walker) ------------------------ */
+ * src/monte_carlo.f90:50-99 run on the GPU, one warp per walker; incl. swapping.f90 when p_swap > 0) ---- */
 typedef struct mgpu_step_trace {
     int32_t move, res, mol, accepted;
     double  dE, prob;
