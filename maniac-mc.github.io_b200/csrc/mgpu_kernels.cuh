@@ -900,11 +900,14 @@ __device__ double intra_energy(int res, const double (*pos)[3])
 // compute_atom_phase (ewald_phase.f90:255-280) + compute_phase_factor (:286-312).  One
 // sincos per (atom, dim); higher k by repeated complex multiplication (the reference calls
 // cos/sin per k; the two agree to ~k ulp).  tab layout: [atom][dim][k], stride KW = kmax_max+1.
-__device__ __forceinline__ void fill_phase_tables(double2 *tab, const double (*pos)[3], int n, int tid0, int nthreads)
+// qskip (optional): per-atom charges; atoms whose charge is exactly 0 add exactly nothing to S(k) in the reference
+// (q * phase), so their tables are neither filled nor read (TIP4P oxygen: a quarter of the molecule's k-space work).
+__device__ __forceinline__ void fill_phase_tables(double2 *tab, const double (*pos)[3], int n, int tid0, int nthreads, const double *qskip = nullptr)
 {
     const int KW = c_sys.kmax_max + 1;
     for (int e = tid0; e < n * 3; e += nthreads) {
         const int d = e % 3, a = e / 3;
+        if (qskip && qskip[a] == 0.0) continue;
         double ph = 0.0;
 #pragma unroll
         for (int j = 0; j < 3; ++j) ph = __dadd_rn(ph, __dmul_rn(c_sys.Hinv[j * 3 + d], pos[a][j]));
@@ -960,6 +963,7 @@ __device__ double kspace(const Smem &S, const double *S_in, double *S_out)
         double sr = 0.0, si = 0.0;
         for (int a = 0; a < na; ++a) {
             const double q = c_sys.charge[P.res][a];
+            if (q == 0.0) continue;                          // adds exactly nothing (and its tables were not filled)
             if (kind != MGPU_KIND_DELETE) { const cplx pn = phase_product(S.tab_new, a, kx, ky, kz); sr += q * pn.re; si += q * pn.im; }
             if (kind != MGPU_KIND_CREATE) { const cplx po = phase_product(S.tab_old, a, kx, ky, kz); sr -= q * po.re; si -= q * po.im; }
         }
@@ -1055,8 +1059,8 @@ __device__ void evaluate_trial(const Smem &S, int w, bool store_S, double e_old[
     const double recip_cur = c_sys.energy[(int64_t)w * 6 + MGPU_E_RECIP];
     double recip_new = recip_cur;
     if (do_kspace) {
-        if (P.has_old) fill_phase_tables(S.tab_old, P.po, P.na, Grp<NT>::tid(), NT);
-        if (P.has_new) fill_phase_tables(S.tab_new, P.pn, P.na, Grp<NT>::tid(), NT);
+        if (P.has_old) fill_phase_tables(S.tab_old, P.po, P.na, Grp<NT>::tid(), NT, c_sys.charge[P.res]);
+        if (P.has_new) fill_phase_tables(S.tab_new, P.pn, P.na, Grp<NT>::tid(), NT, c_sys.charge[P.res]);
         Grp<NT>::sync();
         const int cur = c_sys.cur[w];
         const double *S_in = c_sys.S + ((int64_t)w * 2 + cur) * 2 * c_sys.nk;
