@@ -59,7 +59,7 @@ def parse():
     ap.add_argument("--walkers", type=int, default=4736, help="walkers per GPU (weak scaling); 4736 = 2 x 148 SMs x 16 warps")
     ap.add_argument("--inner", type=int, default=INNER_DEFAULT, help="MC steps per walker per launch")
     ap.add_argument("--loading", type=int, default=64, help="initial waters per walker")
-    ap.add_argument("--e2e-walkers", type=int, default=1024)
+    ap.add_argument("--e2e-walkers", type=int, default=2368, help="walkers of the host-driven leg (2368 = one warp-per-trial wave: 148 SMs x 16 warps)")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--widom", type=int, default=1_000_000, help="insertions in the Widom batch (0 = skip)")
     ap.add_argument("--mixture-walkers", type=int, default=2368, help="walkers of the configs[4] leg (0 = skip)")

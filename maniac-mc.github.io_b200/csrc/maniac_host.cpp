@@ -2,10 +2,14 @@
 // The role of src/monte_carlo.f90:50-99 + translation/rotation/creation/deletion/widom.f90:
 // propose on the host, ask the GPU for old/new energies, apply the acceptance rule of
 // src/monte_carlo_utils.f90:204-255, commit or roll back.  Only mgpu_* exports are used.
+#include <atomic>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/maniac_host.h"
@@ -70,6 +74,58 @@ struct mhost_sim {
 
 namespace {
 int hfail(const std::string &m) { h_err = m; return 1; }
+
+// The host loops of a step (propose, fill the batch, decide) touch one walker each and walkers share nothing, so they
+// are split over a small team of threads.  The team only lives inside mhost_run and spins between the three loops of a
+// step (a condition-variable wake-up costs as much as the loop it would start); results do not depend on the split.
+class Team {
+public:
+    explicit Team(int n) : nt_(n < 1 ? 1 : n)
+    {
+        for (int t = 1; t < nt_; ++t) th_.emplace_back([this, t] { work(t); });
+    }
+    ~Team()
+    {
+        stop_.store(true, std::memory_order_release);
+        gen_.fetch_add(1, std::memory_order_acq_rel);
+        for (auto &t : th_) t.join();
+    }
+    void run(int n, const std::function<void(int)> &fn)
+    {
+        if (nt_ == 1 || n < 64) { for (int i = 0; i < n; ++i) fn(i); return; }
+        fn_ = &fn; n_ = n;
+        done_.store(0, std::memory_order_relaxed);
+        gen_.fetch_add(1, std::memory_order_acq_rel);
+        chunk(0);
+        while (done_.load(std::memory_order_acquire) != nt_ - 1) { }
+    }
+private:
+    void chunk(int t) const { const int lo = (int)((long long)n_ * t / nt_), hi = (int)((long long)n_ * (t + 1) / nt_); for (int i = lo; i < hi; ++i) (*fn_)(i); }
+    void work(int t)
+    {
+        unsigned seen = 0;
+        for (;;) {
+            unsigned g;
+            while ((g = gen_.load(std::memory_order_acquire)) == seen) { }
+            seen = g;
+            if (stop_.load(std::memory_order_acquire)) return;
+            chunk(t);
+            done_.fetch_add(1, std::memory_order_acq_rel);
+        }
+    }
+    int nt_, n_ = 0;
+    const std::function<void(int)> *fn_ = nullptr;
+    std::vector<std::thread> th_;
+    std::atomic<unsigned> gen_{0};
+    std::atomic<int> done_{0};
+    std::atomic<bool> stop_{false};
+};
+int team_size()
+{
+    if (const char *e = std::getenv("MHOST_THREADS")) return std::atoi(e);
+    const unsigned hw = std::thread::hardware_concurrency();
+    return (int)(hw >= 16 ? 8 : hw >= 4 ? hw / 2 : 1);
+}
 
 void apply_PBC(const mhost_sim *S, double pos[3])      // geometry_utils.f90:45-97
 {
@@ -156,6 +212,9 @@ void mhost_destroy(mhost_sim *S) { delete S; }
 int mhost_run(mhost_sim *S, int64_t n_steps, int32_t trace_walker, mgpu_step_trace *trace)
 {
     const int nw = S->nw;
+    Team team(nw >= 64 ? team_size() : 1);
+    std::atomic<int> overflow{0};
+    std::vector<int> slot(nw, 0);
     S->b_walker.resize(nw); S->b_res.resize(nw); S->b_mol.resize(nw); S->b_kind.resize(nw); S->b_accept.resize(nw);
     S->b_com.resize((size_t)3 * nw); S->b_off.resize((size_t)3 * MGPU_MAX_SITES * nw);
     S->b_eold.resize((size_t)6 * nw); S->b_enew.resize((size_t)6 * nw);
@@ -163,7 +222,7 @@ int mhost_run(mhost_sim *S, int64_t n_steps, int32_t trace_walker, mgpu_step_tra
     for (int64_t step = 0; step < n_steps; ++step) {
         int nb = 0;
         // ---- propose (host), monte_carlo.f90:53-99 ----
-        for (int w = 0; w < nw; ++w) {
+        const std::function<void(int)> propose_one = [&](int w) {
             Walker &W = S->w[w];
             Pending &P = S->pend[w];
             P.valid = 0; P.move = MGPU_MV_NONE;
@@ -200,7 +259,7 @@ int mhost_run(mhost_sim *S, int64_t n_steps, int32_t trace_walker, mgpu_step_tra
                 }
                 if (res_bis >= 0 && W.count[res_bis] > 0 && mol >= 0) {
                     const int nb2 = W.count[res_bis], nab = S->res[res_bis].natom;
-                    if (nb2 >= S->res[res_bis].cap) return hfail("Trying to insert a molecule beyond the walker's capacity");
+                    if (nb2 >= S->res[res_bis].cap) { overflow.store(1); return; }
                     P.valid = 1; P.move = MGPU_MV_SWAP; P.kind = MGPU_KIND_SWAP; P.res2 = res_bis;
                     std::memcpy(P.com, com + 3 * mol, sizeof(double) * 3);                        // same CoM (:80)
                     std::memcpy(P.off, W.off[res_bis].data(), sizeof(double) * 3 * nab);          // geometry of molecule 1 of the new type
@@ -215,7 +274,7 @@ int mhost_run(mhost_sim *S, int64_t n_steps, int32_t trace_walker, mgpu_step_tra
                 if (S->p_insdel > 0) { if (W.rng.uniform() <= 0.5) create = true; else del = true; }
                 else if (S->p_widom > 0) widom = true;
                 if (create || widom) {
-                    if (n >= cap) return hfail("Trying to insert a molecule beyond the walker's capacity");
+                    if (n >= cap) { overflow.store(1); return; }
                     P.valid = 1; P.move = widom ? MGPU_MV_WIDOM : MGPU_MV_CREATE; P.kind = MGPU_KIND_CREATE; P.mol = n;
                     double t3[3];
                     for (int d = 0; d < 3; ++d) t3[d] = W.rng.uniform();
@@ -233,16 +292,23 @@ int mhost_run(mhost_sim *S, int64_t n_steps, int32_t trace_walker, mgpu_step_tra
                     if (n > 0) { P.valid = 1; P.move = MGPU_MV_DELETE; P.kind = MGPU_KIND_DELETE; }
                 }
             }
-            if (P.valid) {
-                S->b_walker[nb] = w; S->b_res[nb] = P.res; S->b_mol[nb] = P.mol;
-                S->b_kind[nb] = (P.kind == MGPU_KIND_SWAP) ? (MGPU_KIND_SWAP | (P.res2 << 8)) : P.kind;
-                std::memcpy(&S->b_com[(size_t)3 * nb], P.com, sizeof(double) * 3);
-                std::memset(&S->b_off[(size_t)3 * MGPU_MAX_SITES * nb], 0, sizeof(double) * 3 * MGPU_MAX_SITES);
-                const int na_new = (P.kind == MGPU_KIND_SWAP) ? S->res[P.res2].natom : na;
-                if (P.kind != MGPU_KIND_DELETE) std::memcpy(&S->b_off[(size_t)3 * MGPU_MAX_SITES * nb], P.off, sizeof(double) * 3 * na_new);
-                ++nb;
-            }
-        }
+        };
+        team.run(nw, propose_one);
+        if (overflow.load()) return hfail("Trying to insert a molecule beyond the walker's capacity");
+        // batch slots in walker order, then the copies in parallel
+        for (int w = 0; w < nw; ++w) if (S->pend[w].valid) slot[w] = nb++;
+        const std::function<void(int)> fill_one = [&](int w) {
+            const Pending &P = S->pend[w];
+            if (!P.valid) return;
+            const int b = slot[w], na = S->res[P.res].natom;
+            S->b_walker[b] = w; S->b_res[b] = P.res; S->b_mol[b] = P.mol;
+            S->b_kind[b] = (P.kind == MGPU_KIND_SWAP) ? (MGPU_KIND_SWAP | (P.res2 << 8)) : P.kind;
+            std::memcpy(&S->b_com[(size_t)3 * b], P.com, sizeof(double) * 3);
+            std::memset(&S->b_off[(size_t)3 * MGPU_MAX_SITES * b], 0, sizeof(double) * 3 * MGPU_MAX_SITES);
+            const int na_new = (P.kind == MGPU_KIND_SWAP) ? S->res[P.res2].natom : na;
+            if (P.kind != MGPU_KIND_DELETE) std::memcpy(&S->b_off[(size_t)3 * MGPU_MAX_SITES * b], P.off, sizeof(double) * 3 * na_new);
+        };
+        team.run(nw, fill_one);
         // ---- energies (GPU): compute_old_energy + compute_new_energy for every walker ----
         if (nb) {
             if (mgpu_trial_batch(nb, S->b_walker.data(), S->b_res.data(), S->b_mol.data(), S->b_kind.data(), S->b_com.data(),
@@ -252,7 +318,7 @@ int mhost_run(mhost_sim *S, int64_t n_steps, int32_t trace_walker, mgpu_step_tra
             S->trials += nb;
         }
         // ---- Metropolis (host), monte_carlo_utils.f90:204-255 ----
-        for (int b = 0; b < nb; ++b) {
+        const std::function<void(int)> decide_one = [&](int b) {
             const int w = S->b_walker[b];
             Walker &W = S->w[w];
             Pending &P = S->pend[w];
@@ -318,7 +384,8 @@ int mhost_run(mhost_sim *S, int64_t n_steps, int32_t trace_walker, mgpu_step_tra
                 t.move = P.move; t.res = P.res; t.mol = P.mol; t.accepted = acc; t.dE = dU; t.prob = p;
                 std::memcpy(t.e_old, eo, sizeof t.e_old); std::memcpy(t.e_new, en, sizeof t.e_new);
             }
-        }
+        };
+        team.run(nb, decide_one);
         if (trace && trace_walker >= 0 && trace_walker < nw && !S->pend[trace_walker].valid) {
             mgpu_step_trace &t = trace[step];
             std::memset(&t, 0, sizeof t);
