@@ -961,7 +961,8 @@ int mgpu_commit_batch(int32_t n, const int32_t *walker, const int32_t *accept)
     CK(cudaMemcpyAsync(g.d_accept, g.hc_accept, sizeof(int32_t) * n, cudaMemcpyHostToDevice, g.stream));
     k_commit<<<n, 128, 0, g.stream>>>(g.d_task_i, g.d_accept, g.d_err);
     CK(cudaGetLastError());
-    return check_err_flag("mgpu_commit");
+    g.commit_inflight = true;                    // queued like the latency path: the host mirror above already ruled out the one device-side error
+    return 0;
 }
 
 int mgpu_old_energy(int32_t w, int32_t res, int32_t mol, int32_t kind, double out[6])
