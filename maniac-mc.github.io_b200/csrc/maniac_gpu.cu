@@ -49,7 +49,7 @@ struct Context {
     int natom_max = 1;
     size_t smem1 = 0, smem8 = 0, smem_buildS = 0;   // dynamic shared memory: 1 group (CTA) / MGPU_WARPS groups (warps) per CTA
     int sm_count = 0, ctas_per_sm = 1;
-    int phase_sync = 3;                // MGPU_OPT_PHASE_SYNC: bit 0 = barrier at the top of the MC step, bit 1 = before the energy evaluation
+    int phase_sync = 13;               // MGPU_OPT_PHASE_SYNC bits: 1 top of the MC step, 2 before the energy evaluation, 4 before the guest pass, 8 before k-space
     int tri_listed = 0;                // triclinic: candidates listed but provably irrelevant (see mgpu_init)
     int wgroups = MGPU_WGROUPS;        // walkers (warps) per CTA of the warp-per-task kernels
     int tab_emin = 0, tab_noct = 0;
@@ -802,7 +802,7 @@ int mgpu_get_energy(int32_t w, double out[6])
 int mgpu_set_option(int32_t option, int32_t value)
 {
     NEED_READY();
-    if (option == MGPU_OPT_PHASE_SYNC) { g.phase_sync = (value == 1) ? 3 : (value & 3); return 0; }
+    if (option == MGPU_OPT_PHASE_SYNC) { g.phase_sync = (value == 1) ? 13 : (value & 15); return 0; }   // bits: 1 top of step, 2 before the evaluation, 4 before the guest pass, 8 before k-space
     if (option == MGPU_OPT_HOST_CACHE) {
         g.h.use_hcache = value ? 1 : 0;
         if (upload_sys()) return 1;

@@ -350,6 +350,7 @@ struct WalkerLocal {
 struct GroupWS {
     Probe probe;
     int32_t count[MGPU_MAX_RES];
+    int32_t sync_q, sync_k;                 // k_sweep: threads of this warp's quartet if the quartet re-aligns before the guest pass / before k-space, else 0
     SweepShared sh;
     WalkerLocal loc;
     double red[8 * MGPU_WARPS];
@@ -407,7 +408,7 @@ __device__ __forceinline__ Smem smem_setup(unsigned char *base, int natom_max, i
     unsigned char *g = base + smem_common_bytes(c_sys.ntypes, c_sys.tab_nint, REP) + (size_t)group * smem_group_bytes(c_sys.kmax_max, natom_max, REP);
     s.ws = reinterpret_cast<GroupWS *>(g);
     double (*ppos)[3] = reinterpret_cast<double (*)[3]>(g + smem_ws_bytes(REP > 1));
-    if ((REP > 1) ? ((threadIdx.x & 31) == 0) : (threadIdx.x == 0)) { s.ws->probe.po = ppos; s.ws->probe.pn = ppos + natom_max; }
+    if ((REP > 1) ? ((threadIdx.x & 31) == 0) : (threadIdx.x == 0)) { s.ws->probe.po = ppos; s.ws->probe.pn = ppos + natom_max; s.ws->sync_q = 0; s.ws->sync_k = 0; }
     s.tab_old = reinterpret_cast<double2 *>(g + smem_ws_bytes(REP > 1) + ((sizeof(double) * 2 * 3 * (size_t)natom_max + 15) & ~size_t(15)));
     s.tab_new = s.tab_old + (size_t)natom_max * 3 * (c_sys.kmax_max + 1);
     s.stage = nullptr;
@@ -825,6 +826,12 @@ __device__ __forceinline__ void guest_loops(const Probe &P, const double (*pos)[
     }
 }
 
+// named barrier of the four warps that share an SM sub-partition (see k_sweep)
+__device__ __forceinline__ void quartet_sync(int nthreads_in_quartet)
+{
+    asm volatile("bar.sync %0, %1;" :: "r"(1 + (int)((threadIdx.x >> 5) & 3)), "r"(nthreads_in_quartet) : "memory");
+}
+
 // K1: group-cooperative pair sums of the probe against host atoms + the walker's guests.
 // When two geometries need the same kind of pass (old AND new of a move) the group splits in
 // two halves, one per geometry, so every thread works on a single geometry; otherwise the
@@ -851,6 +858,7 @@ __device__ __noinline__ void pair_sums(const Smem &S, int w, double (&out)[8], P
         acc[0] = new_set ? 0.0 : e_lj; acc[1] = new_set ? 0.0 : e_c;
         acc[2] = new_set ? e_lj : 0.0; acc[3] = new_set ? e_c : 0.0;
     }
+    if (NT == 32 && S.ws->sync_q) quartet_sync(S.ws->sync_q);     // k_sweep, MGPU_OPT_PHASE_SYNC bit 2: re-align before the guest pass
     {
         const bool both = P.has_old && P.has_new;
         const bool new_set = both ? (gt >= NT / 2) : (P.has_new != 0);
@@ -1059,6 +1067,7 @@ __device__ void evaluate_trial(const Smem &S, int w, bool store_S, double e_old[
     const double recip_cur = c_sys.energy[(int64_t)w * 6 + MGPU_E_RECIP];
     double recip_new = recip_cur;
     if (do_kspace) {
+        if (NT == 32 && S.ws->sync_k) quartet_sync(S.ws->sync_k);      // k_sweep, MGPU_OPT_PHASE_SYNC bit 3: re-align before k-space
         if (P.has_old) fill_phase_tables(S.tab_old, P.po, P.na, Grp<NT>::tid(), NT, c_sys.charge[P.res]);
         if (P.has_new) fill_phase_tables(S.tab_new, P.pn, P.na, Grp<NT>::tid(), NT, c_sys.charge[P.res]);
         Grp<NT>::sync();
@@ -1159,9 +1168,13 @@ __device__ void evaluate_swap(const Smem &S, int w, bool store_S, int resA, int 
 {
     double e_tmp[6], hc_tmp[2];
     stage_probe<NT>(S, w, MGPU_KIND_DELETE, resA, molA, nullptr, nullptr);
+    const int sq = S.ws->sync_q;                     // one quartet barrier per MC step inside pair_sums: the creation half takes it
+    Grp<NT>::sync();
+    if (Grp<NT>::tid() == 0) S.ws->sync_q = 0;
     Grp<NT>::sync();
     evaluate_trial<TRI, NT>(S, w, false, e_old, e_tmp, hc_tmp, pc, false);
     Grp<NT>::sync();
+    if (Grp<NT>::tid() == 0) S.ws->sync_q = sq;
     stage_probe<NT>(S, w, MGPU_KIND_CREATE, resB, molB, com, off, resA, molA);
     Grp<NT>::sync();
     evaluate_trial<TRI, NT>(S, w, store_S, e_tmp, e_new, hc_new, pc, true);
@@ -1663,16 +1676,13 @@ __device__ __noinline__ void decide_step(int w, GroupWS &ws, const double e_old[
 // Phase alignment.  The four warps with the same (warp id mod 4) share an SM sub-partition, i.e. its
 // issue port and its ~6 KB L0 instruction cache.  Left alone, the walkers of a CTA drift apart in the
 // MC step (the r01k profile: 46 % of all stall samples were "no instruction", in every loop), because
-// four warps in four different loops evict each other's code.  A named barrier per quartet at the top
-// of every MC step (and again before the energy evaluation) keeps those four warps in the same loop at
-// the same time; quartets stay independent of each other, and a walker's serial section (lane 0:
-// RNG, proposal, Metropolis) still only idles its own quartet for as long as the quartet's slowest
-// proposal.
-__device__ __forceinline__ void quartet_sync(int nthreads_in_quartet)
-{
-    asm volatile("bar.sync %0, %1;" :: "r"(1 + (int)((threadIdx.x >> 5) & 3)), "r"(nthreads_in_quartet) : "memory");
-}
-
+// four warps in four different loops evict each other's code.  Named barriers per quartet keep those
+// four warps in the same loop at the same time: at the top of every MC step, before the guest pass
+// (in pair_sums) and before k-space (in evaluate_trial); a barrier before the energy evaluation is
+// available too.  Measured (moves/s): none 10.9 M, top only 20.3 M, top + evaluation 20.6 M,
+// + guest pass 21.8 M, + k-space 22.7 M, top + guest pass + k-space 22.8 M (default).  Quartets stay
+// independent of each other; a step that evaluates nothing takes the same barriers, and a swap (two
+// evaluations) takes them in its creation half, so every warp of a quartet arrives equally often.
 template <bool TRI>
 __global__ void __launch_bounds__(MGPU_WBLOCK, 1) k_sweep(int first_walker, int n_walkers, long long n_steps, int natom_max,
                                                       int trace_walker, mgpu_step_trace *trace, int32_t *err, int phase_sync)
@@ -1693,17 +1703,19 @@ __global__ void __launch_bounds__(MGPU_WBLOCK, 1) k_sweep(int first_walker, int 
         if (lane < MGPU_MAX_RES) { ws.loc.avgN[lane] = 0.0; ws.loc.avgN2[lane] = 0.0; }
         if (lane == 0) { ws.loc.avgE = 0.0; ws.loc.n_samples = 0; }
     }
-    if (lane == 0) ws.sh.valid = 0;
+    if (lane == 0) { ws.sh.valid = 0; ws.sync_q = (phase_sync & 4) ? qthreads : 0; ws.sync_k = (phase_sync & 8) ? qthreads : 0; }
     PairCount pc = { 0u, 0u, 0u, 0u };
     __syncwarp();
 
     for (long long step = 0; step < n_steps; ++step) {
         if (phase_sync & 1) quartet_sync(qthreads);
-        if (!live) { if (phase_sync & 2) quartet_sync(qthreads); continue; }
+        if (!live) { if (phase_sync & 2) quartet_sync(qthreads); if (phase_sync & 4) quartet_sync(qthreads); if (phase_sync & 8) quartet_sync(qthreads); continue; }
         if (lane == 0) propose_step(w, ws, err);
         __syncwarp();
         if (phase_sync & 2) quartet_sync(qthreads);
         const SweepShared &sh = ws.sh;
+        if (!sh.valid && (phase_sync & 4)) quartet_sync(qthreads);       // the barrier pair_sums would have taken
+        if (!sh.valid && (phase_sync & 8)) quartet_sync(qthreads);       // ... and the one before k-space
         if (sh.valid) {
             double e_old[6], e_new[6], hc_new[2];
             if (sh.kind == MGPU_KIND_SWAP) {
