@@ -102,3 +102,29 @@ def test_plan_layout():
             assert (blk == blk[0]).all()
             assert len(set(pts.tolist())) == 64
         assert seen[0] == 0 and seen[-1] == 4736 * world - 1
+
+
+def test_summarize_and_isotherm_table(tmp_path):
+    sys.path.insert(0, str(ROOT))
+    import maniac_b200  # noqa: F401
+    from maniac_b200.isotherm import IsothermPlan, summarize
+    from maniac_b200.outputs import write_isotherm
+    plan = IsothermPlan(n_points=4, walkers_per_rank=32, world_size=1, rank=0)
+    per_walker = np.zeros((32, 6))
+    pts = plan.points()
+    per_walker[:, 0] = 10.0 * (pts + 1) * 5          # sum N over 5 samples, N = 10 (point + 1)
+    per_walker[:, 1] = (10.0 * (pts + 1)) ** 2 * 5
+    per_walker[:, 2] = -3.0 * 5
+    per_walker[:, 3] = 5
+    per_walker[:, 4] = 0.25 * 7
+    per_walker[:, 5] = 7
+    sums = plan.accumulate(per_walker)
+    s = summarize(sums, beta=2.0)
+    np.testing.assert_allclose(s["mean_N"], [10, 20, 30, 40])
+    np.testing.assert_allclose(s["var_N"], 0.0, atol=1e-9)
+    np.testing.assert_allclose(s["mean_E"], -3.0)
+    np.testing.assert_allclose(s["mu_ex"], -np.log(0.25) / 2.0)
+    assert s["samples"].sum() == 32 * 5
+    write_isotherm(tmp_path / "isotherm.dat", [1e-2, 1e-1, 1.0, 10.0], s)
+    lines = (tmp_path / "isotherm.dat").read_text().splitlines()
+    assert len(lines) == 5 and lines[0].startswith("#") and lines[2].split()[1] == "20.000000"
