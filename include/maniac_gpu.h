@@ -149,7 +149,11 @@ enum { MGPU_OPT_HOST_CACHE = 1,
         * share its instructions in the L0 instruction cache.  0 = free-running warps; other values select the barriers
         * bit by bit (1 top of the step, 2 before the energy evaluation, 4 before the guest pass, 8 before k-space;
         * 1 means 1|4|8).  Results are identical either way (walkers never exchange data). */
-       MGPU_OPT_PHASE_SYNC = 2 };
+       MGPU_OPT_PHASE_SYNC = 2,
+       /* MGPU_OPT_BLOCK_SLICES (default 8, at most 16): mgpu_block cuts its walkers into this many slices, each on its
+        * own stream, so that the records of slice i+1 travel host -> device and those of slice i-1 device -> host while
+        * slice i is being swept.  1 = no pipelining (load, sweep, save one after the other).  Same results either way. */
+       MGPU_OPT_BLOCK_SLICES = 3 };
 int mgpu_set_option(int32_t option, int32_t value);
 
 /* ---- energy routines (single walker, drop-in) -------------------------------------- */
@@ -219,8 +223,9 @@ int mgpu_sweep(int32_t first_walker, int32_t n_walkers, int64_t n_steps,
  *   [15..18] RNG state (raw bits) | [19..30] counters%... (trials, successes) x 6 | [31] 0 |
  *   [32..63] block averages [res][sum N, sum N^2, sum E, samples] | [64] translation_step [65] rotation_step_angle
  *   [66..71] 0 | [72..72+2 nk) ewald%Ak (re[nk], im[nk]) |
- *   then for every active residue type, for mol = 1..count: guest%com(:,res,mol), guest%offset(:,res,mol,1:natom),
- *   and the molecule's cached framework energy {lj, coulomb (e^2/A)}.
+ *   then for every active residue type, for mol = 1..max(count,1): guest%com(:,res,mol), guest%offset(:,res,mol,1:natom),
+ *   and the molecule's cached framework energy {lj, coulomb (e^2/A)}.  (Slot 1 is stored even for an empty type: it is
+ *   the geometry template of the next insertion, src/monte_carlo_utils.f90:563-564.)
  * Record i starts at blob[offsets[i]]; offsets[n] is the total length.  mgpu_save_walkers fills
  * blob and offsets (capacity in doubles; mgpu_record_doubles_max() bounds one record);
  * mgpu_load_walkers restores walkers from records (no recompute: the record is the full state);

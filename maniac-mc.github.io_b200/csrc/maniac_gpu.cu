@@ -71,6 +71,20 @@ struct Context {
     std::vector<char> dirty;          // per walker: coordinates changed outside commit
     std::vector<double> rmax2;        // host mirror of DevSys::rmax2 (grown by mgpu_set_molecule)
     std::vector<char> pending;        // per walker: a trial is pending (host mirror of MgpuTrial::active)
+    std::vector<int32_t> pend_kind, pend_res, pend_res2;   // ... and what it would change (host mirror of the counts below)
+    std::vector<int32_t> counts;      // host mirror of DevSys::count [W][MGPU_MAX_RES]; refreshed lazily (counts_valid)
+    bool counts_valid = false;
+    std::vector<uint32_t> batch_stamp; uint32_t batch_id = 0;   // duplicate walkers inside one mgpu_trial_batch
+    // pipelined mgpu_block: slices of walkers on several streams (copy of slice i+1 / i-1 under the sweep of slice i)
+    static const int NPIPE = 16;
+    cudaStream_t pstream[NPIPE] = {};
+    cudaEvent_t pevent[NPIPE] = {};
+    double *p_in[NPIPE] = {}, *p_out[NPIPE] = {};                 // device staging of the slice's records, in / out
+    size_t p_in_cap[NPIPE] = {}, p_out_cap[NPIPE] = {};
+    long long *p_off_in[NPIPE] = {}, *p_off_out[NPIPE] = {};      // device: record offsets local to the slice
+    long long *ph_off_in[NPIPE] = {}, *ph_off_out[NPIPE] = {};    // pinned host mirrors of the two
+    size_t p_off_cap[NPIPE] = {};
+    int block_slices = 8;             // MGPU_OPT_BLOCK_SLICES (0 / 1 = the unpipelined load -> sweep -> save)
     // latency path (few trials per call, e.g. one unchanged Fortran process): the kernels read the task and write
     // the energies straight from / to page-locked host memory (UVA), so a call is one launch + one synchronisation
     int32_t *hc_walker = nullptr, *hc_accept = nullptr;    // pinned, commit arguments
@@ -171,6 +185,17 @@ int rebuild(int first, int n)
     return 0;
 }
 int ensure_clean(int w) { if (g.dirty[w]) return rebuild(w, 1); return 0; }
+// host mirror of the molecule counts (argument checks of the host-driven trials): kept current by commits and
+// mgpu_set_count, re-read from the device after anything that changes counts there (sweeps, record loads)
+int ensure_counts()
+{
+    if (g.counts_valid) return 0;
+    g.counts.resize((size_t)g.h.n_walkers * MGPU_MAX_RES);
+    CK(cudaMemcpyAsync(g.counts.data(), g.h.count, sizeof(int32_t) * g.counts.size(), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    g.counts_valid = true;
+    return 0;
+}
 } // namespace
 
 // =====================================================================================
@@ -182,6 +207,12 @@ void mgpu_finalize(void)
 {
     if (g.d_blob) { cudaFree(g.d_blob); g.d_blob = nullptr; g.blob_cap = 0; }
     if (g.d_rec_off) { cudaFree(g.d_rec_off); g.d_rec_off = nullptr; g.rec_cap = 0; }
+    for (int i = 0; i < Context::NPIPE; ++i) {
+        if (g.pstream[i]) { cudaStreamSynchronize(g.pstream[i]); cudaStreamDestroy(g.pstream[i]); cudaEventDestroy(g.pevent[i]); }
+        if (g.p_in[i]) cudaFree(g.p_in[i]);
+        if (g.p_out[i]) cudaFree(g.p_out[i]);
+        if (g.p_off_in[i]) { cudaFree(g.p_off_in[i]); cudaFree(g.p_off_out[i]); cudaFreeHost(g.ph_off_in[i]); cudaFreeHost(g.ph_off_out[i]); }
+    }
     if (g.stream) cudaStreamSynchronize(g.stream);
     for (void *p : g.allocs) cudaFree(p);
     g.allocs.clear();
@@ -254,6 +285,7 @@ int mgpu_init(const mgpu_system *sys)
         for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) h.Hinv[i * 3 + j] = rcp * adj[i][j];
     }
     for (int d = 0; d < 3; ++d) { h.L[d] = M[d][d]; h.invL[d] = 1.0 / M[d][d]; }
+    h.rint_magic = MGPU_RINT_MAGIC;
     h.tri_nrel = 0; g.tri_listed = 0;
     if (h.triclinic) {
         // lattice vectors that can beat the fractionally rounded image (min_image_r2<true>): m is relevant iff
@@ -583,6 +615,9 @@ int mgpu_init(const mgpu_system *sys)
     }
     g.dirty.assign(W, 0);
     g.pending.assign(W, 0);
+    g.pend_kind.assign(W, 0); g.pend_res.assign(W, 0); g.pend_res2.assign(W, 0);
+    g.batch_stamp.assign(W, 0); g.batch_id = 0;
+    g.counts_valid = false;
     g.commit_inflight = false;
 
     // ---- shared-memory budgets ----
@@ -755,6 +790,7 @@ int mgpu_set_count(int32_t w, int32_t res, int32_t n)
     if (check_walker(w) || check_guest(res)) return 1;
     if (n < 0 || n > g.h.cap[res]) return fail("mgpu_set_count: count out of range");
     CK(cudaMemcpy(g.h.count + (int64_t)w * MGPU_MAX_RES + res, &n, sizeof n, cudaMemcpyHostToDevice));
+    if (g.counts_valid) g.counts[(size_t)w * MGPU_MAX_RES + res] = n;
     g.dirty[w] = 1;
     return 0;
 }
@@ -803,6 +839,7 @@ int mgpu_set_option(int32_t option, int32_t value)
 {
     NEED_READY();
     if (option == MGPU_OPT_PHASE_SYNC) { g.phase_sync = (value == 1) ? 13 : (value & 15); return 0; }   // bits: 1 top of step, 2 before the evaluation, 4 before the guest pass, 8 before k-space
+    if (option == MGPU_OPT_BLOCK_SLICES) { g.block_slices = value < 1 ? 1 : (value > Context::NPIPE ? (int)Context::NPIPE : value); return 0; }
     if (option == MGPU_OPT_HOST_CACHE) {
         g.h.use_hcache = value ? 1 : 0;
         if (upload_sys()) return 1;
@@ -886,15 +923,29 @@ int mgpu_trial_batch(int32_t n, const int32_t *walker, const int32_t *res, const
 {
     NEED_READY_NOSYNC();
     if (n <= 0) return 0;
-    if (ensure_task_cap(n)) return 1;
+    if (ensure_task_cap(n) || ensure_counts()) return 1;
+    // one trial per walker: a second task on a walker would race with the first on the walker's spare S(k) buffer and
+    // on its pending-trial record, and a trial on top of a pending one would be committed onto flipped buffers
+    ++g.batch_id;
+    if (g.batch_id == 0) { std::fill(g.batch_stamp.begin(), g.batch_stamp.end(), 0u); g.batch_id = 1; }
     for (int t = 0; t < n; ++t) {
         if (check_walker(walker[t]) || check_guest(res[t])) return 1;
+        if (g.pending[walker[t]]) return fail("mgpu_trial_batch: walker already has a pending trial (commit or roll it back first)");
+        if (g.batch_stamp[walker[t]] == g.batch_id) return fail("mgpu_trial_batch: a walker is listed twice in one batch");
+        g.batch_stamp[walker[t]] = g.batch_id;
+    }
+    for (int t = 0; t < n; ++t) {
         const int k = kind[t] & 0xff, res2 = kind[t] >> 8;
         if (k < MGPU_KIND_MOVE || k > MGPU_KIND_SWAP || (k != MGPU_KIND_SWAP && res2 != 0)) return fail("mgpu_trial_batch: unknown kind");
         if (mol[t] < 0 || mol[t] >= g.h.cap[res[t]]) return fail("Trying to insert / move a molecule with an index beyond the walker's capacity");
+        const int cnt = g.counts[(size_t)walker[t] * MGPU_MAX_RES + res[t]];
+        if (k == MGPU_KIND_CREATE ? (mol[t] != cnt) : (mol[t] >= cnt))
+            return fail(k == MGPU_KIND_CREATE ? "mgpu_trial_batch: a creation trial goes into slot N + 1 (mol must equal the current count)"
+                                              : "mgpu_trial_batch: molecule index beyond the walker's current count");
         if (k == MGPU_KIND_SWAP) {
             if (check_guest(res2)) return 1;
             if (res2 == res[t]) return fail("mgpu_trial_batch: swap needs two different residue types");
+            if (g.counts[(size_t)walker[t] * MGPU_MAX_RES + res2] >= g.h.cap[res2]) return fail("Trying to insert a molecule beyond the walker's capacity (NB_MAX_MOLECULE analogue)");
         }
         if (ensure_clean(walker[t])) return 1;
         g.h_task_i[4 * t] = walker[t]; g.h_task_i[4 * t + 1] = res[t]; g.h_task_i[4 * t + 2] = mol[t]; g.h_task_i[4 * t + 3] = kind[t];
@@ -932,6 +983,7 @@ int mgpu_trial_batch(int32_t n, const int32_t *walker, const int32_t *res, const
     }
     for (int t = 0; t < n; ++t) {
         g.pending[walker[t]] = 1;
+        g.pend_kind[walker[t]] = kind[t] & 0xff; g.pend_res[walker[t]] = res[t]; g.pend_res2[walker[t]] = kind[t] >> 8;
         if (e_old) std::memcpy(e_old + 6 * (size_t)t, g.h_task_out + 12 * (size_t)t, sizeof(double) * 6);
         if (e_new) std::memcpy(e_new + 6 * (size_t)t, g.h_task_out + 12 * (size_t)t + 6, sizeof(double) * 6);
     }
@@ -948,7 +1000,16 @@ int mgpu_commit_batch(int32_t n, const int32_t *walker, const int32_t *accept)
         if (!g.pending[walker[t]]) return fail("mgpu_commit: commit without a pending trial");
     }
     if (g.commit_inflight) { CK(cudaStreamSynchronize(g.stream)); g.commit_inflight = false; }   // the argument buffers are being read
-    for (int t = 0; t < n; ++t) { g.hc_walker[t] = walker[t]; g.hc_accept[t] = accept[t] ? 1 : 0; g.pending[walker[t]] = 0; }
+    for (int t = 0; t < n; ++t) {
+        const int w = walker[t];
+        g.hc_walker[t] = w; g.hc_accept[t] = accept[t] ? 1 : 0; g.pending[w] = 0;
+        if (accept[t] && g.counts_valid) {                    // update_counts, mirrored on the host
+            int32_t *c = g.counts.data() + (size_t)w * MGPU_MAX_RES;
+            if (g.pend_kind[w] == MGPU_KIND_CREATE) c[g.pend_res[w]] += 1;
+            else if (g.pend_kind[w] == MGPU_KIND_DELETE) c[g.pend_res[w]] -= 1;
+            else if (g.pend_kind[w] == MGPU_KIND_SWAP) { c[g.pend_res[w]] -= 1; c[g.pend_res2[w]] += 1; }
+        }
+    }
     if (n < g.sm_count) {
         // latency path: arguments read from page-locked host memory, no synchronisation -- the next energy call (or any
         // getter, all of which synchronise the stream) orders after it
@@ -1033,7 +1094,11 @@ int mgpu_sweep(int32_t first, int32_t n, int64_t n_steps, int32_t trace_walker, 
     NEED_READY();
     if (n <= 0 || n_steps <= 0) return 0;
     if (check_walker(first) || check_walker(first + n - 1)) return 1;
-    for (int w = first; w < first + n; ++w) if (ensure_clean(w)) return 1;
+    for (int w = first; w < first + n; ++w) {
+        if (g.pending[w]) return fail("mgpu_sweep: a walker has a pending trial (commit or roll it back first)");
+        if (ensure_clean(w)) return 1;
+    }
+    g.counts_valid = false;
     mgpu_step_trace *d_trace = nullptr;
     if (trace) CK(cudaMalloc(&d_trace, sizeof(mgpu_step_trace) * n_steps));
     Timer tm("sweep");
@@ -1062,6 +1127,29 @@ static int ensure_rec_cap(size_t n_walkers, size_t n_doubles)
         if (g.d_blob) cudaFree(g.d_blob);
         g.blob_cap = n_doubles + n_doubles / 8;
         CK(cudaMalloc(&g.d_blob, sizeof(double) * g.blob_cap));
+    }
+    return 0;
+}
+// Validation of a batch of records on the host, BEFORE anything is uploaded or written: offsets start at 0, every
+// record is at least as long as its fixed part, its counts are integers inside the capacity, and its length field,
+// its offsets and its counts agree.  A malformed batch leaves the engine untouched.
+static int validate_records(int n, const double *blob, const int64_t *offsets)
+{
+    if (offsets[0] != 0) return fail("mgpu_load_walkers: offsets[0] must be 0");
+    const int64_t lmin = MGPU_REC_HDR + 2 * (int64_t)g.h.nk;
+    for (int i = 0; i < n; ++i) {
+        const int64_t len = offsets[i + 1] - offsets[i];
+        if (len < lmin) return fail("mgpu_load_walkers: malformed walker record (length / counts / capacity)");
+        const double *rec = blob + offsets[i];
+        int64_t L = lmin;
+        for (int r = 0; r < g.h.nres; ++r) {
+            if (!g.h.active[r]) continue;
+            const double c = rec[1 + r];
+            if (!(c >= 0.0 && c <= (double)g.h.cap[r]) || c != std::floor(c)) return fail("mgpu_load_walkers: malformed walker record (length / counts / capacity)");
+            const int64_t stored = c > 0.0 ? (int64_t)c : 1;
+            L += stored * (3 + 3 * g.h.natom[r] + 2);
+        }
+        if (rec[0] != (double)L || len != L) return fail("mgpu_load_walkers: malformed walker record (length / counts / capacity)");
     }
     return 0;
 }
@@ -1108,23 +1196,115 @@ int mgpu_load_walkers(int32_t first, int32_t n, const double *blob, const int64_
     if (n <= 0) return 0;
     if (!blob || !offsets) return fail("mgpu_load_walkers: null buffer");
     if (check_walker(first) || check_walker(first + n - 1)) return 1;
-    if (offsets[0] != 0) return fail("mgpu_load_walkers: offsets[0] must be 0");
-    for (int i = 0; i < n; ++i) if (offsets[i + 1] <= offsets[i]) return fail("mgpu_load_walkers: offsets must increase");
+    if (validate_records(n, blob, offsets)) return 1;
     if (ensure_rec_cap(n, (size_t)offsets[n])) return 1;
     CK(cudaMemcpyAsync(g.d_rec_off, offsets, sizeof(long long) * (n + 1), cudaMemcpyHostToDevice, g.stream));
     CK(cudaMemcpyAsync(g.d_blob, blob, sizeof(double) * offsets[n], cudaMemcpyHostToDevice, g.stream));
+    g.h2d_bytes += (long long)sizeof(double) * offsets[n] + (long long)sizeof(long long) * (n + 1);
     Timer tm("unpack");
-    k_unpack<<<(n + 7) / 8, 256, 0, g.stream>>>(first, n, g.d_rec_off, g.d_blob, g.d_err);
+    k_unpack<<<(n + 7) / 8, 256, 0, g.stream>>>(first, n, g.d_rec_off, g.d_blob);
     tm.stop();
     CK(cudaGetLastError());
-    g.h2d_bytes += (long long)sizeof(double) * offsets[n] + (long long)sizeof(long long) * (n + 1);
-    if (check_err_flag("mgpu_load_walkers")) return 1;
     for (int w = first; w < first + n; ++w) { g.dirty[w] = 0; g.pending[w] = 0; }   // the record carries S(k), energies and the cache rows
+    g.counts_valid = false;
     return 0;
 }
+// mgpu_block, pipelined: the walkers are cut into slices of whole sweep CTAs, every slice gets its own stream and
+// staging buffers and runs  records H2D -> k_unpack -> k_sweep -> record offsets (device scan) -> k_pack -> records D2H
+// in stream order.  All slices are in flight at once: the copy engines move slice i+1 in and slice i-1 out while the
+// SMs sweep slice i (a slice's CTAs start as soon as SMs are free, whichever stream they come from).  The only host
+// round trip per slice is its record lengths (a few KB), needed to size the D2H copy and to place the slice in the
+// caller's blob.  Walkers are independent, so the results equal the unpipelined load -> sweep -> save bit for bit.
+static int block_pipelined(int32_t first, int32_t n, int64_t n_steps, const double *blob_in, const int64_t *offsets_in,
+                           double *blob_out, int64_t capacity_out, int64_t *offsets_out)
+{
+    const int gran = g.wgroups;
+    int S = std::min(g.block_slices, (int)Context::NPIPE);
+    int per = ((n + S - 1) / S + gran - 1) / gran * gran;
+    S = (n + per - 1) / per;
+    const int64_t rec_max = mgpu_record_doubles_max();
+    int64_t molmax = 0;
+    for (int r = 0; r < g.h.nres; ++r) if (g.h.active[r]) molmax = std::max<int64_t>(molmax, 3 + 3 * g.h.natom[r] + 2);
+    for (int i = 0; i < S; ++i) {
+        if (!g.pstream[i]) { CK(cudaStreamCreateWithFlags(&g.pstream[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&g.pevent[i], cudaEventDisableTiming)); }
+        const int m = std::min(per, n - i * per);
+        if ((size_t)m + 1 > g.p_off_cap[i]) {
+            if (g.p_off_in[i]) { cudaFree(g.p_off_in[i]); cudaFree(g.p_off_out[i]); cudaFreeHost(g.ph_off_in[i]); cudaFreeHost(g.ph_off_out[i]); }
+            g.p_off_cap[i] = (size_t)per + 1;
+            CK(cudaMalloc(&g.p_off_in[i], sizeof(long long) * g.p_off_cap[i]));
+            CK(cudaMalloc(&g.p_off_out[i], sizeof(long long) * g.p_off_cap[i]));
+            CK(cudaMallocHost(&g.ph_off_in[i], sizeof(long long) * g.p_off_cap[i]));
+            CK(cudaMallocHost(&g.ph_off_out[i], sizeof(long long) * g.p_off_cap[i]));
+        }
+        const int64_t in_len = offsets_in[i * per + m] - offsets_in[i * per];
+        if ((size_t)in_len > g.p_in_cap[i]) {
+            if (g.p_in[i]) cudaFree(g.p_in[i]);
+            g.p_in_cap[i] = (size_t)(in_len + in_len / 8);
+            CK(cudaMalloc(&g.p_in[i], sizeof(double) * g.p_in_cap[i]));
+        }
+        // a walker gains at most one molecule per MC step
+        int64_t out_bound = 0;
+        for (int k = 0; k < m; ++k) out_bound += std::min<int64_t>(rec_max, (offsets_in[i * per + k + 1] - offsets_in[i * per + k]) + n_steps * molmax);
+        if ((size_t)out_bound > g.p_out_cap[i]) {
+            if (g.p_out[i]) cudaFree(g.p_out[i]);
+            g.p_out_cap[i] = (size_t)out_bound;
+            CK(cudaMalloc(&g.p_out[i], sizeof(double) * g.p_out_cap[i]));
+        }
+    }
+    CK(cudaStreamSynchronize(g.stream));
+    for (int i = 0; i < S; ++i) {                      // stage 1 of every slice, back to back
+        cudaStream_t st = g.pstream[i];
+        const int w0 = first + i * per, m = std::min(per, n - i * per);
+        const int64_t b0 = offsets_in[i * per], in_len = offsets_in[i * per + m] - b0;
+        for (int k = 0; k <= m; ++k) g.ph_off_in[i][k] = offsets_in[i * per + k] - b0;
+        CK(cudaMemcpyAsync(g.p_off_in[i], g.ph_off_in[i], sizeof(long long) * (m + 1), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(g.p_in[i], blob_in + b0, sizeof(double) * in_len, cudaMemcpyHostToDevice, st));
+        g.h2d_bytes += (long long)sizeof(double) * in_len + (long long)sizeof(long long) * (m + 1);
+        k_unpack<<<(m + 7) / 8, 256, 0, st>>>(w0, m, g.p_off_in[i], g.p_in[i]);
+        const int nb = (m + g.wgroups - 1) / g.wgroups;
+        if (g.h.triclinic) k_sweep<true><<<nb, 32 * g.wgroups, g.smem8, st>>>(w0, m, n_steps, g.natom_max, -1, nullptr, g.d_err, g.phase_sync);
+        else k_sweep<false><<<nb, 32 * g.wgroups, g.smem8, st>>>(w0, m, n_steps, g.natom_max, -1, nullptr, g.d_err, g.phase_sync);
+        k_record_offsets<<<1, 256, 0, st>>>(w0, m, g.p_off_out[i]);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(g.ph_off_out[i], g.p_off_out[i], sizeof(long long) * (m + 1), cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(g.pevent[i], st));
+    }
+    int rc = 0;
+    int64_t base = 0;
+    offsets_out[0] = 0;
+    for (int i = 0; i < S; ++i) {                      // stage 2 as the slices finish, in order
+        cudaStream_t st = g.pstream[i];
+        const int w0 = first + i * per, m = std::min(per, n - i * per);
+        CK(cudaEventSynchronize(g.pevent[i]));
+        const int64_t total = g.ph_off_out[i][m];
+        if (!rc && (total > (int64_t)g.p_out_cap[i] || base + total > capacity_out))
+            rc = fail("mgpu_block: output buffer too small, need more than " + std::to_string((long long)(base + total)) + " doubles");
+        for (int k = 1; k <= m; ++k) offsets_out[i * per + k] = base + g.ph_off_out[i][k];
+        if (!rc) {
+            k_pack<<<(m + 7) / 8, 256, 0, st>>>(w0, m, g.p_off_out[i], g.p_out[i]);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(blob_out + base, g.p_out[i], sizeof(double) * total, cudaMemcpyDeviceToHost, st));
+            g.d2h_bytes += (long long)sizeof(double) * total + (long long)sizeof(long long) * (m + 1);
+        }
+        base += total;
+    }
+    for (int i = 0; i < S; ++i) CK(cudaStreamSynchronize(g.pstream[i]));
+    for (int w = first; w < first + n; ++w) { g.dirty[w] = 0; g.pending[w] = 0; }
+    g.counts_valid = false;
+    if (check_err_flag("mgpu_block")) return 1;
+    return rc;
+}
+
 int mgpu_block(int32_t first, int32_t n, int64_t n_steps, const double *blob_in, const int64_t *offsets_in,
                double *blob_out, int64_t capacity_out, int64_t *offsets_out)
 {
+    NEED_READY();
+    if (n <= 0) return 0;
+    if (check_walker(first) || check_walker(first + n - 1)) return 1;
+    if (blob_in && blob_out && offsets_in && offsets_out && n_steps > 0 && g.block_slices > 1 && n >= 2 * g.wgroups) {
+        if (validate_records(n, blob_in, offsets_in)) return 1;
+        return block_pipelined(first, n, n_steps, blob_in, offsets_in, blob_out, capacity_out, offsets_out);
+    }
     if (blob_in && mgpu_load_walkers(first, n, blob_in, offsets_in)) return 1;
     if (mgpu_sweep(first, n, n_steps, -1, nullptr)) return 1;
     if (blob_out && mgpu_save_walkers(first, n, blob_out, capacity_out, offsets_out)) return 1;

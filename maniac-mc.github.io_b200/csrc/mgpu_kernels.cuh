@@ -31,22 +31,20 @@
 
 __constant__ DevSys c_sys;
 
-// software prefetch (register rotation) switches: framework pass with U > 1 targets per thread, guest pass, k-space loop.
-// Measured on B200 (4736 walkers x 256 steps): none 18.22, k-space only 19.10, guest only 18.56, framework-U only 18.86,
-// all three 18.36 M moves/s -- at 128 registers per thread the rotations compete for registers, so only k-space is on.
+// software prefetch (register rotation) switches: framework pass with U > 1 targets per thread, k-space loop.
+// Measured on B200 in round 1 (4736 walkers x 256 steps): none 18.22, k-space only 19.10, guest pass only 18.56,
+// framework-U only 18.86, all three 18.36 M moves/s -- at 128 registers per thread the rotations compete for
+// registers, so only k-space is on (the guest-pass rotation was removed).
 #ifndef MGPU_PF_HOSTU
 #define MGPU_PF_HOSTU 0
 #endif
-#ifndef MGPU_PF_GUEST
-#define MGPU_PF_GUEST 0
+// (a cp.async staging of the framework atoms two iterations ahead was measured in round 1: 19.45 M moves/s against
+// 20.5 M with the register rotation -- two more LDS.128 + two LDGSTS per iteration on an LSU that already serves the
+// table gather; removed.)
+// count the LJ terms inside the cutoff per pair (roofline accounting); 0 = production build without it
+#ifndef MGPU_COUNT_LJ
+#define MGPU_COUNT_LJ 1
 #endif
-// framework atoms of the 1-target-per-thread passes staged global -> shared with cp.async, two iterations ahead.
-// Measured: 19.45 M moves/s against 20.5 M with the register rotation (two more LDS.128 + two LDGSTS per iteration on an
-// LSU that already serves the table gather) -- off.
-#ifndef MGPU_STAGE
-#define MGPU_STAGE 0
-#endif
-#define MGPU_STAGE_BYTES 2048            // per warp: 2 stages x 32 lanes x {xy, zq}
 // framework atoms per thread and iteration in the 3-probe-atom passes (1: three pair chains per thread; 2: six)
 #ifndef MGPU_HOST_U3
 #define MGPU_HOST_U3 1
@@ -56,9 +54,6 @@ __constant__ DevSys c_sys;
 #endif
 #ifndef MGPU_ACC_PER_ATOM
 #define MGPU_ACC_PER_ATOM 0
-#endif
-#ifndef MGPU_PINGPONG
-#define MGPU_PINGPONG 0
 #endif
 #ifndef MGPU_PF_KSPACE
 #define MGPU_PF_KSPACE 1
@@ -158,6 +153,21 @@ __device__ __forceinline__ void apply_PBC(double pos[3])
 // minimum image (geometry_utils.f90:210-284) -> squared distance
 // ------------------------------------------------------------------------------------
 #define MGPU_RINT_MAGIC 6755399441055744.0     // 1.5 * 2^52: (x + M) - M = rint(x) for |x| < 2^51
+// The rounding constant as an opaque REGISTER value: with the literal, ptxas encodes it as the immediate of
+// DFMA/DADD and must then bring the box constants (1/L, L) into registers -- LDC/LDCU + R2UR every iteration of
+// the pair loops (r01z SASS: 15 of 138 instructions).  With the constant in a register the box constants are
+// read straight from the constant bank as the instruction's c[3][..] operand.
+#ifndef MGPU_MAGIC_REG
+#define MGPU_MAGIC_REG 1
+#endif
+__device__ __forceinline__ double rint_magic()
+{
+#if MGPU_MAGIC_REG
+    return c_sys.rint_magic;              // a run-time value as far as ptxas can tell
+#else
+    return MGPU_RINT_MAGIC;
+#endif
+}
 // The reference's triclinic branch, literally: minimum over the 27 shifts i c1 + j c2 + k c3 of the RAW
 // difference vector, c = COLUMNS of matrix (geometry_utils.f90:263-280).
 __device__ __noinline__ double min_image_27(double dx, double dy, double dz)
@@ -184,9 +194,10 @@ __device__ __forceinline__ double min_image_r2(double dx, double dy, double dz)
     if (!TRI) {
         // delta_d = modulo(delta_d + L/2, L) - L/2 restated as delta - L*rint(delta/L): the same
         // image except on the exact tie |delta| = L/2, where both images have the same length.
-        const double nx = fma(dx, c_sys.invL[0], MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC;
-        const double ny = fma(dy, c_sys.invL[1], MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC;
-        const double nz = fma(dz, c_sys.invL[2], MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC;
+        const double M = rint_magic();
+        const double nx = fma(dx, c_sys.invL[0], M) - M;
+        const double ny = fma(dy, c_sys.invL[1], M) - M;
+        const double nz = fma(dz, c_sys.invL[2], M) - M;
         dx = fma(-c_sys.L[0], nx, dx);
         dy = fma(-c_sys.L[1], ny, dy);
         dz = fma(-c_sys.L[2], nz, dz);
@@ -203,8 +214,8 @@ __device__ __forceinline__ double min_image_r2(double dx, double dy, double dz)
         const double f0 = fma(c_sys.Hinv[0], dx, fma(c_sys.Hinv[3], dy, c_sys.Hinv[6] * dz));
         const double f1 = fma(c_sys.Hinv[1], dx, fma(c_sys.Hinv[4], dy, c_sys.Hinv[7] * dz));
         const double f2 = fma(c_sys.Hinv[2], dx, fma(c_sys.Hinv[5], dy, c_sys.Hinv[8] * dz));
-        const double n0 = (f0 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC, n1 = (f1 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC,
-                     n2 = (f2 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC;
+        const double M = rint_magic();
+        const double n0 = (f0 + M) - M, n1 = (f1 + M) - M, n2 = (f2 + M) - M;
         const double tx = dx - fma(c_sys.H[0], n0, fma(c_sys.H[1], n1, c_sys.H[2] * n2));
         const double ty = dy - fma(c_sys.H[3], n0, fma(c_sys.H[4], n1, c_sys.H[5] * n2));
         const double tz = dz - fma(c_sys.H[6], n0, fma(c_sys.H[7], n1, c_sys.H[8] * n2));
@@ -266,6 +277,31 @@ __device__ __noinline__ double2 pair_exact(double s, double A, double B, double 
     return make_double2(e_lj, e_c);
 }
 
+// g(s) = erfc(alpha sqrt(s)) / sqrt(s) from this lane's replica of the table (three LDS.128, conflict free).  hi = high
+// word of s.  The unsigned clamp sends s below the first interval AND beyond the last one to the all-zero closing row.
+// The polynomial variable is the position inside the interval on a UNIT octave: t = the mantissa of s (exponent
+// replaced by 0, one LOP3 on the high word) minus the interval centre 1 + (j + 1/2) / 32, which for the bits kept is
+// just t' = (mantissa with the interval bits cleared) - (1 + 1/64): exact, one DADD with an immediate; the per-octave
+// scale 2^(e k) is folded into the row's coefficients by the table builder.
+template <int REP>
+__device__ __forceinline__ double coulomb_g(double s, int hi, const double2 *__restrict__ ctab)
+{
+    const unsigned idx = min((unsigned)((hi >> (20 - MGPU_TAB_K)) - c_sys.tab_ibase), (unsigned)c_sys.tab_nint);
+    const int mhi = (hi & ((1 << (20 - MGPU_TAB_K)) - 1)) | 0x3ff00000;
+    const double uu = __hiloint2double(mhi, __double2loint(s)) - (1.0 + 1.0 / (double)(2 << MGPU_TAB_K));
+    const double2 *t = ctab + idx * (3 * REP);
+    const double2 c01 = t[0], c23 = t[REP], c45 = t[2 * REP];
+    const float uf = (float)uu;
+    const float pf = fmaf(__int_as_float(__double2hiint(c45.y)), uf, __int_as_float(__double2loint(c45.y)));
+    double p = (double)pf;
+    p = fma(p, uu, c45.x);
+    p = fma(p, uu, c23.y);
+    p = fma(p, uu, c23.x);
+    p = fma(p, uu, c01.y);
+    p = fma(p, uu, c01.x);
+    return p;
+}
+
 // One atom pair on the hot path.  tab = this lane's replica of the Coulomb table in shared
 // memory (double2 units, see mgpu_internal.h).  qq = q_i q_j with either factor already zeroed
 // when |q| < 1e-10 (:157).  AB = {4 eps sigma^12, 4 eps sigma^6}.
@@ -292,19 +328,7 @@ __device__ __forceinline__ void pair_terms(double s, double2 AB, double qq, cons
         pc.lj += in;
     }
     if (doC) {
-        const int chi = (hi & ~((1 << (20 - MGPU_TAB_K)) - 1)) | (1 << (19 - MGPU_TAB_K));
-        const double u = s - __hiloint2double(chi, 0);          // exact: same binade
-        const double2 *t = tab + idx * (3 * REP);
-        const double2 c01 = t[0], c23 = t[REP], c45 = t[2 * REP];
-        const float uf = (float)u;
-        const float pf = fmaf(__int_as_float(__double2hiint(c45.y)), uf, __int_as_float(__double2loint(c45.y)));
-        double p = (double)pf;
-        p = fma(p, u, c45.x);
-        p = fma(p, u, c23.y);
-        p = fma(p, u, c23.x);
-        p = fma(p, u, c01.y);
-        p = fma(p, u, c01.x);
-        e_c = fma(qq, p, e_c);
+        e_c = fma(qq, coulomb_g<REP>(s, hi, tab), e_c);
         pc.coul += 1u;
     }
 }
@@ -374,7 +398,6 @@ template <int REP> __device__ __forceinline__ const double2 *smem_ljAB() { retur
 struct Smem {
     GroupWS *ws;
     double2 *tab_old, *tab_new;
-    double2 *stage;                          // this warp's cp.async staging area (warp groups only), or nullptr
 };
 __host__ __device__ inline size_t smem_group_bytes(int kmax_max, int natom_max, int rep)
 {
@@ -389,8 +412,7 @@ __host__ __device__ inline size_t smem_common_bytes(int ntypes, int tab_nint, in
 }
 __host__ __device__ inline size_t smem_bytes(int ntypes, int tab_nint, int kmax_max, int natom_max, int groups, int rep)
 {
-    return smem_common_bytes(ntypes, tab_nint, rep) + groups * smem_group_bytes(kmax_max, natom_max, rep) + 16
-           + ((MGPU_STAGE && rep > 1) ? (size_t)groups * MGPU_STAGE_BYTES : 0);
+    return smem_common_bytes(ntypes, tab_nint, rep) + groups * smem_group_bytes(kmax_max, natom_max, rep) + 16;
 }
 // Carve the CTA's dynamic shared memory and (cooperatively, whole CTA) load the common part.
 // Every thread of the CTA must call this; it ends with __syncthreads().
@@ -411,13 +433,6 @@ __device__ __forceinline__ Smem smem_setup(unsigned char *base, int natom_max, i
     if ((REP > 1) ? ((threadIdx.x & 31) == 0) : (threadIdx.x == 0)) { s.ws->probe.po = ppos; s.ws->probe.pn = ppos + natom_max; s.ws->sync_q = 0; s.ws->sync_k = 0; }
     s.tab_old = reinterpret_cast<double2 *>(g + smem_ws_bytes(REP > 1) + ((sizeof(double) * 2 * 3 * (size_t)natom_max + 15) & ~size_t(15)));
     s.tab_new = s.tab_old + (size_t)natom_max * 3 * (c_sys.kmax_max + 1);
-    s.stage = nullptr;
-    if (MGPU_STAGE && REP > 1) {
-        const int ngroups = (int)(blockDim.x >> 5);
-        size_t o = smem_common_bytes(c_sys.ntypes, c_sys.tab_nint, REP) + (size_t)ngroups * smem_group_bytes(c_sys.kmax_max, natom_max, REP);
-        o = (o + 15) & ~size_t(15);
-        s.stage = reinterpret_cast<double2 *>(base + o + (size_t)group * MGPU_STAGE_BYTES);
-    }
     __syncthreads();
     return s;
 }
@@ -462,26 +477,26 @@ struct HostPass {
 
     // vmask: bit u set = target u is real (guest passes mask the tail / the excluded molecule;
     // framework passes hand in a constant all-ones mask and the tests fold away).
-    // Coulomb sums are kept per probe atom WITHOUT its charge (acc[i] += q_j g(s)); the caller multiplies by
-    // q_i once per pass.  Pairs below the table start (r < 1 A, incl. the overlap sentinel) read the all-zero
-    // row that closes the table (the unsigned clamp sends both ends there), are left out of the LJ sum, and
-    // are redone with the exact formulas when the block's smallest r^2 says there was one (e_x: their sum).
+    // Pairs below the table start (r < 1 A, incl. the overlap sentinel) read the all-zero row that closes the
+    // table (the unsigned clamp sends both ends there) and are left out of the LJ sum; block() only REPORTS that
+    // there was one (return value).  The caller remembers the range of iterations that reported and redoes just
+    // those with fix() after its loop, so the loop body holds no call: a CALL inside it made ptxas reload every
+    // box / table constant and the global-memory descriptor in each iteration (r01z SASS: 19 of the 138
+    // instructions of the 3-atom Coulomb loop were LDC / LDCU / R2UR).
     template <int UU>
-    __device__ __forceinline__ void block(const Atoms<UU> &A, const unsigned vmask, double &e_lj, double (&acc)[N], double2 &e_x, PairCount &pc) const
+    __device__ __forceinline__ bool block(const Atoms<UU> &A, const unsigned vmask, double &e_lj, double (&acc)[N], PairCount &pc) const
     {
         const double2 (&txy)[UU] = A.xy; const double2 (&tzq)[UU] = A.zq; const int (&tt)[UU] = A.tt;
         const double2 *ctab = smem_ctab<REP>(), *ljAB = smem_ljAB<REP>();
         const bool all = (vmask == (1u << UU) - 1u);
         int hmin = 0x7fffffff;
-        double sv[UU][N];
 #pragma unroll
         for (int u = 0; u < UU; ++u) {
             const bool val = (vmask >> u) & 1u;
 #pragma unroll
             for (int i = 0; i < N; ++i) {
                 double s = min_image_r2<TRI>(txy[u].x - px[i], txy[u].y - py[i], tzq[u].x - pz[i]);
-                if (!all) s = val ? s : 1.0e30;                                 // not a target: beyond every range (and (float)(s - centre) stays finite)
-                sv[u][i] = s;
+                if (!all) s = val ? s : 1.0e30;                                 // not a target: beyond every range
                 const int hi = __double2hiint(s);
                 hmin = min(hmin, hi);
                 if ((MODE & 1) && (!TRI || __any_sync(__activemask(), s < c_sys.rc2))) {     // triclinic (large cells): whole warps are beyond the cutoff
@@ -490,106 +505,59 @@ struct HostPass {
                     const double e = (AB.x * y3 - AB.y) * y3;
                     const bool in = (s < c_sys.rc2) && (hi >= c_sys.tab_hi_lo);
                     e_lj += in ? e : 0.0;
-                    pc.lj += (in && (AB.x != 0.0 || AB.y != 0.0));
+                    if (MGPU_COUNT_LJ) pc.lj += (in && (AB.x != 0.0 || AB.y != 0.0));
                 }
                 if (MODE & 2) {
-                    const unsigned idx = min((unsigned)((hi >> (20 - MGPU_TAB_K)) - c_sys.tab_ibase), (unsigned)c_sys.tab_nint);
-                    const int chi = (hi & ~((1 << (20 - MGPU_TAB_K)) - 1)) | (1 << (19 - MGPU_TAB_K));
-                    const double uu = s - __hiloint2double(chi, 0);         // exact: same binade
-                    const double2 *t = ctab + idx * (3 * REP);
-                    const double2 c01 = t[0], c23 = t[REP], c45 = t[2 * REP];
-                    const float uf = (float)uu;
-                    const float pf = fmaf(__int_as_float(__double2hiint(c45.y)), uf, __int_as_float(__double2loint(c45.y)));
-                    double p = (double)pf;
-                    p = fma(p, uu, c45.x);
-                    p = fma(p, uu, c23.y);
-                    p = fma(p, uu, c23.x);
-                    p = fma(p, uu, c01.y);
-                    p = fma(p, uu, c01.x);
+                    const double p = coulomb_g<REP>(s, hi, ctab);
                     if (MGPU_ACC_PER_ATOM) acc[i] = fma(tzq[u].y, p, acc[i]);
                     else acc[0] = fma(q[i] * tzq[u].y, p, acc[0]);
                 }
             }
         }
-        if (hmin < c_sys.tab_hi_lo) {                               // rare: some r < 1 A (incl. overlap)
-#pragma unroll
-            for (int u = 0; u < UU; ++u)
-#pragma unroll
-                for (int i = 0; i < N; ++i)
-                    if (__double2hiint(sv[u][i]) < c_sys.tab_hi_lo) {
-                        const double s = sv[u][i];
-                        double2 AB = make_double2(0.0, 0.0);
-                        if (MODE & 1) AB = ljAB[trow[i] + tt[u]];
-                        const double qq = (MODE & 2) ? q[i] * tzq[u].y : 0.0;
-                        const double2 e = pair_exact(s, AB.x, AB.y, qq, qq != 0.0);
-                        e_x.x += e.x; e_x.y += e.y;
-                        if (MODE & 1) pc.lj += ((AB.x != 0.0 || AB.y != 0.0) && s < c_sys.rc2);
-                    }
+        return hmin < c_sys.tab_hi_lo;                                          // rare: some r < 1 A (incl. overlap)
+    }
+
+    // the pairs of a block that fell below the table start, with the reference's exact formulas (e_x: their sum)
+    template <int UU>
+    __device__ __forceinline__ void fix(const Atoms<UU> &A, const unsigned vmask, double2 &e_x, PairCount &pc) const
+    {
+        const double2 *ljAB = smem_ljAB<REP>();
+#pragma unroll 1
+        for (int u = 0; u < UU; ++u) {
+            if (!((vmask >> u) & 1u)) continue;
+#pragma unroll 1
+            for (int i = 0; i < N; ++i) {
+                const double s = min_image_r2<TRI>(A.xy[u].x - px[i], A.xy[u].y - py[i], A.zq[u].x - pz[i]);
+                if (__double2hiint(s) >= c_sys.tab_hi_lo) continue;
+                double2 AB = make_double2(0.0, 0.0);
+                if (MODE & 1) AB = ljAB[trow[i] + A.tt[u]];
+                const double qq = (MODE & 2) ? q[i] * A.zq[u].y : 0.0;
+                const double2 e = pair_exact(s, AB.x, AB.y, qq, qq != 0.0);
+                e_x.x += e.x; e_x.y += e.y;
+                if ((MODE & 1) && MGPU_COUNT_LJ) pc.lj += ((AB.x != 0.0 || AB.y != 0.0) && s < c_sys.rc2);
+            }
         }
     }
 
     // software-pipelined: the next block's atoms are in flight (L1 / L2 latency) while this one is evaluated
     // (plain register rotation; the last fetch reloads the current block).  Accumulators are taken and
     // returned by value so they stay in registers.
-    __device__ __forceinline__ void run(int t0, int stride, double &e_lj_io, double &e_c_io, PairCount &pc_io, double2 *stg = nullptr) const
+    __device__ __forceinline__ void run(int t0, int stride, double &e_lj_io, double &e_c_io, PairCount &pc_io) const
     {
         double e_lj = e_lj_io;
         double acc[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) acc[i] = 0.0;
-        double2 e_x = make_double2(0.0, 0.0);
         PairCount pc = pc_io;
         const int n = c_sys.n_host;
         const int step = U * stride, reach = (U - 1) * stride;
         int j = t0;
-        if (MGPU_STAGE && U == 1 && REP > 1) {
-            // cp.async pipeline, distance two iterations: every lane copies the {x,y} and {z,q} words of ITS next-but-one
-            // framework atom into its own slots of the warp's staging area and reads them back when their turn comes
-            // (no registers held across iterations, no exposed L2 latency).  Slots: stage s -> [s*64 + lane] = xy, [s*64 + 32 + lane] = zq.
-            const double2 *__restrict__ hxy = c_sys.host_xy;
-            const double2 *__restrict__ hzq = c_sys.host_zq;
-            const int32_t *__restrict__ ht = c_sys.host_type;
-            double2 *my = stg + (threadIdx.x & 31);
-            const unsigned sa = (unsigned)__cvta_generic_to_shared(my);
-            auto issue = [&](int jj, int st) {
-                if (jj < n) {
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(sa + (unsigned)st * 1024u), "l"(hxy + jj) : "memory");
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" :: "r"(sa + (unsigned)st * 1024u + 512u), "l"(hzq + jj) : "memory");
-                }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-            };
-            issue(j, 0);
-            issue(j + stride, 1);
-            int st = 0;
-            for (; j < n; j += stride) {
-                asm volatile("cp.async.wait_group 1;" ::: "memory");
-                Atoms<1> a1;
-                a1.xy[0] = my[st * 64]; a1.zq[0] = my[st * 64 + 32];
-                a1.tt[0] = (MODE & 1) ? __ldg(ht + j) : 0;
-                issue(j + 2 * stride, st);
-                block<1>(a1, 1u, e_lj, acc, e_x, pc);
-                st ^= 1;
-            }
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        } else if (!MGPU_PF_HOSTU && U > 1) {
-            for (; j + reach < n; j += step) { Atoms<U> a; fetch<U>(a, j, stride); block<U>(a, (1u << U) - 1u, e_lj, acc, e_x, pc); }
-        } else if (MGPU_PINGPONG && j + reach < n) {
-            // two register sets used in turn, so the rotation costs no moves
-            Atoms<U> A, B;
-            fetch<U>(A, j, stride);
-            for (;;) {
-                int jn = j + step;
-                bool more = jn + reach < n;
-                fetch<U>(B, more ? jn : j, stride);
-                block<U>(A, (1u << U) - 1u, e_lj, acc, e_x, pc);
-                j = jn;
-                if (!more) break;
-                jn = j + step;
-                more = jn + reach < n;
-                fetch<U>(A, more ? jn : j, stride);
-                block<U>(B, (1u << U) - 1u, e_lj, acc, e_x, pc);
-                j = jn;
-                if (!more) break;
+        int jb0 = 0x7fffffff, jb1 = -1;                        // first / last index of this thread that reported a pair below the table
+        if (!MGPU_PF_HOSTU && U > 1) {
+            for (; j + reach < n; j += step) {
+                Atoms<U> a; fetch<U>(a, j, stride);
+                const bool bad = block<U>(a, (1u << U) - 1u, e_lj, acc, pc);
+                jb0 = bad ? min(jb0, j) : jb0; jb1 = bad ? j + reach : jb1;
             }
         } else if (j + reach < n) {
             Atoms<U> cur;
@@ -599,13 +567,20 @@ struct HostPass {
                 const bool more = jn + reach < n;
                 Atoms<U> nxt;
                 fetch<U>(nxt, more ? jn : j, stride);
-                block<U>(cur, (1u << U) - 1u, e_lj, acc, e_x, pc);
+                const bool bad = block<U>(cur, (1u << U) - 1u, e_lj, acc, pc);
+                jb0 = bad ? min(jb0, j) : jb0; jb1 = bad ? j + reach : jb1;
                 j = jn;
                 if (!more) break;
                 cur = nxt;
             }
         }
-        for (; j < n; j += stride) { Atoms<1> a1; fetch<1>(a1, j, stride); block<1>(a1, 1u, e_lj, acc, e_x, pc); }
+        for (; j < n; j += stride) {
+            Atoms<1> a1; fetch<1>(a1, j, stride);
+            const bool bad = block<1>(a1, 1u, e_lj, acc, pc);
+            jb0 = bad ? min(jb0, j) : jb0; jb1 = bad ? j : jb1;
+        }
+        double2 e_x = make_double2(0.0, 0.0);
+        for (int jj = jb0; jj <= jb1; jj += stride) { Atoms<1> a1; fetch<1>(a1, jj, stride); fix<1>(a1, 1u, e_x, pc); }
         double e_c = e_x.y;
         if (MGPU_ACC_PER_ATOM) {
 #pragma unroll
@@ -623,18 +598,22 @@ struct HostPass {
     // in memory, so the lanes' loads coalesce); tq / ttype are the target atom's charge (0 if tiny)
     // and type.  Molecule m_skip is left out (the probe itself), and so is every m <= m_order
     // (ordering check of pairwise_energy_for_molecule, :60-62; -1 = none).
-    template <int UU> struct GRaw { double c[UU][3], o[UU][3]; };
-    template <int UU>
-    __device__ __forceinline__ void fetch_guest(GRaw<UU> &R, const double *__restrict__ com, const double *__restrict__ offb,
-                                                int cap, int n, int m, int stride) const
+    // target atom b of molecules m, m + stride, ... of a guest residue type as a block of U targets + validity mask
+    __device__ __forceinline__ unsigned guest_targets(Atoms<U> &A, const double *__restrict__ com, const double *__restrict__ offb,
+                                                      int cap, int n, int m, int stride, int m_skip, int m_order, double tq, int ttype) const
     {
+        unsigned vm = 0u;
 #pragma unroll
-        for (int u = 0; u < UU; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int mm = m + u * stride;
+            const bool ok = (mm < n) && (mm != m_skip) && (mm > m_order);
             const int mc = (mm < n) ? mm : m;
-#pragma unroll
-            for (int d = 0; d < 3; ++d) { R.c[u][d] = com[d * cap + mc]; R.o[u][d] = offb[d * cap + mc]; }
+            A.xy[u] = make_double2(com[mc] + offb[mc], com[cap + mc] + offb[cap + mc]);
+            A.zq[u] = make_double2(com[2 * cap + mc] + offb[2 * cap + mc], tq);
+            A.tt[u] = ttype;
+            vm |= ok ? (1u << u) : 0u;
         }
+        return vm;
     }
     __device__ __forceinline__ void run_guest(const double *__restrict__ com, const double *__restrict__ offb, int cap, int n,
                                               int t0, int stride, int m_skip, int m_order, double tq, int ttype,
@@ -644,48 +623,19 @@ struct HostPass {
         double acc[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) acc[i] = 0.0;
-        double2 e_x = make_double2(0.0, 0.0);
         PairCount pc = pc_io;
-        if (!MGPU_PF_GUEST) {
-            for (int m = t0; m < n; m += U * stride) {
-                Atoms<U> A;
-                unsigned vm = 0u;
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int mm = m + u * stride;
-                    const bool ok = (mm < n) && (mm != m_skip) && (mm > m_order);
-                    const int mc = (mm < n) ? mm : m;
-                    A.xy[u] = make_double2(com[mc] + offb[mc], com[cap + mc] + offb[cap + mc]);
-                    A.zq[u] = make_double2(com[2 * cap + mc] + offb[2 * cap + mc], tq);
-                    A.tt[u] = ttype;
-                    vm |= ok ? (1u << u) : 0u;
-                }
-                block<U>(A, vm, e_lj, acc, e_x, pc);
-            }
-        } else {
-            int m = t0;
-            GRaw<U> cur;
-            fetch_guest<U>(cur, com, offb, cap, n, m, stride);
-            for (;;) {                                   // next chunk's coordinates in flight while this one is evaluated
-                const int mn = m + U * stride;
-                const bool more = mn < n;
-                GRaw<U> nxt;
-                fetch_guest<U>(nxt, com, offb, cap, n, more ? mn : m, stride);
-                Atoms<U> A;
-                unsigned vm = 0u;
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int mm = m + u * stride;
-                    const bool ok = (mm < n) && (mm != m_skip) && (mm > m_order);
-                    A.xy[u] = make_double2(cur.c[u][0] + cur.o[u][0], cur.c[u][1] + cur.o[u][1]);
-                    A.zq[u] = make_double2(cur.c[u][2] + cur.o[u][2], tq);
-                    A.tt[u] = ttype;
-                    vm |= ok ? (1u << u) : 0u;
-                }
-                block<U>(A, vm, e_lj, acc, e_x, pc);
-                if (!more) break;
-                cur = nxt; m = mn;
-            }
+        int mb0 = 0x7fffffff, mb1 = -1;                        // first / last chunk of this thread that reported a pair below the table
+        for (int m = t0; m < n; m += U * stride) {
+            Atoms<U> A;
+            const unsigned vm = guest_targets(A, com, offb, cap, n, m, stride, m_skip, m_order, tq, ttype);
+            const bool bad = block<U>(A, vm, e_lj, acc, pc);
+            mb0 = bad ? min(mb0, m) : mb0; mb1 = bad ? m : mb1;
+        }
+        double2 e_x = make_double2(0.0, 0.0);
+        for (int m = mb0; m <= mb1; m += U * stride) {
+            Atoms<U> A;
+            const unsigned vm = guest_targets(A, com, offb, cap, n, m, stride, m_skip, m_order, tq, ttype);
+            fix<U>(A, vm, e_x, pc);
         }
         double e_c = e_x.y;
         if (MGPU_ACC_PER_ATOM) {
@@ -709,8 +659,8 @@ __device__ __forceinline__ void host_list(const Smem &S, const Probe &P, const d
     // chunks of at most 3 probe atoms: ~3 independent pair chains per thread fit the 128-register budget
     for (int base = 0; base < n; base += 3) {
         const int m = min(3, n - base);
-        if (m == 3) { HostPass<TRI, MODE, 3, MGPU_HOST_U3, REP> hp; hp.load(P, pos, list + base); hp.run(t0, stride, e_lj, e_c, pc, S.stage); }
-        else if (m == 2) { HostPass<TRI, MODE, 2, 1, REP> hp; hp.load(P, pos, list + base); hp.run(t0, stride, e_lj, e_c, pc, S.stage); }
+        if (m == 3) { HostPass<TRI, MODE, 3, MGPU_HOST_U3, REP> hp; hp.load(P, pos, list + base); hp.run(t0, stride, e_lj, e_c, pc); }
+        else if (m == 2) { HostPass<TRI, MODE, 2, 1, REP> hp; hp.load(P, pos, list + base); hp.run(t0, stride, e_lj, e_c, pc); }
         else { HostPass<TRI, MODE, 1, 3, REP> hp; hp.load(P, pos, list + base); hp.run(t0, stride, e_lj, e_c, pc); }
     }
 }
@@ -1120,13 +1070,15 @@ __device__ __forceinline__ void grow_rmax2(int res, const double (*off)[3], int 
 // Apply an accepted trial to the walker (group-cooperative).
 // accept_molecule_move / accept_creation_move / accept_deletion_move + remove_molecule +
 // update_counts (monte_carlo_utils.f90:429-442,642-672; creation.f90:82-116; deletion.f90:83-122).
-__device__ void commit_trial(int w, int kind, int res, int mol, const double *com, const double (*off)[3],
+// n = the walker's count of `res` BEFORE the commit, read by the caller while no thread of the group can have
+// written it yet (thread 0 overwrites c_sys.count below; with more than one warp a late reader would otherwise
+// pick the wrong "last" slot).
+__device__ void commit_trial(int w, int kind, int res, int mol, int n, const double *com, const double (*off)[3],
                              const double e_old[6], const double e_new[6], const double hc_new[2], int tid, int nthreads)
 {
     double *wc = c_sys.coords + (int64_t)w * c_sys.coord_stride + c_sys.goff[res];
     const int cap = c_sys.cap[res], na = c_sys.natom[res];
     double *offs = wc + 3 * (int64_t)cap;
-    const int n = c_sys.count[(int64_t)w * MGPU_MAX_RES + res];
     if (kind == MGPU_KIND_DELETE) {
         const int last = n - 1;
         if (mol != last) {                  // the last molecule moves into the hole, with its cache rows (na*3, na*3+1)
@@ -1183,20 +1135,20 @@ __device__ void evaluate_swap(const Smem &S, int w, bool store_S, int resA, int 
 // accept_swap_move (swapping.f90:143-155) + the coordinate / count changes the reference made
 // before the accept test (:66-81): (resA, molA) removed by swap-with-last, the new molecule of type
 // resB appended, S flipped, all five components updated.
-__device__ void commit_swap(int w, int resA, int molA, int resB, const double *com, const double (*off)[3],
+// nA, nB = the walker's counts of the two types BEFORE the commit (read by the caller, see commit_trial).
+__device__ void commit_swap(int w, int resA, int molA, int nA, int resB, int nB, const double *com, const double (*off)[3],
                             const double e_old[6], const double e_new[6], const double hc_new[2], int tid, int nthreads)
 {
     {
         double *wc = c_sys.coords + (int64_t)w * c_sys.coord_stride + c_sys.goff[resA];
         const int cap = c_sys.cap[resA], na = c_sys.natom[resA];
         double *offs = wc + 3 * (int64_t)cap;
-        const int last = c_sys.count[(int64_t)w * MGPU_MAX_RES + resA] - 1;
+        const int last = nA - 1;
         if (molA != last) {
             if (tid < 3) wc[tid * cap + molA] = wc[tid * cap + last];
             for (int e = tid; e < na * 3 + 2; e += nthreads) offs[(int64_t)e * cap + molA] = offs[(int64_t)e * cap + last];
         }
     }
-    const int nB = c_sys.count[(int64_t)w * MGPU_MAX_RES + resB];
     {
         double *wc = c_sys.coords + (int64_t)w * c_sys.coord_stride + c_sys.goff[resB];
         const int cap = c_sys.cap[resB], na = c_sys.natom[resB];
@@ -1207,7 +1159,7 @@ __device__ void commit_swap(int w, int resA, int molA, int resB, const double *c
         grow_rmax2(resB, off, na, tid, nthreads);
     }
     if (tid == 0) {
-        c_sys.count[(int64_t)w * MGPU_MAX_RES + resA] -= 1;
+        c_sys.count[(int64_t)w * MGPU_MAX_RES + resA] = nA - 1;
         c_sys.count[(int64_t)w * MGPU_MAX_RES + resB] = nB + 1;
         c_sys.cur[w] ^= 1;
         double *E = c_sys.energy + (int64_t)w * 6;
@@ -1299,9 +1251,14 @@ __global__ void __launch_bounds__(128) k_commit(const int32_t *walker, const int
     const int w = walker[t];
     MgpuTrial *tr = c_sys.trial + w;
     if (!tr->active) { if (threadIdx.x == 0) atomicExch(err, 1); return; }
+    // every thread reads the counts, THEN the CTA meets, and only then may thread 0 overwrite them: molecules of
+    // 11+ sites spread the row copies over several warps (na * 3 + 2 > 32)
+    const int nA = c_sys.count[(int64_t)w * MGPU_MAX_RES + tr->res];
+    const int nB = (tr->kind == MGPU_KIND_SWAP) ? c_sys.count[(int64_t)w * MGPU_MAX_RES + tr->res2] : 0;
+    __syncthreads();
     if (accept[t]) {
-        if (tr->kind == MGPU_KIND_SWAP) commit_swap(w, tr->res, tr->mol, tr->res2, tr->com, tr->off, tr->e_old, tr->e_new, tr->hc_new, threadIdx.x, blockDim.x);
-        else commit_trial(w, tr->kind, tr->res, tr->mol, tr->com, tr->off, tr->e_old, tr->e_new, tr->hc_new, threadIdx.x, blockDim.x);
+        if (tr->kind == MGPU_KIND_SWAP) commit_swap(w, tr->res, tr->mol, nA, tr->res2, nB, tr->com, tr->off, tr->e_old, tr->e_new, tr->hc_new, threadIdx.x, blockDim.x);
+        else commit_trial(w, tr->kind, tr->res, tr->mol, nA, tr->com, tr->off, tr->e_old, tr->e_new, tr->hc_new, threadIdx.x, blockDim.x);
     } else if (tr->kind == MGPU_KIND_CREATE && tr->mol == 0) write_slot(w, tr->res, 0, tr->com, tr->off, threadIdx.x, blockDim.x);
     __syncthreads();
     if (threadIdx.x == 0) tr->active = 0;
@@ -1728,8 +1685,10 @@ __global__ void __launch_bounds__(MGPU_WBLOCK, 1) k_sweep(int first_walker, int 
             if (lane == 0) decide_step(w, ws, e_old, e_new);
             __syncwarp();
             if (sh.accept) {
-                if (sh.kind == MGPU_KIND_SWAP) commit_swap(w, sh.res, sh.mol, sh.res2, sh.com, sh.off, sh.e_old, sh.e_new, hc_new, lane, 32);
-                else commit_trial(w, sh.kind, sh.res, sh.mol, sh.com, sh.off, sh.e_old, sh.e_new, hc_new, lane, 32);
+                const int nA = ws.count[sh.res], nB = (sh.kind == MGPU_KIND_SWAP) ? ws.count[sh.res2] : 0;
+                __syncwarp();
+                if (sh.kind == MGPU_KIND_SWAP) commit_swap(w, sh.res, sh.mol, nA, sh.res2, nB, sh.com, sh.off, sh.e_old, sh.e_new, hc_new, lane, 32);
+                else commit_trial(w, sh.kind, sh.res, sh.mol, nA, sh.com, sh.off, sh.e_old, sh.e_new, hc_new, lane, 32);
                 if (lane == 0) {
                     if (sh.kind == MGPU_KIND_CREATE) ws.count[sh.res] += 1;
                     if (sh.kind == MGPU_KIND_DELETE) ws.count[sh.res] -= 1;
@@ -1870,8 +1829,8 @@ __global__ void k_selftest(double s_lo, double s_hi, int n, double *out)
         const int hi = __double2hiint(s);
         const int idx = (hi >> (20 - MGPU_TAB_K)) - c_sys.tab_ibase;
         if ((unsigned)idx < (unsigned)c_sys.tab_nint) {
-            const int chi = (hi & ~((1 << (20 - MGPU_TAB_K)) - 1)) | (1 << (19 - MGPU_TAB_K));
-            const double u = s - __hiloint2double(chi, 0);
+            const int mhi = (hi & ((1 << (20 - MGPU_TAB_K)) - 1)) | 0x3ff00000;
+            const double u = __hiloint2double(mhi, __double2loint(s)) - (1.0 + 1.0 / (double)(2 << MGPU_TAB_K));
             const double *row = c_sys.ctab + (size_t)idx * MGPU_TAB_ROW;
             const float uf = (float)u;
             double p = (double)fmaf(__int_as_float(__double2hiint(row[5])), uf, __int_as_float(__double2loint(row[5])));

@@ -12,14 +12,18 @@
 //   [32 .. 63]     block averages [res][sum N, sum N^2, sum E, samples]
 //   [64], [65]     mc_input%translation_step, mc_input%rotation_step_angle of the walker;  [66 .. 71] reserved (0)
 //   [72 .. 72+2nk) S(k) = ewald%Ak: re[nk], im[nk]
-//   then, for every ACTIVE residue type in index order, count(res) molecules of
+//   then, for every ACTIVE residue type in index order, max(count(res), 1) molecules of
 //   { com[3], offset[natom][3], framework-energy cache {lj, coulomb} }   (guest%com(:,res,mol), guest%offset(:,res,mol,1:natom))
+//   -- slot 1 travels even when the walker holds no molecule of the type: it is the geometry template of the next
+//   insertion (insert_and_orient_molecule copies offset(:,res,1,:), monte_carlo_utils.f90:563-564) and a rejected
+//   creation leaves its trial geometry there (:579-591), so an empty walker's future depends on it.
 #pragma once
 #include "mgpu_kernels.cuh"
 
 #define MGPU_REC_HDR 72
 
 __device__ __forceinline__ int rec_molsize(int res) { return 3 + 3 * c_sys.natom[res] + 2; }
+__device__ __forceinline__ int rec_stored(int count) { return count > 0 ? count : 1; }      // molecules of a type stored in a record
 
 __global__ void k_record_len(int first, int n, long long *len)
 {
@@ -28,8 +32,27 @@ __global__ void k_record_len(int first, int n, long long *len)
     const int w = first + i;
     long long L = MGPU_REC_HDR + 2 * (long long)c_sys.nk;
     for (int r = 0; r < c_sys.nres; ++r)
-        if (c_sys.active[r]) L += (long long)c_sys.count[(int64_t)w * MGPU_MAX_RES + r] * rec_molsize(r);
+        if (c_sys.active[r]) L += (long long)rec_stored(c_sys.count[(int64_t)w * MGPU_MAX_RES + r]) * rec_molsize(r);
     len[i] = L;
+}
+
+// record lengths of walkers [first, first + n) and their exclusive prefix sum, in one launch of ONE CTA (pipelined
+// mgpu_block: no host round trip between the sweep and the pack).  off[0] = 0, off[n] = total.
+__global__ void __launch_bounds__(256) k_record_offsets(int first, int n, long long *off)
+{
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int w = first + i;
+        long long L = MGPU_REC_HDR + 2 * (long long)c_sys.nk;
+        for (int r = 0; r < c_sys.nres; ++r)
+            if (c_sys.active[r]) L += (long long)rec_stored(c_sys.count[(int64_t)w * MGPU_MAX_RES + r]) * rec_molsize(r);
+        off[i + 1] = L;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long run = 0;
+        off[0] = 0;
+        for (int i = 0; i < n; ++i) { run += off[i + 1]; off[i + 1] = run; }
+    }
 }
 
 // one warp per walker
@@ -54,7 +77,7 @@ __global__ void __launch_bounds__(256) k_pack(int first, int n, const long long 
     const double *wc = c_sys.coords + (int64_t)w * c_sys.coord_stride;
     for (int r = 0; r < c_sys.nres; ++r) {
         if (!c_sys.active[r]) continue;
-        const int cnt = c_sys.count[(int64_t)w * MGPU_MAX_RES + r], ms = rec_molsize(r), cap = c_sys.cap[r];
+        const int cnt = rec_stored(c_sys.count[(int64_t)w * MGPU_MAX_RES + r]), ms = rec_molsize(r), cap = c_sys.cap[r];
         const double *src = wc + c_sys.goff[r];         // rows: com x,y,z | offset rows (atom, dim) | cache lj, coulomb; each cap long
         for (int t = lane; t < cnt * ms; t += 32) {
             const int m = t / ms, e = t - m * ms;
@@ -64,22 +87,14 @@ __global__ void __launch_bounds__(256) k_pack(int first, int n, const long long 
     }
 }
 
-__global__ void __launch_bounds__(256) k_unpack(int first, int n, const long long *off, const double *blob, int32_t *err)
+// (Records are validated on the host before anything is uploaded: validate_records in maniac_gpu.cu.)
+__global__ void __launch_bounds__(256) k_unpack(int first, int n, const long long *off, const double *blob)
 {
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (i >= n) return;
     const int w = first + i;
     const double *rec = blob + off[i];
     const int nk = c_sys.nk;
-    long long L = MGPU_REC_HDR + 2 * (long long)nk;
-    bool ok = true;
-    for (int r = 0; r < c_sys.nres; ++r) {
-        const int cnt = (int)rec[1 + r];
-        if (!c_sys.active[r]) continue;
-        if (cnt < 0 || cnt > c_sys.cap[r]) ok = false;
-        L += (long long)cnt * rec_molsize(r);
-    }
-    if (!ok || (long long)rec[0] != L || off[i + 1] - off[i] != L) { if (lane == 0) atomicExch(err, 4); return; }
     if (lane < MGPU_MAX_RES && c_sys.active[lane]) c_sys.count[(int64_t)w * MGPU_MAX_RES + lane] = (int)rec[1 + lane];
     if (lane < 6) c_sys.energy[(int64_t)w * 6 + lane] = rec[9 + lane];
     if (lane < 4) c_sys.rng[(int64_t)w * 4 + lane] = (uint64_t)__double_as_longlong(rec[15 + lane]);
@@ -93,7 +108,7 @@ __global__ void __launch_bounds__(256) k_unpack(int first, int n, const long lon
     double *wc = c_sys.coords + (int64_t)w * c_sys.coord_stride;
     for (int r = 0; r < c_sys.nres; ++r) {
         if (!c_sys.active[r]) continue;
-        const int cnt = (int)rec[1 + r], ms = rec_molsize(r), cap = c_sys.cap[r];
+        const int cnt = rec_stored((int)rec[1 + r]), ms = rec_molsize(r), cap = c_sys.cap[r];
         double *dst = wc + c_sys.goff[r];
         for (int t = lane; t < cnt * ms; t += 32) {
             const int m = t / ms, e = t - m * ms;

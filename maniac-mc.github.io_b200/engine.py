@@ -21,7 +21,7 @@ from .inputs import ERROR, System
 
 E_NON_COULOMB, E_COULOMB, E_RECIP, E_SELF, E_INTRA, E_TOTAL = range(6)
 KIND_MOVE, KIND_CREATE, KIND_DELETE, KIND_SWAP = 0, 1, 2, 3
-OPT_HOST_CACHE, OPT_PHASE_SYNC = 1, 2
+OPT_HOST_CACHE, OPT_PHASE_SYNC, OPT_BLOCK_SLICES = 1, 2, 3
 MV_NONE, MV_TRANSLATE, MV_ROTATE, MV_CREATE, MV_DELETE, MV_SWAP, MV_WIDOM = range(7)
 
 TRACE_DTYPE = np.dtype([("move", "i4"), ("res", "i4"), ("mol", "i4"), ("accepted", "i4"),
@@ -384,9 +384,11 @@ class Engine:
             if not active:
                 continue
             ms, cnt = 3 + 3 * na + 2, int(rec[1 + r])
-            m = rec[p:p + cnt * ms].reshape(cnt, ms)
-            out["molecules"][r] = dict(com=m[:, :3].copy(), offset=m[:, 3:3 + 3 * na].reshape(cnt, na, 3).copy(), cache=m[:, -2:].copy())
-            p += cnt * ms
+            stored = max(cnt, 1)                   # slot 1 is stored even when the type is empty (insertion template)
+            m = rec[p:p + stored * ms].reshape(stored, ms)
+            out["molecules"][r] = dict(com=m[:cnt, :3].copy(), offset=m[:cnt, 3:3 + 3 * na].reshape(cnt, na, 3).copy(), cache=m[:cnt, -2:].copy(),
+                                       template_offset=m[0, 3:3 + 3 * na].reshape(na, 3).copy())
+            p += stored * ms
         return out
 
     # ---- multi-GPU: the one exchange of the path -----------------------------------
