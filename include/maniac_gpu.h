@@ -153,7 +153,13 @@ enum { MGPU_OPT_HOST_CACHE = 1,
        /* MGPU_OPT_BLOCK_SLICES (default 8, at most 16): mgpu_block cuts its walkers into this many slices, each on its
         * own stream, so that the records of slice i+1 travel host -> device and those of slice i-1 device -> host while
         * slice i is being swept.  1 = no pipelining (load, sweep, save one after the other).  Same results either way. */
-       MGPU_OPT_BLOCK_SLICES = 3 };
+       MGPU_OPT_BLOCK_SLICES = 3,
+       /* MGPU_OPT_SWEEP_TEAM (default -1 = automatic): shape of mgpu_sweep / mgpu_block launches.  0 = one warp per
+        * walker (16 walkers per CTA: the throughput shape, fills the GPU from 2368 walkers up).  1 = a team of four
+        * warps per walker (4 walkers per CTA): the energy loops of a trial are split over 128 threads, for launches
+        * with few walkers per GPU (a fixed isotherm spread over more GPUs).  -1 picks teams when the walkers would
+        * fill less than half of the GPU's warp slots.  Same trajectories either way (sums are reduced in another order). */
+       MGPU_OPT_SWEEP_TEAM = 4 };
 int mgpu_set_option(int32_t option, int32_t value);
 
 /* ---- energy routines (single walker, drop-in) -------------------------------------- */

@@ -9,7 +9,8 @@
 ! no CPU fallback on this path.
 !
 ! NOTE: the build image of this repository has no Fortran compiler, so this
-! file is shipped as source and is exercised through tests/c_abi_driver.c,
+! file is shipped as source (never compiled here) and its calling conventions are exercised by tests/c_abi_driver.c
+! (built and run by tests/test_c_abi_driver.py),
 ! which makes the same calls with the same argument conventions (by-value
 ! scalars, contiguous column-major arrays, 0-based ids after the shim's -1).
 !-------------------------------------------------------------------------------

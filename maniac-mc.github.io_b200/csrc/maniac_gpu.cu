@@ -52,6 +52,8 @@ struct Context {
     int phase_sync = 13;               // MGPU_OPT_PHASE_SYNC bits: 1 top of the MC step, 2 before the energy evaluation, 4 before the guest pass, 8 before k-space
     int tri_listed = 0;                // triclinic: candidates listed but provably irrelevant (see mgpu_init)
     int wgroups = MGPU_WGROUPS;        // walkers (warps) per CTA of the warp-per-task kernels
+    size_t smem_team = 0;              // dynamic shared memory of the team sweep (wgroups * 32 / MGPU_TEAM walkers per CTA)
+    int sweep_team = -1;               // MGPU_OPT_SWEEP_TEAM: -1 auto (teams when the walkers fill less than half the warp slots), 0 never, 1 always
     int tab_emin = 0, tab_noct = 0;
     std::vector<void *> allocs;
     // host-side mirrors needed by the API
@@ -185,6 +187,29 @@ int rebuild(int first, int n)
     return 0;
 }
 int ensure_clean(int w) { if (g.dirty[w]) return rebuild(w, 1); return 0; }
+// One launch of the device-resident drivers for walkers [first, first + n).  Shape: one warp per walker (16 walkers per
+// CTA) when the walkers fill the GPU's warp slots; a team of four warps per walker (4 walkers per CTA) when they fill less
+// than half of them (few walkers per GPU: strong scaling of a fixed isotherm).
+bool sweep_uses_teams(int n)
+{
+    if (g.wgroups * 32 < MGPU_TEAM) return false;
+    if (g.sweep_team >= 0) return g.sweep_team != 0;
+    return (long long)n * (MGPU_TEAM / 32) * 2 <= (long long)g.sm_count * g.wgroups;
+}
+// n_total: the walkers in flight together (the call's, when it is cut into slices on several streams)
+void launch_sweep(cudaStream_t st, int first, int n, long long n_steps, int trace_walker, mgpu_step_trace *d_trace, int n_total)
+{
+    const int threads = 32 * g.wgroups;
+    if (sweep_uses_teams(n_total)) {
+        const int per_cta = threads / MGPU_TEAM, nb = (n + per_cta - 1) / per_cta;
+        if (g.h.triclinic) k_sweep<true, MGPU_TEAM><<<nb, threads, g.smem_team, st>>>(first, n, n_steps, g.natom_max, trace_walker, d_trace, g.d_err, g.phase_sync);
+        else k_sweep<false, MGPU_TEAM><<<nb, threads, g.smem_team, st>>>(first, n, n_steps, g.natom_max, trace_walker, d_trace, g.d_err, g.phase_sync);
+    } else {
+        const int nb = (n + g.wgroups - 1) / g.wgroups;
+        if (g.h.triclinic) k_sweep<true, 32><<<nb, threads, g.smem8, st>>>(first, n, n_steps, g.natom_max, trace_walker, d_trace, g.d_err, g.phase_sync);
+        else k_sweep<false, 32><<<nb, threads, g.smem8, st>>>(first, n, n_steps, g.natom_max, trace_walker, d_trace, g.d_err, g.phase_sync);
+    }
+}
 // host mirror of the molecule counts (argument checks of the host-driven trials): kept current by commits and
 // mgpu_set_count, re-read from the device after anything that changes counts there (sweeps, record loads)
 int ensure_counts()
@@ -285,7 +310,6 @@ int mgpu_init(const mgpu_system *sys)
         for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) h.Hinv[i * 3 + j] = rcp * adj[i][j];
     }
     for (int d = 0; d < 3; ++d) { h.L[d] = M[d][d]; h.invL[d] = 1.0 / M[d][d]; }
-    h.rint_magic = MGPU_RINT_MAGIC;
     h.tri_nrel = 0; g.tri_listed = 0;
     if (h.triclinic) {
         // lattice vectors that can beat the fractionally rounded image (min_image_r2<true>): m is relevant iff
@@ -621,10 +645,10 @@ int mgpu_init(const mgpu_system *sys)
     g.commit_inflight = false;
 
     // ---- shared-memory budgets ----
-    g.smem1 = smem_bytes(h.ntypes, h.tab_nint, h.kmax_max, g.natom_max, 1, 1);
+    g.smem1 = smem_bytes(h.ntypes, h.tab_nint, h.kmax_max, g.natom_max, 1, 1, true);
     g.wgroups = MGPU_WGROUPS;
-    while (g.wgroups > 1 && smem_bytes(h.ntypes, h.tab_nint, h.kmax_max, g.natom_max, g.wgroups, MGPU_TAB_REP) > 227 * 1024) --g.wgroups;
-    g.smem8 = smem_bytes(h.ntypes, h.tab_nint, h.kmax_max, g.natom_max, g.wgroups, MGPU_TAB_REP);
+    while (g.wgroups > 4 && smem_bytes(h.ntypes, h.tab_nint, h.kmax_max, g.natom_max, g.wgroups, MGPU_TAB_REP, false) > 227 * 1024) g.wgroups -= 4;   // whole quartets / teams
+    g.smem8 = smem_bytes(h.ntypes, h.tab_nint, h.kmax_max, g.natom_max, g.wgroups, MGPU_TAB_REP, false);
     g.smem_buildS = sizeof(double2) * (size_t)MGPU_STILE * 3 * (h.kmax_max + 1);
     const size_t smem_max = std::max(g.smem8, g.smem_buildS);
     if (smem_max > 227 * 1024) return fail("mgpu_init: kmax / ntypes / molecule size need more than 227 KB of shared memory per CTA");
@@ -632,7 +656,9 @@ int mgpu_init(const mgpu_system *sys)
 #define SET_SMEM(k, b) CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(b)))
     SET_SMEM((k_trial<false, 32>), g.smem8); SET_SMEM((k_trial<true, 32>), g.smem8);
     SET_SMEM((k_trial<false, MGPU_BLOCK>), g.smem1); SET_SMEM((k_trial<true, MGPU_BLOCK>), g.smem1);
-    SET_SMEM(k_sweep<false>, g.smem8); SET_SMEM(k_sweep<true>, g.smem8);
+    g.smem_team = smem_bytes(h.ntypes, h.tab_nint, h.kmax_max, g.natom_max, std::max(1, g.wgroups * 32 / MGPU_TEAM), MGPU_TAB_REP, true);
+    SET_SMEM((k_sweep<false, 32>), g.smem8); SET_SMEM((k_sweep<true, 32>), g.smem8);
+    SET_SMEM((k_sweep<false, MGPU_TEAM>), g.smem_team); SET_SMEM((k_sweep<true, MGPU_TEAM>), g.smem_team);
     SET_SMEM(k_total_energy<false>, g.smem1); SET_SMEM(k_total_energy<true>, g.smem1);
     SET_SMEM(k_pair_molecule<false>, g.smem1); SET_SMEM(k_pair_molecule<true>, g.smem1);
     SET_SMEM(k_widom_batch<false>, g.smem8); SET_SMEM(k_widom_batch<true>, g.smem8);
@@ -645,8 +671,8 @@ int mgpu_init(const mgpu_system *sys)
         int pct = (int)((g.smem8 + 1024 + 2048) * 100 / (228 * 1024)) + 1;
         if (pct > 100) pct = 100;
         if (const char *e = std::getenv("MGPU_CARVEOUT")) pct = std::atoi(e);
-        cudaFuncSetAttribute(k_sweep<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-        cudaFuncSetAttribute(k_sweep<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute((k_sweep<false, 32>), cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute((k_sweep<true, 32>), cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         cudaFuncSetAttribute(k_widom_batch<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         cudaFuncSetAttribute(k_widom_batch<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         cudaFuncSetAttribute((k_trial<false, 32>), cudaFuncAttributePreferredSharedMemoryCarveout, pct);
@@ -839,6 +865,7 @@ int mgpu_set_option(int32_t option, int32_t value)
 {
     NEED_READY();
     if (option == MGPU_OPT_PHASE_SYNC) { g.phase_sync = (value == 1) ? 13 : (value & 15); return 0; }   // bits: 1 top of step, 2 before the evaluation, 4 before the guest pass, 8 before k-space
+    if (option == MGPU_OPT_SWEEP_TEAM) { g.sweep_team = value < 0 ? -1 : (value ? 1 : 0); return 0; }
     if (option == MGPU_OPT_BLOCK_SLICES) { g.block_slices = value < 1 ? 1 : (value > Context::NPIPE ? (int)Context::NPIPE : value); return 0; }
     if (option == MGPU_OPT_HOST_CACHE) {
         g.h.use_hcache = value ? 1 : 0;
@@ -972,7 +999,7 @@ int mgpu_trial_batch(int32_t n, const int32_t *walker, const int32_t *res, const
         int grp = (n + g.sm_count - 1) / g.sm_count;
         if (grp > g.wgroups) grp = g.wgroups;
         const int nb = (n + grp - 1) / grp;
-        const size_t sm = smem_bytes(g.h.ntypes, g.h.tab_nint, g.h.kmax_max, g.natom_max, grp, MGPU_TAB_REP);
+        const size_t sm = smem_bytes(g.h.ntypes, g.h.tab_nint, g.h.kmax_max, g.natom_max, grp, MGPU_TAB_REP, false);
         if (g.h.triclinic) k_trial<true, 32><<<nb, 32 * grp, sm, g.stream>>>(T, n, g.natom_max);
         else k_trial<false, 32><<<nb, 32 * grp, sm, g.stream>>>(T, n, g.natom_max);
         tm.stop();
@@ -1102,9 +1129,7 @@ int mgpu_sweep(int32_t first, int32_t n, int64_t n_steps, int32_t trace_walker, 
     mgpu_step_trace *d_trace = nullptr;
     if (trace) CK(cudaMalloc(&d_trace, sizeof(mgpu_step_trace) * n_steps));
     Timer tm("sweep");
-    const int nb_sweep = (n + g.wgroups - 1) / g.wgroups;
-    if (g.h.triclinic) k_sweep<true><<<nb_sweep, 32 * g.wgroups, g.smem8, g.stream>>>(first, n, n_steps, g.natom_max, trace_walker, d_trace, g.d_err, g.phase_sync);
-    else k_sweep<false><<<nb_sweep, 32 * g.wgroups, g.smem8, g.stream>>>(first, n, n_steps, g.natom_max, trace_walker, d_trace, g.d_err, g.phase_sync);
+    launch_sweep(g.stream, first, n, n_steps, trace_walker, d_trace, n);
     tm.stop();
     cudaError_t le = cudaGetLastError();
     if (le != cudaSuccess) { if (d_trace) cudaFree(d_trace); return fail(std::string("k_sweep: ") + cudaGetErrorString(le)); }
@@ -1261,9 +1286,7 @@ static int block_pipelined(int32_t first, int32_t n, int64_t n_steps, const doub
         CK(cudaMemcpyAsync(g.p_in[i], blob_in + b0, sizeof(double) * in_len, cudaMemcpyHostToDevice, st));
         g.h2d_bytes += (long long)sizeof(double) * in_len + (long long)sizeof(long long) * (m + 1);
         k_unpack<<<(m + 7) / 8, 256, 0, st>>>(w0, m, g.p_off_in[i], g.p_in[i]);
-        const int nb = (m + g.wgroups - 1) / g.wgroups;
-        if (g.h.triclinic) k_sweep<true><<<nb, 32 * g.wgroups, g.smem8, st>>>(w0, m, n_steps, g.natom_max, -1, nullptr, g.d_err, g.phase_sync);
-        else k_sweep<false><<<nb, 32 * g.wgroups, g.smem8, st>>>(w0, m, n_steps, g.natom_max, -1, nullptr, g.d_err, g.phase_sync);
+        launch_sweep(st, w0, m, n_steps, -1, nullptr, n);
         k_record_offsets<<<1, 256, 0, st>>>(w0, m, g.p_off_out[i]);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(g.ph_off_out[i], g.p_off_out[i], sizeof(long long) * (m + 1), cudaMemcpyDeviceToHost, st));

@@ -57,7 +57,6 @@ struct MgpuTrial {
 struct DevSys {
     // box (type_cell, src/simulation_state.f90:103-112)
     double H[9], Hinv[9], lo[3], L[3], invL[3], volume;
-    double rint_magic;            // 1.5 * 2^52, kept out of the instruction stream on purpose (see rint_magic() in mgpu_kernels.cuh)
     int32_t triclinic;
     // triclinic minimum image without the 27-image loop (see min_image_r2<true>): lattice vectors
     // C m (tri_rel) that can beat the fractionally rounded image, and their integer coefficients m

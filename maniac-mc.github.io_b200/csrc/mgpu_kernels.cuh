@@ -41,10 +41,6 @@ __constant__ DevSys c_sys;
 // (a cp.async staging of the framework atoms two iterations ahead was measured in round 1: 19.45 M moves/s against
 // 20.5 M with the register rotation -- two more LDS.128 + two LDGSTS per iteration on an LSU that already serves the
 // table gather; removed.)
-// count the LJ terms inside the cutoff per pair (roofline accounting); 0 = production build without it
-#ifndef MGPU_COUNT_LJ
-#define MGPU_COUNT_LJ 1
-#endif
 // framework atoms per thread and iteration in the 3-probe-atom passes (1: three pair chains per thread; 2: six)
 #ifndef MGPU_HOST_U3
 #define MGPU_HOST_U3 1
@@ -80,7 +76,10 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-// Thread-group abstraction: NT = 32 (one warp) or MGPU_BLOCK (the whole CTA).
+// Thread-group abstraction: NT = 32 (one warp), MGPU_TEAM (a team of four warps, one per SM sub-partition, meeting
+// at its own named barrier) or MGPU_BLOCK (the whole CTA).
+#define MGPU_TEAM 128
+#define MGPU_BAR_PHASE 15                 // named barrier of the CTA-wide phase alignment of the team sweep
 template <int NT> struct Grp;
 template <> struct Grp<32> {
     static __device__ __forceinline__ int tid() { return threadIdx.x & 31; }
@@ -91,6 +90,30 @@ template <> struct Grp<32> {
     {
 #pragma unroll
         for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+    }
+};
+template <> struct Grp<MGPU_TEAM> {
+    static __device__ __forceinline__ int tid() { return threadIdx.x & (MGPU_TEAM - 1); }
+    static __device__ __forceinline__ int id() { return threadIdx.x / MGPU_TEAM; }
+    static __device__ __forceinline__ void sync() { asm volatile("bar.sync %0, %1;" :: "r"(1 + (int)(threadIdx.x / MGPU_TEAM)), "n"(MGPU_TEAM) : "memory"); }
+    template <int NV> static __device__ __forceinline__ void sum(double (&v)[NV], double *red)
+    {
+        const int lane = threadIdx.x & 31, wid = (threadIdx.x & (MGPU_TEAM - 1)) >> 5;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+        sync();                                // protect red from a previous use
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) red[i * MGPU_WARPS + wid] = v[i];
+        }
+        sync();
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < MGPU_TEAM / 32; ++w) s += red[i * MGPU_WARPS + w];   // fixed order
+            v[i] = s;
+        }
     }
 };
 template <> struct Grp<MGPU_BLOCK> {
@@ -153,21 +176,6 @@ __device__ __forceinline__ void apply_PBC(double pos[3])
 // minimum image (geometry_utils.f90:210-284) -> squared distance
 // ------------------------------------------------------------------------------------
 #define MGPU_RINT_MAGIC 6755399441055744.0     // 1.5 * 2^52: (x + M) - M = rint(x) for |x| < 2^51
-// The rounding constant as an opaque REGISTER value: with the literal, ptxas encodes it as the immediate of
-// DFMA/DADD and must then bring the box constants (1/L, L) into registers -- LDC/LDCU + R2UR every iteration of
-// the pair loops (r01z SASS: 15 of 138 instructions).  With the constant in a register the box constants are
-// read straight from the constant bank as the instruction's c[3][..] operand.
-#ifndef MGPU_MAGIC_REG
-#define MGPU_MAGIC_REG 1
-#endif
-__device__ __forceinline__ double rint_magic()
-{
-#if MGPU_MAGIC_REG
-    return c_sys.rint_magic;              // a run-time value as far as ptxas can tell
-#else
-    return MGPU_RINT_MAGIC;
-#endif
-}
 // The reference's triclinic branch, literally: minimum over the 27 shifts i c1 + j c2 + k c3 of the RAW
 // difference vector, c = COLUMNS of matrix (geometry_utils.f90:263-280).
 __device__ __noinline__ double min_image_27(double dx, double dy, double dz)
@@ -194,10 +202,9 @@ __device__ __forceinline__ double min_image_r2(double dx, double dy, double dz)
     if (!TRI) {
         // delta_d = modulo(delta_d + L/2, L) - L/2 restated as delta - L*rint(delta/L): the same
         // image except on the exact tie |delta| = L/2, where both images have the same length.
-        const double M = rint_magic();
-        const double nx = fma(dx, c_sys.invL[0], M) - M;
-        const double ny = fma(dy, c_sys.invL[1], M) - M;
-        const double nz = fma(dz, c_sys.invL[2], M) - M;
+        const double nx = fma(dx, c_sys.invL[0], MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC;
+        const double ny = fma(dy, c_sys.invL[1], MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC;
+        const double nz = fma(dz, c_sys.invL[2], MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC;
         dx = fma(-c_sys.L[0], nx, dx);
         dy = fma(-c_sys.L[1], ny, dy);
         dz = fma(-c_sys.L[2], nz, dz);
@@ -214,8 +221,8 @@ __device__ __forceinline__ double min_image_r2(double dx, double dy, double dz)
         const double f0 = fma(c_sys.Hinv[0], dx, fma(c_sys.Hinv[3], dy, c_sys.Hinv[6] * dz));
         const double f1 = fma(c_sys.Hinv[1], dx, fma(c_sys.Hinv[4], dy, c_sys.Hinv[7] * dz));
         const double f2 = fma(c_sys.Hinv[2], dx, fma(c_sys.Hinv[5], dy, c_sys.Hinv[8] * dz));
-        const double M = rint_magic();
-        const double n0 = (f0 + M) - M, n1 = (f1 + M) - M, n2 = (f2 + M) - M;
+        const double n0 = (f0 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC, n1 = (f1 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC,
+                     n2 = (f2 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC;
         const double tx = dx - fma(c_sys.H[0], n0, fma(c_sys.H[1], n1, c_sys.H[2] * n2));
         const double ty = dy - fma(c_sys.H[3], n0, fma(c_sys.H[4], n1, c_sys.H[5] * n2));
         const double tz = dz - fma(c_sys.H[6], n0, fma(c_sys.H[7], n1, c_sys.H[8] * n2));
@@ -277,31 +284,6 @@ __device__ __noinline__ double2 pair_exact(double s, double A, double B, double 
     return make_double2(e_lj, e_c);
 }
 
-// g(s) = erfc(alpha sqrt(s)) / sqrt(s) from this lane's replica of the table (three LDS.128, conflict free).  hi = high
-// word of s.  The unsigned clamp sends s below the first interval AND beyond the last one to the all-zero closing row.
-// The polynomial variable is the position inside the interval on a UNIT octave: t = the mantissa of s (exponent
-// replaced by 0, one LOP3 on the high word) minus the interval centre 1 + (j + 1/2) / 32, which for the bits kept is
-// just t' = (mantissa with the interval bits cleared) - (1 + 1/64): exact, one DADD with an immediate; the per-octave
-// scale 2^(e k) is folded into the row's coefficients by the table builder.
-template <int REP>
-__device__ __forceinline__ double coulomb_g(double s, int hi, const double2 *__restrict__ ctab)
-{
-    const unsigned idx = min((unsigned)((hi >> (20 - MGPU_TAB_K)) - c_sys.tab_ibase), (unsigned)c_sys.tab_nint);
-    const int mhi = (hi & ((1 << (20 - MGPU_TAB_K)) - 1)) | 0x3ff00000;
-    const double uu = __hiloint2double(mhi, __double2loint(s)) - (1.0 + 1.0 / (double)(2 << MGPU_TAB_K));
-    const double2 *t = ctab + idx * (3 * REP);
-    const double2 c01 = t[0], c23 = t[REP], c45 = t[2 * REP];
-    const float uf = (float)uu;
-    const float pf = fmaf(__int_as_float(__double2hiint(c45.y)), uf, __int_as_float(__double2loint(c45.y)));
-    double p = (double)pf;
-    p = fma(p, uu, c45.x);
-    p = fma(p, uu, c23.y);
-    p = fma(p, uu, c23.x);
-    p = fma(p, uu, c01.y);
-    p = fma(p, uu, c01.x);
-    return p;
-}
-
 // One atom pair on the hot path.  tab = this lane's replica of the Coulomb table in shared
 // memory (double2 units, see mgpu_internal.h).  qq = q_i q_j with either factor already zeroed
 // when |q| < 1e-10 (:157).  AB = {4 eps sigma^12, 4 eps sigma^6}.
@@ -328,7 +310,19 @@ __device__ __forceinline__ void pair_terms(double s, double2 AB, double qq, cons
         pc.lj += in;
     }
     if (doC) {
-        e_c = fma(qq, coulomb_g<REP>(s, hi, tab), e_c);
+        const int chi = (hi & ~((1 << (20 - MGPU_TAB_K)) - 1)) | (1 << (19 - MGPU_TAB_K));
+        const double u = s - __hiloint2double(chi, 0);          // exact: same binade
+        const double2 *t = tab + idx * (3 * REP);
+        const double2 c01 = t[0], c23 = t[REP], c45 = t[2 * REP];
+        const float uf = (float)u;
+        const float pf = fmaf(__int_as_float(__double2hiint(c45.y)), uf, __int_as_float(__double2loint(c45.y)));
+        double p = (double)pf;
+        p = fma(p, u, c45.x);
+        p = fma(p, u, c23.y);
+        p = fma(p, u, c23.x);
+        p = fma(p, u, c01.y);
+        p = fma(p, u, c01.x);
+        e_c = fma(qq, p, e_c);
         pc.coul += 1u;
     }
 }
@@ -379,9 +373,9 @@ struct GroupWS {
     WalkerLocal loc;
     double red[8 * MGPU_WARPS];
 };
-__host__ __device__ inline size_t smem_ws_bytes(bool warp_group)
+__host__ __device__ inline size_t smem_ws_bytes(bool with_red)
 {
-    return ((warp_group ? offsetof(GroupWS, red) : sizeof(GroupWS)) + 15) & ~size_t(15);
+    return ((with_red ? sizeof(GroupWS) : offsetof(GroupWS, red)) + 15) & ~size_t(15);
 }
 
 // The dynamic shared memory of every kernel here starts with the replicated Coulomb table,
@@ -390,7 +384,7 @@ __host__ __device__ inline size_t smem_ws_bytes(bool warp_group)
 extern __shared__ __align__(16) unsigned char mgpu_smem[];
 // REP = number of replicas: MGPU_TAB_REP in the warp-per-task kernels (one CTA per SM, filled once
 // per launch), 1 in the CTA-per-task kernels (latency path: a 15 KB fill per task, not 123 KB).
-template <int NT> struct TabRep { static constexpr int v = (NT == 32) ? MGPU_TAB_REP : 1; };
+template <int NT> struct TabRep { static constexpr int v = (NT == 32 || NT == MGPU_TEAM) ? MGPU_TAB_REP : 1; };
 template <int REP> __device__ __forceinline__ const double2 *smem_ctab() { return reinterpret_cast<const double2 *>(mgpu_smem) + (threadIdx.x & (REP - 1)); }
 template <int REP> __device__ __forceinline__ const double2 *smem_ljAB() { return reinterpret_cast<const double2 *>(mgpu_smem) + (size_t)(c_sys.tab_nint + 1) * 3 * REP; }
 
@@ -399,9 +393,10 @@ struct Smem {
     GroupWS *ws;
     double2 *tab_old, *tab_new;
 };
-__host__ __device__ inline size_t smem_group_bytes(int kmax_max, int natom_max, int rep)
+// with_red: the group spans more than one warp and needs the cross-warp reduction scratch
+__host__ __device__ inline size_t smem_group_bytes(int kmax_max, int natom_max, bool with_red)
 {
-    size_t b = smem_ws_bytes(rep > 1);
+    size_t b = smem_ws_bytes(with_red);
     b += (sizeof(double) * 2 * 3 * (size_t)natom_max + 15) & ~size_t(15);          // probe positions, old and new
     b += sizeof(double2) * 2 * (size_t)natom_max * 3 * (kmax_max + 1);
     return b;
@@ -410,16 +405,18 @@ __host__ __device__ inline size_t smem_common_bytes(int ntypes, int tab_nint, in
 {
     return sizeof(double2) * ((size_t)(tab_nint + 1) * 3 * rep + (size_t)ntypes * ntypes);      // + the all-zero row that closes the table
 }
-__host__ __device__ inline size_t smem_bytes(int ntypes, int tab_nint, int kmax_max, int natom_max, int groups, int rep)
+__host__ __device__ inline size_t smem_bytes(int ntypes, int tab_nint, int kmax_max, int natom_max, int groups, int rep, bool with_red)
 {
-    return smem_common_bytes(ntypes, tab_nint, rep) + groups * smem_group_bytes(kmax_max, natom_max, rep) + 16;
+    return smem_common_bytes(ntypes, tab_nint, rep) + groups * smem_group_bytes(kmax_max, natom_max, with_red) + 16;
 }
 // Carve the CTA's dynamic shared memory and (cooperatively, whole CTA) load the common part.
 // Every thread of the CTA must call this; it ends with __syncthreads().
-template <int REP>
-__device__ __forceinline__ Smem smem_setup(unsigned char *base, int natom_max, int group)
+template <int REP, int NT>
+__device__ __forceinline__ Smem smem_setup(unsigned char *base, int natom_max)
 {
     Smem s;
+    const int group = Grp<NT>::id();
+    constexpr bool with_red = (NT != 32);
     double2 *d = reinterpret_cast<double2 *>(base);
     const int nt2 = c_sys.ntypes * c_sys.ntypes;
     const int nchunk = (c_sys.tab_nint + 1) * 3;              // ctab holds tab_nint rows + one all-zero row
@@ -427,11 +424,11 @@ __device__ __forceinline__ Smem smem_setup(unsigned char *base, int natom_max, i
     for (int i = threadIdx.x; i < nchunk * REP; i += blockDim.x) d[i] = src[i / REP];
     double2 *lj = d + (size_t)nchunk * REP;
     for (int i = threadIdx.x; i < nt2; i += blockDim.x) lj[i] = make_double2(c_sys.ljA[i], c_sys.ljB[i]);
-    unsigned char *g = base + smem_common_bytes(c_sys.ntypes, c_sys.tab_nint, REP) + (size_t)group * smem_group_bytes(c_sys.kmax_max, natom_max, REP);
+    unsigned char *g = base + smem_common_bytes(c_sys.ntypes, c_sys.tab_nint, REP) + (size_t)group * smem_group_bytes(c_sys.kmax_max, natom_max, with_red);
     s.ws = reinterpret_cast<GroupWS *>(g);
-    double (*ppos)[3] = reinterpret_cast<double (*)[3]>(g + smem_ws_bytes(REP > 1));
-    if ((REP > 1) ? ((threadIdx.x & 31) == 0) : (threadIdx.x == 0)) { s.ws->probe.po = ppos; s.ws->probe.pn = ppos + natom_max; s.ws->sync_q = 0; s.ws->sync_k = 0; }
-    s.tab_old = reinterpret_cast<double2 *>(g + smem_ws_bytes(REP > 1) + ((sizeof(double) * 2 * 3 * (size_t)natom_max + 15) & ~size_t(15)));
+    double (*ppos)[3] = reinterpret_cast<double (*)[3]>(g + smem_ws_bytes(with_red));
+    if (Grp<NT>::tid() == 0) { s.ws->probe.po = ppos; s.ws->probe.pn = ppos + natom_max; s.ws->sync_q = 0; s.ws->sync_k = 0; }
+    s.tab_old = reinterpret_cast<double2 *>(g + smem_ws_bytes(with_red) + ((sizeof(double) * 2 * 3 * (size_t)natom_max + 15) & ~size_t(15)));
     s.tab_new = s.tab_old + (size_t)natom_max * 3 * (c_sys.kmax_max + 1);
     __syncthreads();
     return s;
@@ -477,26 +474,26 @@ struct HostPass {
 
     // vmask: bit u set = target u is real (guest passes mask the tail / the excluded molecule;
     // framework passes hand in a constant all-ones mask and the tests fold away).
-    // Pairs below the table start (r < 1 A, incl. the overlap sentinel) read the all-zero row that closes the
-    // table (the unsigned clamp sends both ends there) and are left out of the LJ sum; block() only REPORTS that
-    // there was one (return value).  The caller remembers the range of iterations that reported and redoes just
-    // those with fix() after its loop, so the loop body holds no call: a CALL inside it made ptxas reload every
-    // box / table constant and the global-memory descriptor in each iteration (r01z SASS: 19 of the 138
-    // instructions of the 3-atom Coulomb loop were LDC / LDCU / R2UR).
+    // Coulomb sums are kept per probe atom WITHOUT its charge (acc[i] += q_j g(s)); the caller multiplies by
+    // q_i once per pass.  Pairs below the table start (r < 1 A, incl. the overlap sentinel) read the all-zero
+    // row that closes the table (the unsigned clamp sends both ends there), are left out of the LJ sum, and
+    // are redone with the exact formulas when the block's smallest r^2 says there was one (e_x: their sum).
     template <int UU>
-    __device__ __forceinline__ bool block(const Atoms<UU> &A, const unsigned vmask, double &e_lj, double (&acc)[N], PairCount &pc) const
+    __device__ __forceinline__ void block(const Atoms<UU> &A, const unsigned vmask, double &e_lj, double (&acc)[N], double2 &e_x, PairCount &pc) const
     {
         const double2 (&txy)[UU] = A.xy; const double2 (&tzq)[UU] = A.zq; const int (&tt)[UU] = A.tt;
         const double2 *ctab = smem_ctab<REP>(), *ljAB = smem_ljAB<REP>();
         const bool all = (vmask == (1u << UU) - 1u);
         int hmin = 0x7fffffff;
+        double sv[UU][N];
 #pragma unroll
         for (int u = 0; u < UU; ++u) {
             const bool val = (vmask >> u) & 1u;
 #pragma unroll
             for (int i = 0; i < N; ++i) {
                 double s = min_image_r2<TRI>(txy[u].x - px[i], txy[u].y - py[i], tzq[u].x - pz[i]);
-                if (!all) s = val ? s : 1.0e30;                                 // not a target: beyond every range
+                if (!all) s = val ? s : 1.0e30;                                 // not a target: beyond every range (and (float)(s - centre) stays finite)
+                sv[u][i] = s;
                 const int hi = __double2hiint(s);
                 hmin = min(hmin, hi);
                 if ((MODE & 1) && (!TRI || __any_sync(__activemask(), s < c_sys.rc2))) {     // triclinic (large cells): whole warps are beyond the cutoff
@@ -505,37 +502,41 @@ struct HostPass {
                     const double e = (AB.x * y3 - AB.y) * y3;
                     const bool in = (s < c_sys.rc2) && (hi >= c_sys.tab_hi_lo);
                     e_lj += in ? e : 0.0;
-                    if (MGPU_COUNT_LJ) pc.lj += (in && (AB.x != 0.0 || AB.y != 0.0));
+                    pc.lj += (in && (AB.x != 0.0 || AB.y != 0.0));
                 }
                 if (MODE & 2) {
-                    const double p = coulomb_g<REP>(s, hi, ctab);
+                    const unsigned idx = min((unsigned)((hi >> (20 - MGPU_TAB_K)) - c_sys.tab_ibase), (unsigned)c_sys.tab_nint);
+                    const int chi = (hi & ~((1 << (20 - MGPU_TAB_K)) - 1)) | (1 << (19 - MGPU_TAB_K));
+                    const double uu = s - __hiloint2double(chi, 0);         // exact: same binade
+                    const double2 *t = ctab + idx * (3 * REP);
+                    const double2 c01 = t[0], c23 = t[REP], c45 = t[2 * REP];
+                    const float uf = (float)uu;
+                    const float pf = fmaf(__int_as_float(__double2hiint(c45.y)), uf, __int_as_float(__double2loint(c45.y)));
+                    double p = (double)pf;
+                    p = fma(p, uu, c45.x);
+                    p = fma(p, uu, c23.y);
+                    p = fma(p, uu, c23.x);
+                    p = fma(p, uu, c01.y);
+                    p = fma(p, uu, c01.x);
                     if (MGPU_ACC_PER_ATOM) acc[i] = fma(tzq[u].y, p, acc[i]);
                     else acc[0] = fma(q[i] * tzq[u].y, p, acc[0]);
                 }
             }
         }
-        return hmin < c_sys.tab_hi_lo;                                          // rare: some r < 1 A (incl. overlap)
-    }
-
-    // the pairs of a block that fell below the table start, with the reference's exact formulas (e_x: their sum)
-    template <int UU>
-    __device__ __forceinline__ void fix(const Atoms<UU> &A, const unsigned vmask, double2 &e_x, PairCount &pc) const
-    {
-        const double2 *ljAB = smem_ljAB<REP>();
-#pragma unroll 1
-        for (int u = 0; u < UU; ++u) {
-            if (!((vmask >> u) & 1u)) continue;
-#pragma unroll 1
-            for (int i = 0; i < N; ++i) {
-                const double s = min_image_r2<TRI>(A.xy[u].x - px[i], A.xy[u].y - py[i], A.zq[u].x - pz[i]);
-                if (__double2hiint(s) >= c_sys.tab_hi_lo) continue;
-                double2 AB = make_double2(0.0, 0.0);
-                if (MODE & 1) AB = ljAB[trow[i] + A.tt[u]];
-                const double qq = (MODE & 2) ? q[i] * A.zq[u].y : 0.0;
-                const double2 e = pair_exact(s, AB.x, AB.y, qq, qq != 0.0);
-                e_x.x += e.x; e_x.y += e.y;
-                if ((MODE & 1) && MGPU_COUNT_LJ) pc.lj += ((AB.x != 0.0 || AB.y != 0.0) && s < c_sys.rc2);
-            }
+        if (hmin < c_sys.tab_hi_lo) {                               // rare: some r < 1 A (incl. overlap)
+#pragma unroll
+            for (int u = 0; u < UU; ++u)
+#pragma unroll
+                for (int i = 0; i < N; ++i)
+                    if (__double2hiint(sv[u][i]) < c_sys.tab_hi_lo) {
+                        const double s = sv[u][i];
+                        double2 AB = make_double2(0.0, 0.0);
+                        if (MODE & 1) AB = ljAB[trow[i] + tt[u]];
+                        const double qq = (MODE & 2) ? q[i] * tzq[u].y : 0.0;
+                        const double2 e = pair_exact(s, AB.x, AB.y, qq, qq != 0.0);
+                        e_x.x += e.x; e_x.y += e.y;
+                        if (MODE & 1) pc.lj += ((AB.x != 0.0 || AB.y != 0.0) && s < c_sys.rc2);
+                    }
         }
     }
 
@@ -548,17 +549,13 @@ struct HostPass {
         double acc[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) acc[i] = 0.0;
+        double2 e_x = make_double2(0.0, 0.0);
         PairCount pc = pc_io;
         const int n = c_sys.n_host;
         const int step = U * stride, reach = (U - 1) * stride;
         int j = t0;
-        int jb0 = 0x7fffffff, jb1 = -1;                        // first / last index of this thread that reported a pair below the table
         if (!MGPU_PF_HOSTU && U > 1) {
-            for (; j + reach < n; j += step) {
-                Atoms<U> a; fetch<U>(a, j, stride);
-                const bool bad = block<U>(a, (1u << U) - 1u, e_lj, acc, pc);
-                jb0 = bad ? min(jb0, j) : jb0; jb1 = bad ? j + reach : jb1;
-            }
+            for (; j + reach < n; j += step) { Atoms<U> a; fetch<U>(a, j, stride); block<U>(a, (1u << U) - 1u, e_lj, acc, e_x, pc); }
         } else if (j + reach < n) {
             Atoms<U> cur;
             fetch<U>(cur, j, stride);
@@ -567,20 +564,13 @@ struct HostPass {
                 const bool more = jn + reach < n;
                 Atoms<U> nxt;
                 fetch<U>(nxt, more ? jn : j, stride);
-                const bool bad = block<U>(cur, (1u << U) - 1u, e_lj, acc, pc);
-                jb0 = bad ? min(jb0, j) : jb0; jb1 = bad ? j + reach : jb1;
+                block<U>(cur, (1u << U) - 1u, e_lj, acc, e_x, pc);
                 j = jn;
                 if (!more) break;
                 cur = nxt;
             }
         }
-        for (; j < n; j += stride) {
-            Atoms<1> a1; fetch<1>(a1, j, stride);
-            const bool bad = block<1>(a1, 1u, e_lj, acc, pc);
-            jb0 = bad ? min(jb0, j) : jb0; jb1 = bad ? j : jb1;
-        }
-        double2 e_x = make_double2(0.0, 0.0);
-        for (int jj = jb0; jj <= jb1; jj += stride) { Atoms<1> a1; fetch<1>(a1, jj, stride); fix<1>(a1, 1u, e_x, pc); }
+        for (; j < n; j += stride) { Atoms<1> a1; fetch<1>(a1, j, stride); block<1>(a1, 1u, e_lj, acc, e_x, pc); }
         double e_c = e_x.y;
         if (MGPU_ACC_PER_ATOM) {
 #pragma unroll
@@ -598,23 +588,6 @@ struct HostPass {
     // in memory, so the lanes' loads coalesce); tq / ttype are the target atom's charge (0 if tiny)
     // and type.  Molecule m_skip is left out (the probe itself), and so is every m <= m_order
     // (ordering check of pairwise_energy_for_molecule, :60-62; -1 = none).
-    // target atom b of molecules m, m + stride, ... of a guest residue type as a block of U targets + validity mask
-    __device__ __forceinline__ unsigned guest_targets(Atoms<U> &A, const double *__restrict__ com, const double *__restrict__ offb,
-                                                      int cap, int n, int m, int stride, int m_skip, int m_order, double tq, int ttype) const
-    {
-        unsigned vm = 0u;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int mm = m + u * stride;
-            const bool ok = (mm < n) && (mm != m_skip) && (mm > m_order);
-            const int mc = (mm < n) ? mm : m;
-            A.xy[u] = make_double2(com[mc] + offb[mc], com[cap + mc] + offb[cap + mc]);
-            A.zq[u] = make_double2(com[2 * cap + mc] + offb[2 * cap + mc], tq);
-            A.tt[u] = ttype;
-            vm |= ok ? (1u << u) : 0u;
-        }
-        return vm;
-    }
     __device__ __forceinline__ void run_guest(const double *__restrict__ com, const double *__restrict__ offb, int cap, int n,
                                               int t0, int stride, int m_skip, int m_order, double tq, int ttype,
                                               double &e_lj_io, double &e_c_io, PairCount &pc_io) const
@@ -623,20 +596,24 @@ struct HostPass {
         double acc[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) acc[i] = 0.0;
+        double2 e_x = make_double2(0.0, 0.0);
         PairCount pc = pc_io;
-        int mb0 = 0x7fffffff, mb1 = -1;                        // first / last chunk of this thread that reported a pair below the table
         for (int m = t0; m < n; m += U * stride) {
             Atoms<U> A;
-            const unsigned vm = guest_targets(A, com, offb, cap, n, m, stride, m_skip, m_order, tq, ttype);
-            const bool bad = block<U>(A, vm, e_lj, acc, pc);
-            mb0 = bad ? min(mb0, m) : mb0; mb1 = bad ? m : mb1;
+            unsigned vm = 0u;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int mm = m + u * stride;
+                const bool ok = (mm < n) && (mm != m_skip) && (mm > m_order);
+                const int mc = (mm < n) ? mm : m;
+                A.xy[u] = make_double2(com[mc] + offb[mc], com[cap + mc] + offb[cap + mc]);
+                A.zq[u] = make_double2(com[2 * cap + mc] + offb[2 * cap + mc], tq);
+                A.tt[u] = ttype;
+                vm |= ok ? (1u << u) : 0u;
+            }
+            block<U>(A, vm, e_lj, acc, e_x, pc);
         }
-        double2 e_x = make_double2(0.0, 0.0);
-        for (int m = mb0; m <= mb1; m += U * stride) {
-            Atoms<U> A;
-            const unsigned vm = guest_targets(A, com, offb, cap, n, m, stride, m_skip, m_order, tq, ttype);
-            fix<U>(A, vm, e_x, pc);
-        }
+
         double e_c = e_x.y;
         if (MGPU_ACC_PER_ATOM) {
 #pragma unroll
@@ -781,6 +758,14 @@ __device__ __forceinline__ void quartet_sync(int nthreads_in_quartet)
 {
     asm volatile("bar.sync %0, %1;" :: "r"(1 + (int)((threadIdx.x >> 5) & 3)), "r"(nthreads_in_quartet) : "memory");
 }
+// Phase alignment of the sweep kernels.  One warp per walker (NT = 32): the quartet barrier above, n = threads of the
+// quartet.  One TEAM per walker (NT = MGPU_TEAM; every team has a warp on every sub-partition): all teams of the CTA
+// meet, n = threads of the CTA.
+template <int NT> __device__ __forceinline__ void phase_barrier(int n)
+{
+    if (NT == 32) quartet_sync(n);
+    else asm volatile("bar.sync %0, %1;" :: "n"(MGPU_BAR_PHASE), "r"(n) : "memory");
+}
 
 // K1: group-cooperative pair sums of the probe against host atoms + the walker's guests.
 // When two geometries need the same kind of pass (old AND new of a move) the group splits in
@@ -808,7 +793,7 @@ __device__ __noinline__ void pair_sums(const Smem &S, int w, double (&out)[8], P
         acc[0] = new_set ? 0.0 : e_lj; acc[1] = new_set ? 0.0 : e_c;
         acc[2] = new_set ? e_lj : 0.0; acc[3] = new_set ? e_c : 0.0;
     }
-    if (NT == 32 && S.ws->sync_q) quartet_sync(S.ws->sync_q);     // k_sweep, MGPU_OPT_PHASE_SYNC bit 2: re-align before the guest pass
+    if (NT != MGPU_BLOCK && S.ws->sync_q) phase_barrier<NT>(S.ws->sync_q);     // k_sweep, MGPU_OPT_PHASE_SYNC bit 2: re-align before the guest pass
     {
         const bool both = P.has_old && P.has_new;
         const bool new_set = both ? (gt >= NT / 2) : (P.has_new != 0);
@@ -1017,7 +1002,7 @@ __device__ void evaluate_trial(const Smem &S, int w, bool store_S, double e_old[
     const double recip_cur = c_sys.energy[(int64_t)w * 6 + MGPU_E_RECIP];
     double recip_new = recip_cur;
     if (do_kspace) {
-        if (NT == 32 && S.ws->sync_k) quartet_sync(S.ws->sync_k);      // k_sweep, MGPU_OPT_PHASE_SYNC bit 3: re-align before k-space
+        if (NT != MGPU_BLOCK && S.ws->sync_k) phase_barrier<NT>(S.ws->sync_k);      // k_sweep, MGPU_OPT_PHASE_SYNC bit 3: re-align before k-space
         if (P.has_old) fill_phase_tables(S.tab_old, P.po, P.na, Grp<NT>::tid(), NT, c_sys.charge[P.res]);
         if (P.has_new) fill_phase_tables(S.tab_new, P.pn, P.na, Grp<NT>::tid(), NT, c_sys.charge[P.res]);
         Grp<NT>::sync();
@@ -1211,7 +1196,7 @@ struct TaskArrays {
 template <bool TRI, int NT>
 __global__ void __launch_bounds__(NT == 32 ? MGPU_WBLOCK : MGPU_BLOCK, 1) k_trial(TaskArrays T, int n_tasks, int natom_max)
 {
-    const Smem S = smem_setup<TabRep<NT>::v>(mgpu_smem, natom_max, Grp<NT>::id());
+    const Smem S = smem_setup<TabRep<NT>::v, NT>(mgpu_smem, natom_max);
     const int t = blockIdx.x * (NT == 32 ? (int)(blockDim.x >> 5) : 1) + Grp<NT>::id();
     if (t >= n_tasks) return;                       // whole groups leave together (no later CTA barrier for NT = 32)
     const int4 meta = T.meta[t];
@@ -1270,7 +1255,7 @@ __global__ void __launch_bounds__(MGPU_BLOCK) k_pair_molecule(int w, int res, in
                                                               const double *geom /* com[3] + off[na][3] or NULL */,
                                                               double *out2, int natom_max)
 {
-    const Smem S = smem_setup<1>(mgpu_smem, natom_max, 0);
+    const Smem S = smem_setup<1, MGPU_BLOCK>(mgpu_smem, natom_max);
     stage_counts<MGPU_BLOCK>(S, w);
     Probe &P = S.ws->probe;
     const int na = c_sys.natom[res];
@@ -1400,7 +1385,7 @@ __global__ void __launch_bounds__(MGPU_BLOCK) k_host_host(const int32_t *host_mo
 template <bool TRI>
 __global__ void __launch_bounds__(MGPU_BLOCK) k_total_energy(int first_walker, int natom_max)
 {
-    const Smem S = smem_setup<1>(mgpu_smem, natom_max, 0);
+    const Smem S = smem_setup<1, MGPU_BLOCK>(mgpu_smem, natom_max);
     const int w = first_walker + blockIdx.x;
     stage_counts<MGPU_BLOCK>(S, w);
     __syncthreads();
@@ -1640,21 +1625,28 @@ __device__ __noinline__ void decide_step(int w, GroupWS &ws, const double e_old[
 // + guest pass 21.8 M, + k-space 22.7 M, top + guest pass + k-space 22.8 M (default).  Quartets stay
 // independent of each other; a step that evaluates nothing takes the same barriers, and a swap (two
 // evaluations) takes them in its creation half, so every warp of a quartet arrives equally often.
-template <bool TRI>
+// NT = 32: one warp per walker (the throughput shape: 16 walkers per CTA).  NT = MGPU_TEAM: a team of four warps per
+// walker, used when a launch has fewer walkers than half the GPU's warp slots (strong scaling of a FIXED isotherm over
+// more GPUs): the energy loops split over 128 threads, the driver part (RNG, proposal, Metropolis) still
+// runs on one thread.  Same arithmetic per pair; sums are reduced in a different order (parity 1e-10, like the
+// CTA-per-trial kernels that share these templates).
+template <bool TRI, int NT>
 __global__ void __launch_bounds__(MGPU_WBLOCK, 1) k_sweep(int first_walker, int n_walkers, long long n_steps, int natom_max,
                                                       int trace_walker, mgpu_step_trace *trace, int32_t *err, int phase_sync)
 {
-    const Smem S = smem_setup<MGPU_TAB_REP>(mgpu_smem, natom_max, Grp<32>::id());
-    const int wl = blockIdx.x * (int)(blockDim.x >> 5) + Grp<32>::id();
+    const Smem S = smem_setup<MGPU_TAB_REP, NT>(mgpu_smem, natom_max);
+    const int ngroups = (int)blockDim.x / NT;
+    const int wl = blockIdx.x * ngroups + Grp<NT>::id();
     const bool live = wl < n_walkers;
     if (!live && !phase_sync) return;
     const int nwarps = (int)(blockDim.x >> 5);
-    const int qthreads = 32 * ((nwarps - (int)((threadIdx.x >> 5) & 3) + 3) / 4);
+    // threads that meet at a phase barrier: the warps of this warp's sub-partition (NT = 32) or the whole CTA (teams)
+    const int qthreads = (NT == 32) ? 32 * ((nwarps - (int)((threadIdx.x >> 5) & 3) + 3) / 4) : (int)blockDim.x;
     const int w = first_walker + (live ? wl : 0);
-    const int lane = threadIdx.x & 31;
+    const int lane = Grp<NT>::tid();                    // index inside the walker's group; 0 plays the Fortran driver
     GroupWS &ws = *S.ws;
     if (live) {
-        stage_counts<32>(S, w);
+        stage_counts<NT>(S, w);
         if (lane < 4) ws.loc.rng[lane] = c_sys.rng[(int64_t)w * 4 + lane];
         if (lane < 12) ws.loc.cnt[lane] = 0;
         if (lane < MGPU_MAX_RES) { ws.loc.avgN[lane] = 0.0; ws.loc.avgN2[lane] = 0.0; }
@@ -1662,43 +1654,43 @@ __global__ void __launch_bounds__(MGPU_WBLOCK, 1) k_sweep(int first_walker, int 
     }
     if (lane == 0) { ws.sh.valid = 0; ws.sync_q = (phase_sync & 4) ? qthreads : 0; ws.sync_k = (phase_sync & 8) ? qthreads : 0; }
     PairCount pc = { 0u, 0u, 0u, 0u };
-    __syncwarp();
+    Grp<NT>::sync();
 
     for (long long step = 0; step < n_steps; ++step) {
-        if (phase_sync & 1) quartet_sync(qthreads);
-        if (!live) { if (phase_sync & 2) quartet_sync(qthreads); if (phase_sync & 4) quartet_sync(qthreads); if (phase_sync & 8) quartet_sync(qthreads); continue; }
+        if (phase_sync & 1) phase_barrier<NT>(qthreads);
+        if (!live) { if (phase_sync & 2) phase_barrier<NT>(qthreads); if (phase_sync & 4) phase_barrier<NT>(qthreads); if (phase_sync & 8) phase_barrier<NT>(qthreads); continue; }
         if (lane == 0) propose_step(w, ws, err);
-        __syncwarp();
-        if (phase_sync & 2) quartet_sync(qthreads);
+        Grp<NT>::sync();
+        if (phase_sync & 2) phase_barrier<NT>(qthreads);
         const SweepShared &sh = ws.sh;
-        if (!sh.valid && (phase_sync & 4)) quartet_sync(qthreads);       // the barrier pair_sums would have taken
-        if (!sh.valid && (phase_sync & 8)) quartet_sync(qthreads);       // ... and the one before k-space
+        if (!sh.valid && (phase_sync & 4)) phase_barrier<NT>(qthreads);       // the barrier pair_sums would have taken
+        if (!sh.valid && (phase_sync & 8)) phase_barrier<NT>(qthreads);       // ... and the one before k-space
         if (sh.valid) {
             double e_old[6], e_new[6], hc_new[2];
             if (sh.kind == MGPU_KIND_SWAP) {
-                evaluate_swap<TRI, 32>(S, w, true, sh.res, sh.mol, sh.res2, ws.count[sh.res2], sh.com, sh.off, e_old, e_new, hc_new, pc);
+                evaluate_swap<TRI, NT>(S, w, true, sh.res, sh.mol, sh.res2, ws.count[sh.res2], sh.com, sh.off, e_old, e_new, hc_new, pc);
             } else {
-                stage_probe<32>(S, w, sh.kind, sh.res, sh.mol, sh.com, sh.off);
-                __syncwarp();
-                evaluate_trial<TRI, 32>(S, w, sh.move != MGPU_MV_WIDOM, e_old, e_new, hc_new, pc);
+                stage_probe<NT>(S, w, sh.kind, sh.res, sh.mol, sh.com, sh.off);
+                Grp<NT>::sync();
+                evaluate_trial<TRI, NT>(S, w, sh.move != MGPU_MV_WIDOM, e_old, e_new, hc_new, pc);
             }
             if (lane == 0) decide_step(w, ws, e_old, e_new);
-            __syncwarp();
+            Grp<NT>::sync();
             if (sh.accept) {
                 const int nA = ws.count[sh.res], nB = (sh.kind == MGPU_KIND_SWAP) ? ws.count[sh.res2] : 0;
-                __syncwarp();
-                if (sh.kind == MGPU_KIND_SWAP) commit_swap(w, sh.res, sh.mol, nA, sh.res2, nB, sh.com, sh.off, sh.e_old, sh.e_new, hc_new, lane, 32);
-                else commit_trial(w, sh.kind, sh.res, sh.mol, nA, sh.com, sh.off, sh.e_old, sh.e_new, hc_new, lane, 32);
+                Grp<NT>::sync();
+                if (sh.kind == MGPU_KIND_SWAP) commit_swap(w, sh.res, sh.mol, nA, sh.res2, nB, sh.com, sh.off, sh.e_old, sh.e_new, hc_new, lane, NT);
+                else commit_trial(w, sh.kind, sh.res, sh.mol, nA, sh.com, sh.off, sh.e_old, sh.e_new, hc_new, lane, NT);
                 if (lane == 0) {
                     if (sh.kind == MGPU_KIND_CREATE) ws.count[sh.res] += 1;
                     if (sh.kind == MGPU_KIND_DELETE) ws.count[sh.res] -= 1;
                     if (sh.kind == MGPU_KIND_SWAP) { ws.count[sh.res] -= 1; ws.count[sh.res2] += 1; }
                 }
             } else if (sh.kind == MGPU_KIND_CREATE && sh.mol == 0) {
-                write_slot(w, sh.res, 0, sh.com, sh.off, lane, 32);      // rejected / Widom insertion into an empty walker
+                write_slot(w, sh.res, 0, sh.com, sh.off, lane, NT);      // rejected / Widom insertion into an empty walker
             }
         }
-        __syncwarp();
+        Grp<NT>::sync();
         if (lane == 0) {
             if (trace && w == trace_walker) {
                 mgpu_step_trace *t = trace + step;
@@ -1721,7 +1713,7 @@ __global__ void __launch_bounds__(MGPU_WBLOCK, 1) k_sweep(int first_walker, int 
             ws.loc.n_samples += 1;
         }
         __threadfence_block();
-        __syncwarp();        // commit visible (coordinates, S flip, counts) to every lane before the next step
+        Grp<NT>::sync();     // commit visible (coordinates, S flip, counts) to every thread of the group before the next step
     }
     if (!live) return;
     flush_pair_count(pc);
@@ -1766,7 +1758,7 @@ __global__ void __launch_bounds__(MGPU_WBLOCK, 1) k_widom_batch(int w, int res, 
                                                             unsigned long long seed, double *dE_out,
                                                             double *warp_sum_w, long long *warp_n_ok, int natom_max)
 {
-    const Smem S = smem_setup<MGPU_TAB_REP>(mgpu_smem, natom_max, Grp<32>::id());
+    const Smem S = smem_setup<MGPU_TAB_REP, 32>(mgpu_smem, natom_max);
     const int lane = threadIdx.x & 31;
     const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + Grp<32>::id();
     const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
@@ -1829,8 +1821,8 @@ __global__ void k_selftest(double s_lo, double s_hi, int n, double *out)
         const int hi = __double2hiint(s);
         const int idx = (hi >> (20 - MGPU_TAB_K)) - c_sys.tab_ibase;
         if ((unsigned)idx < (unsigned)c_sys.tab_nint) {
-            const int mhi = (hi & ((1 << (20 - MGPU_TAB_K)) - 1)) | 0x3ff00000;
-            const double u = __hiloint2double(mhi, __double2loint(s)) - (1.0 + 1.0 / (double)(2 << MGPU_TAB_K));
+            const int chi = (hi & ~((1 << (20 - MGPU_TAB_K)) - 1)) | (1 << (19 - MGPU_TAB_K));
+            const double u = s - __hiloint2double(chi, 0);
             const double *row = c_sys.ctab + (size_t)idx * MGPU_TAB_ROW;
             const float uf = (float)u;
             double p = (double)fmaf(__int_as_float(__double2hiint(row[5])), uf, __int_as_float(__double2loint(row[5])));

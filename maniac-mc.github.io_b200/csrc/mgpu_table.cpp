@@ -4,7 +4,7 @@
 // (src/pairwise_energy_utils.f90:175).  On the GPU that one call is ~60 FP64 instructions;
 // here g is fitted per interval of s = r^2 (intervals = top MGPU_TAB_K mantissa bits within
 // each binary octave) by a truncated Chebyshev series of degree 6 computed in long double
-// from 28 Chebyshev nodes, and converted to a monomial in u' = (s - centre) / 2^octave.
+// from 28 Chebyshev nodes, and converted to a monomial in u = s - centre.
 // The fit error is checked in tests/test_host_logic.py (no GPU needed) through
 // mgpu_coulomb_table_check.
 #include <cmath>
@@ -51,16 +51,13 @@ void mgpu_build_coulomb_table(double alpha, double r_lo, double r_hi, int *emin_
                 for (int m = 0; m < NC; ++m) b[m] += a[n] * T2[m];
                 T0 = T1; T1 = T2;
             }
-            // t = u / h with u = s - centre; the device evaluates in u' = u / 2^(emin + e) (the position inside the
-            // interval on a unit octave: mantissa of s minus (1 + (j + 1/2) / NI)), so the octave's scale is folded
-            // into the coefficients: c_m = b_m / (h / base)^m.  c5, c6 stored in single precision, packed into the sixth double
+            // t = u / h; c5, c6 stored in single precision, packed into the sixth double
             double *row = tab.data() + (size_t)(e * NI + j) * MGPU_TAB_ROW;
-            const long double hu = 0.5L / NI;
             long double hp = 1.0L;
             float cf[2] = { 0.f, 0.f };
             for (int m = 0; m < NC; ++m) {
                 if (m < 5) row[m] = (double)(b[m] / hp); else cf[m - 5] = (float)(b[m] / hp);
-                hp *= hu;
+                hp *= h;
             }
             std::memcpy(&row[5], cf, 8);
         }
@@ -74,9 +71,10 @@ bool mgpu_eval_coulomb_table(const std::vector<double> &tab, int emin, int noct,
     const int32_t hi = (int32_t)(bits >> 32);
     const int idx = (hi >> (20 - K)) - ((1023 + emin) << K);
     if (idx < 0 || idx >= (noct << K)) return false;
-    const uint64_t mb = (bits & ((1ull << (52 - K)) - 1)) | 0x3ff0000000000000ull;      // mantissa of s below the interval bits, exponent 0
-    double t; std::memcpy(&t, &mb, 8);
-    const double u = t - (1.0 + 1.0 / (double)(2 << K));
+    const int32_t chi = (hi & ~((1 << (20 - K)) - 1)) | (1 << (19 - K));
+    const uint64_t cb = (uint64_t)(uint32_t)chi << 32;
+    double c; std::memcpy(&c, &cb, 8);
+    const double u = s - c;
     const double *row = tab.data() + (size_t)idx * MGPU_TAB_ROW;
     float cf[2]; std::memcpy(cf, &row[5], 8);
     const float uf = (float)u;

@@ -21,7 +21,7 @@ from .inputs import ERROR, System
 
 E_NON_COULOMB, E_COULOMB, E_RECIP, E_SELF, E_INTRA, E_TOTAL = range(6)
 KIND_MOVE, KIND_CREATE, KIND_DELETE, KIND_SWAP = 0, 1, 2, 3
-OPT_HOST_CACHE, OPT_PHASE_SYNC, OPT_BLOCK_SLICES = 1, 2, 3
+OPT_HOST_CACHE, OPT_PHASE_SYNC, OPT_BLOCK_SLICES, OPT_SWEEP_TEAM = 1, 2, 3, 4
 MV_NONE, MV_TRANSLATE, MV_ROTATE, MV_CREATE, MV_DELETE, MV_SWAP, MV_WIDOM = range(7)
 
 TRACE_DTYPE = np.dtype([("move", "i4"), ("res", "i4"), ("mol", "i4"), ("accepted", "i4"),

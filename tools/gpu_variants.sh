@@ -9,7 +9,7 @@ OUT=gpurun_out/variants_$TAG.jsonl
 for v in "$@"; do
   if [ "$v" = default ]; then unset MANIAC_GPU_LIB; else export MANIAC_GPU_LIB=$PWD/maniac-mc.github.io_b200/variants/libmaniac_gpu_$v.so; fi
   for rep in 1 2; do
-    timeout 300 python bench.py --quick ${QUICK_ARGS:-"--steps 6 --warmup 3"} >> $OUT 2>> gpurun_out/variants_$TAG.err
+    timeout 300 python bench.py --quick ${QUICK_ARGS:---steps 6 --warmup 3} >> $OUT 2>> gpurun_out/variants_$TAG.err
   done
 done
 unset MANIAC_GPU_LIB
