@@ -5,31 +5,37 @@ Contract (driver):  python bench.py --gpus N --steps K --warmup W     (N > 1 via
 prints ONE JSON line on rank 0.
 
   step      one launch of the device-resident sweep kernel: INNER Monte Carlo steps for every
-            walker of this rank (one warp per walker, zero host round trips inside the launch)
-  workload  BASELINE.json configs[1]: ZIF-8 2x2x2 + TIP4P water GCMC, move mix 0.4/0.4/0.2
-            (translate / rotate / insert-delete), 64 waters per walker initially, walkers
-            spread over a 64-point fugacity grid (the isotherm sweep of configs[3])
-  value     trial moves / s over all ranks, state resident in HBM, device-timed (CUDA events on
-            the launching stream), max over ranks
-  e2e       the same metric through the block-level C-ABI call with HOST buffers (mgpu_block):
-            every step the walkers' whole state travels pinned host -> device, the MC steps run,
-            and the updated state travels back; wall clock
-  host_driven  the Fortran drivers' role: host RNG / proposal / Metropolis, one mgpu_trial_batch +
-            mgpu_commit_batch per MC step (proposals H2D, energies D2H)
-  single_walker_dropin  one walker, one trial per call: the latency one unchanged Fortran process sees
-  roofline  the sweep kernel against the FP64-pipe peak measured on this GPU by a DFMA loop
-            (the binding roof of K1; SURVEY.md 8d convention C1): frac = C1 FLOPs of the pairs
-            EVALUATED; frac_reference_ops = the reference's full operation count per move at this
-            rate (the framework-energy cache and the per-molecule screen skip pairs); traffic =
-            DRAM bytes per launch from the committed ncu capture
-  no_host_cache / no_phase_sync   the same sweep with MGPU_OPT_HOST_CACHE / MGPU_OPT_PHASE_SYNC off
-  widom     BASELINE configs[2]: 10^6 CO2 test insertions in empty ZIF-8, one launch
-  mixture   BASELINE configs[4]: CO2/N2 with identity swaps in the 17 664-atom triclinic supercell
-  isotherm  per-point averages summed over ranks by the library's NCCL reduction (the one exchange)
-  cpu_baseline  the CPU oracle (a C restatement of the reference's serial algorithm) on the
-            host cores, bounded sample of the same workload
-  --impl reference   times that CPU path as the main line (no Fortran compiler in the image,
-            so the reference itself cannot be built; kind = "port")
+            walker of this rank (zero host round trips inside the launch)
+  workload  BASELINE.json configs[1] (SURVEY 8d M1): ZIF-8 2x2x2 + TIP4P water GCMC, move mix 0.4/0.4/0.2
+            (translate / rotate / insert-delete), EVERY WALKER PINNED AT 64 WATERS: before anything is
+            timed a pool of walkers is run under a feedback on ln(fugacity) until <N> sits at the target
+            and the configurations have relaxed, then the fugacity is frozen and the pool is cloned
+            (records through host memory, fresh RNG streams) into the timed walkers.  The loading at the
+            start and at the end of the timed region is in the line (`stationarity`): moves/s does not
+            depend on --steps
+  value     trial moves / s over all ranks (weak scaling: --walkers per GPU), state resident in HBM,
+            device-timed (CUDA events on the launching stream), max over ranks; the L2 is flushed
+            between timed launches
+  e2e       the same metric through the block-level C-ABI call with HOST buffers (mgpu_block): every
+            step the walkers' whole state travels pinned host -> device, the MC steps run, and the
+            updated state travels back, in slices on several streams (copies under compute); wall clock
+  roofline  the sweep kernel against the FP64-pipe peak measured on this GPU in this run (DFMA loop);
+            achieved = convention-C1 FLOPs (SURVEY 8d) of the pairs the launch EVALUATED / event time;
+            fp64_pipe_pct / issue_active_pct = executed-instruction utilisation from the committed ncu
+            capture of the same kernel; roofline_k2 = the k-space traffic against a measured L2 peak
+  grid      SURVEY 8d M1: loadings N in {0,16,64,128} x walkers W in {64,1024,4096,16384}, each pinned
+            and relaxed the same way (N = 1 only)
+  strong_scaling  SURVEY 8d M3 / BASELINE configs[3]: a FIXED isotherm of 64 fugacity points x 64
+            replicas = 4096 walkers split over the N GPUs (few walkers per GPU -> team shape of the
+            sweep kernel: four warps per walker); per-point sums reduced once with NCCL
+  widom     BASELINE configs[2]: 10^6 CO2 test insertions in empty ZIF-8 in 16 blocks, mu_ex +- sigma;
+            sum w / n reduced over ranks through mgpu_reduce_averages
+  mixture   BASELINE configs[4]: CO2/N2 with swaps in the 17 664-atom triclinic supercell
+  host_driven / single_walker_dropin   the Fortran drivers' role over the batched / single-trial ABI
+  cpu_baseline   the CPU oracle (C restatement of the reference's serial Fortran, gcc -O3) on all host
+            cores, bounded sample of the same workload state (same loading, same fugacity)
+  --impl reference   times that CPU path as the main line (no Fortran compiler in the image, so the
+            reference itself cannot be built; kind = "port")
 """
 import argparse
 import json
@@ -46,8 +52,10 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 INNER_DEFAULT = 256
-CAPACITY = 1024          # molecules per walker (NB_MAX_MOLECULE analogue): room for the pore-filling points of the fugacity grid
+CAPACITY = 320           # molecules per walker (NB_MAX_MOLECULE analogue); loadings up to 128 pinned
+POOL = 2368              # walkers of the equilibration pool: one full wave of the warp-per-walker shape
 FLOP_GEOM, FLOP_LJ, FLOP_COUL, FLOP_SINCOS = 29.0, 8.0, 69.0, 64.0      # SURVEY.md 8d, convention C1
+FUG_FILE = ROOT / "tests" / "golden" / "bench_fugacity.json"              # ln f that pins each loading (written by a GPU run)
 
 
 def parse():
@@ -58,16 +66,20 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--walkers", type=int, default=4736, help="walkers per GPU (weak scaling); 4736 = 2 x 148 SMs x 16 warps")
     ap.add_argument("--inner", type=int, default=INNER_DEFAULT, help="MC steps per walker per launch")
-    ap.add_argument("--loading", type=int, default=64, help="initial waters per walker")
-    ap.add_argument("--e2e-walkers", type=int, default=2368, help="walkers of the host-driven leg (2368 = one warp-per-trial wave: 148 SMs x 16 warps)")
+    ap.add_argument("--loading", type=int, default=64, help="waters per walker the headline is pinned at")
+    ap.add_argument("--equil", type=int, default=80, help="launches of the pinning / relaxation stage")
+    ap.add_argument("--grid", type=int, default=-1, help="SURVEY 8d M1 grid: 1 on, 0 off, -1 = on for N = 1")
+    ap.add_argument("--strong-walkers", type=int, default=4096, help="walkers of the fixed isotherm (64 points x 64 replicas), split over the GPUs (0 = skip)")
+    ap.add_argument("--e2e-walkers", type=int, default=2368, help="walkers of the host-driven leg (one warp-per-trial wave)")
     ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--widom", type=int, default=1_000_000, help="insertions in the Widom batch (0 = skip)")
     ap.add_argument("--mixture-walkers", type=int, default=2368, help="walkers of the configs[4] leg (0 = skip)")
     ap.add_argument("--mixture-steps", type=int, default=32)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--phase-sync", type=int, default=-1, help="experiment: MGPU_OPT_PHASE_SYNC value (2 = top-of-step barrier only, 3 = both)")
-    ap.add_argument("--quick", action="store_true", help="kernel-variant experiments: the timed sweep only, prints a short line")
+    ap.add_argument("--phase-sync", type=int, default=-1, help="experiment: MGPU_OPT_PHASE_SYNC value")
+    ap.add_argument("--quick", action="store_true", help="kernel-variant experiments: pinning + the timed sweep only, prints a short line")
+    ap.add_argument("--write-fugacity", action="store_true", help="store the pinning fugacities found by this run in tests/golden/bench_fugacity.json")
     return ap.parse_args()
 
 
@@ -76,9 +88,16 @@ def workload(loading):
     from maniac_b200.snapshot import load_snapshot
     from maniac_b200.workloads import load_pore
     s = load_snapshot(ROOT / "tests" / "golden" / "zif8_h2o_gcmc.npz")
-    s = load_pore(s, 0, loading, seed=12345)
+    s = load_pore(s, 0, max(1, loading), seed=12345)
     s.p_translation, s.p_rotation, s.p_insertion_deletion, s.p_swap, s.p_widom = 0.4, 0.4, 0.2, 0.0, 0.0
     return s
+
+
+def stored_lnf():
+    try:
+        return {int(k): float(v) for k, v in json.loads(FUG_FILE.read_text())["ln_fugacity"].items()}
+    except Exception:
+        return {}
 
 
 class ClockSampler:
@@ -147,13 +166,23 @@ def kspace_flops(counters_delta, na, kmax, nk):
     return tr * (2 * tab + nk * (30 * na + 7)) + (cr + de) * (tab + nk * (14 * na + 7))
 
 
-def cpu_sample(system, seconds, threads, capacity):
+def kspace_bytes(counters_delta, nk):
+    """Algorithmic bytes of K2 unique to a walker: S(k) read by every trial that reaches k-space
+    (16 nk), S_trial written back when the trial is accepted (16 nk)."""
+    trials = counters_delta[0, 0] + counters_delta[1, 0] + (counters_delta[2, 0] - counters_delta[2, 1]) + (counters_delta[3, 0] - counters_delta[3, 1])
+    commits = counters_delta[0, 1] + counters_delta[1, 1] + counters_delta[2, 1] + counters_delta[3, 1]
+    return 16.0 * nk * trials + 16.0 * nk * commits
+
+
+def cpu_sample(system, seconds, threads, capacity, fugacity=None):
     """Aggregate moves/s of the CPU oracle on `threads` host threads, one walker each (-O3 build of the oracle source)."""
     os.environ["MANIAC_ORACLE_VARIANT"] = "o3"
     from oracle.oracle import Oracle
     oracles = []
     for t in range(threads):
         o = Oracle(system, capacity=capacity)
+        if fugacity is not None:
+            o.set_fugacity(0, float(fugacity))
         o.update_system_energy()
         o.seed(12345 + 104729 * t)
         oracles.append(o)
@@ -173,7 +202,48 @@ def cpu_sample(system, seconds, threads, capacity):
     for th in ths:
         th.join()
     dt = time.perf_counter() - t0
-    return sum(done) / dt, n, dt
+    return sum(done) / dt, n, dt, float(np.mean([o.count(0) for o in oracles]))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# pinning a loading: feedback on ln(fugacity), then frozen
+# ---------------------------------------------------------------------------------------------------------
+def pin_loading(eng, n_walkers, target, launches, inner, lnf0):
+    """Run walkers [0, n_walkers) of `eng` for `launches` launches of `inner` MC steps under a PD feedback on
+    ln f (one fugacity for all of them) that holds <N> at `target`; returns (ln f averaged over the last third,
+    history of <N>).  target = 0: a vanishing fugacity empties the walkers."""
+    lnf = float(lnf0) if target > 0 else -60.0
+    hist, lnfs = [], []
+    prev = float(eng.counts(0, 0, n_walkers).mean())
+    scale = float(max(target, 4))
+    for it in range(launches):
+        eng.set_fugacities(0, np.full(n_walkers, np.exp(lnf)), 0)
+        eng.sweep(inner, 0, n_walkers)
+        nbar = float(eng.counts(0, 0, n_walkers).mean())
+        hist.append(nbar)
+        lnfs.append(lnf)
+        if target > 0:
+            lnf -= 0.5 * (nbar - target) / scale + 4.0 * (nbar - prev) / scale
+        prev = nbar
+    if target > 0:
+        lnf = float(np.mean(lnfs[-max(1, launches // 3):]))
+    return lnf, hist
+
+
+def clone_records(eng, blob_pool, off_pool, n_pool, n_target):
+    """Tile the pool's records into a pinned buffer for n_target walkers (record i <- pool record i mod n_pool)."""
+    reps = (n_target + n_pool - 1) // n_pool
+    lens = np.diff(off_pool)
+    lens_t = np.tile(lens, reps)[:n_target]
+    off = np.zeros(n_target + 1, dtype=np.int64)
+    np.cumsum(lens_t, out=off[1:])
+    buf = eng.host_buffer(int(off[-1]))
+    full = int(off_pool[-1])
+    for r in range(reps):
+        a = r * full
+        b = min(a + full, int(off[-1]))
+        buf[a:b] = blob_pool[:b - a]
+    return buf, off
 
 
 def main():
@@ -182,32 +252,34 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    cfg = {"workload": "ZIF-8 2x2x2 (2208 atoms, 34.02 A cubic) + TIP4P H2O GCMC, BASELINE configs[1]; "
-                       f"{a.loading} waters/walker initially, mix 0.4/0.4/0.2 translate/rotate/insert-delete, "
-                       "walkers over a 64-point log fugacity grid 1e-2..1e4 (configs[3])",
+    lnf_known = stored_lnf()
+    cfg = {"workload": "ZIF-8 2x2x2 (2208 atoms, 34.02 A cubic) + TIP4P H2O GCMC, BASELINE configs[1] / SURVEY 8d M1; "
+                       f"every walker pinned at {a.loading} waters (fugacity found by feedback during an untimed relaxation "
+                       "stage, then frozen), mix 0.4/0.4/0.2 translate/rotate/insert-delete",
            "walkers_per_gpu": a.walkers, "mc_steps_per_launch": a.inner, "r_cut": 17.0, "nkvec": 297,
-           "l2": "per-walker state (~45 KB x walkers) exceeds the 126 MB L2 for >= 3000 walkers; the 88 KB "
-                 "framework block is meant to stay cache-resident"}
+           "l2": "flushed between timed launches (256 MB write); per-walker state (~25 KB x walkers) is of the order of the 126 MB L2"}
     s = workload(a.loading)
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if a.impl == "reference":
         if rank != 0:
             return
+        lnf = lnf_known.get(a.loading)
         per_s = []
         for i in range(a.warmup + a.steps):
-            v, n, dt = cpu_sample(s, max(2.0, a.cpu_seconds / max(1, a.steps)), cores, 512)
+            v, n, dt, nbar = cpu_sample(s, max(2.0, a.cpu_seconds / max(1, a.steps)), cores, 512, None if lnf is None else np.exp(lnf))
             if i >= a.warmup:
-                per_s.append((v, n, dt))
+                per_s.append((v, n, dt, nbar))
         v = float(np.mean([x[0] for x in per_s]))
         line = {"impl": "reference", "metric": "mc_trial_moves_per_s", "value": v, "unit": "moves/s", "n_gpus": a.gpus,
                 "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * float(np.mean([x[2] for x in per_s])),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": cfg,
                 "cpu_baseline": {"value": v, "unit": "moves/s", "cores": cores, "kind": "port",
-                                 "sample": f"{cores} independent walkers (one per host thread) x {per_s[0][1]} MC steps per step; "
-                                           "C restatement of the reference's serial Fortran algorithm, gcc -O3 -ffp-contract=off "
-                                           "(no Fortran compiler in the image: the reference itself cannot be built)"},
+                                 "sample": f"{cores} independent walkers (one per host thread) x {per_s[0][1]} MC steps per step from the {a.loading}-water "
+                                           f"configuration at the pinning fugacity (mean loading at the end {per_s[-1][3]:.1f}); C restatement of the "
+                                           "reference's serial Fortran algorithm with a compact per-type-pair LJ table, gcc -O3 -ffp-contract=off, "
+                                           "no -march=native (no Fortran compiler in the image: the reference itself cannot be built)"},
                 "e2e": {"value": v, "unit": "moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -215,9 +287,8 @@ def main():
     # ------------------------------------------------------------------ B200 arm
     import torch
     import torch.distributed as dist
-    from maniac_b200.engine import Engine
+    from maniac_b200.engine import OPT_HOST_CACHE, OPT_PHASE_SYNC, Engine
     from maniac_b200.hostmc import HostMonteCarlo
-    from maniac_b200.workloads import isotherm_fugacities
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the energy path has no CPU fallback")
     torch.cuda.set_device(local)
@@ -229,162 +300,243 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    W = a.walkers
-    eng = Engine(s, n_walkers=W, capacity=CAPACITY, device=local)
-    fug = isotherm_fugacities(64)
+    def max_over_ranks(*vals):
+        if world == 1:
+            return vals if len(vals) > 1 else vals[0]
+        t = torch.tensor(list(vals), device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out = [float(x) for x in t]
+        return out if len(out) > 1 else out[0]
 
-    def point(w):
-        # replica -> isotherm point: the four walkers (warps) of a CTA that share an SM sub-partition
-        # (w, w+4, w+8, w+12) are replicas of the SAME fugacity point, so their loadings -- hence the
-        # lengths of their MC steps -- are statistically alike and the per-quartet phase barrier waits little
-        return ((rank * W + w) // 16 * 4 + w % 4) % 64
-    for w in range(W):
-        eng.set_fugacity(0, float(fug[point(w)]), walker=w)
-    eng.seed(12345 + 7919 * rank)
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+
+    def flush_l2():
+        flush_buf.zero_()
+        torch.cuda.synchronize()
+
+    do_grid = (a.grid == 1) or (a.grid < 0 and world == 1 and not a.quick)
+    W = a.walkers
+    Wmax = max(W, 16384 if do_grid else 0, POOL)
+    n_pool = min(POOL, Wmax)
+    eng = Engine(s, n_walkers=Wmax, capacity=CAPACITY, device=local)
     if a.phase_sync >= 0:
-        from maniac_b200.engine import OPT_PHASE_SYNC as _OPS
-        eng.set_option(_OPS, a.phase_sync)
+        eng.set_option(OPT_PHASE_SYNC, a.phase_sync)
     peak_tf, _ = eng.measure_fp64_peak()
+    l2_peak = eng.measure_l2_peak()
     ew = eng.ewald()
+    beta = eng.thermo(0)["beta"]
     na = 4
 
+    def prepare(loading, n_target, seed):
+        """Pin `loading` on the pool (walkers [0, n_pool)), then clone the relaxed pool into walkers [0, n_target)."""
+        lnf, hist = pin_loading(eng, n_pool, loading, a.equil, a.inner, lnf_known.get(loading, 0.0))
+        blob_pool = eng.host_buffer(n_pool * (72 + 2 * ew["nk"] + (int(1.3 * max(loading, 8)) + 48) * (3 + 3 * na + 2)))
+        off_pool = eng.save_walkers(blob_pool, 0, n_pool)
+        buf, off = clone_records(eng, blob_pool, off_pool, n_pool, n_target)
+        eng.load_walkers(buf, off, 0)
+        eng.set_fugacities(0, np.full(n_target, np.exp(lnf)), 0)
+        eng.seed(seed)
+        eng.reset_averages()
+        return lnf, hist
+
     sampler = ClockSampler(local)
-    sampler.start()                                    # nvidia-smi needs ~0.5 s before its first row: start before the warm-up
+    sampler.start()
+    t_prep = time.perf_counter()
+    lnf_head, hist_head = prepare(a.loading, Wmax if do_grid else W, 12345 + 7919 * rank)
+    t_prep = time.perf_counter() - t_prep
+    found_lnf = {a.loading: lnf_head}
+
+    def timed_sweeps(n_walkers, n_launch, n_warm):
+        for _ in range(n_warm):
+            eng.sweep(a.inner, 0, n_walkers)
+        eng.reset_pair_counts()
+        eng.timing_reset()
+        for _ in range(n_launch):
+            flush_l2()
+            eng.sweep(a.inner, 0, n_walkers)
+        ms, launches = eng.timing("sweep")
+        return ms * 1e-3, int(launches)
+
+    # ---- headline: W walkers pinned at the loading --------------------------------------------------
     for _ in range(a.warmup):
-        eng.sweep(a.inner)
-    c0 = np.array([eng.counters(w) for w in range(0, W, max(1, W // 256))]).sum(axis=0)   # sampled walkers
-    n_sampled = len(range(0, W, max(1, W // 256)))
+        eng.sweep(a.inner, 0, W)
+    stride = max(1, W // 256)
+    c0 = np.array([eng.counters(w) for w in range(0, W, stride)]).sum(axis=0)
+    n_sampled = len(range(0, W, stride))
+    n_begin = float(eng.counts(0, 0, W).mean())
     eng.reset_pair_counts()
     eng.timing_reset()
     barrier()
     sampler.mark_begin()
     t0 = time.perf_counter()
     for _ in range(a.steps):
-        eng.sweep(a.inner)
+        flush_l2()
+        eng.sweep(a.inner, 0, W)
     barrier()
     wall = time.perf_counter() - t0
     sampler.mark_end()
     clocks = sampler.stop()
     ms_total, launches = eng.timing("sweep")
     pc = eng.pair_counts()
-    c1 = np.array([eng.counters(w) for w in range(0, W, max(1, W // 256))]).sum(axis=0)
+    c1 = np.array([eng.counters(w) for w in range(0, W, stride)]).sum(axis=0)
+    n_end = float(eng.counts(0, 0, W).mean())
     dcount = (c1 - c0) * (W / n_sampled)
-    t_dev = ms_total * 1e-3
-    if world > 1:
-        t = torch.tensor([t_dev, wall], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_dev, wall = float(t[0]), float(t[1])
+    t_dev, wall = max_over_ranks(ms_total * 1e-3, wall)
     moves = float(W) * a.inner * a.steps * world
     value = moves / t_dev
 
     if a.quick:
         if rank == 0:
             print(json.dumps({"quick": True, "lib": os.environ.get("MANIAC_GPU_LIB", "default"), "moves_per_s": value,
-                              "ms_per_step": 1e3 * t_dev / a.steps, "clocks": clocks}))
+                              "ms_per_step": 1e3 * t_dev / a.steps, "loading": [n_begin, n_end], "ln_fugacity": lnf_head,
+                              "clocks": clocks}))
         eng.close()
         return
     flops = FLOP_GEOM * pc["pairs"] + FLOP_LJ * pc["lj"] + FLOP_COUL * pc["coulomb"] + kspace_flops(dcount, na, ew["kmax"], ew["nk"])
     ach_tf = flops / (ms_total * 1e-3) / 1e12
-    nmean = float(np.mean([eng.count(0, walker=w) for w in range(0, W, max(1, W // 64))]))
-    bytes_alg = float(W) * a.inner * a.steps * (32.0 * ew["nk"] + 8.0 * 15 * nmean + 36.0 * 2208)
     peaks = {}
     try:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
     except Exception:
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    traffic, traffic_note = None, "no ncu capture committed"
+    cap_info, traffic, traffic_note = {}, None, "no ncu capture committed"
     try:
-        tj = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())["k_sweep"]
-        traffic = tj["dram_bytes_per_move"] * float(W) * a.inner
-        traffic_note = (f"dram__bytes_read.sum + dram__bytes_write.sum of {tj['capture']} ({tj['walkers']} walkers x {tj['steps']} MC steps, "
-                        f"{tj['dram_bytes']:.4g} B) scaled per move to this launch")
+        cap_info = json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text())["k_sweep"]
+        traffic = cap_info["dram_bytes_per_move"] * float(W) * a.inner
+        traffic_note = (f"dram__bytes_read.sum + dram__bytes_write.sum of {cap_info['capture']} ({cap_info['walkers']} walkers x {cap_info['steps']} MC steps, "
+                        f"{cap_info['dram_bytes']:.4g} B) scaled per move to this launch")
     except Exception:
         pass
     roofline = {"bound": "fp64", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf if peak_tf else None,
-                "traffic": traffic, "traffic_note": traffic_note, "kernel": "k_sweep<false>",
-                "note": "K1/K2 are FP64-pipe bound, not HBM/tensor bound (SURVEY 8d): peak = DFMA loop measured on this GPU in this "
-                        "run (mgpu_measure_fp64_peak, 2 FLOP per FMA); achieved = convention-C1 FLOPs (29/pair geometry, 8/LJ term, "
-                        "69/erfc-Coulomb term, k-space per SURVEY 8d) of the pairs this launch EVALUATED / event-timed kernel time; "
-                        "the framework-energy cache and the per-molecule screen skip pairs the reference evaluates, "
-                        "frac_reference_ops credits the reference's full operation count per move (measured by the no_host_cache leg)",
-                "pairs_per_launch": pc["pairs"] / max(1, launches), "screened_pairs_per_launch": pc.get("screened", 0) / max(1, launches), "lj_terms_per_launch": pc["lj"] / max(1, launches),
-                "coulomb_terms_per_launch": pc["coulomb"] / max(1, launches),
-                "hbm": {"achieved": bytes_alg / t_dev / 1e9 / world, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": bytes_alg / t_dev / 1e9 / world / hbm_peak,
-                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6.65 TB/s"}}
+                "fp64_pipe_pct": cap_info.get("fp64_pipe_pct"), "issue_active_pct": cap_info.get("issue_active_pct"),
+                "traffic": traffic, "traffic_note": traffic_note, "kernel": "k_sweep<false, 32>",
+                "note": "K1 is FP64-pipe bound, not HBM/tensor bound (SURVEY 8d): peak = DFMA loop measured on this GPU in this run "
+                        "(mgpu_measure_fp64_peak, 2 FLOP per FMA); achieved = convention-C1 FLOPs (29/pair geometry, 8/LJ term, "
+                        "69/erfc-Coulomb term, k-space per SURVEY 8d) of the pairs this launch EVALUATED / event-timed kernel time. C1 counts the "
+                        "reference's arithmetic (erfc = 64), the kernel evaluates erfc(ar)/r with 8 FP64 instructions: fp64_pipe_pct / "
+                        "issue_active_pct (ncu, committed capture) are the executed-instruction utilisations",
+                "pairs_per_launch": pc["pairs"] / max(1, launches), "screened_pairs_per_launch": pc.get("screened", 0) / max(1, launches),
+                "lj_terms_per_launch": pc["lj"] / max(1, launches), "coulomb_terms_per_launch": pc["coulomb"] / max(1, launches)}
+    k2_bytes = kspace_bytes(dcount, ew["nk"])
+    roofline_k2 = {"bound": "l2", "achieved": k2_bytes / (ms_total * 1e-3) / 1e9, "peak": l2_peak, "unit": "GB/s",
+                   "frac": k2_bytes / (ms_total * 1e-3) / 1e9 / l2_peak if l2_peak else None, "nkvec": ew["nk"],
+                   "note": "K2 (k-space) is fused into the sweep kernel, so its algorithmic bytes (16 nk read per trial + 16 nk written per commit, "
+                           "SURVEY 8d) are divided by the WHOLE kernel's time: an upper bound of how far K2 is from its roof; peak = "
+                           "mgpu_measure_l2_peak (48 MB L2-resident buffer read by all SMs, this run)"}
+    stationarity = {"target_loading": a.loading, "mean_loading_begin": n_begin, "mean_loading_end": n_end, "ln_fugacity": lnf_head,
+                    "pinning_launches": a.equil, "pinning_seconds": t_prep,
+                    "loading_during_pinning": [hist_head[i] for i in range(0, len(hist_head), max(1, len(hist_head) // 8))]}
 
-    # ---- the one exchange of the path: per-point sums over ranks, once, after the sampling -----
-    from maniac_b200.isotherm import IsothermPlan, reduce_sums, summarize
-    plan = IsothermPlan(n_points=64, walkers_per_rank=W, world_size=world, rank=rank)
-    assert all(plan.point_of(rank * W + w) == point(w) for w in range(0, W, 97))
-    per_walker = np.zeros((W, 6))
-    per_walker[:, :4] = eng.all_averages(0)
-    local_sums = plan.accumulate(per_walker)
-    if world > 1:
-        eng.nccl_init_from_torch()
-    total = reduce_sums(local_sums, engine=eng)
-    if world > 1:
-        eng.nccl_finalize()
-    summ = summarize(total, eng.thermo(0)["beta"])
-    isotherm = {"points": 64, "replicas_per_point": float(W * world) / 64.0,
-                "reduction": "mgpu_reduce_averages (one ncclAllReduce of 384 doubles)" if world > 1 else "single rank: none",
-                "fugacity": [float(fug[i]) for i in range(0, 64, 9)],
-                "mean_waters": [float(summ["mean_N"][i]) for i in range(0, 64, 9)],
-                "note": "block averages since the start of the run (not equilibrated: a throughput benchmark)"}
-
-    # ---- the same sweep with the per-molecule framework-energy cache off (framework swept for the old
-    #      AND the new geometry of every move, the reference's operation count) --------------------
-    from maniac_b200.engine import OPT_HOST_CACHE
+    # ---- the same sweep with the per-molecule framework-energy cache off (the reference's operation count) -----
     eng.set_option(OPT_HOST_CACHE, 0)
-    eng.sweep(a.inner)
-    eng.timing_reset()
-    eng.reset_pair_counts()
-    barrier()
-    for _ in range(2):
-        eng.sweep(a.inner)
-    barrier()
-    ms_nc, l_nc = eng.timing("sweep")
+    t_nc, l_nc = timed_sweeps(W, 2, 1)
     pc_nc = eng.pair_counts()
-    t_nc = ms_nc * 1e-3
-    if world > 1:
-        t = torch.tensor([t_nc], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_nc = float(t[0])
+    ms_nc = t_nc * 1e3
+    t_nc = max_over_ranks(t_nc)
     fl_nc = FLOP_GEOM * (pc_nc["pairs"] + pc_nc.get("screened", 0)) + FLOP_LJ * pc_nc["lj"] + FLOP_COUL * pc_nc["coulomb"] + kspace_flops(dcount, na, ew["kmax"], ew["nk"]) * 2 / a.steps
     no_cache = {"moves_per_s": float(W) * a.inner * 2 * world / t_nc, "launches": int(l_nc),
                 "roofline_frac_c1": fl_nc / (ms_nc * 1e-3) / 1e12 / peak_tf if peak_tf else None,
-                "note": "mgpu_set_option(MGPU_OPT_HOST_CACHE, 0): old-geometry framework sums recomputed every trial"}
+                "note": "mgpu_set_option(MGPU_OPT_HOST_CACHE, 0): old-geometry framework sums recomputed every trial, like the reference"}
     eng.set_option(OPT_HOST_CACHE, 1)
-    # the reference's own operation count per move on this workload state (no cache: every pair the Fortran loops visit),
-    # credited to the cached run: "how fast would the FP64 pipe have to be to do the reference's arithmetic at this rate"
-    ref_flops_per_move = fl_nc / (float(W) * a.inner * 2)
-    roofline["reference_ops_per_move_c1"] = ref_flops_per_move
-    roofline["achieved_reference_ops"] = ref_flops_per_move * value / world / 1e12
-    roofline["frac_reference_ops"] = roofline["achieved_reference_ops"] / peak_tf if peak_tf else None
-
-    # ---- the same sweep without the per-quartet phase alignment (MGPU_OPT_PHASE_SYNC) -------------
-    from maniac_b200.engine import OPT_PHASE_SYNC
     eng.set_option(OPT_PHASE_SYNC, 0)
-    eng.sweep(a.inner)
-    eng.timing_reset()
-    barrier()
-    for _ in range(2):
-        eng.sweep(a.inner)
-    barrier()
-    ms_ns, _ = eng.timing("sweep")
-    t_ns = ms_ns * 1e-3
-    if world > 1:
-        t = torch.tensor([t_ns], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_ns = float(t[0])
+    t_ns, _ = timed_sweeps(W, 2, 1)
+    t_ns = max_over_ranks(t_ns)
     no_sync = {"moves_per_s": float(W) * a.inner * 2 * world / t_ns,
                "note": "mgpu_set_option(MGPU_OPT_PHASE_SYNC, 0): walkers of a CTA free-running (no per-quartet barrier)"}
-    eng.set_option(OPT_PHASE_SYNC, 1)
+    eng.set_option(OPT_PHASE_SYNC, 1 if a.phase_sync < 0 else a.phase_sync)
 
-    # ---- Widom batch (configs[2]) ------------------------------------------------------------
-    widom = None
+    # ---- e2e: the block-level C-ABI entry with HOST buffers (mgpu_block, pipelined) ---------------------
+    rec_max = eng.record_doubles_max()
+    per_walker = 72 + 2 * ew["nk"] + (int(1.3 * max(a.loading, 8)) + 48) * (3 + 3 * na + 2)
+    blob = [eng.host_buffer(min(rec_max, per_walker) * W) for _ in range(2)]
+    off = eng.save_walkers(blob[0], 0, W)
+    cur = 0
+    for i in range(max(1, min(2, a.warmup))):
+        off = eng.block(a.inner, blob[cur], off, blob[cur ^ 1], 0, W)
+        cur ^= 1
+    eng.traffic(reset=True)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(a.steps):
+        off = eng.block(a.inner, blob[cur], off, blob[cur ^ 1], 0, W)
+        cur ^= 1
+    barrier()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    tr1 = eng.traffic()
+    e2e = {"value": float(W) * a.inner * a.steps * world / t_e2e, "unit": "moves/s",
+           "h2d_bytes_per_step": tr1["h2d_bytes"] / a.steps, "d2h_bytes_per_step": tr1["d2h_bytes"] / a.steps,
+           "walkers_per_gpu": W, "mc_steps_per_call": a.inner, "ms_per_step": 1e3 * t_e2e / a.steps,
+           "path": "mgpu_block: walker records (guest%com / guest%offset, ewald%Ak, energy, RNG, counters) H2D from pinned host "
+                   "memory -> k_unpack -> k_sweep -> k_pack -> records D2H, every step, in 8 slices on 8 streams (copies under compute); "
+                   "wall clock, max over ranks"}
+    del blob
+
+    # ---- SURVEY 8d M1 grid: loadings x walker counts, each pinned and relaxed (N = 1 only) --------------
+    grid = None
+    if do_grid:
+        grid = {"loadings": [0, 16, 64, 128], "walkers": [64, 1024, 4096, 16384], "mc_steps_per_launch": a.inner, "cells": []}
+        order = [a.loading] + [x for x in grid["loadings"] if x != a.loading]      # the headline state is already on the device
+        for loading in order:
+            if loading != a.loading:
+                eng.close()                               # the pool restarts from a configuration holding about that many waters
+                eng = Engine(workload(loading), n_walkers=Wmax, capacity=CAPACITY, device=local)
+                found_lnf[loading], _ = prepare(loading, Wmax, 999 + loading)
+            for Wg in grid["walkers"]:
+                nb = float(eng.counts(0, 0, Wg).mean())
+                t_g, l_g = timed_sweeps(Wg, 3, 1)
+                pcg = eng.pair_counts()
+                fl_g = FLOP_GEOM * pcg["pairs"] + FLOP_LJ * pcg["lj"] + FLOP_COUL * pcg["coulomb"]      # real-space part only
+                grid["cells"].append({"loading": loading, "walkers": Wg, "moves_per_s": float(Wg) * a.inner * l_g / t_g,
+                                      "frac_c1_realspace": fl_g / t_g / 1e12 / peak_tf if peak_tf else None,
+                                      "mean_loading": [nb, float(eng.counts(0, 0, Wg).mean())], "ln_fugacity": found_lnf[loading],
+                                      "shape": "team (4 warps / walker)" if Wg * 8 <= 148 * 16 else "warp / walker"})
+        grid["cells"].sort(key=lambda c: (c["loading"], c["walkers"]))
+        eng.close()                                       # back to the headline state for the legs below
+        eng = Engine(s, n_walkers=max(a.strong_walkers // world, POOL), capacity=CAPACITY, device=local)
+        prepare(a.loading, max(a.strong_walkers // world, POOL), 4242 + rank)
+
+    # ---- SURVEY 8d M3: a FIXED isotherm (64 points x replicas) split over the GPUs ----------------------
+    strong = None
+    if a.strong_walkers > 0:
+        from maniac_b200.isotherm import IsothermPlan, reduce_sums, summarize
+        Ws = a.strong_walkers // world
+        plan = IsothermPlan(n_points=64, walkers_per_rank=Ws, world_size=world, rank=rank)
+        # one decade of fugacity centred on the pinning value: the points drift towards their own loadings while timed
+        fug = np.exp(lnf_head + (np.arange(64) / 63.0 - 0.5) * np.log(10.0))
+        eng.set_fugacities(0, fug[plan.points()], 0)
+        eng.seed(31337 + 7919 * rank)
+        eng.reset_averages()
+        for _ in range(2):
+            eng.sweep(a.inner, 0, Ws)
+        eng.timing_reset()
+        barrier()
+        for _ in range(a.steps):
+            flush_l2()
+            eng.sweep(a.inner, 0, Ws)
+        barrier()
+        ms_s, l_s = eng.timing("sweep")
+        t_s = max_over_ranks(ms_s * 1e-3)
+        per_walker_acc = np.zeros((Ws, 6))
+        per_walker_acc[:, :4] = eng.all_averages(0)[:Ws]
+        local_sums = plan.accumulate(per_walker_acc)
+        if world > 1:
+            eng.nccl_init_from_torch()
+        total = reduce_sums(local_sums, engine=eng)
+        if world > 1:
+            eng.nccl_finalize()
+        summ = summarize(total, beta)
+        strong = {"metric": "mc_trial_moves_per_s", "scaling": "strong", "walkers_total": Ws * world, "walkers_per_gpu": Ws,
+                  "value": float(Ws) * world * a.inner * a.steps / t_s, "ms_per_step": 1e3 * t_s / a.steps,
+                  "shape": "team (4 warps / walker)" if Ws * 8 <= 148 * 16 else "warp / walker",
+                  "points": 64, "replicas_per_point": Ws * world / 64.0,
+                  "reduction": "mgpu_reduce_averages (one ncclAllReduce of 384 doubles)" if world > 1 else "single rank: none",
+                  "fugacity": [float(fug[i]) for i in range(0, 64, 9)],
+                  "mean_waters": [float(summ["mean_N"][i]) for i in range(0, 64, 9)]}
     eng.close()
+
+    # ---- Widom batches (configs[2]) in 16 blocks: mu_ex +- sigma, sums reduced over ranks ----------------
+    widom = None
     if a.widom > 0:
         from maniac_b200.snapshot import load_snapshot
         sw = load_snapshot(ROOT / "tests" / "golden" / "zif8_co2_widom.npz")
@@ -395,24 +547,41 @@ def main():
         engw.widom_batch(1, min(a.widom, 100_000), seed=1)
         engw.timing_reset()
         engw.reset_pair_counts()
+        nblk = 16
+        per_blk = a.widom // nblk
+        blocks = np.zeros((nblk, 2))
         barrier()
-        _, sw_sum, n_ok = engw.widom_batch(1, a.widom, seed=2024 + rank)
+        for b in range(nblk):
+            _, sw_sum, n_ok = engw.widom_batch(1, per_blk, seed=2024, first_id=(rank * nblk + b) * per_blk)
+            blocks[b] = (sw_sum, per_blk)
         barrier()
         ms_w, _ = engw.timing("widom")
         pcw = engw.pair_counts()
-        fl = FLOP_GEOM * pcw["pairs"] + FLOP_LJ * pcw["lj"] + FLOP_COUL * pcw["coulomb"] + a.widom * (
+        done = nblk * per_blk
+        fl = FLOP_GEOM * pcw["pairs"] + FLOP_LJ * pcw["lj"] + FLOP_COUL * pcw["coulomb"] + done * (
             sum(k + 1 for k in engw.ewald()["kmax"]) * 3 * FLOP_SINCOS + engw.ewald()["nk"] * (14 * 3 + 7))
-        t_w = ms_w * 1e-3
-        if world > 1:
-            t = torch.tensor([t_w], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            t_w = float(t[0])
-        beta = engw.thermo(1)["beta"]
-        widom = {"workload": "CO2 test-particle insertion in empty ZIF-8 2x2x2 (BASELINE configs[2])", "batch": a.widom,
-                 "insertions_per_s": a.widom * world / t_w, "ms": ms_w,
-                 "mu_ex_kcal_mol": float(-np.log(max(sw_sum, 1e-300) / a.widom) / beta), "accepted_weights": int(n_ok),
+        t_w = max_over_ranks(ms_w * 1e-3)
+        beta_w = engw.thermo(1)["beta"]
+        if world > 1:                                   # every rank's blocks, through the library's NCCL sum
+            allb = np.zeros((world, nblk, 2))
+            allb[rank] = blocks
+            engw.nccl_init_from_torch()
+            flat = allb.reshape(-1).copy()
+            engw.reduce_averages(flat)
+            engw.nccl_finalize()
+            allb = flat.reshape(world * nblk, 2)
+        else:
+            allb = blocks
+        mu_b = -np.log(np.maximum(allb[:, 0], 1e-300) / allb[:, 1]) / beta_w
+        mu_all = float(-np.log(allb[:, 0].sum() / allb[:, 1].sum()) / beta_w)
+        widom = {"workload": "CO2 test-particle insertion in empty ZIF-8 2x2x2 (BASELINE configs[2])", "batch_per_gpu": done,
+                 "insertions_per_s": done * world / t_w, "ms": ms_w,
+                 "mu_ex_kcal_mol": mu_all, "mu_ex_sigma": float(mu_b.std(ddof=1) / np.sqrt(len(mu_b))), "blocks": int(len(mu_b)),
+                 "insertions_total": int(allb[:, 1].sum()),
                  "roofline": {"bound": "fp64", "achieved": fl / (ms_w * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
-                              "frac": fl / (ms_w * 1e-3) / 1e12 / peak_tf if peak_tf else None, "kernel": "k_widom_batch<false>"}}
+                              "frac": fl / (ms_w * 1e-3) / 1e12 / peak_tf if peak_tf else None, "kernel": "k_widom_batch<false>",
+                              "fp64_pipe_pct": json.loads((ROOT / "profiles" / "ncu_traffic.json").read_text()).get("k_widom_batch", {}).get("fp64_pipe_pct")
+                              if (ROOT / "profiles" / "ncu_traffic.json").exists() else None}}
         engw.close()
 
     # ---- configs[4]: CO2 / N2 mixture with swaps in the 17 664-atom triclinic supercell ---------------
@@ -435,82 +604,37 @@ def main():
         ms_m, _ = engm.timing("sweep")
         cm1 = np.array([engm.counters(w) for w in range(0, Wm, max(1, Wm // 64))]).sum(axis=0)
         pcm = engm.pair_counts()
-        t_m = ms_m * 1e-3
-        if world > 1:
-            t = torch.tensor([t_m], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            t_m = float(t[0])
+        t_m = max_over_ranks(ms_m * 1e-3)
         ewm = engm.ewald()
         fl_m = FLOP_GEOM * pcm["pairs"] + FLOP_LJ * pcm["lj"] + FLOP_COUL * pcm["coulomb"]      # geometry counted at the orthorhombic 29 / pair
-        dcm = (cm1 - cm0).reshape(6, 2)
+        dcm = (cm1 - cm0).reshape(6, 2) * (Wm / len(range(0, Wm, max(1, Wm // 64))))
+        k2m = kspace_bytes(dcm, ewm["nk"]) + 16.0 * ewm["nk"] * (dcm[4, 0] - dcm[4, 1] + dcm[4, 1])
         mixture = {"workload": "CO2/N2 mixture GCMC with identity swaps (0.3/0.3/0.2/0.2 translate/rotate/swap/insert-delete), ZIF-8 4x4x4 "
                                "unit cells = 17 664 framework atoms, triclinic (xy tilt 3 A), BASELINE configs[4]",
                    "walkers_per_gpu": Wm, "mc_steps_per_launch": a.mixture_steps, "nkvec": ewm["nk"], "kmax": ewm["kmax"],
                    "moves_per_s": float(Wm) * a.mixture_steps * world / t_m, "ms": ms_m,
                    "triclinic_candidates": engm.triclinic_candidates(),
                    "swap_trials_sampled": int(dcm[4, 0] - dcm[4, 1]), "swap_accepted_sampled": int(dcm[4, 1]),
-                   "roofline_frac_c1_realspace": fl_m / (ms_m * 1e-3) / 1e12 / peak_tf if peak_tf else None}
+                   "roofline_frac_c1_realspace": fl_m / (ms_m * 1e-3) / 1e12 / peak_tf if peak_tf else None,
+                   "roofline_k2": {"bound": "l2", "achieved": k2m / (ms_m * 1e-3) / 1e9, "peak": l2_peak, "unit": "GB/s",
+                                   "frac": k2m / (ms_m * 1e-3) / 1e9 / l2_peak if l2_peak else None, "nkvec": ewm["nk"]}}
         engm.close()
-
-    # ---- e2e: the block-level C-ABI entry with HOST buffers (mgpu_block) ------------------------
-    # every step = one block of the MC loop: the walkers' records (coordinates, S(k), energies, RNG,
-    # counters) are copied from pinned host memory to the device, `inner` MC steps run, the updated records
-    # are copied back -- the same moves as `value`, plus the host<->device traffic of the whole state.
-    enge = Engine(s, n_walkers=W, capacity=CAPACITY, device=local)
-    for w in range(W):
-        enge.set_fugacity(0, float(fug[point(w)]), walker=w)
-    enge.seed(4321 + 7919 * rank)
-    for _ in range(2):
-        enge.sweep(a.inner)                          # move towards the steady-state loading before records are sized
-    rec_max = enge.record_doubles_max()
-    nmax = max(enge.count(0, walker=w) for w in range(0, W, max(1, W // 128)))
-    per_walker = 72 + 2 * ew["nk"] + int(1.5 * nmax + 64) * (3 + 3 * na + 2)
-    blob = [enge.host_buffer(min(rec_max, per_walker) * W) for _ in range(2)]
-    off = enge.save_walkers(blob[0])
-    for i in range(max(1, a.warmup)):
-        off = enge.block(a.inner, blob[i % 2], off, blob[(i + 1) % 2])
-        cur = (i + 1) % 2
-    enge.traffic(reset=True)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(a.steps):
-        off = enge.block(a.inner, blob[cur], off, blob[cur ^ 1])
-        cur ^= 1
-    barrier()
-    t_e2e = time.perf_counter() - t0
-    tr1 = enge.traffic()
-    if world > 1:
-        t = torch.tensor([t_e2e], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_e2e = float(t[0])
-    e2e = {"value": float(W) * a.inner * a.steps * world / t_e2e, "unit": "moves/s",
-           "h2d_bytes_per_step": tr1["h2d_bytes"] / a.steps, "d2h_bytes_per_step": tr1["d2h_bytes"] / a.steps,
-           "walkers_per_gpu": W, "mc_steps_per_call": a.inner, "ms_per_step": 1e3 * t_e2e / a.steps,
-           "path": "mgpu_block: walker records (guest%com / guest%offset, ewald%Ak, energy, RNG, counters) H2D from pinned host "
-                   "memory -> k_unpack -> k_sweep -> k_pack -> records D2H, every step; wall clock, max over ranks"}
-    enge.close()
 
     # ---- the Fortran drivers' role: host-driven trials (host RNG / proposal / Metropolis per MC step) ----
     We = min(a.e2e_walkers, W)
     enge = Engine(s, n_walkers=We, capacity=CAPACITY, device=local)
-    for w in range(We):
-        enge.set_fugacity(0, float(fug[(rank * We + w) % 64]), walker=w)
+    enge.set_fugacities(0, np.full(We, np.exp(lnf_head)), 0)
     hm = HostMonteCarlo(enge, seed=999 + rank)
-    beta_e = enge.thermo(0)["beta"]
-    for w in range(We):
-        hm.set_chemical_potential(0, float(np.log(fug[(rank * We + w) % 64]) / beta_e), walker=w)
+    for w in range(0, We):
+        hm.set_chemical_potential(0, lnf_head / beta, walker=w)
     hm.run(3)
     tr0 = hm.traffic()
     barrier()
     t0 = time.perf_counter()
     hm.run(a.e2e_steps)
     barrier()
-    t_hd = time.perf_counter() - t0
+    t_hd = max_over_ranks(time.perf_counter() - t0)
     tr1 = hm.traffic()
-    if world > 1:
-        t = torch.tensor([t_hd], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_hd = float(t[0])
     host_driven = {"value": (tr1["trials"] - tr0["trials"]) * world / t_hd, "unit": "moves/s",
                    "h2d_bytes_per_mc_step": (tr1["h2d_bytes"] - tr0["h2d_bytes"]) / a.e2e_steps,
                    "d2h_bytes_per_mc_step": (tr1["d2h_bytes"] - tr0["d2h_bytes"]) / a.e2e_steps,
@@ -523,6 +647,7 @@ def main():
     # ---- the literal drop-in: ONE walker, one trial per call (what a single unchanged Fortran process does) ----
     eng1 = Engine(s, n_walkers=1, capacity=CAPACITY, device=local)
     hm1 = HostMonteCarlo(eng1, seed=5 + rank)
+    hm1.set_chemical_potential(0, lnf_head / beta, walker=0)
     hm1.run(200)
     eng1.timing_reset()
     t0 = time.perf_counter()
@@ -539,10 +664,19 @@ def main():
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
-        v, n, dt = cpu_sample(s, a.cpu_seconds, cores, 512)
+        v, n, dt, nbar = cpu_sample(s, a.cpu_seconds, cores, 512, np.exp(lnf_head))
         cpu = {"value": v, "unit": "moves/s", "cores": cores, "kind": "port",
-               "sample": f"{cores} independent walkers (one per host thread) x {n} MC steps of the same workload ({dt:.1f} s); "
-                         "CPU oracle = C restatement of the reference's serial algorithm, gcc -O3 (no Fortran compiler in the image)"}
+               "sample": f"{cores} independent walkers (one per host thread) x {n} MC steps from the {a.loading}-water configuration at the same "
+                         f"pinning fugacity ({dt:.1f} s, mean loading at the end {nbar:.1f}); CPU oracle = C restatement of the reference's serial "
+                         "algorithm with a compact per-type-pair LJ table (friendlier than the reference's 4-D arrays), gcc -O3 "
+                         "-ffp-contract=off, no -march=native (no Fortran compiler in the image)"}
+    if a.write_fugacity and rank == 0:
+        old = stored_lnf()
+        old.update(found_lnf)
+        FUG_FILE.write_text(json.dumps({"ln_fugacity": {str(k): v for k, v in sorted(old.items())},
+                                        "note": "ln(fugacity) that holds <N> at the keyed loading for ZIF-8 2x2x2 + TIP4P at 300 K with the 0.4/0.4/0.2 "
+                                                "mix (bench.py feedback stage, written with --write-fugacity on a B200); the CPU arm and the "
+                                                "feedback's starting point read it"}, indent=1) + "\n")
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -551,8 +685,10 @@ def main():
     line = {"metric": "mc_trial_moves_per_s", "value": value, "unit": "moves/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": 1e3 * t_dev / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg, "clocks": clocks,
-            "e2e": e2e, "host_driven": host_driven, "single_walker_dropin": single, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "widom": widom, "no_host_cache": no_cache, "no_phase_sync": no_sync, "mixture": mixture, "isotherm": isotherm,
-            "wall_s_timed_region": wall, "mean_waters_per_walker": nmean, "fp64_peak_tflops_measured": peak_tf}
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "roofline_k2": roofline_k2, "cpu_baseline": cpu,
+            "stationarity": stationarity, "strong_scaling": strong, "grid": grid, "widom": widom, "mixture": mixture,
+            "host_driven": host_driven, "single_walker_dropin": single, "no_host_cache": no_cache, "no_phase_sync": no_sync,
+            "wall_s_timed_region": wall, "fp64_peak_tflops_measured": peak_tf, "l2_peak_gbs_measured": l2_peak}
     print(json.dumps(line))
 
 

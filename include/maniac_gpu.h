@@ -132,6 +132,9 @@ int mgpu_get_count(int32_t walker, int32_t res, int32_t *n);
 /* thermo%chemical_potential(res) / fugacity of one walker (isotherm points) */
 int mgpu_set_chemical_potential(int32_t walker, int32_t res, double mu);
 int mgpu_set_fugacity(int32_t walker, int32_t res, double fugacity);
+/* the same for a run of walkers in one copy (mu[n_walkers], kcal/mol), and their molecule counts of one type */
+int mgpu_set_chemical_potentials(int32_t first_walker, int32_t n_walkers, int32_t res, const double *mu);
+int mgpu_get_counts(int32_t first_walker, int32_t n_walkers, int32_t res, int32_t *counts);
 /* S(k) of a walker (ewald%Ak), interleaved re,im */
 int mgpu_get_Ak(int32_t walker, double *re_im);
 /* running totals `energy` of a walker */
@@ -296,6 +299,9 @@ int mgpu_reset_pair_counts(void);
 /* achieved FP64 FMA throughput of a register-resident DFMA loop (TFLOP/s) and the SM
  * clock it ran at: the roofline denominator for the FP64-bound kernels */
 int mgpu_measure_fp64_peak(double *tflops, double *seconds);
+/* achieved read bandwidth (GB/s) of a 48 MB buffer that stays resident in L2, all SMs streaming it with 16-byte loads:
+ * the roofline denominator of the k-space traffic (S(k) of the resident walkers lives in L2) */
+int mgpu_measure_l2_peak(double *gbytes_per_s);
 /* accuracy of the two fast per-pair primitives on the device, measured against the exact
  * forms over the whole tabulated range: max relative error of 1/r^2 (MUFU seed + Newton) and
  * max error of the erfc(alpha r)/r table relative to the pair's Coulomb scale */

@@ -65,6 +65,8 @@ SIGNATURES = {
     "mgpu_get_count": (C.c_int, [I, I, _pi]),
     "mgpu_set_chemical_potential": (C.c_int, [I, I, D]),
     "mgpu_set_fugacity": (C.c_int, [I, I, D]),
+    "mgpu_set_chemical_potentials": (C.c_int, [I, I, I, _pd]),
+    "mgpu_get_counts": (C.c_int, [I, I, I, _pi]),
     "mgpu_get_Ak": (C.c_int, [I, _pd]),
     "mgpu_get_energy": (C.c_int, [I, _pd]),
     "mgpu_set_option": (C.c_int, [I, I]),
@@ -109,6 +111,7 @@ SIGNATURES = {
     "mgpu_get_screened_pairs": (C.c_int, [_pl]),
     "mgpu_reset_pair_counts": (C.c_int, []),
     "mgpu_measure_fp64_peak": (C.c_int, [_pd, _pd]),
+    "mgpu_measure_l2_peak": (C.c_int, [_pd]),
     "mgpu_selftest_math": (C.c_int, [_pd, _pd]),
     "mgpu_coulomb_table_check": (C.c_int, [D, D, D, I, _pd, _pd]),
 }

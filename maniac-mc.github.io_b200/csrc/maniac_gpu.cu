@@ -416,7 +416,7 @@ int mgpu_init(const mgpu_system *sys)
             if (R.natom > g.natom_max) g.natom_max = R.natom;
             for (int a = 0; a < R.natom; ++a) { h.charge[r][a] = R.charges[a]; h.type[r][a] = R.types[a]; }
             h.goff[r] = stride;
-            stride += (int64_t)(3 + 3 * R.natom + 2) * R.capacity;      // com, offsets, framework-energy cache rows
+            stride += (int64_t)(3 + 3 * R.natom + 2 + 3 * R.natom) * R.capacity;      // com, offsets, framework-energy cache rows, absolute atom positions
             // prepare_monte_carlo, prepare_utils.f90:231-259
             const double mass = R.mass * G_TO_KG / NA();
             double lam = H_PLANCK / std::sqrt(TWOPI * mass * KB * sys->temperature);
@@ -604,8 +604,12 @@ int mgpu_init(const mgpu_system *sys)
             double *com = img.data() + h.goff[r], *off = com + 3 * (size_t)R.capacity;
             for (int m = 0; m < R.nmol; ++m) {
                 for (int d = 0; d < 3; ++d) com[(size_t)d * R.capacity + m] = R.com[(size_t)m * 3 + d];
+                double *pos = off + (size_t)(3 * R.natom + 2) * R.capacity;      // com + offset per atom (geometry_utils.f90:235-241), kept next to them
                 for (int a = 0; a < R.natom; ++a)
-                    for (int d = 0; d < 3; ++d) off[((size_t)a * 3 + d) * R.capacity + m] = R.offset[((size_t)m * R.natom + a) * 3 + d];
+                    for (int d = 0; d < 3; ++d) {
+                        off[((size_t)a * 3 + d) * R.capacity + m] = R.offset[((size_t)m * R.natom + a) * 3 + d];
+                        pos[((size_t)a * 3 + d) * R.capacity + m] = R.com[(size_t)m * 3 + d] + R.offset[((size_t)m * R.natom + a) * 3 + d];
+                    }
             }
         }
         std::vector<double> all(W * (size_t)(stride ? stride : 1)); std::vector<int32_t> allc(W * MGPU_MAX_RES); std::vector<double> allmu(W * MGPU_MAX_RES);
@@ -786,6 +790,9 @@ int mgpu_set_molecule(int32_t w, int32_t res, int32_t mol, const double com[3], 
     for (int d = 0; d < 3; ++d) tmp[d] = com[d];
     for (int e = 0; e < 3 * na; ++e) tmp[3 + e] = offset[e];
     CK(cudaMemcpy2DAsync(base + mol, sizeof(double) * cap, tmp.data(), sizeof(double), sizeof(double), 3 + 3 * na, cudaMemcpyHostToDevice, g.stream));
+    std::vector<double> pos(3 * na);                          // the molecule's absolute-position rows, behind the cache rows
+    for (int e = 0; e < 3 * na; ++e) pos[e] = com[e % 3] + offset[e];
+    CK(cudaMemcpy2DAsync(base + (size_t)(3 + 3 * na + 2) * cap + mol, sizeof(double) * cap, pos.data(), sizeof(double), sizeof(double), 3 * na, cudaMemcpyHostToDevice, g.stream));
     CK(cudaStreamSynchronize(g.stream));
     double r2 = 0.0;
     for (int a = 0; a < na; ++a) r2 = std::fmax(r2, offset[3 * a] * offset[3 * a] + offset[3 * a + 1] * offset[3 * a + 1] + offset[3 * a + 2] * offset[3 * a + 2]);
@@ -834,6 +841,24 @@ int mgpu_set_chemical_potential(int32_t w, int32_t res, double mu)
     NEED_READY();
     if (check_walker(w) || check_guest(res)) return 1;
     CK(cudaMemcpy(g.h.mu + (int64_t)w * MGPU_MAX_RES + res, &mu, sizeof mu, cudaMemcpyHostToDevice));
+    return 0;
+}
+int mgpu_set_chemical_potentials(int32_t first, int32_t n, int32_t res, const double *mu)
+{
+    NEED_READY();
+    if (n <= 0) return 0;
+    if (check_walker(first) || check_walker(first + n - 1) || check_guest(res)) return 1;
+    if (!mu) return fail("mgpu_set_chemical_potentials: null array");
+    // element (w, res) of the [W][MGPU_MAX_RES] array: a strided scatter in one copy
+    CK(cudaMemcpy2D(g.h.mu + (int64_t)first * MGPU_MAX_RES + res, sizeof(double) * MGPU_MAX_RES, mu, sizeof(double), sizeof(double), n, cudaMemcpyHostToDevice));
+    return 0;
+}
+int mgpu_get_counts(int32_t first, int32_t n, int32_t res, int32_t *counts)
+{
+    NEED_READY();
+    if (n <= 0) return 0;
+    if (check_walker(first) || check_walker(first + n - 1) || check_guest(res)) return 1;
+    CK(cudaMemcpy2D(counts, sizeof(int32_t), g.h.count + (int64_t)first * MGPU_MAX_RES + res, sizeof(int32_t) * MGPU_MAX_RES, sizeof(int32_t), n, cudaMemcpyDeviceToHost));
     return 0;
 }
 int mgpu_set_fugacity(int32_t w, int32_t res, double f)
@@ -1476,6 +1501,40 @@ int mgpu_selftest_math(double *max_rel_rcp, double *max_err_table)
     cudaFree(d_out);
     if (max_rel_rcp) *max_rel_rcp = out[0];
     if (max_err_table) *max_err_table = out[1];
+    return 0;
+}
+// L2 read bandwidth (roofline denominator of K2): every SM streams a 48 MB buffer that stays resident in
+// the 126 MB L2, 16-byte loads, several passes; the first pass (DRAM) is not timed.
+int mgpu_measure_l2_peak(double *gbytes_per_s)
+{
+    int dev = 0, sms = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    cudaStream_t st = g.stream;
+    bool own = false;
+    if (!st) { CK(cudaStreamCreate(&st)); own = true; }
+    const size_t n16 = (size_t)48 * 1024 * 1024 / 16;
+    double2 *buf; double *out;
+    CK(cudaMalloc(&buf, n16 * 16));
+    CK(cudaMalloc(&out, sizeof(double) * sms * 8 * 256));
+    CK(cudaMemsetAsync(buf, 0, n16 * 16, st));
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    const int passes = 20;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(a, st));
+        k_l2_read<<<sms * 8, 256, 0, st>>>(buf, n16, rep == 0 ? 1 : passes, out);
+        CK(cudaEventRecord(b, st));
+        CK(cudaEventSynchronize(b));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, a, b));
+        if (rep > 0) best = std::fmax(best, (double)n16 * 16.0 * passes / (ms * 1e-3) / 1e9);
+    }
+    CK(cudaGetLastError());
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(buf); cudaFree(out);
+    if (own) cudaStreamDestroy(st);
+    if (gbytes_per_s) *gbytes_per_s = best;
     return 0;
 }
 int mgpu_measure_fp64_peak(double *tflops, double *seconds)

@@ -51,6 +51,13 @@ __constant__ DevSys c_sys;
 #ifndef MGPU_ACC_PER_ATOM
 #define MGPU_ACC_PER_ATOM 0
 #endif
+// guest passes read the molecules' stored absolute atom positions (and prefetch the next molecule's) instead of com + offset
+#ifndef MGPU_GUEST_POS
+#define MGPU_GUEST_POS 1
+#endif
+#ifndef MGPU_GUEST_PF
+#define MGPU_GUEST_PF 1
+#endif
 #ifndef MGPU_PF_KSPACE
 #define MGPU_PF_KSPACE 1
 #endif
@@ -588,7 +595,8 @@ struct HostPass {
     // in memory, so the lanes' loads coalesce); tq / ttype are the target atom's charge (0 if tiny)
     // and type.  Molecule m_skip is left out (the probe itself), and so is every m <= m_order
     // (ordering check of pairwise_energy_for_molecule, :60-62; -1 = none).
-    __device__ __forceinline__ void run_guest(const double *__restrict__ com, const double *__restrict__ offb, int cap, int n,
+    // posb = the stored absolute positions of atom b (rows x, y, z; cap long): what com + offb adds up to
+    __device__ __forceinline__ void run_guest(const double *__restrict__ com, const double *__restrict__ offb, const double *__restrict__ posb, int cap, int n,
                                               int t0, int stride, int m_skip, int m_order, double tq, int ttype,
                                               double &e_lj_io, double &e_c_io, PairCount &pc_io) const
     {
@@ -598,6 +606,28 @@ struct HostPass {
         for (int i = 0; i < N; ++i) acc[i] = 0.0;
         double2 e_x = make_double2(0.0, 0.0);
         PairCount pc = pc_io;
+        if (MGPU_GUEST_POS && MGPU_GUEST_PF && U == 1) {
+            // the target atom's stored absolute position (the same com + offset sum, formed when the molecule was written):
+            // three loads instead of six per target, and the next molecule's three are in flight while this one is
+            // evaluated -- the r02b capture showed half of all long-scoreboard stalls on the six unprefetched loads
+            // (7.5 % of the kernel's samples)
+            const double *__restrict__ px_ = posb, *__restrict__ py_ = posb + cap, *__restrict__ pz_ = posb + 2 * cap;
+            int m = t0;
+            if (m < n) {
+                double cx = px_[m], cy = py_[m], cz = pz_[m];
+                for (;;) {
+                    const int mn = m + stride;
+                    const int mp = mn < n ? mn : m;
+                    const double nx = px_[mp], ny = py_[mp], nz = pz_[mp];
+                    Atoms<1> A;
+                    A.xy[0] = make_double2(cx, cy); A.zq[0] = make_double2(cz, tq); A.tt[0] = ttype;
+                    const unsigned vm = ((m != m_skip) && (m > m_order)) ? 1u : 0u;
+                    block<1>(A, vm, e_lj, acc, e_x, pc);
+                    if (mn >= n) break;
+                    m = mn; cx = nx; cy = ny; cz = nz;
+                }
+            }
+        } else
         for (int m = t0; m < n; m += U * stride) {
             Atoms<U> A;
             unsigned vm = 0u;
@@ -606,8 +636,13 @@ struct HostPass {
                 const int mm = m + u * stride;
                 const bool ok = (mm < n) && (mm != m_skip) && (mm > m_order);
                 const int mc = (mm < n) ? mm : m;
-                A.xy[u] = make_double2(com[mc] + offb[mc], com[cap + mc] + offb[cap + mc]);
-                A.zq[u] = make_double2(com[2 * cap + mc] + offb[2 * cap + mc], tq);
+                if (MGPU_GUEST_POS) {
+                    A.xy[u] = make_double2(posb[mc], posb[cap + mc]);
+                    A.zq[u] = make_double2(posb[2 * cap + mc], tq);
+                } else {
+                    A.xy[u] = make_double2(com[mc] + offb[mc], com[cap + mc] + offb[cap + mc]);
+                    A.zq[u] = make_double2(com[2 * cap + mc] + offb[2 * cap + mc], tq);
+                }
                 A.tt[u] = ttype;
                 vm |= ok ? (1u << u) : 0u;
             }
@@ -675,14 +710,14 @@ __device__ __forceinline__ int gl_index(int ri, int g, int b, int mode) { return
 
 template <bool TRI, int MODE, int REP>
 __device__ __forceinline__ void guest_list(const Probe &P, const double (*pos)[3], const int8_t *list, int nl,
-                                           const double *com, const double *offb, int cap, int n, int t0, int stride,
+                                           const double *com, const double *offb, const double *posb, int cap, int n, int t0, int stride,
                                            int m_skip, int m_order, double tq, int ttype, double &e_lj, double &e_c, PairCount &pc)
 {
     for (int base = 0; base < nl; base += 3) {
         const int k = min(3, nl - base);
-        if (k == 3) { HostPass<TRI, MODE, 3, 1, REP> hp; hp.load(P, pos, list + base); hp.run_guest(com, offb, cap, n, t0, stride, m_skip, m_order, tq, ttype, e_lj, e_c, pc); }
-        else if (k == 2) { HostPass<TRI, MODE, 2, 1, REP> hp; hp.load(P, pos, list + base); hp.run_guest(com, offb, cap, n, t0, stride, m_skip, m_order, tq, ttype, e_lj, e_c, pc); }
-        else { HostPass<TRI, MODE, 1, 3, REP> hp; hp.load(P, pos, list + base); hp.run_guest(com, offb, cap, n, t0, stride, m_skip, m_order, tq, ttype, e_lj, e_c, pc); }
+        if (k == 3) { HostPass<TRI, MODE, 3, 1, REP> hp; hp.load(P, pos, list + base); hp.run_guest(com, offb, posb, cap, n, t0, stride, m_skip, m_order, tq, ttype, e_lj, e_c, pc); }
+        else if (k == 2) { HostPass<TRI, MODE, 2, 1, REP> hp; hp.load(P, pos, list + base); hp.run_guest(com, offb, posb, cap, n, t0, stride, m_skip, m_order, tq, ttype, e_lj, e_c, pc); }
+        else { HostPass<TRI, MODE, 1, 3, REP> hp; hp.load(P, pos, list + base); hp.run_guest(com, offb, posb, cap, n, t0, stride, m_skip, m_order, tq, ttype, e_lj, e_c, pc); }
     }
 }
 
@@ -734,17 +769,18 @@ __device__ __forceinline__ void guest_loops(const Probe &P, const double (*pos)[
         }
         for (int b = 0; b < na_g; ++b) {
             const double *offb = off + (int64_t)b * 3 * cap;
+            const double *posb = off + (int64_t)(na_g * 3 + 2 + b * 3) * cap;
             double tq = c_sys.charge[g][b];
             if (fabs(tq) < MGPU_ERR_TOL) tq = 0.0;
             const int ttype = c_sys.type[g][b];
             const int gi = gl_index(P.res, g, b, 0);
             const int8_t *L = c_sys.gl_list + (int64_t)gi * MGPU_MAX_SITES;
             const int8_t *N = c_sys.gl_n + gi;
-            guest_list<TRI, 1, REP>(P, pos, L + 1 * MGPU_MAX_SITES, N[1], com, offb, cap, n, t0, stride, m_skip, m_order, tq, ttype, e_lj, e_c, pc);
-            guest_list<TRI, 2, REP>(P, pos, L + 2 * MGPU_MAX_SITES, N[2], com, offb, cap, n, t0, stride, m_skip, m_order, tq, ttype, e_lj, e_c, pc);
-            guest_list<TRI, 3, REP>(P, pos, L + 3 * MGPU_MAX_SITES, N[3], com, offb, cap, n, t0, stride, m_skip, m_order, tq, ttype, e_lj, e_c, pc);
+            guest_list<TRI, 1, REP>(P, pos, L + 1 * MGPU_MAX_SITES, N[1], com, offb, posb, cap, n, t0, stride, m_skip, m_order, tq, ttype, e_lj, e_c, pc);
+            guest_list<TRI, 2, REP>(P, pos, L + 2 * MGPU_MAX_SITES, N[2], com, offb, posb, cap, n, t0, stride, m_skip, m_order, tq, ttype, e_lj, e_c, pc);
+            guest_list<TRI, 3, REP>(P, pos, L + 3 * MGPU_MAX_SITES, N[3], com, offb, posb, cap, n, t0, stride, m_skip, m_order, tq, ttype, e_lj, e_c, pc);
             if (nothing_lists)
-                guest_list<TRI, 0, REP>(P, pos, L + 0 * MGPU_MAX_SITES, N[0], com, offb, cap, n, t0, stride, m_skip, m_order, tq, ttype, e_lj, e_c, pc);
+                guest_list<TRI, 0, REP>(P, pos, L + 0 * MGPU_MAX_SITES, N[0], com, offb, posb, cap, n, t0, stride, m_skip, m_order, tq, ttype, e_lj, e_c, pc);
             else if (t0 == 0) {                                  // this thread's share is not known per list; credit the whole list once
                 const int first = m_order + 1;
                 pc.scr += (unsigned)(N[0] * ((n - first) - ((m_skip >= first && m_skip < n) ? 1 : 0)));
@@ -1066,13 +1102,16 @@ __device__ void commit_trial(int w, int kind, int res, int mol, int n, const dou
     double *offs = wc + 3 * (int64_t)cap;
     if (kind == MGPU_KIND_DELETE) {
         const int last = n - 1;
-        if (mol != last) {                  // the last molecule moves into the hole, with its cache rows (na*3, na*3+1)
+        if (mol != last) {                  // the last molecule moves into the hole, with its cache rows (na*3, na*3+1) and position rows
             if (tid < 3) wc[tid * cap + mol] = wc[tid * cap + last];
-            for (int e = tid; e < na * 3 + 2; e += nthreads) offs[(int64_t)e * cap + mol] = offs[(int64_t)e * cap + last];
+            for (int e = tid; e < na * 6 + 2; e += nthreads) offs[(int64_t)e * cap + mol] = offs[(int64_t)e * cap + last];
         }
     } else {
         if (tid < 3) wc[tid * cap + mol] = com[tid];
-        for (int e = tid; e < na * 3; e += nthreads) offs[(int64_t)e * cap + mol] = off[e / 3][e % 3];
+        for (int e = tid; e < na * 3; e += nthreads) {
+            offs[(int64_t)e * cap + mol] = off[e / 3][e % 3];
+            offs[(int64_t)(na * 3 + 2 + e) * cap + mol] = com[e % 3] + off[e / 3][e % 3];
+        }
         if (tid < 2) offs[(int64_t)(na * 3 + tid) * cap + mol] = hc_new[tid];
         grow_rmax2(res, off, na, tid, nthreads);
     }
@@ -1131,7 +1170,7 @@ __device__ void commit_swap(int w, int resA, int molA, int nA, int resB, int nB,
         const int last = nA - 1;
         if (molA != last) {
             if (tid < 3) wc[tid * cap + molA] = wc[tid * cap + last];
-            for (int e = tid; e < na * 3 + 2; e += nthreads) offs[(int64_t)e * cap + molA] = offs[(int64_t)e * cap + last];
+            for (int e = tid; e < na * 6 + 2; e += nthreads) offs[(int64_t)e * cap + molA] = offs[(int64_t)e * cap + last];
         }
     }
     {
@@ -1139,7 +1178,10 @@ __device__ void commit_swap(int w, int resA, int molA, int nA, int resB, int nB,
         const int cap = c_sys.cap[resB], na = c_sys.natom[resB];
         double *offs = wc + 3 * (int64_t)cap;
         if (tid < 3) wc[tid * cap + nB] = com[tid];
-        for (int e = tid; e < na * 3; e += nthreads) offs[(int64_t)e * cap + nB] = off[e / 3][e % 3];
+        for (int e = tid; e < na * 3; e += nthreads) {
+            offs[(int64_t)e * cap + nB] = off[e / 3][e % 3];
+            offs[(int64_t)(na * 3 + 2 + e) * cap + nB] = com[e % 3] + off[e / 3][e % 3];
+        }
         if (tid < 2) offs[(int64_t)(na * 3 + tid) * cap + nB] = hc_new[tid];
         grow_rmax2(resB, off, na, tid, nthreads);
     }
@@ -1167,7 +1209,10 @@ __device__ __forceinline__ void write_slot(int w, int res, int mol, const double
     const int cap = c_sys.cap[res], na = c_sys.natom[res];
     double *offs = wc + 3 * (int64_t)cap;
     if (tid < 3) wc[tid * cap + mol] = com[tid];
-    for (int e = tid; e < na * 3; e += nthreads) offs[(int64_t)e * cap + mol] = off[e / 3][e % 3];
+    for (int e = tid; e < na * 3; e += nthreads) {
+        offs[(int64_t)e * cap + mol] = off[e / 3][e % 3];
+        offs[(int64_t)(na * 3 + 2 + e) * cap + mol] = com[e % 3] + off[e / 3][e % 3];
+    }
     grow_rmax2(res, off, na, tid, nthreads);
 }
 
@@ -1834,6 +1879,28 @@ __global__ void k_selftest(double s_lo, double s_hi, int n, double *out)
     // non-negative doubles order like their bit patterns
     atomicMax(reinterpret_cast<unsigned long long *>(out + 0), (unsigned long long)__double_as_longlong(e_r));
     atomicMax(reinterpret_cast<unsigned long long *>(out + 1), (unsigned long long)__double_as_longlong(e_g));
+}
+
+// ------------------------------------------------------------------------------------
+// L2 read-bandwidth microbenchmark (roofline denominator of K2): grid-stride 16-byte loads over an L2-resident buffer
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_l2_read(const double2 *__restrict__ buf, size_t n16, int passes, double *out)
+{
+    double ax = 0.0, ay = 0.0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (int p = 0; p < passes; ++p) {
+        size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; i + 3 * stride < n16; i += 4 * stride) {          // four independent loads in flight per thread
+            double2 v0, v1, v2, v3;
+            asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v0.x), "=d"(v0.y) : "l"(buf + i));
+            asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v1.x), "=d"(v1.y) : "l"(buf + i + stride));
+            asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v2.x), "=d"(v2.y) : "l"(buf + i + 2 * stride));
+            asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v3.x), "=d"(v3.y) : "l"(buf + i + 3 * stride));
+            ax += v0.x + v1.x + v2.x + v3.x; ay += v0.y + v1.y + v2.y + v3.y;
+        }
+        for (; i < n16; i += stride) { const double2 v = buf[i]; ax += v.x; ay += v.y; }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ax + ay;
 }
 
 // ------------------------------------------------------------------------------------

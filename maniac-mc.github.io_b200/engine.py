@@ -205,6 +205,17 @@ class Engine:
     def set_fugacity(self, res, f, walker=0):
         self._ck(self.L.mgpu_set_fugacity(walker, res, float(f)))
 
+    def set_fugacities(self, res, f, first_walker=0):
+        """thermo%fugacity(res) of a run of walkers in one copy (mu = ln f / beta, prepare_utils.f90:245-247)."""
+        mu = np.ascontiguousarray(np.log(np.asarray(f, dtype=np.float64)) / self.thermo(res)["beta"])
+        self._ck(self.L.mgpu_set_chemical_potentials(first_walker, mu.size, res, _pd(mu)))
+
+    def counts(self, res, first_walker=0, n_walkers=None):
+        n = self.n_walkers - first_walker if n_walkers is None else n_walkers
+        out = np.zeros(n, dtype=np.int32)
+        self._ck(self.L.mgpu_get_counts(first_walker, n, res, _pi(out)))
+        return out
+
     def Ak(self, walker=0):
         nk = self.ewald()["nk"]
         a = np.zeros(2 * nk)
@@ -491,6 +502,11 @@ class Engine:
         a, b = C.c_double(), C.c_double()
         self._ck(self.L.mgpu_selftest_math(C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def measure_l2_peak(self):
+        gb = C.c_double()
+        self._ck(self.L.mgpu_measure_l2_peak(C.byref(gb)))
+        return gb.value
 
     def measure_fp64_peak(self):
         tf, s = C.c_double(), C.c_double()

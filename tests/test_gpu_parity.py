@@ -24,20 +24,34 @@ def assert_e(a, b, rel=REL_E, what=""):
     assert close_e(a, b, rel), f"{what}: gpu={np.asarray(a)!r} ref={np.asarray(b)!r} diff={np.asarray(a) - np.asarray(b)!r}"
 
 
+def _engine_variant(param):
+    from maniac_b200.engine import OPT_HOST_CACHE, OPT_SWEEP_TEAM, Engine
+
+    class EngineVariant(Engine):
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+            # the device-resident drivers in their throughput shape (one warp per walker) unless the variant asks for
+            # the team shape; left to itself the engine would pick teams for the handful of walkers a test uses
+            self.set_option(OPT_SWEEP_TEAM, 1 if param == "team" else 0)
+            if param == "nocache":
+                self.set_option(OPT_HOST_CACHE, 0)
+    EngineVariant.__name__ = f"Engine_{param}"
+    return EngineVariant
+
+
 @pytest.fixture(params=["hcache", "nocache"])
 def engine_cls(request):
     """Every parity test runs twice: with the per-molecule framework-energy cache (default: the old
     geometry of a move / deletion reads the molecule's cached framework sum) and without it (the
     framework is swept for old and new geometry, like the reference does)."""
-    from maniac_b200.engine import OPT_HOST_CACHE, Engine
-    if request.param == "hcache":
-        return Engine
+    return _engine_variant(request.param)
 
-    class EngineNoCache(Engine):
-        def __init__(self, *a, **k):
-            super().__init__(*a, **k)
-            self.set_option(OPT_HOST_CACHE, 0)
-    return EngineNoCache
+
+@pytest.fixture(params=["hcache", "nocache", "team"])
+def sweep_engine_cls(request):
+    """Tests of the device-resident drivers run a third time in the team shape of the sweep kernel (four warps per
+    walker, MGPU_OPT_SWEEP_TEAM = 1): the shape launches with few walkers per GPU use."""
+    return _engine_variant(request.param)
 
 
 ALL = ["lj_gas", "zif8_h2o", "h2o_gas", "methanol", "two_atoms", "dipole", "two_dipole", "dipole_triclinic",
@@ -238,7 +252,8 @@ def _compare_traces(tr, ref, n_check=None):
     assert (d <= lim).all(), (d.max(), np.argmax(d - lim))
 
 
-def test_sweep_10k_moves_accept_reject_sequence(load, engine_cls):
+def test_sweep_10k_moves_accept_reject_sequence(load, sweep_engine_cls):
+    engine_cls = sweep_engine_cls
     """North-star gate: identical accept/reject sequence over the first 10^4 moves and
     per-move dE within 1e-9, GCMC mix of BASELINE configs[1] (0.4/0.4/0.2)."""
     s = load("zif8_h2o_gcmc")
@@ -264,7 +279,8 @@ def test_sweep_10k_moves_accept_reject_sequence(load, engine_cls):
 
 
 @pytest.mark.parametrize("name,steps", [("methanol", 3000), ("dipole_triclinic", 400), ("lj_gas", 2000)])
-def test_sweep_other_systems(name, steps, load, engine_cls):
+def test_sweep_other_systems(name, steps, load, sweep_engine_cls):
+    engine_cls = sweep_engine_cls
     s = load(name)
     if name == "lj_gas":
         s.p_translation, s.p_rotation, s.p_insertion_deletion = 0.5, 0.0, 0.5
@@ -285,7 +301,8 @@ def test_sweep_other_systems(name, steps, load, engine_cls):
         assert_e(eng.energy(), o.energy(), rel=1e-9)
 
 
-def test_sweep_from_empty_and_widom_moves(load, engine_cls):
+def test_sweep_from_empty_and_widom_moves(load, sweep_engine_cls):
+    engine_cls = sweep_engine_cls
     """Edge cases: N = 0 (moves return early, creations use the slot-1 template) and Widom trials
     inside the loop (state never changes; statistic%weight / sample)."""
     s = load("zif8_co2_widom")
@@ -500,7 +517,8 @@ def test_swap_energy_commit_rollback(load, engine_cls):
 
 
 @pytest.mark.parametrize("steps", [1500])
-def test_sweep_mixture_with_swaps(steps, load, engine_cls):
+def test_sweep_mixture_with_swaps(steps, load, sweep_engine_cls):
+    engine_cls = sweep_engine_cls
     """Device-resident drivers incl. swapping.f90 on the triclinic mixture: same move / accept sequence,
     per-move energies within 1e-9, same final state as the oracle."""
     s = _mixture(load)
@@ -541,7 +559,8 @@ def test_host_driven_mixture_with_swaps(load, engine_cls):
         hm.close()
 
 
-def test_large_triclinic_supercell(load, engine_cls):
+def test_large_triclinic_supercell(load, sweep_engine_cls):
+    engine_cls = sweep_engine_cls
     """configs[4] at full size: 2x2x2 blocks = 17 664 framework atoms, dense k set; total energy and a short
     trajectory against the oracle, then a longer device run audited by a full recompute (drift gate)."""
     s = _mixture(load, reps=(2, 2, 2), tilt=3.0, n_co2=24, n_n2=24)
@@ -567,7 +586,8 @@ def test_large_triclinic_supercell(load, engine_cls):
 # ---------------------------------------------------------------------------------------------
 # walker records and the block-level entry (host state in, host state out)
 # ---------------------------------------------------------------------------------------------
-def test_walker_records_roundtrip_and_block(load, engine_cls):
+def test_walker_records_roundtrip_and_block(load, sweep_engine_cls):
+    engine_cls = sweep_engine_cls
     """mgpu_save_walkers / mgpu_load_walkers / mgpu_block: the record is the whole state, so
     (a) save -> load into another walker reproduces that walker exactly, (b) a trajectory cut into
     blocks that travel through host memory equals the uninterrupted device-resident one and the
@@ -638,7 +658,8 @@ def test_walker_records_roundtrip_and_block(load, engine_cls):
             eng.save_walkers(small)
 
 
-def test_step_size_adaptation_per_block(load, engine_cls):
+def test_step_size_adaptation_per_block(load, sweep_engine_cls):
+    engine_cls = sweep_engine_cls
     """adjust_move_step_sizes (src/monte_carlo_utils.f90:98-134) at the end of every block, on the device, per walker:
     same step sizes and same trajectory as the oracle doing the same."""
     s = load("zif8_h2o_gcmc")
