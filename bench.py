@@ -56,6 +56,7 @@ CAPACITY = 320           # molecules per walker (NB_MAX_MOLECULE analogue); load
 POOL = 2368              # walkers of the equilibration pool: one full wave of the warp-per-walker shape
 FLOP_GEOM, FLOP_LJ, FLOP_COUL, FLOP_SINCOS = 29.0, 8.0, 69.0, 64.0      # SURVEY.md 8d, convention C1
 FUG_FILE = ROOT / "tests" / "golden" / "bench_fugacity.json"              # ln f that pins each loading (written by a GPU run)
+STATES_FILE = ROOT / "tests" / "golden" / "bench_states.npz"              # relaxed configurations of 32 GPU walkers at the headline loading (same run)
 
 
 def parse():
@@ -91,6 +92,17 @@ def workload(loading):
     s = load_pore(s, 0, max(1, loading), seed=12345)
     s.p_translation, s.p_rotation, s.p_insertion_deletion, s.p_swap, s.p_widom = 0.4, 0.4, 0.2, 0.0, 0.0
     return s
+
+
+def stored_states(loading):
+    """[(com[n,3], offset[n,natom,3])] relaxed at `loading` (written by a GPU run with --write-fugacity), or None"""
+    try:
+        z = np.load(STATES_FILE)
+        if int(z["loading"]) != loading:
+            return None
+        return [(z[f"com{i}"], z[f"off{i}"]) for i in range(int(z["n"]))]
+    except Exception:
+        return None
 
 
 def stored_lnf():
@@ -174,60 +186,92 @@ def kspace_bytes(counters_delta, nk):
     return 16.0 * nk * trials + 16.0 * nk * commits
 
 
-def cpu_sample(system, seconds, threads, capacity, fugacity=None):
-    """Aggregate moves/s of the CPU oracle on `threads` host threads, one walker each (-O3 build of the oracle source)."""
+def cpu_sample(system, seconds, threads, capacity, target, lnf, states=None, chunk=256):
+    """Aggregate moves/s of the CPU oracle on `threads` host threads, one walker each (-O3 build of the oracle source),
+    under the same loading controller as the GPU legs (ln f moved between chunks of `chunk` MC steps from the mean loading
+    of the walkers).  states: optional list of (com[n,3], offset[n,natom,3]) -- relaxed configurations handed over from
+    the GPU walkers, so that both sides sample the same state."""
     os.environ["MANIAC_ORACLE_VARIANT"] = "o3"
     from oracle.oracle import Oracle
     oracles = []
     for t in range(threads):
         o = Oracle(system, capacity=capacity)
-        if fugacity is not None:
-            o.set_fugacity(0, float(fugacity))
+        if states:
+            com, off = states[t % len(states)]
+            o.set_count(0, len(com))
+            for m in range(len(com)):
+                o.set_molecule(0, m, com[m], off[m])
         o.update_system_energy()
         o.seed(12345 + 104729 * t)
         oracles.append(o)
-    t0 = time.perf_counter()
-    oracles[0].monte_carlo_steps(100, trace=False)
-    per = (time.perf_counter() - t0) / 100
-    n = max(100, int(seconds / per))
-    done = [0] * threads
+    ctl = LoadingController(target, -14.0 if lnf is None else lnf)
+    ctl.prev = float(np.mean([o.count(0) for o in oracles]))
+    for o in oracles:
+        o.set_fugacity(0, float(np.exp(ctl.lnf)))
 
     def run(i):
-        oracles[i].monte_carlo_steps(n, trace=False)
-        done[i] = n
-    ths = [threading.Thread(target=run, args=(i,)) for i in range(threads)]
-    t0 = time.perf_counter()
-    for th in ths:
-        th.start()
-    for th in ths:
-        th.join()
+        oracles[i].monte_carlo_steps(chunk, trace=False)
+    done, t0 = 0, time.perf_counter()
+    while True:
+        ths = [threading.Thread(target=run, args=(i,)) for i in range(threads)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+        done += chunk * threads
+        ctl.update(float(np.mean([o.count(0) for o in oracles])))
+        for o in oracles:
+            o.set_fugacity(0, float(np.exp(ctl.lnf)))
+        if time.perf_counter() - t0 >= seconds:
+            break
     dt = time.perf_counter() - t0
-    return sum(done) / dt, n, dt, float(np.mean([o.count(0) for o in oracles]))
+    return done / dt, done // threads, dt, ctl.hist[-1]
 
 
 # ---------------------------------------------------------------------------------------------------------
 # pinning a loading: feedback on ln(fugacity), then frozen
 # ---------------------------------------------------------------------------------------------------------
+class LoadingController:
+    """PID feedback on ln(fugacity), one value for all walkers of a leg, applied BETWEEN launches: holds <N> at the
+    target.  It has to stay on: TIP4P water in the hydrophobic ZIF-8 cage adsorbs cooperatively (the pinning fugacity
+    FALLS with loading: ln f = -13.5 / -14.7 / -15.0 at N = 16 / 64 / 128), so at a frozen fugacity an intermediate
+    loading runs away to the empty or to the filled branch.  target = 0: a vanishing fugacity keeps the walkers empty."""
+
+    def __init__(self, target, lnf0):
+        self.target, self.scale = target, float(max(target, 4))
+        self.lnf = float(lnf0) if target > 0 else -60.0
+        self.prev = None
+        self.integral = 0.0
+        self.hist, self.lnfs = [], []
+
+    def apply(self, eng, n_walkers):
+        eng.set_fugacities(0, np.full(n_walkers, np.exp(self.lnf)), 0)
+
+    def update(self, nbar):
+        self.hist.append(float(nbar))
+        self.lnfs.append(self.lnf)
+        if self.target > 0:
+            d = 0.0 if self.prev is None else nbar - self.prev
+            e = (nbar - self.target) / self.scale
+            self.integral = float(np.clip(self.integral + e, -3.0, 3.0))      # removes the offset the runaway drift would leave under P + D alone
+            self.lnf -= 0.5 * e + 4.0 * d / self.scale + 0.08 * self.integral
+        self.prev = float(nbar)
+
+    def step(self, eng, n_walkers):
+        """after a launch: read <N>, move ln f, hand it to the walkers"""
+        self.update(float(eng.counts(0, 0, n_walkers).mean()))
+        self.apply(eng, n_walkers)
+
+
 def pin_loading(eng, n_walkers, target, launches, inner, lnf0):
-    """Run walkers [0, n_walkers) of `eng` for `launches` launches of `inner` MC steps under a PD feedback on
-    ln f (one fugacity for all of them) that holds <N> at `target`; returns (ln f averaged over the last third,
-    history of <N>).  target = 0: a vanishing fugacity empties the walkers."""
-    lnf = float(lnf0) if target > 0 else -60.0
-    hist, lnfs = [], []
-    prev = float(eng.counts(0, 0, n_walkers).mean())
-    scale = float(max(target, 4))
+    """Run walkers [0, n_walkers) of `eng` for `launches` launches of `inner` MC steps under the controller; returns it."""
+    ctl = LoadingController(target, lnf0)
+    ctl.prev = float(eng.counts(0, 0, n_walkers).mean())
+    ctl.apply(eng, n_walkers)
     for it in range(launches):
-        eng.set_fugacities(0, np.full(n_walkers, np.exp(lnf)), 0)
         eng.sweep(inner, 0, n_walkers)
-        nbar = float(eng.counts(0, 0, n_walkers).mean())
-        hist.append(nbar)
-        lnfs.append(lnf)
-        if target > 0:
-            lnf -= 0.5 * (nbar - target) / scale + 4.0 * (nbar - prev) / scale
-        prev = nbar
-    if target > 0:
-        lnf = float(np.mean(lnfs[-max(1, launches // 3):]))
-    return lnf, hist
+        ctl.step(eng, n_walkers)
+    return ctl
 
 
 def clone_records(eng, blob_pool, off_pool, n_pool, n_target):
@@ -265,9 +309,10 @@ def main():
         if rank != 0:
             return
         lnf = lnf_known.get(a.loading)
+        states = stored_states(a.loading)
         per_s = []
         for i in range(a.warmup + a.steps):
-            v, n, dt, nbar = cpu_sample(s, max(2.0, a.cpu_seconds / max(1, a.steps)), cores, 512, None if lnf is None else np.exp(lnf))
+            v, n, dt, nbar = cpu_sample(s, max(2.0, a.cpu_seconds / max(1, a.steps)), cores, 512, a.loading, lnf, states)
             if i >= a.warmup:
                 per_s.append((v, n, dt, nbar))
         v = float(np.mean([x[0] for x in per_s]))
@@ -276,8 +321,9 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": cfg,
                 "cpu_baseline": {"value": v, "unit": "moves/s", "cores": cores, "kind": "port",
-                                 "sample": f"{cores} independent walkers (one per host thread) x {per_s[0][1]} MC steps per step from the {a.loading}-water "
-                                           f"configuration at the pinning fugacity (mean loading at the end {per_s[-1][3]:.1f}); C restatement of the "
+                                 "sample": f"{cores} independent walkers (one per host thread) x {per_s[0][1]} MC steps per step from "
+                                           + ("relaxed configurations of GPU walkers (tests/golden/bench_states.npz) " if states else f"the unrelaxed {a.loading}-water configuration ")
+                                           + f"under the same loading controller as the GPU legs (mean loading at the end {per_s[-1][3]:.1f}); C restatement of the "
                                            "reference's serial Fortran algorithm with a compact per-type-pair LJ table, gcc -O3 -ffp-contract=off, "
                                            "no -march=native (no Fortran compiler in the image: the reference itself cannot be built)"},
                 "e2e": {"value": v, "unit": "moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -329,37 +375,42 @@ def main():
 
     def prepare(loading, n_target, seed):
         """Pin `loading` on the pool (walkers [0, n_pool)), then clone the relaxed pool into walkers [0, n_target)."""
-        lnf, hist = pin_loading(eng, n_pool, loading, a.equil, a.inner, lnf_known.get(loading, 0.0))
+        ctl = pin_loading(eng, n_pool, loading, a.equil, a.inner, lnf_known.get(loading, -14.0))
         blob_pool = eng.host_buffer(n_pool * (72 + 2 * ew["nk"] + (int(1.3 * max(loading, 8)) + 48) * (3 + 3 * na + 2)))
         off_pool = eng.save_walkers(blob_pool, 0, n_pool)
         buf, off = clone_records(eng, blob_pool, off_pool, n_pool, n_target)
         eng.load_walkers(buf, off, 0)
-        eng.set_fugacities(0, np.full(n_target, np.exp(lnf)), 0)
+        ctl.apply(eng, n_target)
         eng.seed(seed)
         eng.reset_averages()
-        return lnf, hist
+        return ctl
 
     sampler = ClockSampler(local)
     sampler.start()
     t_prep = time.perf_counter()
-    lnf_head, hist_head = prepare(a.loading, Wmax if do_grid else W, 12345 + 7919 * rank)
+    ctl_head = prepare(a.loading, Wmax if do_grid else W, 12345 + 7919 * rank)
     t_prep = time.perf_counter() - t_prep
-    found_lnf = {a.loading: lnf_head}
+    hist_head = list(ctl_head.hist)
+    found_lnf = {a.loading: float(np.mean(ctl_head.lnfs[-max(1, a.equil // 3):]))}
+    lnf_head = found_lnf[a.loading]
 
-    def timed_sweeps(n_walkers, n_launch, n_warm):
+    def timed_sweeps(ctl, n_walkers, n_launch, n_warm):
         for _ in range(n_warm):
             eng.sweep(a.inner, 0, n_walkers)
+            ctl.step(eng, n_walkers)
         eng.reset_pair_counts()
         eng.timing_reset()
         for _ in range(n_launch):
             flush_l2()
             eng.sweep(a.inner, 0, n_walkers)
+            ctl.step(eng, n_walkers)
         ms, launches = eng.timing("sweep")
         return ms * 1e-3, int(launches)
 
     # ---- headline: W walkers pinned at the loading --------------------------------------------------
     for _ in range(a.warmup):
         eng.sweep(a.inner, 0, W)
+        ctl_head.step(eng, W)
     stride = max(1, W // 256)
     c0 = np.array([eng.counters(w) for w in range(0, W, stride)]).sum(axis=0)
     n_sampled = len(range(0, W, stride))
@@ -372,6 +423,7 @@ def main():
     for _ in range(a.steps):
         flush_l2()
         eng.sweep(a.inner, 0, W)
+        ctl_head.step(eng, W)                   # between launches: 19 KB of counts D2H, 38 KB of mu H2D (outside the event-timed kernel)
     barrier()
     wall = time.perf_counter() - t0
     sampler.mark_end()
@@ -388,7 +440,7 @@ def main():
     if a.quick:
         if rank == 0:
             print(json.dumps({"quick": True, "lib": os.environ.get("MANIAC_GPU_LIB", "default"), "moves_per_s": value,
-                              "ms_per_step": 1e3 * t_dev / a.steps, "loading": [n_begin, n_end], "ln_fugacity": lnf_head,
+                              "ms_per_step": 1e3 * t_dev / a.steps, "loading": [n_begin, n_end], "ln_fugacity": ctl_head.lnf,
                               "clocks": clocks}))
         eng.close()
         return
@@ -424,13 +476,26 @@ def main():
                    "note": "K2 (k-space) is fused into the sweep kernel, so its algorithmic bytes (16 nk read per trial + 16 nk written per commit, "
                            "SURVEY 8d) are divided by the WHOLE kernel's time: an upper bound of how far K2 is from its roof; peak = "
                            "mgpu_measure_l2_peak (48 MB L2-resident buffer read by all SMs, this run)"}
-    stationarity = {"target_loading": a.loading, "mean_loading_begin": n_begin, "mean_loading_end": n_end, "ln_fugacity": lnf_head,
+    stationarity = {"target_loading": a.loading, "mean_loading_begin": n_begin, "mean_loading_end": n_end,
+                    "ln_fugacity_begin": ctl_head.lnfs[-a.steps] if len(ctl_head.lnfs) >= a.steps else None, "ln_fugacity_end": ctl_head.lnf,
+                    "controller": "PID feedback on ln f between launches (all legs at a pinned loading): d ln f = -(0.5 e + 4 de + 0.08 sum e), e = (<N> - N0) / N0",
                     "pinning_launches": a.equil, "pinning_seconds": t_prep,
                     "loading_during_pinning": [hist_head[i] for i in range(0, len(hist_head), max(1, len(hist_head) // 8))]}
 
+    # relaxed configurations for the CPU baseline (rank 0): the first `cores` walkers' records
+    cpu_states = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        nst = min(max(cores, 32), W)
+        tmp = eng.host_buffer(nst * eng.record_doubles_max())
+        off_st = eng.save_walkers(tmp, 0, nst)
+        cpu_states = []
+        for i in range(nst):
+            rec = Engine.parse_record(tmp[off_st[i]:off_st[i + 1]], ew["nk"], [(r.active, r.natom) for r in s.residues])
+            cpu_states.append((rec["molecules"][0]["com"].copy(), rec["molecules"][0]["offset"].copy()))
+
     # ---- the same sweep with the per-molecule framework-energy cache off (the reference's operation count) -----
     eng.set_option(OPT_HOST_CACHE, 0)
-    t_nc, l_nc = timed_sweeps(W, 2, 1)
+    t_nc, l_nc = timed_sweeps(ctl_head, W, 2, 1)
     pc_nc = eng.pair_counts()
     ms_nc = t_nc * 1e3
     t_nc = max_over_ranks(t_nc)
@@ -440,7 +505,7 @@ def main():
                 "note": "mgpu_set_option(MGPU_OPT_HOST_CACHE, 0): old-geometry framework sums recomputed every trial, like the reference"}
     eng.set_option(OPT_HOST_CACHE, 1)
     eng.set_option(OPT_PHASE_SYNC, 0)
-    t_ns, _ = timed_sweeps(W, 2, 1)
+    t_ns, _ = timed_sweeps(ctl_head, W, 2, 1)
     t_ns = max_over_ranks(t_ns)
     no_sync = {"moves_per_s": float(W) * a.inner * 2 * world / t_ns,
                "note": "mgpu_set_option(MGPU_OPT_PHASE_SYNC, 0): walkers of a CTA free-running (no per-quartet barrier)"}
@@ -461,6 +526,7 @@ def main():
     for i in range(a.steps):
         off = eng.block(a.inner, blob[cur], off, blob[cur ^ 1], 0, W)
         cur ^= 1
+        ctl_head.step(eng, W)                   # the host's part between blocks (inside the wall clock)
     barrier()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
     tr1 = eng.traffic()
@@ -478,23 +544,28 @@ def main():
         grid = {"loadings": [0, 16, 64, 128], "walkers": [64, 1024, 4096, 16384], "mc_steps_per_launch": a.inner, "cells": []}
         order = [a.loading] + [x for x in grid["loadings"] if x != a.loading]      # the headline state is already on the device
         for loading in order:
+            ctl_g = ctl_head
             if loading != a.loading:
                 eng.close()                               # the pool restarts from a configuration holding about that many waters
                 eng = Engine(workload(loading), n_walkers=Wmax, capacity=CAPACITY, device=local)
-                found_lnf[loading], _ = prepare(loading, Wmax, 999 + loading)
+                ctl_g = prepare(loading, Wmax, 999 + loading)
+                found_lnf[loading] = float(np.mean(ctl_g.lnfs[-max(1, a.equil // 3):]))
             for Wg in grid["walkers"]:
                 nb = float(eng.counts(0, 0, Wg).mean())
-                t_g, l_g = timed_sweeps(Wg, 3, 1)
+                ctl_w = LoadingController(loading, ctl_g.lnf)      # its own feedback: the leg's walkers only
+                ctl_w.prev = nb
+                t_g, l_g = timed_sweeps(ctl_w, Wg, 3, 1)
                 pcg = eng.pair_counts()
                 fl_g = FLOP_GEOM * pcg["pairs"] + FLOP_LJ * pcg["lj"] + FLOP_COUL * pcg["coulomb"]      # real-space part only
                 grid["cells"].append({"loading": loading, "walkers": Wg, "moves_per_s": float(Wg) * a.inner * l_g / t_g,
                                       "frac_c1_realspace": fl_g / t_g / 1e12 / peak_tf if peak_tf else None,
                                       "mean_loading": [nb, float(eng.counts(0, 0, Wg).mean())], "ln_fugacity": found_lnf[loading],
-                                      "shape": "team (4 warps / walker)" if Wg * 8 <= 148 * 16 else "warp / walker"})
+                                      "shape": "team (4 warps / walker)" if Wg * 4 <= 148 * 16 * 3 else "warp / walker"})
         grid["cells"].sort(key=lambda c: (c["loading"], c["walkers"]))
         eng.close()                                       # back to the headline state for the legs below
         eng = Engine(s, n_walkers=max(a.strong_walkers // world, POOL), capacity=CAPACITY, device=local)
-        prepare(a.loading, max(a.strong_walkers // world, POOL), 4242 + rank)
+        ctl_head = prepare(a.loading, max(a.strong_walkers // world, POOL), 4242 + rank)
+        lnf_head = ctl_head.lnf
 
     # ---- a FIXED isotherm (64 points x replicas) split over the GPUs ----------------------
     strong = None
@@ -528,7 +599,7 @@ def main():
         summ = summarize(total, beta)
         strong = {"metric": "mc_trial_moves_per_s", "scaling": "strong", "walkers_total": Ws * world, "walkers_per_gpu": Ws,
                   "value": float(Ws) * world * a.inner * a.steps / t_s, "ms_per_step": 1e3 * t_s / a.steps,
-                  "shape": "team (4 warps / walker)" if Ws * 8 <= 148 * 16 else "warp / walker",
+                  "shape": "team (4 warps / walker)" if Ws * 4 <= 148 * 16 * 3 else "warp / walker",
                   "points": 64, "replicas_per_point": Ws * world / 64.0,
                   "reduction": "mgpu_reduce_averages (one ncclAllReduce of 384 doubles)" if world > 1 else "single rank: none",
                   "fugacity": [float(fug[i]) for i in range(0, 64, 9)],
@@ -664,12 +735,15 @@ def main():
     # ---- CPU baseline (rank 0, N = 1 only) ------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
-        v, n, dt, nbar = cpu_sample(s, a.cpu_seconds, cores, 512, np.exp(lnf_head))
+        v, n, dt, nbar = cpu_sample(s, a.cpu_seconds, cores, 512, a.loading, lnf_head, cpu_states)
         cpu = {"value": v, "unit": "moves/s", "cores": cores, "kind": "port",
-               "sample": f"{cores} independent walkers (one per host thread) x {n} MC steps from the {a.loading}-water configuration at the same "
-                         f"pinning fugacity ({dt:.1f} s, mean loading at the end {nbar:.1f}); CPU oracle = C restatement of the reference's serial "
+               "sample": f"{cores} independent walkers (one per host thread) x {n} MC steps, started from relaxed configurations of the GPU walkers "
+                         f"(records through host memory) under the same loading controller ({dt:.1f} s, mean loading at the end {nbar:.1f}); CPU oracle = C restatement of the reference's serial "
                          "algorithm with a compact per-type-pair LJ table (friendlier than the reference's 4-D arrays), gcc -O3 "
                          "-ffp-contract=off, no -march=native (no Fortran compiler in the image)"}
+    if a.write_fugacity and rank == 0 and cpu_states:
+        np.savez_compressed(STATES_FILE, loading=a.loading, n=min(32, len(cpu_states)),
+                            **{f"com{i}": c for i, (c, o) in enumerate(cpu_states[:32])}, **{f"off{i}": o for i, (c, o) in enumerate(cpu_states[:32])})
     if a.write_fugacity and rank == 0:
         old = stored_lnf()
         old.update(found_lnf)

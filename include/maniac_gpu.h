@@ -161,7 +161,7 @@ enum { MGPU_OPT_HOST_CACHE = 1,
         * walker (16 walkers per CTA: the throughput shape, fills the GPU from 2368 walkers up).  1 = a team of four
         * warps per walker (4 walkers per CTA): the energy loops of a trial are split over 128 threads, for launches
         * with few walkers per GPU (a fixed isotherm spread over more GPUs).  -1 picks teams when the walkers would
-        * fill less than half of the GPU's warp slots.  Same trajectories either way (sums are reduced in another order). */
+        * fill at most three quarters of the GPU's warp slots (three short team waves beat one partly empty warp wave).  Same trajectories either way (sums are reduced in another order). */
        MGPU_OPT_SWEEP_TEAM = 4 };
 int mgpu_set_option(int32_t option, int32_t value);
 

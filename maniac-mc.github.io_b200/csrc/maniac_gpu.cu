@@ -53,7 +53,7 @@ struct Context {
     int tri_listed = 0;                // triclinic: candidates listed but provably irrelevant (see mgpu_init)
     int wgroups = MGPU_WGROUPS;        // walkers (warps) per CTA of the warp-per-task kernels
     size_t smem_team = 0;              // dynamic shared memory of the team sweep (wgroups * 32 / MGPU_TEAM walkers per CTA)
-    int sweep_team = -1;               // MGPU_OPT_SWEEP_TEAM: -1 auto (teams when the walkers fill less than half the warp slots), 0 never, 1 always
+    int sweep_team = -1;               // MGPU_OPT_SWEEP_TEAM: -1 auto (teams when the walkers fill at most 3/4 of the warp slots), 0 never, 1 always
     int tab_emin = 0, tab_noct = 0;
     std::vector<void *> allocs;
     // host-side mirrors needed by the API
@@ -188,13 +188,15 @@ int rebuild(int first, int n)
 }
 int ensure_clean(int w) { if (g.dirty[w]) return rebuild(w, 1); return 0; }
 // One launch of the device-resident drivers for walkers [first, first + n).  Shape: one warp per walker (16 walkers per
-// CTA) when the walkers fill the GPU's warp slots; a team of four warps per walker (4 walkers per CTA) when they fill less
-// than half of them (few walkers per GPU: strong scaling of a fixed isotherm).
+// CTA) when the walkers fill the GPU's warp slots; a team of four warps per walker (4 walkers per CTA) when there are few
+// walkers per GPU (strong scaling of a fixed isotherm).  A team step is about 3.5x shorter than a warp step
+// (the driver part does not shrink), a team wave holds a quarter of the walkers: up to three team waves
+// (n <= 3/4 of the warp slots) beat the single, partly empty warp wave.
 bool sweep_uses_teams(int n)
 {
     if (g.wgroups * 32 < MGPU_TEAM) return false;
     if (g.sweep_team >= 0) return g.sweep_team != 0;
-    return (long long)n * (MGPU_TEAM / 32) * 2 <= (long long)g.sm_count * g.wgroups;
+    return (long long)n * 4 <= (long long)g.sm_count * g.wgroups * 3;
 }
 // n_total: the walkers in flight together (the call's, when it is cut into slices on several streams)
 void launch_sweep(cudaStream_t st, int first, int n, long long n_steps, int trace_walker, mgpu_step_trace *d_trace, int n_total)
@@ -332,6 +334,30 @@ int mgpu_init(const mgpu_system *sys)
         h.tri_nrel = n;
         h.tri_safe2 = 1e300;
         for (int k = 0; k < n; ++k) h.tri_safe2 = std::fmin(h.tri_safe2, 0.25 * h.tri_len2[k]);
+        // Gate of the candidate loop in fractional space.  With f_d = +-(1/2 - u_d), u_d in [0, 1/2]:
+        //   |t|^2 - |t -+ C m|^2 = 2 |f . G m| - m.G.m  <=  s1 - m.G.m - 2 sum_d u_d |(G m)_d|,   s1 = sum_d |(G m)_d|,
+        // so m can only help when u_d |(G m)_d| < (s1 - m.G.m) / 2 for every d, in particular for its dominant axis d*.
+        // tri_eps[d] = the largest such bound over the listed vectors whose dominant axis is d.
+        h.tri_eps[0] = h.tri_eps[1] = h.tri_eps[2] = 0.0;
+        h.tri_gain_max = 0.0;
+        for (int k = 0; k < n; ++k) {
+            double Gm[3], mGm = 0.0, s1 = 0.0;
+            for (int d = 0; d < 3; ++d) { Gm[d] = G[d][0] * h.tri_m[k][0] + G[d][1] * h.tri_m[k][1] + G[d][2] * h.tri_m[k][2]; mGm += h.tri_m[k][d] * Gm[d]; s1 += std::fabs(Gm[d]); }
+            int ds = 0;
+            for (int d = 1; d < 3; ++d) if (std::fabs(Gm[d]) > std::fabs(Gm[ds])) ds = d;
+            const double slack = 0.5 * (s1 - mGm);
+            h.tri_eps[ds] = std::fmax(h.tri_eps[ds], slack / std::fabs(Gm[ds]) * (1.0 + 1e-9) + 1e-12);
+            h.tri_gain_max = std::fmax(h.tri_gain_max, (s1 - mGm) * (1.0 + 1e-9));
+        }
+    }
+    h.tri_lower = (M[0][1] == 0.0 && M[0][2] == 0.0 && M[1][2] == 0.0) ? 1 : 0;
+    for (int d = 0; d < 3; ++d) {
+        h.tri_thr_hi[d] = 0x7ff00000;                           // never
+        if (h.triclinic && h.tri_nrel > 0 && h.tri_eps[d] > 0.0) {
+            const double thr = std::fmax(0.0, 0.5 - h.tri_eps[d]);
+            uint64_t bits; std::memcpy(&bits, &thr, 8);
+            h.tri_thr_hi[d] = (int32_t)(bits >> 32);             // hi(|f|) >= hi(thr) is implied by |f| >= thr: a superset
+        }
     }
 
     // ---- Ewald: setup_ewald, prepare_utils.f90:110-226 ----
@@ -416,7 +442,7 @@ int mgpu_init(const mgpu_system *sys)
             if (R.natom > g.natom_max) g.natom_max = R.natom;
             for (int a = 0; a < R.natom; ++a) { h.charge[r][a] = R.charges[a]; h.type[r][a] = R.types[a]; }
             h.goff[r] = stride;
-            stride += (int64_t)(3 + 3 * R.natom + 2 + 3 * R.natom) * R.capacity;      // com, offsets, framework-energy cache rows, absolute atom positions
+            stride += (int64_t)(3 + 3 * R.natom + 2) * R.capacity;      // com, offsets, framework-energy cache rows
             // prepare_monte_carlo, prepare_utils.f90:231-259
             const double mass = R.mass * G_TO_KG / NA();
             double lam = H_PLANCK / std::sqrt(TWOPI * mass * KB * sys->temperature);
@@ -492,6 +518,41 @@ int mgpu_init(const mgpu_system *sys)
         CK(cudaMemcpy(d_xy, hxy.data(), sizeof(double2) * hxy.size(), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(d_zq, hzq.data(), sizeof(double2) * hzq.size(), cudaMemcpyHostToDevice));
         h.host_xy = d_xy; h.host_zq = d_zq;
+        h.host_fxy = nullptr; h.host_fzq = nullptr; h.host_blk = nullptr;
+        if (h.triclinic && h.tri_nrel >= 0 && n_host > 0) {
+            // framework in fractional coordinates wrapped into [0, 1) (Hinv = transposed inverse: f_d = sum_j Hinv[j][d] x_j),
+            // and the bounding spheres of every 16 consecutive atoms (of the wrapped images, which is what Morton order groups)
+            std::vector<double2> fxy(hx.size()), fzq(hx.size());
+            std::vector<double> wx(3 * hx.size());
+            for (size_t i = 0; i < (size_t)n_host; ++i) {
+                const double x[3] = { hx[i].x, hx[i].y, hx[i].z };
+                double f[3];
+                for (int d = 0; d < 3; ++d) { f[d] = h.Hinv[0 * 3 + d] * x[0] + h.Hinv[1 * 3 + d] * x[1] + h.Hinv[2 * 3 + d] * x[2]; f[d] -= std::floor(f[d]); }
+                fxy[i] = make_double2(f[0], f[1]); fzq[i] = make_double2(f[2], hx[i].w);
+                for (int r = 0; r < 3; ++r) wx[3 * i + r] = M[r][0] * f[0] + M[r][1] * f[1] + M[r][2] * f[2];
+            }
+            const size_t nb = ((size_t)n_host + 15) / 16;
+            std::vector<double4> blk(nb);
+            for (size_t b = 0; b < nb; ++b) {
+                const size_t i0 = b * 16, i1 = std::min<size_t>(i0 + 16, (size_t)n_host);
+                double c[3] = { 0, 0, 0 };
+                for (size_t i = i0; i < i1; ++i) for (int r = 0; r < 3; ++r) c[r] += wx[3 * i + r];
+                for (int r = 0; r < 3; ++r) c[r] /= (double)(i1 - i0);
+                double rad2 = 0.0;
+                for (size_t i = i0; i < i1; ++i) {
+                    double d2 = 0.0;
+                    for (int r = 0; r < 3; ++r) d2 += (wx[3 * i + r] - c[r]) * (wx[3 * i + r] - c[r]);
+                    rad2 = std::fmax(rad2, d2);
+                }
+                blk[b] = make_double4(c[0], c[1], c[2], std::sqrt(rad2) * (1.0 + 1e-12) + 1e-9);
+            }
+            double2 *d_fxy, *d_fzq; double4 *d_blk;
+            if (dalloc(&d_fxy, fxy.size()) || dalloc(&d_fzq, fzq.size()) || dalloc(&d_blk, blk.size())) return 1;
+            CK(cudaMemcpy(d_fxy, fxy.data(), sizeof(double2) * fxy.size(), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(d_fzq, fzq.data(), sizeof(double2) * fzq.size(), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(d_blk, blk.data(), sizeof(double4) * blk.size(), cudaMemcpyHostToDevice));
+            h.host_fxy = d_fxy; h.host_fzq = d_fzq; h.host_blk = d_blk;
+        }
         // classes of guest atoms with respect to the framework
         std::vector<char> type_present(sys->ntypes, 0);
         bool host_charged = false;
@@ -554,6 +615,23 @@ int mgpu_init(const mgpu_system *sys)
                                   : 0.5 * std::sqrt(metrics[0] * metrics[0] + metrics[1] * metrics[1] + metrics[2] * metrics[2]) + 1.0;
         const double r_zero = MGPU_TAB_XCUT / alpha;         // erfc(7)/r < 1e-24: below the rounding of any sum it enters
         h.s_zero = r_zero * r_zero;
+        {
+            // Pruning radius of the triclinic framework passes: beyond it a pair has no LJ term (r > r_c) and the erfc-Coulomb
+            // terms of ALL such pairs of a trial together stay below 1e-13 kcal/mol (bound: targets x MGPU_MAX_SITES x max|q|^2 x
+            // erfc(alpha r)/r x EPS0_INV_real), four orders below the 1e-9 tolerance on dE.  The rounded image may be longer than
+            // the true one by at most tri_gain_max in r^2, hence the margin.
+            double qmax = 0.0; long long targets = 0;
+            for (int r = 0; r < sys->nres; ++r) {
+                const mgpu_residue &R = sys->residues[r];
+                for (int a = 0; a < R.natom; ++a) qmax = std::fmax(qmax, std::fabs(R.charges[a]));
+                targets += (long long)R.natom * (R.is_active ? R.capacity : R.nmol);
+            }
+            auto bound = [&](double r) { return (double)targets * MGPU_MAX_SITES * qmax * qmax * std::erfc(alpha * r) / r * EPS0_INV_real(); };
+            double lo_r = rc, hi_r = r_zero;
+            if (bound(lo_r) < 1.0e-13) hi_r = lo_r;
+            for (int it = 0; it < 60 && hi_r - lo_r > 1e-6; ++it) { const double mid = 0.5 * (lo_r + hi_r); if (bound(mid) < 1.0e-13) hi_r = mid; else lo_r = mid; }
+            h.r_skip2 = hi_r * hi_r + (h.triclinic && h.tri_nrel > 0 ? h.tri_gain_max : 0.0);
+        }
         if (r_hi > r_zero) r_hi = r_zero;
         std::vector<double> tab;
         mgpu_build_coulomb_table(alpha, MGPU_TAB_RLO, r_hi, &g.tab_emin, &g.tab_noct, tab);
@@ -604,12 +682,8 @@ int mgpu_init(const mgpu_system *sys)
             double *com = img.data() + h.goff[r], *off = com + 3 * (size_t)R.capacity;
             for (int m = 0; m < R.nmol; ++m) {
                 for (int d = 0; d < 3; ++d) com[(size_t)d * R.capacity + m] = R.com[(size_t)m * 3 + d];
-                double *pos = off + (size_t)(3 * R.natom + 2) * R.capacity;      // com + offset per atom (geometry_utils.f90:235-241), kept next to them
                 for (int a = 0; a < R.natom; ++a)
-                    for (int d = 0; d < 3; ++d) {
-                        off[((size_t)a * 3 + d) * R.capacity + m] = R.offset[((size_t)m * R.natom + a) * 3 + d];
-                        pos[((size_t)a * 3 + d) * R.capacity + m] = R.com[(size_t)m * 3 + d] + R.offset[((size_t)m * R.natom + a) * 3 + d];
-                    }
+                    for (int d = 0; d < 3; ++d) off[((size_t)a * 3 + d) * R.capacity + m] = R.offset[((size_t)m * R.natom + a) * 3 + d];
             }
         }
         std::vector<double> all(W * (size_t)(stride ? stride : 1)); std::vector<int32_t> allc(W * MGPU_MAX_RES); std::vector<double> allmu(W * MGPU_MAX_RES);
@@ -790,9 +864,6 @@ int mgpu_set_molecule(int32_t w, int32_t res, int32_t mol, const double com[3], 
     for (int d = 0; d < 3; ++d) tmp[d] = com[d];
     for (int e = 0; e < 3 * na; ++e) tmp[3 + e] = offset[e];
     CK(cudaMemcpy2DAsync(base + mol, sizeof(double) * cap, tmp.data(), sizeof(double), sizeof(double), 3 + 3 * na, cudaMemcpyHostToDevice, g.stream));
-    std::vector<double> pos(3 * na);                          // the molecule's absolute-position rows, behind the cache rows
-    for (int e = 0; e < 3 * na; ++e) pos[e] = com[e % 3] + offset[e];
-    CK(cudaMemcpy2DAsync(base + (size_t)(3 + 3 * na + 2) * cap + mol, sizeof(double) * cap, pos.data(), sizeof(double), sizeof(double), 3 * na, cudaMemcpyHostToDevice, g.stream));
     CK(cudaStreamSynchronize(g.stream));
     double r2 = 0.0;
     for (int a = 0; a < na; ++a) r2 = std::fmax(r2, offset[3 * a] * offset[3 * a] + offset[3 * a + 1] * offset[3 * a + 1] + offset[3 * a + 2] * offset[3 * a + 2]);

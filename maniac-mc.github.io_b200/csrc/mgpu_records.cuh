@@ -114,11 +114,6 @@ __global__ void __launch_bounds__(256) k_unpack(int first, int n, const long lon
             const int m = t / ms, e = t - m * ms;
             dst[(int64_t)e * cap + m] = p[t];
         }
-        // the absolute-position rows are not part of the record: com + offset, as every other writer forms them
-        for (int t = lane; t < cnt * 3 * c_sys.natom[r]; t += 32) {
-            const int m = t / (3 * c_sys.natom[r]), e = t - m * 3 * c_sys.natom[r];
-            dst[(int64_t)(ms + e) * cap + m] = p[(long long)m * ms + e % 3] + p[(long long)m * ms + 3 + e];
-        }
         // keep the bound on |offset|^2 of this residue type valid for whatever the record brings in
         double r2 = 0.0;
         const int na = c_sys.natom[r];
