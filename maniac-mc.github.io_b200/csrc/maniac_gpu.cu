@@ -334,32 +334,7 @@ int mgpu_init(const mgpu_system *sys)
         h.tri_nrel = n;
         h.tri_safe2 = 1e300;
         for (int k = 0; k < n; ++k) h.tri_safe2 = std::fmin(h.tri_safe2, 0.25 * h.tri_len2[k]);
-        // Gate of the candidate loop in fractional space.  With f_d = +-(1/2 - u_d), u_d in [0, 1/2]:
-        //   |t|^2 - |t -+ C m|^2 = 2 |f . G m| - m.G.m  <=  s1 - m.G.m - 2 sum_d u_d |(G m)_d|,   s1 = sum_d |(G m)_d|,
-        // so m can only help when u_d |(G m)_d| < (s1 - m.G.m) / 2 for every d, in particular for its dominant axis d*.
-        // tri_eps[d] = the largest such bound over the listed vectors whose dominant axis is d.
-        h.tri_eps[0] = h.tri_eps[1] = h.tri_eps[2] = 0.0;
-        h.tri_gain_max = 0.0;
-        for (int k = 0; k < n; ++k) {
-            double Gm[3], mGm = 0.0, s1 = 0.0;
-            for (int d = 0; d < 3; ++d) { Gm[d] = G[d][0] * h.tri_m[k][0] + G[d][1] * h.tri_m[k][1] + G[d][2] * h.tri_m[k][2]; mGm += h.tri_m[k][d] * Gm[d]; s1 += std::fabs(Gm[d]); }
-            int ds = 0;
-            for (int d = 1; d < 3; ++d) if (std::fabs(Gm[d]) > std::fabs(Gm[ds])) ds = d;
-            const double slack = 0.5 * (s1 - mGm);
-            h.tri_eps[ds] = std::fmax(h.tri_eps[ds], slack / std::fabs(Gm[ds]) * (1.0 + 1e-9) + 1e-12);
-            h.tri_gain_max = std::fmax(h.tri_gain_max, (s1 - mGm) * (1.0 + 1e-9));
-        }
     }
-    h.tri_lower = (M[0][1] == 0.0 && M[0][2] == 0.0 && M[1][2] == 0.0) ? 1 : 0;
-    for (int d = 0; d < 3; ++d) {
-        h.tri_thr_hi[d] = 0x7ff00000;                           // never
-        if (h.triclinic && h.tri_nrel > 0 && h.tri_eps[d] > 0.0) {
-            const double thr = std::fmax(0.0, 0.5 - h.tri_eps[d]);
-            uint64_t bits; std::memcpy(&bits, &thr, 8);
-            h.tri_thr_hi[d] = (int32_t)(bits >> 32);             // hi(|f|) >= hi(thr) is implied by |f| >= thr: a superset
-        }
-    }
-
     // ---- Ewald: setup_ewald, prepare_utils.f90:110-226 ----
     double rc = sys->real_space_cutoff;
     if (rc > metrics[0] || rc > metrics[1] || rc > metrics[2]) rc = std::fmin(metrics[0], std::fmin(metrics[1], metrics[2])) / 2.0;
@@ -518,41 +493,6 @@ int mgpu_init(const mgpu_system *sys)
         CK(cudaMemcpy(d_xy, hxy.data(), sizeof(double2) * hxy.size(), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(d_zq, hzq.data(), sizeof(double2) * hzq.size(), cudaMemcpyHostToDevice));
         h.host_xy = d_xy; h.host_zq = d_zq;
-        h.host_fxy = nullptr; h.host_fzq = nullptr; h.host_blk = nullptr;
-        if (h.triclinic && h.tri_nrel >= 0 && n_host > 0) {
-            // framework in fractional coordinates wrapped into [0, 1) (Hinv = transposed inverse: f_d = sum_j Hinv[j][d] x_j),
-            // and the bounding spheres of every 16 consecutive atoms (of the wrapped images, which is what Morton order groups)
-            std::vector<double2> fxy(hx.size()), fzq(hx.size());
-            std::vector<double> wx(3 * hx.size());
-            for (size_t i = 0; i < (size_t)n_host; ++i) {
-                const double x[3] = { hx[i].x, hx[i].y, hx[i].z };
-                double f[3];
-                for (int d = 0; d < 3; ++d) { f[d] = h.Hinv[0 * 3 + d] * x[0] + h.Hinv[1 * 3 + d] * x[1] + h.Hinv[2 * 3 + d] * x[2]; f[d] -= std::floor(f[d]); }
-                fxy[i] = make_double2(f[0], f[1]); fzq[i] = make_double2(f[2], hx[i].w);
-                for (int r = 0; r < 3; ++r) wx[3 * i + r] = M[r][0] * f[0] + M[r][1] * f[1] + M[r][2] * f[2];
-            }
-            const size_t nb = ((size_t)n_host + 15) / 16;
-            std::vector<double4> blk(nb);
-            for (size_t b = 0; b < nb; ++b) {
-                const size_t i0 = b * 16, i1 = std::min<size_t>(i0 + 16, (size_t)n_host);
-                double c[3] = { 0, 0, 0 };
-                for (size_t i = i0; i < i1; ++i) for (int r = 0; r < 3; ++r) c[r] += wx[3 * i + r];
-                for (int r = 0; r < 3; ++r) c[r] /= (double)(i1 - i0);
-                double rad2 = 0.0;
-                for (size_t i = i0; i < i1; ++i) {
-                    double d2 = 0.0;
-                    for (int r = 0; r < 3; ++r) d2 += (wx[3 * i + r] - c[r]) * (wx[3 * i + r] - c[r]);
-                    rad2 = std::fmax(rad2, d2);
-                }
-                blk[b] = make_double4(c[0], c[1], c[2], std::sqrt(rad2) * (1.0 + 1e-12) + 1e-9);
-            }
-            double2 *d_fxy, *d_fzq; double4 *d_blk;
-            if (dalloc(&d_fxy, fxy.size()) || dalloc(&d_fzq, fzq.size()) || dalloc(&d_blk, blk.size())) return 1;
-            CK(cudaMemcpy(d_fxy, fxy.data(), sizeof(double2) * fxy.size(), cudaMemcpyHostToDevice));
-            CK(cudaMemcpy(d_fzq, fzq.data(), sizeof(double2) * fzq.size(), cudaMemcpyHostToDevice));
-            CK(cudaMemcpy(d_blk, blk.data(), sizeof(double4) * blk.size(), cudaMemcpyHostToDevice));
-            h.host_fxy = d_fxy; h.host_fzq = d_fzq; h.host_blk = d_blk;
-        }
         // classes of guest atoms with respect to the framework
         std::vector<char> type_present(sys->ntypes, 0);
         bool host_charged = false;
@@ -615,24 +555,6 @@ int mgpu_init(const mgpu_system *sys)
                                   : 0.5 * std::sqrt(metrics[0] * metrics[0] + metrics[1] * metrics[1] + metrics[2] * metrics[2]) + 1.0;
         const double r_zero = MGPU_TAB_XCUT / alpha;         // erfc(7)/r < 1e-24: below the rounding of any sum it enters
         h.s_zero = r_zero * r_zero;
-        {
-            // Pruning radius of the triclinic framework passes: beyond it a pair has no LJ term (r > r_c) and the erfc-Coulomb
-            // terms of ALL such pairs of a trial together stay below 1e-13 kcal/mol (bound: targets x MGPU_MAX_SITES x max|q|^2 x
-            // erfc(alpha r)/r x EPS0_INV_real), four orders below the 1e-9 tolerance on dE.  The rounded image may be longer than
-            // the true one by at most tri_gain_max in r^2, hence the margin.
-            double qmax = 0.0; long long targets = 0;
-            for (int r = 0; r < sys->nres; ++r) {
-                const mgpu_residue &R = sys->residues[r];
-                for (int a = 0; a < R.natom; ++a) qmax = std::fmax(qmax, std::fabs(R.charges[a]));
-                targets += (long long)R.natom * (R.is_active ? R.capacity : R.nmol);
-            }
-            auto bound = [&](double r) { return (double)targets * MGPU_MAX_SITES * qmax * qmax * std::erfc(alpha * r) / r * EPS0_INV_real(); };
-            double lo_r = rc, hi_r = r_zero;
-            if (bound(lo_r) < 1.0e-13) hi_r = lo_r;
-            for (int it = 0; it < 60 && hi_r - lo_r > 1e-6; ++it) { const double mid = 0.5 * (lo_r + hi_r); if (bound(mid) < 1.0e-13) hi_r = mid; else lo_r = mid; }
-            h.r_skip2 = hi_r * hi_r + (h.triclinic && h.tri_nrel > 0 ? h.tri_gain_max : 0.0);
-        }
-        if (r_hi > r_zero) r_hi = r_zero;
         std::vector<double> tab;
         mgpu_build_coulomb_table(alpha, MGPU_TAB_RLO, r_hi, &g.tab_emin, &g.tab_noct, tab);
         // the hot loops send everything beyond the last interval to an all-zero row, so the table has to reach

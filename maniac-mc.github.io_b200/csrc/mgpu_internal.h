@@ -64,15 +64,6 @@ struct DevSys {
     int32_t tri_nrel;
     double tri_safe2;             // a listed vector can only shorten t when |t|^2 > tri_safe2 = min |C m|^2 / 4
     double tri_rel[MGPU_TRI_MAXREL][3], tri_m[MGPU_TRI_MAXREL][3], tri_len2[MGPU_TRI_MAXREL];   // one of every +-m pair
-    // framework passes of triclinic cells work on FRACTIONAL coordinates (min_image_frac): wrapping is a rounding of the
-    // coordinate difference itself, and the projection back costs 6 FMAs when the cell matrix is lower triangular
-    int32_t tri_lower;            // matrix(0,1) = matrix(0,2) = matrix(1,2) = 0 (LAMMPS-style cell in the reference's column convention)
-    double tri_eps[3];            // a listed lattice vector can only matter when 1/2 - |f_d| < tri_eps[d] for some axis d
-    int32_t tri_thr_hi[3];        // ... as a compare on the high word of |f_d|: candidates are tried when hi(|f_d|) >= tri_thr_hi[d]
-    double tri_gain_max;          // largest |t|^2 - |t -+ C m|^2 a listed vector can bring
-    double r_skip2;               // a pair farther apart than sqrt(r_skip2) (rounded image) contributes nothing: no LJ, erfc term below the sum's rounding
-    const double2 *host_fxy, *host_fzq;   // framework atoms {f0, f1}, {f2, q}: fractional coordinates wrapped into [0, 1)  (triclinic cells only)
-    const double4 *host_blk;      // [ceil(n_host / 16)] bounding sphere {x, y, z, radius} of 16 consecutive (Morton-ordered) framework atoms
     // ewald / constants
     double rc, rc2, alpha, eps0_inv_real, twopi, beta, overlap;
     int32_t kmax[3], kmax_max, nk;

@@ -251,59 +251,6 @@ __device__ __forceinline__ double min_image_r2(double dx, double dy, double dz)
     }
 }
 
-// The same minimum image from the FRACTIONAL coordinate difference g = f(target) - f(probe) (framework passes of
-// triclinic cells: the framework is stored in fractional coordinates, the probe atoms are converted once per pass).
-// Rounding g itself wraps it (no projection of a Cartesian difference: 9 FMAs less per pair), and t = C (g - n) costs 6
-// FMAs for a lower-triangular cell matrix.  The listed lattice vectors are only tried when the rounded vector sits
-// within tri_eps of a face of the fractional cube (see mgpu_init: elsewhere no listed vector can shorten it), which with
-// the Morton-ordered framework is a whole-warp fact almost everywhere; the reference's 27-image search is the fallback
-// whenever the winning shift leaves {-1,0,1}^3 (atoms far outside the cell), exactly as in min_image_r2<true>.
-// All "rare" tests are integer compares on the high words.
-__device__ __forceinline__ double min_image_frac(double g0, double g1, double g2)
-{
-    const double n0 = (g0 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC, n1 = (g1 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC,
-                 n2 = (g2 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC;
-    const double f0 = g0 - n0, f1 = g1 - n1, f2 = g2 - n2;                 // in [-1/2, 1/2]
-    double tx, ty, tz;
-    if (c_sys.tri_lower) {
-        tx = c_sys.H[0] * f0;
-        ty = fma(c_sys.H[3], f0, c_sys.H[4] * f1);
-        tz = fma(c_sys.H[6], f0, fma(c_sys.H[7], f1, c_sys.H[8] * f2));
-    } else {
-        tx = fma(c_sys.H[0], f0, fma(c_sys.H[1], f1, c_sys.H[2] * f2));
-        ty = fma(c_sys.H[3], f0, fma(c_sys.H[4], f1, c_sys.H[5] * f2));
-        tz = fma(c_sys.H[6], f0, fma(c_sys.H[7], f1, c_sys.H[8] * f2));
-    }
-    const double t2 = fma(tx, tx, fma(ty, ty, tz * tz));
-    const int a0 = __double2hiint(f0) & 0x7fffffff, a1 = __double2hiint(f1) & 0x7fffffff, a2 = __double2hiint(f2) & 0x7fffffff;
-    const bool near = (a0 >= c_sys.tri_thr_hi[0]) | (a1 >= c_sys.tri_thr_hi[1]) | (a2 >= c_sys.tri_thr_hi[2]);
-    const int b0 = __double2hiint(g0) & 0x7fffffff, b1 = __double2hiint(g1) & 0x7fffffff, b2 = __double2hiint(g2) & 0x7fffffff;
-    const bool far = (max(b0, max(b1, b2)) >= 0x3ff80000);                 // |g_d| >= 1.5: the rounded image is beyond the reference's 27
-    if (__any_sync(__activemask(), near | far)) {
-        double gain = 0.0, bsign = 0.0;
-        int bk = -1;
-        const int nrel = (near && t2 > c_sys.tri_safe2) ? c_sys.tri_nrel : 0;
-        for (int k = 0; k < nrel; ++k) {
-            const double dot = fma(tx, c_sys.tri_rel[k][0], fma(ty, c_sys.tri_rel[k][1], tz * c_sys.tri_rel[k][2]));
-            const double gk = fma(-2.0, fabs(dot), c_sys.tri_len2[k]);
-            if (gk < gain) { gain = gk; bk = k; bsign = dot > 0.0 ? -1.0 : 1.0; }
-        }
-        double cx = tx, cy = ty, cz = tz, o0 = n0, o1 = n1, o2 = n2;
-        if (bk >= 0) {
-            cx = fma(bsign, c_sys.tri_rel[bk][0], tx); cy = fma(bsign, c_sys.tri_rel[bk][1], ty); cz = fma(bsign, c_sys.tri_rel[bk][2], tz);
-            o0 = fma(-bsign, c_sys.tri_m[bk][0], n0); o1 = fma(-bsign, c_sys.tri_m[bk][1], n1); o2 = fma(-bsign, c_sys.tri_m[bk][2], n2);
-        }
-        if (fmax(fabs(o0), fmax(fabs(o1), fabs(o2))) > 1.0) {              // raw Cartesian difference for the literal search
-            const double dx = fma(c_sys.H[0], g0, fma(c_sys.H[1], g1, c_sys.H[2] * g2));
-            const double dy = fma(c_sys.H[3], g0, fma(c_sys.H[4], g1, c_sys.H[5] * g2));
-            const double dz = fma(c_sys.H[6], g0, fma(c_sys.H[7], g1, c_sys.H[8] * g2));
-            return min_image_27(dx, dy, dz);
-        }
-        return fma(cx, cx, fma(cy, cy, cz * cz));
-    }
-    return t2;
-}
-
 // Work counters for the roofline accounting: pairs evaluated, LJ terms inside the
 // cutoff, erfc-Coulomb terms.  Integer adds on the otherwise idle ALU pipe.
 struct PairCount { unsigned geom, lj, coul, scr; };      // scr: pairs of "nothing" lists settled by the per-molecule screen
@@ -534,10 +481,8 @@ struct HostPass {
     // q_i once per pass.  Pairs below the table start (r < 1 A, incl. the overlap sentinel) read the all-zero
     // row that closes the table (the unsigned clamp sends both ends there), are left out of the LJ sum, and
     // are redone with the exact formulas when the block's smallest r^2 says there was one (e_x: their sum).
-    // (bx, by, bz) = the probe atoms in the coordinates the targets are given in: Cartesian, or fractional (FRAC)
-    template <int UU, bool FRAC>
-    __device__ __forceinline__ void block(const Atoms<UU> &A, const unsigned vmask, const double (&bx)[N], const double (&by)[N], const double (&bz)[N],
-                                          double &e_lj, double (&acc)[N], double2 &e_x, PairCount &pc) const
+    template <int UU>
+    __device__ __forceinline__ void block(const Atoms<UU> &A, const unsigned vmask, double &e_lj, double (&acc)[N], double2 &e_x, PairCount &pc) const
     {
         const double2 (&txy)[UU] = A.xy; const double2 (&tzq)[UU] = A.zq; const int (&tt)[UU] = A.tt;
         const double2 *ctab = smem_ctab<REP>(), *ljAB = smem_ljAB<REP>();
@@ -549,8 +494,7 @@ struct HostPass {
             const bool val = (vmask >> u) & 1u;
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                double s = FRAC ? min_image_frac(txy[u].x - bx[i], txy[u].y - by[i], tzq[u].x - bz[i])
-                                : min_image_r2<TRI>(txy[u].x - bx[i], txy[u].y - by[i], tzq[u].x - bz[i]);
+                double s = min_image_r2<TRI>(txy[u].x - px[i], txy[u].y - py[i], tzq[u].x - pz[i]);
                 if (!all) s = val ? s : 1.0e30;                                 // not a target: beyond every range (and (float)(s - centre) stays finite)
                 sv[u][i] = s;
                 const int hi = __double2hiint(s);
@@ -611,11 +555,10 @@ struct HostPass {
         double2 e_x = make_double2(0.0, 0.0);
         PairCount pc = pc_io;
         const int n = c_sys.n_host;
-        if (TRI && c_sys.host_fxy != nullptr) { run_frac(t0, stride, e_lj_io, e_c_io, pc_io); return; }
         const int step = U * stride, reach = (U - 1) * stride;
         int j = t0;
         if (!MGPU_PF_HOSTU && U > 1) {
-            for (; j + reach < n; j += step) { Atoms<U> a; fetch<U>(a, j, stride); block<U, false>(a, (1u << U) - 1u, px, py, pz, e_lj, acc, e_x, pc); }
+            for (; j + reach < n; j += step) { Atoms<U> a; fetch<U>(a, j, stride); block<U>(a, (1u << U) - 1u, e_lj, acc, e_x, pc); }
         } else if (j + reach < n) {
             Atoms<U> cur;
             fetch<U>(cur, j, stride);
@@ -624,13 +567,13 @@ struct HostPass {
                 const bool more = jn + reach < n;
                 Atoms<U> nxt;
                 fetch<U>(nxt, more ? jn : j, stride);
-                block<U, false>(cur, (1u << U) - 1u, px, py, pz, e_lj, acc, e_x, pc);
+                block<U>(cur, (1u << U) - 1u, e_lj, acc, e_x, pc);
                 j = jn;
                 if (!more) break;
                 cur = nxt;
             }
         }
-        for (; j < n; j += stride) { Atoms<1> a1; fetch<1>(a1, j, stride); block<1, false>(a1, 1u, px, py, pz, e_lj, acc, e_x, pc); }
+        for (; j < n; j += stride) { Atoms<1> a1; fetch<1>(a1, j, stride); block<1>(a1, 1u, e_lj, acc, e_x, pc); }
         double e_c = e_x.y;
         if (MGPU_ACC_PER_ATOM) {
 #pragma unroll
@@ -640,98 +583,6 @@ struct HostPass {
             pc.geom += (unsigned)(N * n);
             if (MODE & 2) pc.coul += (unsigned)(N * c_sys.n_host_charged);
         }
-        e_lj_io = e_lj + e_x.x; e_c_io = e_c_io + e_c; pc_io = pc;
-    }
-
-    // Framework pass of a triclinic cell: fractional coordinates (min_image_frac) and pruning of whole blocks of
-    // framework atoms.  The framework is Morton-ordered, so the `width` consecutive atoms one warp (or half-warp) takes
-    // per iteration sit in one small region; its 16-atom bounding spheres are compared with the sphere of this pass's
-    // probe atoms, and an iteration none of whose pairs can be closer than sqrt(r_skip2) -- beyond the LJ cutoff, and
-    // with erfc-Coulomb terms that sum to < 1e-13 kcal/mol over a whole trial (mgpu_init) -- is not loaded at all.
-    // Lane l of the (half-)warp tests iteration K + l, a ballot hands every lane the surviving iterations, and the
-    // next survivor's atoms are in flight while the current ones are evaluated.
-    __device__ __forceinline__ void run_frac(int t0, int stride, double &e_lj_io, double &e_c_io, PairCount &pc_io) const
-    {
-        double e_lj = e_lj_io;
-        double acc[N];
-#pragma unroll
-        for (int i = 0; i < N; ++i) acc[i] = 0.0;
-        double2 e_x = make_double2(0.0, 0.0);
-        PairCount pc = pc_io;
-        const int n = c_sys.n_host;
-        const double2 *__restrict__ hxy = c_sys.host_fxy;
-        const double2 *__restrict__ hzq = c_sys.host_fzq;
-        const int32_t *__restrict__ ht = c_sys.host_type;
-        // the probe atoms of this pass in fractional coordinates (Hinv = transposed inverse), and their bounding sphere
-        double bx[N], by[N], bz[N];
-        double cx = 0.0, cy = 0.0, cz = 0.0;
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            bx[i] = fma(c_sys.Hinv[0], px[i], fma(c_sys.Hinv[3], py[i], c_sys.Hinv[6] * pz[i]));
-            by[i] = fma(c_sys.Hinv[1], px[i], fma(c_sys.Hinv[4], py[i], c_sys.Hinv[7] * pz[i]));
-            bz[i] = fma(c_sys.Hinv[2], px[i], fma(c_sys.Hinv[5], py[i], c_sys.Hinv[8] * pz[i]));
-            cx += px[i]; cy += py[i]; cz += pz[i];
-        }
-        cx *= 1.0 / N; cy *= 1.0 / N; cz *= 1.0 / N;
-        double rho2 = 0.0;
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-            const double ax = px[i] - cx, ay = py[i] - cy, az = pz[i] - cz;
-            rho2 = fmax(rho2, fma(ax, ax, fma(ay, ay, az * az)));
-        }
-        const double reach0 = sqrt(c_sys.r_skip2) + sqrt(rho2) + 1.0e-9;
-        const int lane = threadIdx.x & 31;
-        const int width = stride < 32 ? stride : 32;                     // consecutive atoms this (half-)warp takes per iteration
-        const int sl = lane & (width - 1);
-        const int nit = (n - (t0 - sl) + stride - 1) / stride;           // iterations of this (half-)warp: the first atom of iteration k is (t0 - sl) + k stride
-        unsigned evaluated = 0u, charged = 0u;
-        for (int K = 0; K < nit; K += width) {
-            // lane sl tests iteration K + sl
-            bool keep = false;
-            const int kt = K + sl;
-            if (kt < nit) {
-                const int js = (t0 - sl) + kt * stride;
-                for (int b = js >> 4; b <= min(js + width - 1, n - 1) >> 4; ++b) {
-                    const double4 sp = c_sys.host_blk[b];
-                    const double d2 = min_image_r2<true>(sp.x - cx, sp.y - cy, sp.z - cz);
-                    const double lim = reach0 + sp.w;
-                    keep |= d2 <= lim * lim;
-                }
-            }
-            unsigned mask = __ballot_sync(0xffffffffu, keep);
-            mask = (width == 32) ? mask : ((mask >> (lane & ~(width - 1))) & ((1u << width) - 1u));
-            if (!mask) continue;
-            int b = __ffs(mask) - 1;
-            mask &= mask - 1;
-            int j = t0 + (K + b) * stride;
-            int jc = j < n ? j : n - 1;
-            Atoms<1> cur;
-            cur.xy[0] = __ldg(hxy + jc); cur.zq[0] = __ldg(hzq + jc); cur.tt[0] = (MODE & 1) ? __ldg(ht + jc) : 0;
-            for (;;) {
-                const bool more = mask != 0u;
-                int jn = j;
-                Atoms<1> nxt;
-                if (more) {
-                    b = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    jn = t0 + (K + b) * stride;
-                    const int jnc = jn < n ? jn : n - 1;
-                    nxt.xy[0] = __ldg(hxy + jnc); nxt.zq[0] = __ldg(hzq + jnc); nxt.tt[0] = (MODE & 1) ? __ldg(ht + jnc) : 0;
-                }
-                const unsigned vm = j < n ? 1u : 0u;
-                block<1, true>(cur, vm, bx, by, bz, e_lj, acc, e_x, pc);
-                evaluated += vm; charged += (vm && cur.zq[0].y != 0.0) ? 1u : 0u;
-                if (!more) break;
-                cur = nxt; j = jn;
-            }
-        }
-        double e_c = e_x.y;
-        if (MGPU_ACC_PER_ATOM) {
-#pragma unroll
-            for (int i = 0; i < N; ++i) e_c = fma(q[i], acc[i], e_c);
-        } else e_c += acc[0];
-        pc.geom += (unsigned)N * evaluated;                      // work counters: the pairs actually evaluated
-        if (MODE & 2) pc.coul += (unsigned)N * charged;
         e_lj_io = e_lj + e_x.x; e_c_io = e_c_io + e_c; pc_io = pc;
     }
 
@@ -763,7 +614,7 @@ struct HostPass {
                 A.tt[u] = ttype;
                 vm |= ok ? (1u << u) : 0u;
             }
-            block<U, false>(A, vm, px, py, pz, e_lj, acc, e_x, pc);
+            block<U>(A, vm, e_lj, acc, e_x, pc);
         }
 
         double e_c = e_x.y;

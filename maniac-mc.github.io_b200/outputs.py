@@ -172,3 +172,78 @@ def lammpstrj_frame(timestep: int, matrix, residues, record_molecules: dict) -> 
     head += [f"{-m[d, d] / 2:15.8f} {m[d, d] / 2:15.8f}" for d in range(3)]
     head.append("ITEM: ATOMS id type x y z")
     return "\n".join(head + rows) + "\n"
+
+
+# ---- topology.data (write_topology_data, src/write_utils.f90:406-636) -------------------------------
+def _ld_int(n: int) -> str:
+    """gfortran list-directed output of a default integer: right-justified in 12 columns (the record's leading blank included)."""
+    return f"{int(n):12d}"
+
+
+def topology_data(matrix, lo, masses, residues, record_molecules: dict, connect: dict | None = None, n_types: dict | None = None) -> str:
+    """The LAMMPS data file (atom_style full) the reference rewrites after every block.
+
+    ``residues`` = list of dict(active, types (1-based atom-type id per site), charges, com [nmol,3], offset [nmol,natom,3]) in
+    residue order; active residues take their molecules from ``record_molecules`` (Engine.parse_record(...)["molecules"]).
+    ``connect`` = optional {"bonds": [per residue: list of (type, i, j)], "angles": [... (type, i, j, k)], "dihedrals": [...],
+    "impropers": [...]} with 1-based atom indices inside the molecule (connect%bonds(res, k, 1:3) etc.); ``n_types`` = declared
+    numbers of bond / angle / dihedral / improper types.  Atoms of INACTIVE residues are wrapped into the box, active molecules
+    are left whole across the boundary (:538-541).  Fixed-format fields (F15.8, I5/F12.6, I6/I6/I4/F12.8/F12.7) are reproduced
+    character by character; the list-directed records (`write(unit,*)`) follow gfortran's conventions (leading blank, integers
+    in 12 columns), which no test of the reference pins and which LAMMPS reads whitespace-insensitively."""
+    m = np.asarray(matrix, dtype=float)
+    lo = np.asarray(lo, dtype=float)
+    connect = connect or {}
+    n_types = n_types or {}
+    kinds = ("bonds", "angles", "dihedrals", "impropers")
+    nmol = []
+    for r, res in enumerate(residues):
+        if res["active"]:
+            mol = record_molecules.get(r)
+            nmol.append(0 if mol is None else len(mol["com"]))
+        else:
+            nmol.append(len(res["com"]))
+    per_res = {k: [len(c) for c in connect.get(k, [[] for _ in residues])] for k in kinds}
+    totals = {k: sum(n * per_res[k][r] for r, n in enumerate(nmol)) for k in kinds}
+    n_atoms = sum(n * len(res["types"]) for n, res in zip(nmol, residues))
+    out = [" ! LAMMPS data file (atom_style full)",
+           _ld_int(n_atoms) + "  atoms", _ld_int(len(masses)) + "  atom types"]
+    for k, label in zip(kinds, ("bond", "angle", "dihedral", "improper")):
+        out += [_ld_int(totals[k]) + f"  {label}s", _ld_int(n_types.get(k, 0)) + f"  {label} types"]
+    out.append("")
+    hi = lo + np.array([m[0, 0], m[1, 1], m[2, 2]])
+    for d, name in enumerate("xyz"):
+        out.append(f"{lo[d]:15.8f} {hi[d]:15.8f} {name}lo {name}hi")
+    tilt = np.array([m[1, 0], m[2, 0], m[2, 1]])                       # readers_utils.f90:256-258: rows of the matrix are a, b, c
+    if np.abs(np.array([m[0, 1], m[0, 2], m[1, 0], m[1, 2], m[2, 0], m[2, 1]])).max() > 1e-10:
+        out += [f"{tilt[0]:15.8f} {tilt[1]:15.8f} {tilt[2]:15.8f} ", "xy xz yz"]
+    out += ["", " Masses", ""]
+    out += [f"{t + 1:5d} {float(mass):12.6f}" for t, mass in enumerate(masses)]
+    out += ["", " Atoms", ""]
+    atom_id = mol_id = 0
+    for r, res in enumerate(residues):
+        if res["active"]:
+            mol = record_molecules.get(r)
+            coms, offs = (mol["com"], mol["offset"]) if mol is not None else (np.zeros((0, 3)), np.zeros((0, len(res["types"]), 3)))
+        else:
+            coms, offs = np.asarray(res["com"]), np.asarray(res["offset"])
+        for k in range(len(coms)):
+            mol_id += 1
+            for a, t in enumerate(res["types"]):
+                atom_id += 1
+                pos = np.asarray(coms[k], dtype=float) + offs[k][a]
+                if not res["active"]:
+                    pos = wrap_into_box(pos, m)
+                out.append(f"{atom_id:6d} {mol_id:6d} {int(t):4d} {float(res['charges'][a]):12.8f} {pos[0]:12.7f} {pos[1]:12.7f} {pos[2]:12.7f}")
+    for k, title in zip(kinds, ("Bonds", "Angles", "Dihedrals", "Impropers")):
+        if totals[k] == 0:
+            continue
+        out += ["", " " + title, ""]
+        cpt, cpt_atom = 1, 0
+        for r, res in enumerate(residues):
+            for _ in range(nmol[r]):
+                for entry in connect[k][r]:
+                    out.append("".join(_ld_int(v) for v in (cpt, entry[0], *[cpt_atom + i for i in entry[1:]])))
+                    cpt += 1
+                cpt_atom += len(res["types"])
+    return "\n".join(out) + "\n"

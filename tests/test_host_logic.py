@@ -209,3 +209,56 @@ def test_lammpstrj_frame_and_wrap():
     assert txt[10] == "     2    4   -4.0000000    0.0000000    0.0000000"          # inactive: the ATOM is wrapped
     assert txt[11] == "     3    1   -3.0000000    0.0000000    0.0000000"          # active: the CoM is wrapped, atoms follow it
     assert txt[12] == "     4    2   -2.5000000    0.0000000    0.0000000"
+
+
+def test_topology_data_writer_roundtrips_through_the_data_reader(tmp_path, load):
+    """write_topology_data (src/write_utils.f90:406-636): the file written from a walker's molecules is a LAMMPS data file the
+    reader of this package (and LAMMPS) takes back: same atoms, types, charges, positions (F12.7), bonds renumbered per molecule."""
+    import numpy as np
+    from maniac_b200 import outputs as out
+    s = load("zif8_h2o_gcmc")
+    residues, mols = [], {}
+    for r, res in enumerate(s.residues):
+        residues.append(dict(active=res.active, types=[int(t) + 1 for t in res.types], charges=res.charges, com=res.com, offset=res.offset))
+        if res.active:
+            mols[r] = dict(com=res.com.copy(), offset=res.offset.copy())
+    masses = np.arange(1, s.ntypes + 1, dtype=float) * 1.5
+    act = [r for r, res in enumerate(s.residues) if res.active][0]
+    connect = {"bonds": [[] for _ in s.residues], "angles": [[] for _ in s.residues]}
+    connect["bonds"][act] = [(1, 1, 3), (1, 1, 4)]                      # O-H, O-H of TIP4P (sites O, M, H, H)
+    connect["angles"][act] = [(1, 3, 1, 4)]
+    txt = out.topology_data(s.matrix, s.lo, masses, residues, mols, connect, {"bonds": 1, "angles": 1})
+    lines = txt.splitlines()
+    n_atoms = sum(res.nmol * res.natom for res in s.residues)
+    assert lines[0] == " ! LAMMPS data file (atom_style full)"
+    assert lines[1] == f"{n_atoms:12d}  atoms" and lines[2] == f"{s.ntypes:12d}  atom types"
+    nw = s.residues[act].nmol
+    assert lines[3] == f"{2 * nw:12d}  bonds" and lines[5] == f"{nw:12d}  angles"
+    assert f"{s.lo[0]:15.8f} {s.lo[0] + s.matrix[0, 0]:15.8f} xlo xhi" in lines
+    i0 = lines.index(" Atoms") + 2
+    rows = [ln.split() for ln in lines[i0:i0 + n_atoms]]
+    assert [int(r[0]) for r in rows] == list(range(1, n_atoms + 1))
+    # last water, last site: charge and unwrapped position, fixed formats
+    w = s.residues[act]
+    pos = w.com[-1] + w.offset[-1][-1]
+    first_water_atom = sum(res.nmol * res.natom for res in s.residues[:act])
+    k_last = first_water_atom + nw * w.natom - 1
+    assert lines[i0 + k_last] == f"{k_last + 1:6d} {int(rows[k_last][1]):6d} {int(w.types[-1]) + 1:4d} {w.charges[-1]:12.8f} {pos[0]:12.7f} {pos[1]:12.7f} {pos[2]:12.7f}"
+    # inactive (framework) atoms are wrapped into the box, active molecules are not
+    inactive = [r for r, res in enumerate(s.residues) if not res.active][0]
+    fw0 = sum(res.nmol * res.natom for res in s.residues[:inactive])
+    fw = rows[fw0:fw0 + s.residues[inactive].nmol * s.residues[inactive].natom]
+    xyz = np.array([[float(v) for v in r[4:7]] for r in fw])
+    L = np.diag(s.matrix)
+    assert np.all(np.abs(xyz) <= L / 2 + 1e-6)
+    # bonds: two per water, atom ids offset by the atoms before the molecule
+    b0 = lines.index(" Bonds") + 2
+    assert [int(v) for v in lines[b0].split()] == [1, 1, first_water_atom + 1, first_water_atom + 3]
+    assert [int(v) for v in lines[b0 + 2].split()] == [3, 1, first_water_atom + w.natom + 1, first_water_atom + w.natom + 3]
+    a0 = lines.index(" Angles") + 2
+    assert [int(v) for v in lines[a0].split()] == [1, 1, first_water_atom + 3, first_water_atom + 1, first_water_atom + 4]
+    # the package's own data reader takes the Atoms section back
+    (tmp_path / "topology.data").write_text(txt)
+    atoms = [ln.split() for ln in (tmp_path / "topology.data").read_text().splitlines()[i0:i0 + n_atoms]]
+    q = np.array([float(r[3]) for r in atoms])
+    assert abs(q.sum() - sum(res.nmol * res.charges.sum() for res in s.residues)) < 1e-5
