@@ -334,7 +334,20 @@ int mgpu_init(const mgpu_system *sys)
         h.tri_nrel = n;
         h.tri_safe2 = 1e300;
         for (int k = 0; k < n; ++k) h.tri_safe2 = std::fmin(h.tri_safe2, 0.25 * h.tri_len2[k]);
+        // Gate of the candidate search in fractional space.  With f_d = +-(1/2 - u_d), u_d in [0, 1/2]:
+        //   |t|^2 - |t -+ C m|^2 = 2 |f . G m| - m.G.m  <=  s1 - m.G.m - 2 sum_d u_d |(G m)_d|,   s1 = sum_d |(G m)_d|,
+        // so m can only help when u_d |(G m)_d| < (s1 - m.G.m) / 2 for every d, in particular for its dominant axis d*.
+        // tri_eps[d] = the largest such bound over the listed vectors whose dominant axis is d.
+        h.tri_eps[0] = h.tri_eps[1] = h.tri_eps[2] = 0.0;
+        for (int k = 0; k < n; ++k) {
+            double Gm[3], mGm = 0.0, s1 = 0.0;
+            for (int d = 0; d < 3; ++d) { Gm[d] = G[d][0] * h.tri_m[k][0] + G[d][1] * h.tri_m[k][1] + G[d][2] * h.tri_m[k][2]; mGm += h.tri_m[k][d] * Gm[d]; s1 += std::fabs(Gm[d]); }
+            int ds = 0;
+            for (int d = 1; d < 3; ++d) if (std::fabs(Gm[d]) > std::fabs(Gm[ds])) ds = d;
+            h.tri_eps[ds] = std::fmax(h.tri_eps[ds], 0.5 * (s1 - mGm) / std::fabs(Gm[ds]) * (1.0 + 1e-9) + 1e-12);
+        }
     }
+    h.tri_lower = (M[0][1] == 0.0 && M[0][2] == 0.0 && M[1][2] == 0.0) ? 1 : 0;
     // ---- Ewald: setup_ewald, prepare_utils.f90:110-226 ----
     double rc = sys->real_space_cutoff;
     if (rc > metrics[0] || rc > metrics[1] || rc > metrics[2]) rc = std::fmin(metrics[0], std::fmin(metrics[1], metrics[2])) / 2.0;
@@ -359,6 +372,14 @@ int mgpu_init(const mgpu_system *sys)
         }
         const double bound = (double)targets * MGPU_MAX_SITES * qmax * qmax * std::erfc(alpha * r_safe) / r_safe * EPS0_INV_real();
         if (rc <= r_safe && bound < 1.0e-12) { g.tri_listed = h.tri_nrel; h.tri_nrel = 0; }
+    }
+    for (int d = 0; d < 3; ++d) {
+        h.tri_thr_hi[d] = (h.triclinic && h.tri_nrel < 0) ? 0 : 0x7ff00000;      // very skewed cell: always the literal search; else never ...
+        if (h.triclinic && h.tri_nrel > 0 && h.tri_eps[d] > 0.0) {                // ... unless a listed vector can matter near this face
+            const double thr = std::fmax(0.0, 0.5 - h.tri_eps[d]);
+            uint64_t bits; std::memcpy(&bits, &thr, 8);
+            h.tri_thr_hi[d] = (int32_t)(bits >> 32);             // hi(|f|) >= hi(thr) is implied by |f| >= thr: a superset
+        }
     }
     for (int d = 0; d < 3; ++d) h.kmax[d] = f_nint(0.25 + metrics[d] * alpha * fprec / PI);
     h.kmax_max = std::max(h.kmax[0], std::max(h.kmax[1], h.kmax[2]));
@@ -493,6 +514,22 @@ int mgpu_init(const mgpu_system *sys)
         CK(cudaMemcpy(d_xy, hxy.data(), sizeof(double2) * hxy.size(), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(d_zq, hzq.data(), sizeof(double2) * hzq.size(), cudaMemcpyHostToDevice));
         h.host_xy = d_xy; h.host_zq = d_zq;
+        h.host_fxy = d_xy; h.host_fzq = d_zq;
+        if (h.triclinic && n_host > 0) {
+            // framework in fractional coordinates wrapped into [0, 1) (Hinv = transposed inverse: f_d = sum_j Hinv[j][d] x_j)
+            std::vector<double2> fxy(hx.size()), fzq(hx.size());
+            for (size_t i = 0; i < (size_t)n_host; ++i) {
+                const double x[3] = { hx[i].x, hx[i].y, hx[i].z };
+                double f[3];
+                for (int d = 0; d < 3; ++d) { f[d] = h.Hinv[0 * 3 + d] * x[0] + h.Hinv[1 * 3 + d] * x[1] + h.Hinv[2 * 3 + d] * x[2]; f[d] -= std::floor(f[d]); }
+                fxy[i] = make_double2(f[0], f[1]); fzq[i] = make_double2(f[2], hx[i].w);
+            }
+            double2 *d_fxy, *d_fzq;
+            if (dalloc(&d_fxy, fxy.size()) || dalloc(&d_fzq, fzq.size())) return 1;
+            CK(cudaMemcpy(d_fxy, fxy.data(), sizeof(double2) * fxy.size(), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(d_fzq, fzq.data(), sizeof(double2) * fzq.size(), cudaMemcpyHostToDevice));
+            h.host_fxy = d_fxy; h.host_fzq = d_fzq;
+        }
         // classes of guest atoms with respect to the framework
         std::vector<char> type_present(sys->ntypes, 0);
         bool host_charged = false;
@@ -555,6 +592,7 @@ int mgpu_init(const mgpu_system *sys)
                                   : 0.5 * std::sqrt(metrics[0] * metrics[0] + metrics[1] * metrics[1] + metrics[2] * metrics[2]) + 1.0;
         const double r_zero = MGPU_TAB_XCUT / alpha;         // erfc(7)/r < 1e-24: below the rounding of any sum it enters
         h.s_zero = r_zero * r_zero;
+        if (r_hi > r_zero) r_hi = r_zero;
         std::vector<double> tab;
         mgpu_build_coulomb_table(alpha, MGPU_TAB_RLO, r_hi, &g.tab_emin, &g.tab_noct, tab);
         // the hot loops send everything beyond the last interval to an all-zero row, so the table has to reach

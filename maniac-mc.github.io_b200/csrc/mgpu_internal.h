@@ -64,6 +64,12 @@ struct DevSys {
     int32_t tri_nrel;
     double tri_safe2;             // a listed vector can only shorten t when |t|^2 > tri_safe2 = min |C m|^2 / 4
     double tri_rel[MGPU_TRI_MAXREL][3], tri_m[MGPU_TRI_MAXREL][3], tri_len2[MGPU_TRI_MAXREL];   // one of every +-m pair
+    // framework passes of triclinic cells work on FRACTIONAL coordinates (min_image_frac): wrapping is a rounding of the
+    // coordinate difference itself, and the projection back costs 6 FMAs when the cell matrix is lower triangular
+    int32_t tri_lower;            // matrix(0,1) = matrix(0,2) = matrix(1,2) = 0 (LAMMPS-style cell in the reference's column convention)
+    int32_t tri_thr_hi[3];        // the listed vectors are tried when hi(|f_d|) >= tri_thr_hi[d] for some axis d (|f_d| within tri_eps of 1/2)
+    double tri_eps[3];
+    const double2 *host_fxy, *host_fzq;   // framework atoms {f0, f1}, {f2, q}: fractional coordinates wrapped into [0, 1)  (triclinic cells only)
     // ewald / constants
     double rc, rc2, alpha, eps0_inv_real, twopi, beta, overlap;
     int32_t kmax[3], kmax_max, nk;

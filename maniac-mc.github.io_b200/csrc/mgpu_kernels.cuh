@@ -35,8 +35,9 @@ __constant__ DevSys c_sys;
 // Measured on B200 in round 1 (4736 walkers x 256 steps): none 18.22, k-space only 19.10, guest pass only 18.56,
 // framework-U only 18.86, all three 18.36 M moves/s -- at 128 registers per thread the rotations compete for
 // registers, so only k-space is on (the guest-pass rotation was removed).
+// (round 2, on the build without the guest-pass rotation: framework-U prefetch on 24.69 -> 25.11 M moves/s, r02i)
 #ifndef MGPU_PF_HOSTU
-#define MGPU_PF_HOSTU 0
+#define MGPU_PF_HOSTU 1
 #endif
 // (a cp.async staging of the framework atoms two iterations ahead was measured in round 1: 19.45 M moves/s against
 // 20.5 M with the register rotation -- two more LDS.128 + two LDGSTS per iteration on an LSU that already serves the
@@ -199,6 +200,48 @@ __device__ __noinline__ double min_image_27(double dx, double dy, double dz)
     return best;
 }
 
+// Triclinic minimum image of a Cartesian difference (guest passes, intramolecular pairs, setup kernels).  Deliberately NOT
+// inlined: with this body inlined into every pair chain of every pass, k_sweep<true> is 34 k instructions; the framework
+// passes, where the time goes, use min_image_frac below and the rest can afford a call.
+__device__ __noinline__ double min_image_tri(double dx, double dy, double dz)
+{
+    // Same minimum as the 27-image search, found in 1 + tri_nrel candidates: round the fractional
+    // coordinates (image n), then try the few lattice vectors +-C m that can shorten ANY vector with
+    // fractional coordinates in [-1/2, 1/2]^3 (m G m < sum_d |(G m)_d|, G = C^T C; listed at init).
+    // That is the global minimum over the lattice; it is the reference's answer whenever its shift
+    // n - m lies in {-1,0,1}^3, which is checked -- otherwise (atoms far outside the cell, extreme
+    // skew) the literal 27-image search decides.
+    if (c_sys.tri_nrel < 0) return min_image_27(dx, dy, dz);
+    // fractional coordinates: c_sys.Hinv holds the reference's "reciprocal" = TRANSPOSE of inverse(matrix)
+    const double f0 = fma(c_sys.Hinv[0], dx, fma(c_sys.Hinv[3], dy, c_sys.Hinv[6] * dz));
+    const double f1 = fma(c_sys.Hinv[1], dx, fma(c_sys.Hinv[4], dy, c_sys.Hinv[7] * dz));
+    const double f2 = fma(c_sys.Hinv[2], dx, fma(c_sys.Hinv[5], dy, c_sys.Hinv[8] * dz));
+    const double n0 = (f0 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC, n1 = (f1 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC,
+                 n2 = (f2 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC;
+    const double tx = dx - fma(c_sys.H[0], n0, fma(c_sys.H[1], n1, c_sys.H[2] * n2));
+    const double ty = dy - fma(c_sys.H[3], n0, fma(c_sys.H[4], n1, c_sys.H[5] * n2));
+    const double tz = dz - fma(c_sys.H[6], n0, fma(c_sys.H[7], n1, c_sys.H[8] * n2));
+    // the list holds one vector of every +-m pair; of the two, only the one pointing against t can
+    // shorten it: |t -+ C m|^2 - |t|^2 = |C m|^2 - 2 |t . C m|
+    double gain = 0.0, bsign = 0.0;
+    int bk = -1;
+    // (framework atoms are Morton-sorted: the lanes of a warp look at one small region, so this is usually unanimous)
+    const double t2 = fma(tx, tx, fma(ty, ty, tz * tz));
+    const int nrel = __any_sync(__activemask(), t2 > c_sys.tri_safe2) ? c_sys.tri_nrel : 0;
+    for (int k = 0; k < nrel; ++k) {
+        const double dot = fma(tx, c_sys.tri_rel[k][0], fma(ty, c_sys.tri_rel[k][1], tz * c_sys.tri_rel[k][2]));
+        const double gk = fma(-2.0, fabs(dot), c_sys.tri_len2[k]);
+        if (gk < gain) { gain = gk; bk = k; bsign = dot > 0.0 ? -1.0 : 1.0; }
+    }
+    double cx = tx, cy = ty, cz = tz, o0 = n0, o1 = n1, o2 = n2;   // o = shift of the winner in the reference's convention, -(n - s m)
+    if (bk >= 0) {
+        cx = fma(bsign, c_sys.tri_rel[bk][0], tx); cy = fma(bsign, c_sys.tri_rel[bk][1], ty); cz = fma(bsign, c_sys.tri_rel[bk][2], tz);
+        o0 = fma(-bsign, c_sys.tri_m[bk][0], n0); o1 = fma(-bsign, c_sys.tri_m[bk][1], n1); o2 = fma(-bsign, c_sys.tri_m[bk][2], n2);
+    }
+    if (fmax(fabs(o0), fmax(fabs(o1), fabs(o2))) > 1.0) return min_image_27(dx, dy, dz);
+    return fma(cx, cx, fma(cy, cy, cz * cz));
+}
+
 template <bool TRI>
 __device__ __forceinline__ double min_image_r2(double dx, double dy, double dz)
 {
@@ -213,42 +256,68 @@ __device__ __forceinline__ double min_image_r2(double dx, double dy, double dz)
         dz = fma(-c_sys.L[2], nz, dz);
         return fma(dx, dx, fma(dy, dy, dz * dz));
     } else {
-        // Same minimum as the 27-image search, found in 1 + tri_nrel candidates: round the fractional
-        // coordinates (image n), then try the few lattice vectors +-C m that can shorten ANY vector with
-        // fractional coordinates in [-1/2, 1/2]^3 (m G m < sum_d |(G m)_d|, G = C^T C; listed at init).
-        // That is the global minimum over the lattice; it is the reference's answer whenever its shift
-        // n - m lies in {-1,0,1}^3, which is checked -- otherwise (atoms far outside the cell, extreme
-        // skew) the literal 27-image search decides.
-        if (c_sys.tri_nrel < 0) return min_image_27(dx, dy, dz);
-        // fractional coordinates: c_sys.Hinv holds the reference's "reciprocal" = TRANSPOSE of inverse(matrix)
-        const double f0 = fma(c_sys.Hinv[0], dx, fma(c_sys.Hinv[3], dy, c_sys.Hinv[6] * dz));
-        const double f1 = fma(c_sys.Hinv[1], dx, fma(c_sys.Hinv[4], dy, c_sys.Hinv[7] * dz));
-        const double f2 = fma(c_sys.Hinv[2], dx, fma(c_sys.Hinv[5], dy, c_sys.Hinv[8] * dz));
-        const double n0 = (f0 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC, n1 = (f1 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC,
-                     n2 = (f2 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC;
-        const double tx = dx - fma(c_sys.H[0], n0, fma(c_sys.H[1], n1, c_sys.H[2] * n2));
-        const double ty = dy - fma(c_sys.H[3], n0, fma(c_sys.H[4], n1, c_sys.H[5] * n2));
-        const double tz = dz - fma(c_sys.H[6], n0, fma(c_sys.H[7], n1, c_sys.H[8] * n2));
-        // the list holds one vector of every +-m pair; of the two, only the one pointing against t can
-        // shorten it: |t -+ C m|^2 - |t|^2 = |C m|^2 - 2 |t . C m|
-        double gain = 0.0, bsign = 0.0;
-        int bk = -1;
-        // (framework atoms are Morton-sorted: the lanes of a warp look at one small region, so this is usually unanimous)
-        const double t2 = fma(tx, tx, fma(ty, ty, tz * tz));
-        const int nrel = __any_sync(__activemask(), t2 > c_sys.tri_safe2) ? c_sys.tri_nrel : 0;
-        for (int k = 0; k < nrel; ++k) {
-            const double dot = fma(tx, c_sys.tri_rel[k][0], fma(ty, c_sys.tri_rel[k][1], tz * c_sys.tri_rel[k][2]));
-            const double gk = fma(-2.0, fabs(dot), c_sys.tri_len2[k]);
-            if (gk < gain) { gain = gk; bk = k; bsign = dot > 0.0 ? -1.0 : 1.0; }
-        }
-        double cx = tx, cy = ty, cz = tz, o0 = n0, o1 = n1, o2 = n2;   // o = shift of the winner in the reference's convention, -(n - s m)
-        if (bk >= 0) {
-            cx = fma(bsign, c_sys.tri_rel[bk][0], tx); cy = fma(bsign, c_sys.tri_rel[bk][1], ty); cz = fma(bsign, c_sys.tri_rel[bk][2], tz);
-            o0 = fma(-bsign, c_sys.tri_m[bk][0], n0); o1 = fma(-bsign, c_sys.tri_m[bk][1], n1); o2 = fma(-bsign, c_sys.tri_m[bk][2], n2);
-        }
-        if (fmax(fabs(o0), fmax(fabs(o1), fabs(o2))) > 1.0) return min_image_27(dx, dy, dz);
-        return fma(cx, cx, fma(cy, cy, cz * cz));
+        return min_image_tri(dx, dy, dz);
     }
+}
+
+// The same minimum image from the FRACTIONAL coordinate difference g = f(target) - f(probe) (framework passes of
+// triclinic cells: the framework is stored in fractional coordinates, the probe atoms are converted once per pass).
+// Rounding g itself wraps it (no projection of a Cartesian difference: 9 FMAs less per pair), and t = C (g - n) costs 6
+// FMAs for a lower-triangular cell matrix.  The listed lattice vectors are only tried when the rounded vector sits
+// within tri_eps of a face of the fractional cube (mgpu_init: elsewhere no listed vector can shorten it); the reference's
+// 27-image search is the fallback whenever the winning shift leaves {-1,0,1}^3 (atoms far outside the cell), exactly as
+// in min_image_tri.  The rare part is a separate function; the "rare" tests are integer compares on high words.
+__device__ __noinline__ double min_image_frac_slow(double g0, double g1, double g2)
+{
+    const double n0 = (g0 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC, n1 = (g1 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC,
+                 n2 = (g2 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC;
+    const double f0 = g0 - n0, f1 = g1 - n1, f2 = g2 - n2;
+    const double tx = fma(c_sys.H[0], f0, fma(c_sys.H[1], f1, c_sys.H[2] * f2));
+    const double ty = fma(c_sys.H[3], f0, fma(c_sys.H[4], f1, c_sys.H[5] * f2));
+    const double tz = fma(c_sys.H[6], f0, fma(c_sys.H[7], f1, c_sys.H[8] * f2));
+    const double t2 = fma(tx, tx, fma(ty, ty, tz * tz));
+    double gain = 0.0, bsign = 0.0;
+    int bk = -1;
+    const int nrel = (c_sys.tri_nrel > 0 && t2 > c_sys.tri_safe2) ? c_sys.tri_nrel : 0;
+    for (int k = 0; k < nrel; ++k) {
+        const double dot = fma(tx, c_sys.tri_rel[k][0], fma(ty, c_sys.tri_rel[k][1], tz * c_sys.tri_rel[k][2]));
+        const double gk = fma(-2.0, fabs(dot), c_sys.tri_len2[k]);
+        if (gk < gain) { gain = gk; bk = k; bsign = dot > 0.0 ? -1.0 : 1.0; }
+    }
+    double cx = tx, cy = ty, cz = tz, o0 = n0, o1 = n1, o2 = n2;
+    if (bk >= 0) {
+        cx = fma(bsign, c_sys.tri_rel[bk][0], tx); cy = fma(bsign, c_sys.tri_rel[bk][1], ty); cz = fma(bsign, c_sys.tri_rel[bk][2], tz);
+        o0 = fma(-bsign, c_sys.tri_m[bk][0], n0); o1 = fma(-bsign, c_sys.tri_m[bk][1], n1); o2 = fma(-bsign, c_sys.tri_m[bk][2], n2);
+    }
+    if (c_sys.tri_nrel < 0 || fmax(fabs(o0), fmax(fabs(o1), fabs(o2))) > 1.0) {      // the literal search, on the raw Cartesian difference
+        const double dx = fma(c_sys.H[0], g0, fma(c_sys.H[1], g1, c_sys.H[2] * g2));
+        const double dy = fma(c_sys.H[3], g0, fma(c_sys.H[4], g1, c_sys.H[5] * g2));
+        const double dz = fma(c_sys.H[6], g0, fma(c_sys.H[7], g1, c_sys.H[8] * g2));
+        return min_image_27(dx, dy, dz);
+    }
+    return fma(cx, cx, fma(cy, cy, cz * cz));
+}
+__device__ __forceinline__ double min_image_frac(double g0, double g1, double g2)
+{
+    const double n0 = (g0 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC, n1 = (g1 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC,
+                 n2 = (g2 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC;
+    const double f0 = g0 - n0, f1 = g1 - n1, f2 = g2 - n2;                 // in [-1/2, 1/2]
+    double tx, ty, tz;
+    if (c_sys.tri_lower) {
+        tx = c_sys.H[0] * f0;
+        ty = fma(c_sys.H[3], f0, c_sys.H[4] * f1);
+        tz = fma(c_sys.H[6], f0, fma(c_sys.H[7], f1, c_sys.H[8] * f2));
+    } else {
+        tx = fma(c_sys.H[0], f0, fma(c_sys.H[1], f1, c_sys.H[2] * f2));
+        ty = fma(c_sys.H[3], f0, fma(c_sys.H[4], f1, c_sys.H[5] * f2));
+        tz = fma(c_sys.H[6], f0, fma(c_sys.H[7], f1, c_sys.H[8] * f2));
+    }
+    const int a0 = __double2hiint(f0) & 0x7fffffff, a1 = __double2hiint(f1) & 0x7fffffff, a2 = __double2hiint(f2) & 0x7fffffff;
+    const bool near = (a0 >= c_sys.tri_thr_hi[0]) | (a1 >= c_sys.tri_thr_hi[1]) | (a2 >= c_sys.tri_thr_hi[2]);
+    const int b0 = __double2hiint(g0) & 0x7fffffff, b1 = __double2hiint(g1) & 0x7fffffff, b2 = __double2hiint(g2) & 0x7fffffff;
+    const bool far = (max(b0, max(b1, b2)) >= 0x3ff80000);                 // |g_d| >= 1.5: the rounded image is beyond the reference's 27
+    if (__any_sync(__activemask(), near | far)) return min_image_frac_slow(g0, g1, g2);
+    return fma(tx, tx, fma(ty, ty, tz * tz));
 }
 
 // Work counters for the roofline accounting: pairs evaluated, LJ terms inside the
@@ -465,8 +534,9 @@ struct HostPass {
     template <int UU>
     __device__ __forceinline__ void fetch(Atoms<UU> &A, int j, int stride) const
     {
-        const double2 *__restrict__ hxy = c_sys.host_xy;
-        const double2 *__restrict__ hzq = c_sys.host_zq;
+        // triclinic cells: the framework in fractional coordinates (min_image_frac)
+        const double2 *__restrict__ hxy = TRI ? c_sys.host_fxy : c_sys.host_xy;
+        const double2 *__restrict__ hzq = TRI ? c_sys.host_fzq : c_sys.host_zq;
         const int32_t *__restrict__ ht = c_sys.host_type;
 #pragma unroll
         for (int u = 0; u < UU; ++u) {
@@ -481,8 +551,10 @@ struct HostPass {
     // q_i once per pass.  Pairs below the table start (r < 1 A, incl. the overlap sentinel) read the all-zero
     // row that closes the table (the unsigned clamp sends both ends there), are left out of the LJ sum, and
     // are redone with the exact formulas when the block's smallest r^2 says there was one (e_x: their sum).
-    template <int UU>
-    __device__ __forceinline__ void block(const Atoms<UU> &A, const unsigned vmask, double &e_lj, double (&acc)[N], double2 &e_x, PairCount &pc) const
+    // (bx, by, bz) = the probe atoms in the coordinates the targets are given in: Cartesian, or fractional (FRAC)
+    template <int UU, bool FRAC>
+    __device__ __forceinline__ void block(const Atoms<UU> &A, const unsigned vmask, const double (&bx)[N], const double (&by)[N], const double (&bz)[N],
+                                          double &e_lj, double (&acc)[N], double2 &e_x, PairCount &pc) const
     {
         const double2 (&txy)[UU] = A.xy; const double2 (&tzq)[UU] = A.zq; const int (&tt)[UU] = A.tt;
         const double2 *ctab = smem_ctab<REP>(), *ljAB = smem_ljAB<REP>();
@@ -494,7 +566,8 @@ struct HostPass {
             const bool val = (vmask >> u) & 1u;
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                double s = min_image_r2<TRI>(txy[u].x - px[i], txy[u].y - py[i], tzq[u].x - pz[i]);
+                double s = FRAC ? min_image_frac(txy[u].x - bx[i], txy[u].y - by[i], tzq[u].x - bz[i])
+                                : min_image_r2<TRI>(txy[u].x - bx[i], txy[u].y - by[i], tzq[u].x - bz[i]);
                 if (!all) s = val ? s : 1.0e30;                                 // not a target: beyond every range (and (float)(s - centre) stays finite)
                 sv[u][i] = s;
                 const int hi = __double2hiint(s);
@@ -555,10 +628,21 @@ struct HostPass {
         double2 e_x = make_double2(0.0, 0.0);
         PairCount pc = pc_io;
         const int n = c_sys.n_host;
+        // the probe atoms in the coordinates the framework is stored in: fractional for triclinic cells
+        // (c_sys.Hinv = transposed inverse of the cell matrix), Cartesian otherwise
+        double bx[N], by[N], bz[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (TRI) {
+                bx[i] = fma(c_sys.Hinv[0], px[i], fma(c_sys.Hinv[3], py[i], c_sys.Hinv[6] * pz[i]));
+                by[i] = fma(c_sys.Hinv[1], px[i], fma(c_sys.Hinv[4], py[i], c_sys.Hinv[7] * pz[i]));
+                bz[i] = fma(c_sys.Hinv[2], px[i], fma(c_sys.Hinv[5], py[i], c_sys.Hinv[8] * pz[i]));
+            } else { bx[i] = px[i]; by[i] = py[i]; bz[i] = pz[i]; }
+        }
         const int step = U * stride, reach = (U - 1) * stride;
         int j = t0;
         if (!MGPU_PF_HOSTU && U > 1) {
-            for (; j + reach < n; j += step) { Atoms<U> a; fetch<U>(a, j, stride); block<U>(a, (1u << U) - 1u, e_lj, acc, e_x, pc); }
+            for (; j + reach < n; j += step) { Atoms<U> a; fetch<U>(a, j, stride); block<U, TRI>(a, (1u << U) - 1u, bx, by, bz, e_lj, acc, e_x, pc); }
         } else if (j + reach < n) {
             Atoms<U> cur;
             fetch<U>(cur, j, stride);
@@ -567,13 +651,13 @@ struct HostPass {
                 const bool more = jn + reach < n;
                 Atoms<U> nxt;
                 fetch<U>(nxt, more ? jn : j, stride);
-                block<U>(cur, (1u << U) - 1u, e_lj, acc, e_x, pc);
+                block<U, TRI>(cur, (1u << U) - 1u, bx, by, bz, e_lj, acc, e_x, pc);
                 j = jn;
                 if (!more) break;
                 cur = nxt;
             }
         }
-        for (; j < n; j += stride) { Atoms<1> a1; fetch<1>(a1, j, stride); block<1>(a1, 1u, e_lj, acc, e_x, pc); }
+        for (; j < n; j += stride) { Atoms<1> a1; fetch<1>(a1, j, stride); block<1, TRI>(a1, 1u, bx, by, bz, e_lj, acc, e_x, pc); }
         double e_c = e_x.y;
         if (MGPU_ACC_PER_ATOM) {
 #pragma unroll
@@ -614,7 +698,7 @@ struct HostPass {
                 A.tt[u] = ttype;
                 vm |= ok ? (1u << u) : 0u;
             }
-            block<U>(A, vm, e_lj, acc, e_x, pc);
+            block<U, false>(A, vm, px, py, pz, e_lj, acc, e_x, pc);
         }
 
         double e_c = e_x.y;
