@@ -12,6 +12,9 @@
 #include <vector>
 #include <map>
 
+#ifndef MGPU_HILBERT
+#define MGPU_HILBERT 1            // framework atoms along a Hilbert curve (0: Z curve, round 1)
+#endif
 #include "mgpu_kernels.cuh"
 #include "mgpu_records.cuh"
 #include "mgpu_table.h"
@@ -457,6 +460,7 @@ int mgpu_init(const mgpu_system *sys)
     h.p_insdel = sys->p_insertion_deletion; h.p_widom = sys->p_widom;
     h.tstep = sys->translation_step; h.rstep = sys->rotation_step_angle;
     h.use_hcache = 1;
+    for (int a = 0; a < MGPU_MAX_SITES; ++a) h.iota[a] = (int8_t)a;
 
     // ---- static arrays ----
     std::vector<double4> hx(n_host ? n_host : 1); std::vector<int32_t> ht(n_host ? n_host : 1), hm(n_host ? n_host : 1); std::vector<double> hq(n_host ? n_host : 1);
@@ -481,7 +485,33 @@ int mgpu_init(const mgpu_system *sys)
         // become warp-uniform facts that whole iterations can act on (triclinic passes).  Sums are order-independent
         // up to rounding; the host-host constant and S_host use the same permuted arrays.
         std::vector<std::pair<uint32_t, int>> key(n_host);
+#if MGPU_HILBERT
+        // Hilbert curve (Skilling's transpose form, 10 bits per axis): unlike the Z curve it has no jumps, so EVERY run of 32
+        // consecutive atoms is one compact cluster -- with Z order 76 % of the warp-level pair evaluations of configs[4] had some
+        // lane near a face of the fractional cube (the rare path of min_image_frac), because a run that straddles a jump of
+        // the curve is two clusters
+        auto curve_key = [](uint32_t x, uint32_t y, uint32_t z) {
+            uint32_t X[3] = { x & 1023u, y & 1023u, z & 1023u };
+            const uint32_t Mb = 1u << 9;
+            for (uint32_t Q = Mb; Q > 1; Q >>= 1) {
+                const uint32_t P = Q - 1;
+                for (int i = 0; i < 3; ++i) {
+                    if (X[i] & Q) X[0] ^= P;
+                    else { const uint32_t t = (X[0] ^ X[i]) & P; X[0] ^= t; X[i] ^= t; }
+                }
+            }
+            for (int i = 1; i < 3; ++i) X[i] ^= X[i - 1];
+            uint32_t t = 0;
+            for (uint32_t Q = Mb; Q > 1; Q >>= 1) if (X[2] & Q) t ^= Q - 1;
+            for (int i = 0; i < 3; ++i) X[i] ^= t;
+            uint32_t k = 0;
+            for (int b = 9; b >= 0; --b) for (int i = 0; i < 3; ++i) k = (k << 1) | ((X[i] >> b) & 1u);
+            return k;
+        };
+#else
         auto spread = [](uint32_t v) { v &= 1023u; v = (v | (v << 16)) & 0x030000FFu; v = (v | (v << 8)) & 0x0300F00Fu; v = (v | (v << 4)) & 0x030C30C3u; v = (v | (v << 2)) & 0x09249249u; return v; };
+        auto curve_key = [&](uint32_t x, uint32_t y, uint32_t z) { return spread(x) | (spread(y) << 1) | (spread(z) << 2); };
+#endif
         for (int k = 0; k < n_host; ++k) {
             const double r[3] = { hx[k].x - h.lo[0], hx[k].y - h.lo[1], hx[k].z - h.lo[2] };
             uint32_t q[3];
@@ -490,7 +520,7 @@ int mgpu_init(const mgpu_system *sys)
                 f -= std::floor(f);
                 q[d] = (uint32_t)std::fmin(1023.0, f * 1024.0);
             }
-            key[k] = { spread(q[0]) | (spread(q[1]) << 1) | (spread(q[2]) << 2), k };
+            key[k] = { curve_key(q[0], q[1], q[2]), k };
         }
         std::stable_sort(key.begin(), key.end());
         std::vector<double4> hx2(n_host); std::vector<int32_t> ht2(n_host), hm2(n_host); std::vector<double> hq2(n_host);

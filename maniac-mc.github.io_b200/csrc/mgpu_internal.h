@@ -102,6 +102,7 @@ struct DevSys {
     // guest atoms of each residue type by what they feel from the framework: 0 nothing, 1 LJ, 2 Coulomb, 3 both
     int32_t hl_n[MGPU_MAX_RES][4];
     int8_t  hl_list[MGPU_MAX_RES][4][MGPU_MAX_SITES];
+    int8_t  iota[MGPU_MAX_SITES];             // 0, 1, 2, ...: "every atom of the probe" as a list (merged passes of triclinic cells)
     // the same classification of a probe residue's atoms against atom b of guest residue g:
     // gl_n[((ri*MAX_RES + g)*MAX_SITES + b)*4 + mode], gl_list[that index][MAX_SITES]   (global memory, warp-uniform reads)
     const int8_t *gl_n, *gl_list;

@@ -55,6 +55,14 @@ __constant__ DevSys c_sys;
 // (Round 2 measured stored absolute atom positions for the guest passes -- three loads per target instead of six, with
 // and without a prefetch of the next molecule: 22.9 / 23.0 M moves/s against 24.2 M for com + offset.  Half of the
 // kernel's long-scoreboard stalls sit on those six loads, but the extra rows and registers cost more than they save.)
+// Triclinic cells (configs[4]): every probe atom goes through the SAME pass instantiation (LJ + Coulomb with zero
+// coefficients where a term is absent) instead of one pass per interaction class.  The r02k capture of k_sweep<true> put
+// 29 % of the warp-stall samples on instruction fetch: with two guest species and four move kinds the four walkers of a
+// quartet rarely run the same instantiation, and the classes multiply the hot code.  Costs the absent terms' arithmetic
+// (N2's centre site: an LJ term with A = B = 0), removes the "nothing"-list screen (those pairs are simply evaluated).
+#ifndef MGPU_TRI_MERGED
+#define MGPU_TRI_MERGED 1
+#endif
 #ifndef MGPU_PF_KSPACE
 #define MGPU_PF_KSPACE 1
 #endif
@@ -529,6 +537,15 @@ struct HostPass {
         }
     }
 
+    // probe atoms of this pass that carry a charge (all of them in a Coulomb list; fewer in the merged passes of triclinic cells)
+    __device__ __forceinline__ int n_charged() const
+    {
+        int c = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) c += (q[i] != 0.0) ? 1 : 0;
+        return c;
+    }
+
     template <int UU> struct Atoms { double2 xy[UU], zq[UU]; int tt[UU]; };
 
     template <int UU>
@@ -665,7 +682,7 @@ struct HostPass {
         } else e_c += acc[0];
         if (t0 == 0) {                                           // work counters of the whole pass, once (SURVEY 8d accounting)
             pc.geom += (unsigned)(N * n);
-            if (MODE & 2) pc.coul += (unsigned)(N * c_sys.n_host_charged);
+            if (MODE & 2) pc.coul += (unsigned)(n_charged() * c_sys.n_host_charged);
         }
         e_lj_io = e_lj + e_x.x; e_c_io = e_c_io + e_c; pc_io = pc;
     }
@@ -710,7 +727,7 @@ struct HostPass {
             const int first = m_order + 1;                       // molecules first .. n-1 except m_skip
             const int nv = (n - first) - ((m_skip >= first && m_skip < n) ? 1 : 0);
             pc.geom += (unsigned)(N * nv);
-            if ((MODE & 2) && tq != 0.0) pc.coul += (unsigned)(N * nv);
+            if ((MODE & 2) && tq != 0.0) pc.coul += (unsigned)(n_charged() * nv);
         }
         e_lj_io = e_lj + e_x.x; e_c_io = e_c_io + e_c; pc_io = pc;
     }
@@ -749,7 +766,11 @@ template <bool TRI, int REP>
 __device__ __forceinline__ void host_loops(const Probe &P, const double (*pos)[3], const Smem &S, int t0, int stride,
                                            double &e_lj, double &e_c, PairCount &pc)
 {
-    if (c_sys.n_host > 0) {
+    if (TRI && MGPU_TRI_MERGED) {
+        // triclinic cells: ONE instantiation for every probe atom (LJ + Coulomb, zero coefficients where a term is absent)
+        // instead of a pass per interaction class -- see MGPU_TRI_MERGED
+        if (c_sys.n_host > 0) host_list<TRI, 3, REP>(S, P, pos, c_sys.iota, P.na, t0, stride, e_lj, e_c, pc);
+    } else if (c_sys.n_host > 0) {
         const int r = P.res;
         host_list<TRI, 1, REP>(S, P, pos, c_sys.hl_list[r][1], c_sys.hl_n[r][1], t0, stride, e_lj, e_c, pc);
         host_list<TRI, 2, REP>(S, P, pos, c_sys.hl_list[r][2], c_sys.hl_n[r][2], t0, stride, e_lj, e_c, pc);
@@ -810,7 +831,7 @@ __device__ __forceinline__ void guest_loops(const Probe &P, const double (*pos)[
         if (P.order_res >= 0) m_order = (g < P.order_res) ? n : (g == P.order_res ? P.order_mol : -1);
         if (m_order >= n - 1 || (n == 1 && m_skip == 0)) continue;
         bool nothing_lists = true;
-        if (MGPU_SCREEN_NOTHING) {
+        if (MGPU_SCREEN_NOTHING && !(TRI && MGPU_TRI_MERGED)) {
             const double rr = sqrt(prad2) + sqrt(c_sys.rmax2[g] * (1.0 + 1.0e-6)) + 1.0e-9;
             const double thr2 = rr * rr;
             nothing_lists = false;
@@ -824,6 +845,10 @@ __device__ __forceinline__ void guest_loops(const Probe &P, const double (*pos)[
             double tq = c_sys.charge[g][b];
             if (fabs(tq) < MGPU_ERR_TOL) tq = 0.0;
             const int ttype = c_sys.type[g][b];
+            if (TRI && MGPU_TRI_MERGED) {
+                guest_list<TRI, 3, REP>(P, pos, c_sys.iota, P.na, com, offb, cap, n, t0, stride, m_skip, m_order, tq, ttype, e_lj, e_c, pc);
+                continue;
+            }
             const int gi = gl_index(P.res, g, b, 0);
             const int8_t *L = c_sys.gl_list + (int64_t)gi * MGPU_MAX_SITES;
             const int8_t *N = c_sys.gl_n + gi;
