@@ -439,7 +439,9 @@ def main():
 
     if a.quick:
         if rank == 0:
-            print(json.dumps({"quick": True, "lib": os.environ.get("MANIAC_GPU_LIB", "default"), "moves_per_s": value,
+            q_flops = FLOP_GEOM * pc["pairs"] + FLOP_LJ * pc["lj"] + FLOP_COUL * pc["coulomb"] + kspace_flops(dcount, na, ew["kmax"], ew["nk"])
+            print(json.dumps({"quick": True, "lib": os.environ.get("MANIAC_GPU_LIB", "default"), "walkers": W, "phase_sync": a.phase_sync, "moves_per_s": value,
+                              "frac_c1": q_flops / (ms_total * 1e-3) / 1e12 / peak_tf,
                               "ms_per_step": 1e3 * t_dev / a.steps, "loading": [n_begin, n_end], "ln_fugacity": ctl_head.lnf,
                               "clocks": clocks}))
         eng.close()
@@ -560,7 +562,7 @@ def main():
                 grid["cells"].append({"loading": loading, "walkers": Wg, "moves_per_s": float(Wg) * a.inner * l_g / t_g,
                                       "frac_c1_realspace": fl_g / t_g / 1e12 / peak_tf if peak_tf else None,
                                       "mean_loading": [nb, float(eng.counts(0, 0, Wg).mean())], "ln_fugacity": found_lnf[loading],
-                                      "shape": "team (4 warps / walker)" if Wg * 4 <= 148 * 16 * 3 else "warp / walker"})
+                                      "shape": eng.sweep_shape(Wg)["text"]})
         grid["cells"].sort(key=lambda c: (c["loading"], c["walkers"]))
         eng.close()                                       # back to the headline state for the legs below
         eng = Engine(s, n_walkers=max(a.strong_walkers // world, POOL), capacity=CAPACITY, device=local)
@@ -599,7 +601,7 @@ def main():
         summ = summarize(total, beta)
         strong = {"metric": "mc_trial_moves_per_s", "scaling": "strong", "walkers_total": Ws * world, "walkers_per_gpu": Ws,
                   "value": float(Ws) * world * a.inner * a.steps / t_s, "ms_per_step": 1e3 * t_s / a.steps,
-                  "shape": "team (4 warps / walker)" if Ws * 4 <= 148 * 16 * 3 else "warp / walker",
+                  "shape": eng.sweep_shape(Ws)["text"],
                   "points": 64, "replicas_per_point": Ws * world / 64.0,
                   "reduction": "mgpu_reduce_averages (one ncclAllReduce of 384 doubles)" if world > 1 else "single rank: none",
                   "fugacity": [float(fug[i]) for i in range(0, 64, 9)],

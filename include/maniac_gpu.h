@@ -119,6 +119,9 @@ int mgpu_get_launch_info(int32_t *walkers_per_cta, int64_t *smem_bytes_per_cta, 
  * evaluated in mgpu_init); -1 = the literal 27-image search of src/geometry_utils.f90:263-280 is used for every
  * pair (very skewed cell) */
 int mgpu_get_triclinic_candidates(int32_t *n);
+/* launch shape mgpu_sweep / mgpu_block would use for n_walkers walkers in flight: threads per walker (32, 64 or 128) and
+ * walkers per CTA (one CTA per SM); see MGPU_OPT_SWEEP_TEAM */
+int mgpu_get_sweep_shape(int32_t n_walkers, int32_t *threads_per_walker, int32_t *walkers_per_cta);
 int mgpu_get_thermo(int32_t res, double *beta, double *lambda, double *mu_walker0);
 
 /* ---- per-walker state --------------------------------------------------------------- */
@@ -159,9 +162,11 @@ enum { MGPU_OPT_HOST_CACHE = 1,
        MGPU_OPT_BLOCK_SLICES = 3,
        /* MGPU_OPT_SWEEP_TEAM (default -1 = automatic): shape of mgpu_sweep / mgpu_block launches.  0 = one warp per
         * walker (16 walkers per CTA: the throughput shape, fills the GPU from 2368 walkers up).  1 = a team of four
-        * warps per walker (4 walkers per CTA): the energy loops of a trial are split over 128 threads, for launches
-        * with few walkers per GPU (a fixed isotherm spread over more GPUs).  -1 picks teams when the walkers would
-        * fill at most three quarters of the GPU's warp slots (three short team waves beat one partly empty warp wave).  Same trajectories either way (sums are reduced in another order). */
+        * warps per walker (4 walkers per CTA), 2 = a team of two warps (8 per CTA): the energy loops of a trial are
+        * split over 128 / 64 threads, for launches with few walkers per GPU (a fixed isotherm spread over more GPUs).
+        * -1 picks the widest team with which one wave of CTAs still holds every walker, and the fewest walkers per CTA
+        * that need no extra round of CTAs (mgpu_get_sweep_shape reports the choice).  Same trajectories either way
+        * (sums are reduced in another order). */
        MGPU_OPT_SWEEP_TEAM = 4 };
 int mgpu_set_option(int32_t option, int32_t value);
 

@@ -58,6 +58,7 @@ SIGNATURES = {
     "mgpu_get_box": (C.c_int, [_pd, _pd, _pd, _pi]),
     "mgpu_get_launch_info": (C.c_int, [_pi, _pl, _pi]),
     "mgpu_get_triclinic_candidates": (C.c_int, [_pi]),
+    "mgpu_get_sweep_shape": (C.c_int, [C.c_int32, _pi, _pi]),
     "mgpu_get_thermo": (C.c_int, [I, _pd, _pd, _pd]),
     "mgpu_set_molecule": (C.c_int, [I, I, I, _pd, _pd]),
     "mgpu_get_molecule": (C.c_int, [I, I, I, _pd, _pd]),

@@ -54,9 +54,11 @@ struct Context {
     int sm_count = 0, ctas_per_sm = 1;
     int phase_sync = 13;               // MGPU_OPT_PHASE_SYNC bits: 1 top of the MC step, 2 before the energy evaluation, 4 before the guest pass, 8 before k-space
     int tri_listed = 0;                // triclinic: candidates listed but provably irrelevant (see mgpu_init)
+    int tri_req[MGPU_TRI_MAXREL] = {};  // faces (bit d = axis d) the rounded vector must be near for listed vector k to matter
     int wgroups = MGPU_WGROUPS;        // walkers (warps) per CTA of the warp-per-task kernels
     size_t smem_team = 0;              // dynamic shared memory of the team sweep (wgroups * 32 / MGPU_TEAM walkers per CTA)
-    int sweep_team = -1;               // MGPU_OPT_SWEEP_TEAM: -1 auto (teams when the walkers fill at most 3/4 of the warp slots), 0 never, 1 always
+    size_t smem_team2 = 0;             // ... of the two-warp team sweep (wgroups * 32 / MGPU_TEAM2 walkers per CTA)
+    int sweep_team = -1;               // MGPU_OPT_SWEEP_TEAM: -1 auto (see sweep_shape), 0 one warp per walker, 1 four warps, 2 two warps
     int tab_emin = 0, tab_noct = 0;
     std::vector<void *> allocs;
     // host-side mirrors needed by the API
@@ -190,30 +192,47 @@ int rebuild(int first, int n)
     return 0;
 }
 int ensure_clean(int w) { if (g.dirty[w]) return rebuild(w, 1); return 0; }
-// One launch of the device-resident drivers for walkers [first, first + n).  Shape: one warp per walker (16 walkers per
-// CTA) when the walkers fill the GPU's warp slots; a team of four warps per walker (4 walkers per CTA) when there are few
-// walkers per GPU (strong scaling of a fixed isotherm).  A team step is about 3.5x shorter than a warp step
-// (the driver part does not shrink), a team wave holds a quarter of the walkers: up to three team waves
-// (n <= 3/4 of the warp slots) beat the single, partly empty warp wave.
-bool sweep_uses_teams(int n)
+// One launch of the device-resident drivers for walkers [first, first + n).  Shape = threads per walker x walkers per CTA
+// (one CTA per SM), chosen from the number of walkers in flight so that ONE wave covers every SM when the walkers allow it:
+//   * a team of four warps per walker (up to wgroups / 4 walkers per CTA) while the walkers fit such a wave,
+//   * a team of two warps (up to wgroups / 2 per CTA) up to twice as many,
+//   * one warp per walker (up to wgroups per CTA: the throughput shape) beyond that;
+// and the walkers per CTA are the smallest number that still needs no extra round of CTAs -- e.g. 4096 walkers on 148 SMs
+// run as 2 rounds of 14-walker CTAs (all SMs busy in both) rather than 1.73 rounds of 16-walker CTAs.  Fixed isotherms
+// spread over more GPUs are the case this is for.  MGPU_OPT_SWEEP_TEAM forces the threads per walker
+// (0: 32, 1: 128, 2: 64) with full CTAs.
+struct SweepShape { int nt, per_cta; };
+SweepShape sweep_shape(int n_total)
 {
-    if (g.wgroups * 32 < MGPU_TEAM) return false;
-    if (g.sweep_team >= 0) return g.sweep_team != 0;
-    return (long long)n * 4 <= (long long)g.sm_count * g.wgroups * 3;
+    const int slots = g.wgroups;                                  // warps of a sweep CTA
+    int nt = 32;
+    const bool can4 = slots * 32 >= MGPU_TEAM, can2 = slots * 32 >= MGPU_TEAM2;
+    if (g.sweep_team == 1 && can4) nt = MGPU_TEAM;
+    else if (g.sweep_team == 2 && can2) nt = MGPU_TEAM2;
+    else if (g.sweep_team < 0) {
+        if (can4 && (long long)n_total <= (long long)g.sm_count * (slots / 4)) nt = MGPU_TEAM;
+        else if (can2 && (long long)n_total <= (long long)g.sm_count * (slots / 2)) nt = MGPU_TEAM2;
+    }
+    const int max_per = std::max(1, slots * 32 / nt);
+    int per = max_per;
+    if (g.sweep_team < 0) {
+        const long long wave = (long long)max_per * g.sm_count;
+        const long long rounds = (n_total + wave - 1) / wave;
+        per = (int)((n_total + rounds * g.sm_count - 1) / (rounds * g.sm_count));
+        per = std::max(1, std::min(per, max_per));
+    }
+    return { nt, per };
 }
 // n_total: the walkers in flight together (the call's, when it is cut into slices on several streams)
 void launch_sweep(cudaStream_t st, int first, int n, long long n_steps, int trace_walker, mgpu_step_trace *d_trace, int n_total)
 {
-    const int threads = 32 * g.wgroups;
-    if (sweep_uses_teams(n_total)) {
-        const int per_cta = threads / MGPU_TEAM, nb = (n + per_cta - 1) / per_cta;
-        if (g.h.triclinic) k_sweep<true, MGPU_TEAM><<<nb, threads, g.smem_team, st>>>(first, n, n_steps, g.natom_max, trace_walker, d_trace, g.d_err, g.phase_sync);
-        else k_sweep<false, MGPU_TEAM><<<nb, threads, g.smem_team, st>>>(first, n, n_steps, g.natom_max, trace_walker, d_trace, g.d_err, g.phase_sync);
-    } else {
-        const int nb = (n + g.wgroups - 1) / g.wgroups;
-        if (g.h.triclinic) k_sweep<true, 32><<<nb, threads, g.smem8, st>>>(first, n, n_steps, g.natom_max, trace_walker, d_trace, g.d_err, g.phase_sync);
-        else k_sweep<false, 32><<<nb, threads, g.smem8, st>>>(first, n, n_steps, g.natom_max, trace_walker, d_trace, g.d_err, g.phase_sync);
-    }
+    const SweepShape sh = sweep_shape(n_total);
+    const int threads = sh.per_cta * sh.nt, nb = (n + sh.per_cta - 1) / sh.per_cta;
+#define SWEEP(TRI, NT, SM) k_sweep<TRI, NT><<<nb, threads, SM, st>>>(first, n, n_steps, g.natom_max, trace_walker, d_trace, g.d_err, g.phase_sync)
+    if (sh.nt == MGPU_TEAM) { if (g.h.triclinic) SWEEP(true, MGPU_TEAM, g.smem_team); else SWEEP(false, MGPU_TEAM, g.smem_team); }
+    else if (sh.nt == MGPU_TEAM2) { if (g.h.triclinic) SWEEP(true, MGPU_TEAM2, g.smem_team2); else SWEEP(false, MGPU_TEAM2, g.smem_team2); }
+    else { if (g.h.triclinic) SWEEP(true, 32, g.smem8); else SWEEP(false, 32, g.smem8); }
+#undef SWEEP
 }
 // host mirror of the molecule counts (argument checks of the host-driven trials): kept current by commits and
 // mgpu_set_count, re-read from the device after anything that changes counts there (sweeps, record loads)
@@ -339,15 +358,21 @@ int mgpu_init(const mgpu_system *sys)
         for (int k = 0; k < n; ++k) h.tri_safe2 = std::fmin(h.tri_safe2, 0.25 * h.tri_len2[k]);
         // Gate of the candidate search in fractional space.  With f_d = +-(1/2 - u_d), u_d in [0, 1/2]:
         //   |t|^2 - |t -+ C m|^2 = 2 |f . G m| - m.G.m  <=  s1 - m.G.m - 2 sum_d u_d |(G m)_d|,   s1 = sum_d |(G m)_d|,
-        // so m can only help when u_d |(G m)_d| < (s1 - m.G.m) / 2 for every d, in particular for its dominant axis d*.
-        // tri_eps[d] = the largest such bound over the listed vectors whose dominant axis is d.
+        // so m can only help when sum_d u_d |(G m)_d| < (s1 - m.G.m) / 2 =: D_m, hence u_d < D_m / |(G m)_d| for EVERY axis d
+        // with (G m)_d != 0.  Axes where that bound is below 1/2 are the faces the rounded vector has to be near for m to
+        // matter (tri_req[k], a 3-bit set); tri_eps[d] = the largest such bound of axis d over the listed vectors.
         h.tri_eps[0] = h.tri_eps[1] = h.tri_eps[2] = 0.0;
         for (int k = 0; k < n; ++k) {
             double Gm[3], mGm = 0.0, s1 = 0.0;
             for (int d = 0; d < 3; ++d) { Gm[d] = G[d][0] * h.tri_m[k][0] + G[d][1] * h.tri_m[k][1] + G[d][2] * h.tri_m[k][2]; mGm += h.tri_m[k][d] * Gm[d]; s1 += std::fabs(Gm[d]); }
-            int ds = 0;
-            for (int d = 1; d < 3; ++d) if (std::fabs(Gm[d]) > std::fabs(Gm[ds])) ds = d;
-            h.tri_eps[ds] = std::fmax(h.tri_eps[ds], 0.5 * (s1 - mGm) / std::fabs(Gm[ds]) * (1.0 + 1e-9) + 1e-12);
+            g.tri_req[k] = 0;
+            for (int d = 0; d < 3; ++d) {
+                if (std::fabs(Gm[d]) == 0.0) continue;
+                const double e = 0.5 * (s1 - mGm) / std::fabs(Gm[d]) * (1.0 + 1e-9) + 1e-12;
+                if (e >= 0.5) continue;                                            // no constraint from this axis
+                g.tri_req[k] |= 1 << d;
+                h.tri_eps[d] = std::fmax(h.tri_eps[d], e);
+            }
         }
     }
     h.tri_lower = (M[0][1] == 0.0 && M[0][2] == 0.0 && M[1][2] == 0.0) ? 1 : 0;
@@ -383,6 +408,17 @@ int mgpu_init(const mgpu_system *sys)
             uint64_t bits; std::memcpy(&bits, &thr, 8);
             h.tri_thr_hi[d] = (int32_t)(bits >> 32);             // hi(|f|) >= hi(thr) is implied by |f| >= thr: a superset
         }
+    }
+    // tri_lut[faces]: which listed vectors have to be tried when the lanes of a warp are near the faces in `faces` (bits 0-2 =
+    // axes, bit 3 = some |g_d| >= 1.5, i.e. an atom far outside the cell).  Bit k = vector k; bit 31 = the complete search
+    // (every vector, then the reference's 27 images if the winner leaves {-1,0,1}^3).  0 = the rounded image is the answer.
+    for (int f = 0; f < 16; ++f) {
+        uint32_t m = 0;
+        if (h.triclinic) {
+            if (h.tri_nrel < 0 || (f & 8)) m = 0x80000000u | ((h.tri_nrel > 0) ? ((1u << h.tri_nrel) - 1u) : 0u);
+            else for (int k = 0; k < h.tri_nrel; ++k) if ((g.tri_req[k] & f) == g.tri_req[k]) m |= 1u << k;
+        }
+        h.tri_lut[f] = m;
     }
     for (int d = 0; d < 3; ++d) h.kmax[d] = f_nint(0.25 + metrics[d] * alpha * fprec / PI);
     h.kmax_max = std::max(h.kmax[0], std::max(h.kmax[1], h.kmax[2]));
@@ -440,6 +476,7 @@ int mgpu_init(const mgpu_system *sys)
             h.active_list[h.nactive++] = r;
             if (R.natom > g.natom_max) g.natom_max = R.natom;
             for (int a = 0; a < R.natom; ++a) { h.charge[r][a] = R.charges[a]; h.type[r][a] = R.types[a]; }
+            for (int a = 0; a < R.natom; ++a) if (R.charges[a] != 0.0) h.qlist[r][h.nq[r]++] = (int8_t)a;
             h.goff[r] = stride;
             stride += (int64_t)(3 + 3 * R.natom + 2) * R.capacity;      // com, offsets, framework-energy cache rows
             // prepare_monte_carlo, prepare_utils.f90:231-259
@@ -727,6 +764,8 @@ int mgpu_init(const mgpu_system *sys)
     g.smem_team = smem_bytes(h.ntypes, h.tab_nint, h.kmax_max, g.natom_max, std::max(1, g.wgroups * 32 / MGPU_TEAM), MGPU_TAB_REP, true);
     SET_SMEM((k_sweep<false, 32>), g.smem8); SET_SMEM((k_sweep<true, 32>), g.smem8);
     SET_SMEM((k_sweep<false, MGPU_TEAM>), g.smem_team); SET_SMEM((k_sweep<true, MGPU_TEAM>), g.smem_team);
+    g.smem_team2 = smem_bytes(h.ntypes, h.tab_nint, h.kmax_max, g.natom_max, std::max(1, g.wgroups * 32 / MGPU_TEAM2), MGPU_TAB_REP, true);
+    SET_SMEM((k_sweep<false, MGPU_TEAM2>), g.smem_team2); SET_SMEM((k_sweep<true, MGPU_TEAM2>), g.smem_team2);
     SET_SMEM(k_total_energy<false>, g.smem1); SET_SMEM(k_total_energy<true>, g.smem1);
     SET_SMEM(k_pair_molecule<false>, g.smem1); SET_SMEM(k_pair_molecule<true>, g.smem1);
     SET_SMEM(k_widom_batch<false>, g.smem8); SET_SMEM(k_widom_batch<true>, g.smem8);
@@ -831,6 +870,14 @@ int mgpu_get_launch_info(int32_t *walkers_per_cta, int64_t *smem_bytes_per_cta, 
     return 0;
 }
 int mgpu_get_triclinic_candidates(int32_t *n) { NEED_READY(); *n = g.h.tri_nrel; return 0; }
+int mgpu_get_sweep_shape(int32_t n_walkers, int32_t *threads_per_walker, int32_t *walkers_per_cta)
+{
+    NEED_READY();
+    const SweepShape sh = sweep_shape(n_walkers < 1 ? 1 : n_walkers);
+    if (threads_per_walker) *threads_per_walker = sh.nt;
+    if (walkers_per_cta) *walkers_per_cta = sh.per_cta;
+    return 0;
+}
 int mgpu_get_thermo(int32_t res, double *beta, double *lambda, double *mu_walker0)
 {
     NEED_READY();
@@ -951,7 +998,7 @@ int mgpu_set_option(int32_t option, int32_t value)
 {
     NEED_READY();
     if (option == MGPU_OPT_PHASE_SYNC) { g.phase_sync = (value == 1) ? 13 : (value & 15); return 0; }   // bits: 1 top of step, 2 before the evaluation, 4 before the guest pass, 8 before k-space
-    if (option == MGPU_OPT_SWEEP_TEAM) { g.sweep_team = value < 0 ? -1 : (value ? 1 : 0); return 0; }
+    if (option == MGPU_OPT_SWEEP_TEAM) { g.sweep_team = value < 0 ? -1 : (value > 2 ? 1 : value); return 0; }
     if (option == MGPU_OPT_BLOCK_SLICES) { g.block_slices = value < 1 ? 1 : (value > Context::NPIPE ? (int)Context::NPIPE : value); return 0; }
     if (option == MGPU_OPT_HOST_CACHE) {
         g.h.use_hcache = value ? 1 : 0;

@@ -69,6 +69,7 @@ struct DevSys {
     int32_t tri_lower;            // matrix(0,1) = matrix(0,2) = matrix(1,2) = 0 (LAMMPS-style cell in the reference's column convention)
     int32_t tri_thr_hi[3];        // the listed vectors are tried when hi(|f_d|) >= tri_thr_hi[d] for some axis d (|f_d| within tri_eps of 1/2)
     double tri_eps[3];
+    uint32_t tri_lut[16];         // listed vectors to try, by the set of faces the lanes of a warp are near (mgpu_init)
     const double2 *host_fxy, *host_fzq;   // framework atoms {f0, f1}, {f2, q}: fractional coordinates wrapped into [0, 1)  (triclinic cells only)
     // ewald / constants
     double rc, rc2, alpha, eps0_inv_real, twopi, beta, overlap;
@@ -89,6 +90,8 @@ struct DevSys {
     int32_t use_hcache;                       // 1: old-geometry framework sums come from the per-molecule cache
     double  charge[MGPU_MAX_RES][MGPU_MAX_SITES];
     int32_t type[MGPU_MAX_RES][MGPU_MAX_SITES];
+    int32_t nq[MGPU_MAX_RES];                 // atoms of the residue type whose charge is not exactly 0 ...
+    int8_t  qlist[MGPU_MAX_RES][MGPU_MAX_SITES];   // ... and their indices (k-space entries of a trial, fill_trial_tables)
     double  e_self[MGPU_MAX_RES];             // ewald_self_energy_single_mol(res)
     double  lambda[MGPU_MAX_RES];             // res%lambda
     double  self_host_total;                  // sum over inactive residues of e_self*count

@@ -46,6 +46,12 @@ __constant__ DevSys c_sys;
 #ifndef MGPU_HOST_U3
 #define MGPU_HOST_U3 1
 #endif
+#ifndef MGPU_ALIGN_GROUPS
+#define MGPU_ALIGN_GROUPS 1               // phase-alignment groups per CTA (warp id mod this): 1 = every warp of the CTA meets at the barriers (measured best, r03c); 4 = the warps of one SM sub-partition (round 1); 8 = pairs
+#endif
+#ifndef MGPU_SWP_COUL
+#define MGPU_SWP_COUL 0                   // hand-pipelined Coulomb-only framework pass (HostPass::run_pipelined)
+#endif
 #ifndef MGPU_SCREEN_NOTHING
 #define MGPU_SCREEN_NOTHING 1
 #endif
@@ -88,9 +94,10 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-// Thread-group abstraction: NT = 32 (one warp), MGPU_TEAM (a team of four warps, one per SM sub-partition, meeting
-// at its own named barrier) or MGPU_BLOCK (the whole CTA).
+// Thread-group abstraction: NT = 32 (one warp), MGPU_TEAM / MGPU_TEAM2 (a team of four / two warps of one walker, on
+// different SM sub-partitions, meeting at the team's own named barrier) or MGPU_BLOCK (the whole CTA).
 #define MGPU_TEAM 128
+#define MGPU_TEAM2 64
 #define MGPU_BAR_PHASE 15                 // named barrier of the CTA-wide phase alignment of the team sweep
 template <int NT> struct Grp;
 template <> struct Grp<32> {
@@ -104,13 +111,13 @@ template <> struct Grp<32> {
         for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
     }
 };
-template <> struct Grp<MGPU_TEAM> {
-    static __device__ __forceinline__ int tid() { return threadIdx.x & (MGPU_TEAM - 1); }
-    static __device__ __forceinline__ int id() { return threadIdx.x / MGPU_TEAM; }
-    static __device__ __forceinline__ void sync() { asm volatile("bar.sync %0, %1;" :: "r"(1 + (int)(threadIdx.x / MGPU_TEAM)), "n"(MGPU_TEAM) : "memory"); }
+template <int NT> struct GrpTeam {        // NT = 64 or 128: at most 8 teams per CTA, named barriers 1 .. 8
+    static __device__ __forceinline__ int tid() { return threadIdx.x & (NT - 1); }
+    static __device__ __forceinline__ int id() { return threadIdx.x / NT; }
+    static __device__ __forceinline__ void sync() { asm volatile("bar.sync %0, %1;" :: "r"(1 + (int)(threadIdx.x / NT)), "n"(NT) : "memory"); }
     template <int NV> static __device__ __forceinline__ void sum(double (&v)[NV], double *red)
     {
-        const int lane = threadIdx.x & 31, wid = (threadIdx.x & (MGPU_TEAM - 1)) >> 5;
+        const int lane = threadIdx.x & 31, wid = (threadIdx.x & (NT - 1)) >> 5;
 #pragma unroll
         for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
         sync();                                // protect red from a previous use
@@ -123,11 +130,13 @@ template <> struct Grp<MGPU_TEAM> {
         for (int i = 0; i < NV; ++i) {
             double s = 0.0;
 #pragma unroll
-            for (int w = 0; w < MGPU_TEAM / 32; ++w) s += red[i * MGPU_WARPS + w];   // fixed order
+            for (int w = 0; w < NT / 32; ++w) s += red[i * MGPU_WARPS + w];   // fixed order
             v[i] = s;
         }
     }
 };
+template <> struct Grp<MGPU_TEAM> : GrpTeam<MGPU_TEAM> {};
+template <> struct Grp<MGPU_TEAM2> : GrpTeam<MGPU_TEAM2> {};
 template <> struct Grp<MGPU_BLOCK> {
     static __device__ __forceinline__ int tid() { return threadIdx.x; }
     static __device__ __forceinline__ int id() { return 0; }
@@ -275,7 +284,7 @@ __device__ __forceinline__ double min_image_r2(double dx, double dy, double dz)
 // within tri_eps of a face of the fractional cube (mgpu_init: elsewhere no listed vector can shorten it); the reference's
 // 27-image search is the fallback whenever the winning shift leaves {-1,0,1}^3 (atoms far outside the cell), exactly as
 // in min_image_tri.  The rare part is a separate function; the "rare" tests are integer compares on high words.
-__device__ __noinline__ double min_image_frac_slow(double g0, double g1, double g2)
+__device__ __noinline__ double min_image_frac_slow(double g0, double g1, double g2, unsigned cand)
 {
     const double n0 = (g0 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC, n1 = (g1 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC,
                  n2 = (g2 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC;
@@ -283,11 +292,12 @@ __device__ __noinline__ double min_image_frac_slow(double g0, double g1, double 
     const double tx = fma(c_sys.H[0], f0, fma(c_sys.H[1], f1, c_sys.H[2] * f2));
     const double ty = fma(c_sys.H[3], f0, fma(c_sys.H[4], f1, c_sys.H[5] * f2));
     const double tz = fma(c_sys.H[6], f0, fma(c_sys.H[7], f1, c_sys.H[8] * f2));
-    const double t2 = fma(tx, tx, fma(ty, ty, tz * tz));
     double gain = 0.0, bsign = 0.0;
     int bk = -1;
-    const int nrel = (c_sys.tri_nrel > 0 && t2 > c_sys.tri_safe2) ? c_sys.tri_nrel : 0;
-    for (int k = 0; k < nrel; ++k) {
+    // cand (warp-uniform, c_sys.tri_lut): the listed vectors that can matter near the faces this warp's lanes are near --
+    // usually one.  A vector that cannot shorten t has gk >= 0 and loses against gain = 0, so trying it is harmless.
+    for (unsigned c = cand & 0x7fffffffu; c; c &= c - 1u) {
+        const int k = __ffs((int)c) - 1;
         const double dot = fma(tx, c_sys.tri_rel[k][0], fma(ty, c_sys.tri_rel[k][1], tz * c_sys.tri_rel[k][2]));
         const double gk = fma(-2.0, fabs(dot), c_sys.tri_len2[k]);
         if (gk < gain) { gain = gk; bk = k; bsign = dot > 0.0 ? -1.0 : 1.0; }
@@ -320,11 +330,16 @@ __device__ __forceinline__ double min_image_frac(double g0, double g1, double g2
         ty = fma(c_sys.H[3], f0, fma(c_sys.H[4], f1, c_sys.H[5] * f2));
         tz = fma(c_sys.H[6], f0, fma(c_sys.H[7], f1, c_sys.H[8] * f2));
     }
+    // faces of the fractional cube this lane's rounded vector is near (bits 0-2), bit 3: |g_d| >= 1.5 for some d (the rounded
+    // image is beyond the reference's 27).  The warp's union selects, through tri_lut, the listed vectors worth trying: a
+    // vector only matters near EVERY face of its tri_req set, so in a mildly tilted cell a warp near one face tries one
+    // vector instead of the whole list, and a warp near no relevant face none (mgpu_init).
     const int a0 = __double2hiint(f0) & 0x7fffffff, a1 = __double2hiint(f1) & 0x7fffffff, a2 = __double2hiint(f2) & 0x7fffffff;
-    const bool near = (a0 >= c_sys.tri_thr_hi[0]) | (a1 >= c_sys.tri_thr_hi[1]) | (a2 >= c_sys.tri_thr_hi[2]);
     const int b0 = __double2hiint(g0) & 0x7fffffff, b1 = __double2hiint(g1) & 0x7fffffff, b2 = __double2hiint(g2) & 0x7fffffff;
-    const bool far = (max(b0, max(b1, b2)) >= 0x3ff80000);                 // |g_d| >= 1.5: the rounded image is beyond the reference's 27
-    if (__any_sync(__activemask(), near | far)) return min_image_frac_slow(g0, g1, g2);
+    const unsigned faces = (a0 >= c_sys.tri_thr_hi[0] ? 1u : 0u) | (a1 >= c_sys.tri_thr_hi[1] ? 2u : 0u) | (a2 >= c_sys.tri_thr_hi[2] ? 4u : 0u) |
+                           (max(b0, max(b1, b2)) >= 0x3ff80000 ? 8u : 0u);
+    const unsigned cand = c_sys.tri_lut[__reduce_or_sync(__activemask(), faces)];
+    if (cand) return min_image_frac_slow(g0, g1, g2, cand);
     return fma(tx, tx, fma(ty, ty, tz * tz));
 }
 
@@ -464,7 +479,7 @@ __host__ __device__ inline size_t smem_ws_bytes(bool with_red)
 extern __shared__ __align__(16) unsigned char mgpu_smem[];
 // REP = number of replicas: MGPU_TAB_REP in the warp-per-task kernels (one CTA per SM, filled once
 // per launch), 1 in the CTA-per-task kernels (latency path: a 15 KB fill per task, not 123 KB).
-template <int NT> struct TabRep { static constexpr int v = (NT == 32 || NT == MGPU_TEAM) ? MGPU_TAB_REP : 1; };
+template <int NT> struct TabRep { static constexpr int v = (NT == 32 || NT == MGPU_TEAM || NT == MGPU_TEAM2) ? MGPU_TAB_REP : 1; };
 template <int REP> __device__ __forceinline__ const double2 *smem_ctab() { return reinterpret_cast<const double2 *>(mgpu_smem) + (threadIdx.x & (REP - 1)); }
 template <int REP> __device__ __forceinline__ const double2 *smem_ljAB() { return reinterpret_cast<const double2 *>(mgpu_smem) + (size_t)(c_sys.tab_nint + 1) * 3 * REP; }
 
@@ -687,6 +702,87 @@ struct HostPass {
         e_lj_io = e_lj + e_x.x; e_c_io = e_c_io + e_c; pc_io = pc;
     }
 
+    // Coulomb-only framework pass (MODE 2, orthorhombic cell, one framework atom per thread and iteration), software
+    // pipelined BY HAND across iterations: the geometry of the NEXT atom (27 back-to-back FP64 instructions that saturate
+    // the pipe) and the table part of the CURRENT one (index -> LDS.128 gather -> conversions -> Horner chain: latency
+    // bound, r02k capture: 70-80 % of the samples on those lines wait for shared memory) are independent instruction
+    // streams inside one loop body, so the in-order issue of a warp always has one of them ready.  In run() / block()
+    // the two sit behind each other and the compiler keeps them there.  Same arithmetic per pair, same order of the sums.
+    __device__ __forceinline__ void run_pipelined(int t0, int stride, double &e_c_io, PairCount &pc_io) const
+    {
+        const double2 *ctab = smem_ctab<REP>();
+        const double2 *__restrict__ hxy = c_sys.host_xy;
+        const double2 *__restrict__ hzq = c_sys.host_zq;
+        double acc = 0.0;
+        const int n = c_sys.n_host;
+        int jfirst = 0x7fffffff, jlast = -1;                 // iterations that saw a pair below the table start (r < 1 A)
+        if (t0 < n) {
+            // the loop runs one round more than there are atoms: round k does the geometry of atom k and the table part of
+            // atom k - 1 (round 0: a dummy "atom" beyond every range, which reads the all-zero row)
+            double s_cur[N], q_cur = 0.0;
+#pragma unroll
+            for (int i = 0; i < N; ++i) s_cur[i] = 1.0e30;
+            int j = t0, jcur = t0;
+            double2 xy = __ldg(hxy + t0), zq = __ldg(hzq + t0);
+            for (;;) {
+                const bool have = j < n;
+                // stream B: geometry of atom j (in registers since the previous round), then its successor's loads go out
+                double s_nxt[N];
+                const double q_nxt = zq.y;
+#pragma unroll
+                for (int i = 0; i < N; ++i) s_nxt[i] = min_image_r2<false>(xy.x - px[i], xy.y - py[i], zq.x - pz[i]);
+                const int jn = j + stride;
+                { const int jc = jn < n ? jn : t0; xy = __ldg(hxy + jc); zq = __ldg(hzq + jc); }
+                // stream A: table part of atom jcur
+                int hmin = 0x7fffffff;
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    const double sI = s_cur[i];
+                    const int hi = __double2hiint(sI);
+                    hmin = min(hmin, hi);
+                    const unsigned idx = min((unsigned)((hi >> (20 - MGPU_TAB_K)) - c_sys.tab_ibase), (unsigned)c_sys.tab_nint);
+                    const int chi = (hi & ~((1 << (20 - MGPU_TAB_K)) - 1)) | (1 << (19 - MGPU_TAB_K));
+                    const double uu = sI - __hiloint2double(chi, 0);
+                    const double2 *t = ctab + idx * (3 * REP);
+                    const double2 c01 = t[0], c23 = t[REP], c45 = t[2 * REP];
+                    const float uf = (float)uu;
+                    const float pf = fmaf(__int_as_float(__double2hiint(c45.y)), uf, __int_as_float(__double2loint(c45.y)));
+                    double p = (double)pf;
+                    p = fma(p, uu, c45.x);
+                    p = fma(p, uu, c23.y);
+                    p = fma(p, uu, c23.x);
+                    p = fma(p, uu, c01.y);
+                    p = fma(p, uu, c01.x);
+                    acc = fma(q[i] * q_cur, p, acc);
+                }
+                const bool hit = hmin < c_sys.tab_hi_lo;             // such pairs read the all-zero row; redone below
+                jfirst = min(jfirst, hit ? jcur : 0x7fffffff);
+                jlast = max(jlast, hit ? jcur : -1);
+                if (!have) break;
+#pragma unroll
+                for (int i = 0; i < N; ++i) s_cur[i] = s_nxt[i];
+                q_cur = q_nxt; jcur = j; j = jn;
+            }
+        }
+        double e_xc = 0.0;
+        for (int j = jfirst; j <= jlast; j += stride) {              // rare: pairs with r < 1 A (incl. overlap), exact formulas
+            const double2 xy = __ldg(hxy + j), zq = __ldg(hzq + j);
+#pragma unroll 1
+            for (int i = 0; i < N; ++i) {
+                const double sI = min_image_r2<false>(xy.x - px[i], xy.y - py[i], zq.x - pz[i]);
+                if (__double2hiint(sI) < c_sys.tab_hi_lo) {
+                    const double qq = q[i] * zq.y;
+                    e_xc += pair_exact(sI, 0.0, 0.0, qq, qq != 0.0).y;
+                }
+            }
+        }
+        if (t0 == 0) {                                               // work counters of the whole pass, once (SURVEY 8d accounting)
+            pc_io.geom += (unsigned)(N * n);
+            pc_io.coul += (unsigned)(n_charged() * c_sys.n_host_charged);
+        }
+        e_c_io = e_c_io + (e_xc + acc);
+    }
+
     // The same body against ONE atom (index b) of every molecule of a guest residue type of the
     // walker: targets are com[m] + off_b[m], m = t0, t0 + stride, ... < n (molecule index fastest
     // in memory, so the lanes' loads coalesce); tq / ttype are the target atom's charge (0 if tiny)
@@ -740,7 +836,8 @@ __device__ __forceinline__ void host_list(const Smem &S, const Probe &P, const d
     // chunks of at most 3 probe atoms: ~3 independent pair chains per thread fit the 128-register budget
     for (int base = 0; base < n; base += 3) {
         const int m = min(3, n - base);
-        if (m == 3) { HostPass<TRI, MODE, 3, MGPU_HOST_U3, REP> hp; hp.load(P, pos, list + base); hp.run(t0, stride, e_lj, e_c, pc); }
+        if (m == 3 && MODE == 2 && !TRI && MGPU_SWP_COUL) { HostPass<TRI, MODE, 3, 1, REP> hp; hp.load(P, pos, list + base); hp.run_pipelined(t0, stride, e_c, pc); }
+        else if (m == 3) { HostPass<TRI, MODE, 3, MGPU_HOST_U3, REP> hp; hp.load(P, pos, list + base); hp.run(t0, stride, e_lj, e_c, pc); }
         else if (m == 2) { HostPass<TRI, MODE, 2, 1, REP> hp; hp.load(P, pos, list + base); hp.run(t0, stride, e_lj, e_c, pc); }
         else { HostPass<TRI, MODE, 1, 3, REP> hp; hp.load(P, pos, list + base); hp.run(t0, stride, e_lj, e_c, pc); }
     }
@@ -868,7 +965,7 @@ __device__ __forceinline__ void guest_loops(const Probe &P, const double (*pos)[
 // named barrier of the four warps that share an SM sub-partition (see k_sweep)
 __device__ __forceinline__ void quartet_sync(int nthreads_in_quartet)
 {
-    asm volatile("bar.sync %0, %1;" :: "r"(1 + (int)((threadIdx.x >> 5) & 3)), "r"(nthreads_in_quartet) : "memory");
+    asm volatile("bar.sync %0, %1;" :: "r"(1 + (int)((threadIdx.x >> 5) & (MGPU_ALIGN_GROUPS - 1))), "r"(nthreads_in_quartet) : "memory");
 }
 // Phase alignment of the sweep kernels.  One warp per walker (NT = 32): the quartet barrier above, n = threads of the
 // quartet.  One TEAM per walker (NT = MGPU_TEAM; every team has a warp on every sub-partition): all teams of the CTA
@@ -996,6 +1093,106 @@ __device__ __forceinline__ cplx phase_product(const double2 *tab, int a, int kx,
     return c_mul(c_mul(a1, a2), a3);
 }
 
+#ifndef MGPU_KSPACE_V2
+#define MGPU_KSPACE_V2 1                  // trial k-space pass on charge-folded entry tables, two k-vectors per thread and iteration
+#endif
+// The phase tables of ONE trial, as a list of ENTRIES: every atom of the probe whose charge is not exactly 0 (c_sys.qlist; the
+// others add exactly nothing to S(k) in the reference, q * phase), first in the new geometry, then in the old one.  The charge
+// is folded into the entry's x-table, with a minus sign for the old geometry, so that dS(k) = sum over entries of
+// tx[kx] ty[ky] tz[kz] with no per-entry branch, charge load or sign.  Old and new geometry are filled in one round (twice
+// the threads busy during the sincos latency).  Layout [entry][dim][k], stride KW = kmax_max + 1, in the space of the
+// group's two tables (S.tab_old onwards).  Returns the number of entries.
+template <int NT>
+__device__ __forceinline__ int fill_trial_tables(const Smem &S, const Probe &P)
+{
+    const int KW = c_sys.kmax_max + 1;
+    const int nq = c_sys.nq[P.res];
+    const int n_new = P.has_new ? nq : 0, ne = n_new + (P.has_old ? nq : 0);
+    for (int idx = Grp<NT>::tid(); idx < ne * 3; idx += NT) {
+        const int e = idx / 3, d = idx - 3 * e;
+        const bool is_new = e < n_new;
+        const int a = c_sys.qlist[P.res][is_new ? e : e - n_new];
+        const double (*pos)[3] = is_new ? P.pn : P.po;
+        double ph = 0.0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) ph = __dadd_rn(ph, __dmul_rn(c_sys.Hinv[j * 3 + d], pos[a][j]));
+        ph = c_sys.twopi * ph;
+        double sn, cs;
+        sincos(ph, &sn, &cs);
+        double sc = 1.0;
+        if (d == 0) { const double q = c_sys.charge[P.res][a]; sc = is_new ? q : -q; }
+        double2 *t = S.tab_old + (int64_t)idx * KW;
+        double cr = 1.0, ci = 0.0;
+        t[0] = make_double2(sc, 0.0);
+        const int km = c_sys.kmax[d];
+        for (int k = 1; k <= km; ++k) {
+            const double nr = cr * cs - ci * sn, ni = cr * sn + ci * cs;
+            cr = nr; ci = ni;
+            if ((k & 7) == 0) sincos((double)k * ph, &ci, &cr);   // re-anchor, as in fill_phase_tables
+            t[k] = make_double2(sc * cr, sc * ci);
+        }
+    }
+    return ne;
+}
+
+// One entry's contribution to dS(k): tx[kx] * ty[|ky|]^(*) * tz[|kz|]^(*) added to (sr, si); 8 FP64 instructions.
+__device__ __forceinline__ void entry_term(const double2 *__restrict__ t, int o1, int o2, int o3, int sy, int sz, double &sr, double &si)
+{
+    const double2 f1 = t[o1], f2 = t[o2], f3 = t[o3];
+    // conjugate for negative ky / kz: flip the sign bit of the imaginary part (sy, sz = 0 or 0x80000000)
+    const double f2i = __hiloint2double(__double2hiint(f2.y) ^ sy, __double2loint(f2.y));
+    const double f3i = __hiloint2double(__double2hiint(f3.y) ^ sz, __double2loint(f3.y));
+    const double pr = fma(-f1.y, f2i, f1.x * f2.x), pi = fma(f1.y, f2.x, f1.x * f2i);
+    sr = fma(-pi, f3i, fma(pr, f3.x, sr));
+    si = fma(pi, f3.x, fma(pr, f3i, si));
+}
+
+// S_trial(k) = S(k) + dS(k) and E = sum_k ffW |S_trial|^2 * EPS0_INV_real * TWOPI / V over the entries of fill_trial_tables.
+// Every thread takes TWO k-vectors per iteration (i and i + NT): two independent dependency chains through the table
+// look-ups and complex products, where one chain per thread left the group latency-bound (r02k capture: 41 % of this
+// function's samples were fixed-latency waits).  The next pair's index triples, weights and S(k) are in flight meanwhile.
+template <int NT>
+__device__ double kspace_entries(const Smem &S, int ne, const double *__restrict__ S_in, double *__restrict__ S_out)
+{
+    const int nk = c_sys.nk, KW = c_sys.kmax_max + 1;
+    const double2 *__restrict__ tab = S.tab_old;
+    const int32_t *__restrict__ gkx = c_sys.kx, *__restrict__ gky = c_sys.ky, *__restrict__ gkz = c_sys.kz;
+    double part[1] = { 0.0 };
+    // S(k) of the next pair is in flight (per-walker data: L2 latency) while this pair is evaluated; the k-vector
+    // triples and weights are shared by every walker of the SM and come from L1
+    int i = Grp<NT>::tid();
+    double reA = 0.0, imA = 0.0, reB = 0.0, imB = 0.0;
+    if (i < nk) { reA = S_in[i]; imA = S_in[nk + i]; const int ib = min(i + NT, nk - 1); reB = S_in[ib]; imB = S_in[nk + ib]; }
+    while (i < nk) {
+        const int ib = min(i + NT, nk - 1);
+        const bool hasB = i + NT < nk;
+        const int kxA = __ldg(gkx + i), kyA = __ldg(gky + i), kzA = __ldg(gkz + i);
+        const int kxB = __ldg(gkx + ib), kyB = __ldg(gky + ib), kzB = __ldg(gkz + ib);
+        const int in = i + 2 * NT;
+        double nreA = 0.0, nimA = 0.0, nreB = 0.0, nimB = 0.0;
+        if (in < nk) { nreA = S_in[in]; nimA = S_in[nk + in]; const int inb = min(in + NT, nk - 1); nreB = S_in[inb]; nimB = S_in[nk + inb]; }
+        const int o2A = KW + abs(kyA), o3A = 2 * KW + abs(kzA), syA = kyA & 0x80000000, szA = kzA & 0x80000000;
+        const int o2B = KW + abs(kyB), o3B = 2 * KW + abs(kzB), syB = kyB & 0x80000000, szB = kzB & 0x80000000;
+        double srA = 0.0, siA = 0.0, srB = 0.0, siB = 0.0;
+        const double2 *t = tab;
+#pragma unroll 2
+        for (int e = 0; e < ne; ++e, t += 3 * KW) {
+            entry_term(t, kxA, o2A, o3A, syA, szA, srA, siA);
+            entry_term(t, kxB, o2B, o3B, syB, szB, srB, siB);
+        }
+        reA += srA; imA += siA; reB += srB; imB += siB;
+        if (S_out) {
+            S_out[i] = reA; S_out[nk + i] = imA;
+            if (hasB) { S_out[ib] = reB; S_out[nk + ib] = imB; }
+        }
+        part[0] += __ldg(c_sys.ffW + i) * (reA * reA + imA * imA);
+        if (hasB) part[0] += __ldg(c_sys.ffW + ib) * (reB * reB + imB * imB);
+        i = in; reA = nreA; imA = nimA; reB = nreB; imB = nimB;
+    }
+    Grp<NT>::template sum<1>(part, S.ws->red);
+    return part[0] * c_sys.eps0_inv_real * c_sys.twopi / c_sys.volume;
+}
+
 // S_trial(k) = S(k) + dS(k) and E = sum_k ffW |S_trial|^2 * EPS0_INV_real * TWOPI / V.
 // S_out may be NULL (Widom: nothing is stored).
 template <int NT>
@@ -1115,13 +1312,19 @@ __device__ void evaluate_trial(const Smem &S, int w, bool store_S, double e_old[
     double recip_new = recip_cur;
     if (do_kspace) {
         if (NT != MGPU_BLOCK && S.ws->sync_k) phase_barrier<NT>(S.ws->sync_k);      // k_sweep, MGPU_OPT_PHASE_SYNC bit 3: re-align before k-space
-        if (P.has_old) fill_phase_tables(S.tab_old, P.po, P.na, Grp<NT>::tid(), NT, c_sys.charge[P.res]);
-        if (P.has_new) fill_phase_tables(S.tab_new, P.pn, P.na, Grp<NT>::tid(), NT, c_sys.charge[P.res]);
-        Grp<NT>::sync();
         const int cur = c_sys.cur[w];
         const double *S_in = c_sys.S + ((int64_t)w * 2 + cur) * 2 * c_sys.nk;
         double *S_out = store_S ? c_sys.S + ((int64_t)w * 2 + (cur ^ 1)) * 2 * c_sys.nk : nullptr;
-        recip_new = kspace<NT>(S, S_in, S_out);
+        if (MGPU_KSPACE_V2) {
+            const int ne = fill_trial_tables<NT>(S, P);
+            Grp<NT>::sync();
+            recip_new = kspace_entries<NT>(S, ne, S_in, S_out);
+        } else {
+            if (P.has_old) fill_phase_tables(S.tab_old, P.po, P.na, Grp<NT>::tid(), NT, c_sys.charge[P.res]);
+            if (P.has_new) fill_phase_tables(S.tab_new, P.pn, P.na, Grp<NT>::tid(), NT, c_sys.charge[P.res]);
+            Grp<NT>::sync();
+            recip_new = kspace<NT>(S, S_in, S_out);
+        }
     }
 #pragma unroll
     for (int i = 0; i < 6; ++i) { e_old[i] = 0.0; e_new[i] = 0.0; }
@@ -1753,7 +1956,7 @@ __global__ void __launch_bounds__(MGPU_WBLOCK, 1) k_sweep(int first_walker, int 
     if (!live && !phase_sync) return;
     const int nwarps = (int)(blockDim.x >> 5);
     // threads that meet at a phase barrier: the warps of this warp's sub-partition (NT = 32) or the whole CTA (teams)
-    const int qthreads = (NT == 32) ? 32 * ((nwarps - (int)((threadIdx.x >> 5) & 3) + 3) / 4) : (int)blockDim.x;
+    const int qthreads = (NT == 32) ? 32 * ((nwarps - (int)((threadIdx.x >> 5) & (MGPU_ALIGN_GROUPS - 1)) + MGPU_ALIGN_GROUPS - 1) / MGPU_ALIGN_GROUPS) : (int)blockDim.x;
     const int w = first_walker + (live ? wl : 0);
     const int lane = Grp<NT>::tid();                    // index inside the walker's group; 0 plays the Fortran driver
     GroupWS &ws = *S.ws;

@@ -169,6 +169,13 @@ class Engine:
         self._ck(self.L.mgpu_get_triclinic_candidates(C.byref(n)))
         return n.value
 
+    def sweep_shape(self, n_walkers):
+        """Launch shape mgpu_sweep / mgpu_block would pick for n_walkers walkers in flight."""
+        t, p = C.c_int32(0), C.c_int32(0)
+        self._ck(self.L.mgpu_get_sweep_shape(int(n_walkers), C.byref(t), C.byref(p)))
+        return dict(threads_per_walker=t.value, walkers_per_cta=p.value,
+                    text={32: "warp / walker", 64: "team (2 warps / walker)", 128: "team (4 warps / walker)"}.get(t.value, "?") + ", %d walkers / CTA" % p.value)
+
     def thermo(self, res):
         b, l, m = C.c_double(), C.c_double(), C.c_double()
         self._ck(self.L.mgpu_get_thermo(res, C.byref(b), C.byref(l), C.byref(m)))

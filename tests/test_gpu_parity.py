@@ -32,7 +32,7 @@ def _engine_variant(param):
             super().__init__(*a, **k)
             # the device-resident drivers in their throughput shape (one warp per walker) unless the variant asks for
             # the team shape; left to itself the engine would pick teams for the handful of walkers a test uses
-            self.set_option(OPT_SWEEP_TEAM, 1 if param == "team" else 0)
+            self.set_option(OPT_SWEEP_TEAM, {"team": 1, "team2": 2}.get(param, 0))
             if param == "nocache":
                 self.set_option(OPT_HOST_CACHE, 0)
     EngineVariant.__name__ = f"Engine_{param}"
@@ -47,10 +47,10 @@ def engine_cls(request):
     return _engine_variant(request.param)
 
 
-@pytest.fixture(params=["hcache", "nocache", "team"])
+@pytest.fixture(params=["hcache", "nocache", "team", "team2"])
 def sweep_engine_cls(request):
-    """Tests of the device-resident drivers run a third time in the team shape of the sweep kernel (four warps per
-    walker, MGPU_OPT_SWEEP_TEAM = 1): the shape launches with few walkers per GPU use."""
+    """Tests of the device-resident drivers run again in the two team shapes of the sweep kernel (four / two warps per
+    walker, MGPU_OPT_SWEEP_TEAM = 1 / 2): the shapes launches with few walkers per GPU use."""
     return _engine_variant(request.param)
 
 

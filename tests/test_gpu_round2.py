@@ -232,3 +232,29 @@ def test_trial_batch_argument_checks(load):
         eng.load_walkers(blob[:offs[-1]], offs)
         for w in range(4):
             np.testing.assert_array_equal(eng.energy(w), e_before[w])
+
+
+@pytest.mark.parametrize("n_walkers,expect_threads", [(5, 128), (450, 128), (1000, 64), (2000, 32)])
+def test_automatic_sweep_shapes(n_walkers, expect_threads, load):
+    """MGPU_OPT_SWEEP_TEAM = -1 (the default): the engine picks the threads per walker and the walkers per CTA from the
+    number of walkers in flight (mgpu_get_sweep_shape) -- CTAs that are not full quartets / not the maximal team count,
+    e.g. 7 two-warp teams or 14 warps.  The traced walker and the last walker of the launch (a partly filled CTA) must
+    follow the oracle whatever the shape."""
+    s = load("zif8_h2o_gcmc")
+    steps = 600
+    from maniac_b200.engine import Engine
+    with Engine(s, n_walkers=n_walkers, capacity=64) as eng:
+        shape = eng.sweep_shape(n_walkers)
+        sm = eng.launch_info()["sm_count"]
+        assert shape["threads_per_walker"] == expect_threads or sm != 148
+        assert shape["walkers_per_cta"] * shape["threads_per_walker"] <= 512
+        eng.seed(4321)
+        last = n_walkers - 1
+        tr = eng.sweep(steps, trace_walker=last)
+        o = Oracle(s, capacity=64)
+        o.update_system_energy()
+        o.seed(4321 + 104729 * last)                      # the walker's own stream: state = splitmix64(seed + 104729 w)
+        ref = o.monte_carlo_steps(steps)
+        _compare_traces(tr, ref)
+        assert eng.count(0, walker=last) == o.count(0)
+        assert close_e(eng.energy(last), o.energy(), 1e-9)

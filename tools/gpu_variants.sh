@@ -17,6 +17,6 @@ cat $OUT | python -c "
 import sys, json
 for l in sys.stdin:
     try:
-        d = json.loads(l); print('%-70s %8.3f M moves/s  %7.2f ms  sm %s' % (d['lib'][-40:], d['moves_per_s']/1e6, d['ms_per_step'], d['clocks'].get('sm_mhz')))
+        d = json.loads(l); print('%-50s %8.3f M moves/s  %7.2f ms  C1 %.4f  N %.1f  sm %s' % (d['lib'][-40:], d['moves_per_s']/1e6, d['ms_per_step'], d.get('frac_c1', 0), d['loading'][1], d['clocks'].get('sm_mhz')))
     except Exception as e: print('bad line', l[:100])
 "
