@@ -150,11 +150,13 @@ int mgpu_get_energy(int32_t walker, double out[6]);
  * 0 = recompute it every trial, like pairwise_energy_for_molecule on the old geometry
  * (src/monte_carlo_utils.f90:367-423) does.  Same energies to rounding either way. */
 enum { MGPU_OPT_HOST_CACHE = 1,
-       /* MGPU_OPT_PHASE_SYNC (default 1 = the measured best set): in mgpu_sweep the four walkers (warps) that share an
-        * SM sub-partition meet at named barriers inside every MC step, so they run the same loop at the same time and
-        * share its instructions in the L0 instruction cache.  0 = free-running warps; other values select the barriers
-        * bit by bit (1 top of the step, 2 before the energy evaluation, 4 before the guest pass, 8 before k-space;
-        * 1 means 1|4|8).  Results are identical either way (walkers never exchange data). */
+       /* MGPU_OPT_PHASE_SYNC (default 1 = the measured best set for the launch shape): in mgpu_sweep the walkers of a
+        * CTA meet at named barriers inside every MC step, so they run the same loop at the same time and share its
+        * instructions and the framework atoms it streams in the caches.  0 = free-running; other values select the
+        * barriers bit by bit (1 top of the step, 2 before the energy evaluation, 4 before the guest pass, 8 before
+        * k-space, 16 = a CTA whose walkers are nearly empty -- fewer than 4 molecules each -- runs free).
+        * 1 means 1|4|16 when one warp owns a walker and 1|4|8 for the team shapes.  Results are identical either way
+        * (walkers never exchange data). */
        MGPU_OPT_PHASE_SYNC = 2,
        /* MGPU_OPT_BLOCK_SLICES (default 8, at most 16): mgpu_block cuts its walkers into this many slices, each on its
         * own stream, so that the records of slice i+1 travel host -> device and those of slice i-1 device -> host while

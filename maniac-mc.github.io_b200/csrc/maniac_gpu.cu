@@ -52,7 +52,7 @@ struct Context {
     int natom_max = 1;
     size_t smem1 = 0, smem8 = 0, smem_buildS = 0;   // dynamic shared memory: 1 group (CTA) / MGPU_WARPS groups (warps) per CTA
     int sm_count = 0, ctas_per_sm = 1;
-    int phase_sync = 13;               // MGPU_OPT_PHASE_SYNC bits: 1 top of the MC step, 2 before the energy evaluation, 4 before the guest pass, 8 before k-space
+    int phase_sync = -1;               // MGPU_OPT_PHASE_SYNC: -1 = the measured best set per launch shape (warps: 1|4 + adaptive groups, teams: 1|4|8); else bits: 1 top of the MC step, 2 before the energy evaluation, 4 before the guest pass, 8 before k-space, 16 nearly empty CTAs run free
     int tri_listed = 0;                // triclinic: candidates listed but provably irrelevant (see mgpu_init)
     int tri_req[MGPU_TRI_MAXREL] = {};  // faces (bit d = axis d) the rounded vector must be near for listed vector k to matter
     int wgroups = MGPU_WGROUPS;        // walkers (warps) per CTA of the warp-per-task kernels
@@ -228,7 +228,11 @@ void launch_sweep(cudaStream_t st, int first, int n, long long n_steps, int trac
 {
     const SweepShape sh = sweep_shape(n_total);
     const int threads = sh.per_cta * sh.nt, nb = (n + sh.per_cta - 1) / sh.per_cta;
-#define SWEEP(TRI, NT, SM) k_sweep<TRI, NT><<<nb, threads, SM, st>>>(first, n, n_steps, g.natom_max, trace_walker, d_trace, g.d_err, g.phase_sync)
+    // phase alignment (see k_sweep): measured best sets -- top of the step + before the guest pass (r03e: 27.65 M moves/s against
+    // 26.9 M with the k-space barrier as well; teams r03f: 14.2 against 13.5 M at 512 walkers); none in the large triclinic cells
+    // of configs[4], where a pass over 17 664 framework atoms dwarfs everything a barrier could align (2.19 against 2.05 M)
+    const int ps = g.phase_sync >= 0 ? g.phase_sync : (g.h.triclinic ? 0 : (sh.nt == 32 ? (1 | 4 | 16) : (1 | 4)));
+#define SWEEP(TRI, NT, SM) k_sweep<TRI, NT><<<nb, threads, SM, st>>>(first, n, n_steps, g.natom_max, trace_walker, d_trace, g.d_err, ps)
     if (sh.nt == MGPU_TEAM) { if (g.h.triclinic) SWEEP(true, MGPU_TEAM, g.smem_team); else SWEEP(false, MGPU_TEAM, g.smem_team); }
     else if (sh.nt == MGPU_TEAM2) { if (g.h.triclinic) SWEEP(true, MGPU_TEAM2, g.smem_team2); else SWEEP(false, MGPU_TEAM2, g.smem_team2); }
     else { if (g.h.triclinic) SWEEP(true, 32, g.smem8); else SWEEP(false, 32, g.smem8); }
@@ -997,7 +1001,7 @@ int mgpu_get_energy(int32_t w, double out[6])
 int mgpu_set_option(int32_t option, int32_t value)
 {
     NEED_READY();
-    if (option == MGPU_OPT_PHASE_SYNC) { g.phase_sync = (value == 1) ? 13 : (value & 15); return 0; }   // bits: 1 top of step, 2 before the evaluation, 4 before the guest pass, 8 before k-space
+    if (option == MGPU_OPT_PHASE_SYNC) { g.phase_sync = (value == 1 || value < 0) ? -1 : (value & 31); return 0; }   // bits: 1 top of step, 2 before the evaluation, 4 before the guest pass, 8 before k-space
     if (option == MGPU_OPT_SWEEP_TEAM) { g.sweep_team = value < 0 ? -1 : (value > 2 ? 1 : value); return 0; }
     if (option == MGPU_OPT_BLOCK_SLICES) { g.block_slices = value < 1 ? 1 : (value > Context::NPIPE ? (int)Context::NPIPE : value); return 0; }
     if (option == MGPU_OPT_HOST_CACHE) {

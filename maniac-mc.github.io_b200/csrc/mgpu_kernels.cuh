@@ -463,7 +463,8 @@ struct WalkerLocal {
 struct GroupWS {
     Probe probe;
     int32_t count[MGPU_MAX_RES];
-    int32_t sync_q, sync_k;                 // k_sweep: threads of this warp's quartet if the quartet re-aligns before the guest pass / before k-space, else 0
+    int32_t sync_q, sync_k;                 // k_sweep: threads of this warp's alignment group if the group re-aligns before the guest pass / before k-space, else 0
+    int32_t sync_top, sync_eval;            // ... at the top of the MC step / before the energy evaluation
     SweepShared sh;
     WalkerLocal loc;
     double red[8 * MGPU_WARPS];
@@ -962,14 +963,17 @@ __device__ __forceinline__ void guest_loops(const Probe &P, const double (*pos)[
     }
 }
 
-// named barrier of the four warps that share an SM sub-partition (see k_sweep)
-__device__ __forceinline__ void quartet_sync(int nthreads_in_quartet)
+// named barrier of an alignment group of warps (see k_sweep): the warps with the same (warp id mod MGPU_ALIGN_GROUPS);
+// MGPU_ALIGN_GROUPS = 1: every warp of the CTA.  The group is a compile-time constant on purpose: the same kernel with the
+// mask in a register ran 6 % slower (r03g: 26.1 against 27.7 M moves/s).
+__device__ __forceinline__ void quartet_sync(int nthreads_in_group)
 {
-    asm volatile("bar.sync %0, %1;" :: "r"(1 + (int)((threadIdx.x >> 5) & (MGPU_ALIGN_GROUPS - 1))), "r"(nthreads_in_quartet) : "memory");
+    if (MGPU_ALIGN_GROUPS == 1) asm volatile("bar.sync 1, %0;" :: "r"(nthreads_in_group) : "memory");
+    else asm volatile("bar.sync %0, %1;" :: "r"(1 + (int)((threadIdx.x >> 5) & (MGPU_ALIGN_GROUPS - 1))), "r"(nthreads_in_group) : "memory");
 }
-// Phase alignment of the sweep kernels.  One warp per walker (NT = 32): the quartet barrier above, n = threads of the
-// quartet.  One TEAM per walker (NT = MGPU_TEAM; every team has a warp on every sub-partition): all teams of the CTA
-// meet, n = threads of the CTA.
+// Phase alignment of the sweep kernels.  One warp per walker (NT = 32): the group barrier above, n = threads of the
+// group.  One TEAM per walker (NT = MGPU_TEAM / MGPU_TEAM2; every team has a warp on every / every other sub-partition):
+// all teams of the CTA meet, n = threads of the CTA.
 template <int NT> __device__ __forceinline__ void phase_barrier(int n)
 {
     if (NT == 32) quartet_sync(n);
@@ -1953,11 +1957,35 @@ __global__ void __launch_bounds__(MGPU_WBLOCK, 1) k_sweep(int first_walker, int 
     const int ngroups = (int)blockDim.x / NT;
     const int wl = blockIdx.x * ngroups + Grp<NT>::id();
     const bool live = wl < n_walkers;
-    if (!live && !phase_sync) return;
-    const int nwarps = (int)(blockDim.x >> 5);
-    // threads that meet at a phase barrier: the warps of this warp's sub-partition (NT = 32) or the whole CTA (teams)
-    const int qthreads = (NT == 32) ? 32 * ((nwarps - (int)((threadIdx.x >> 5) & (MGPU_ALIGN_GROUPS - 1)) + MGPU_ALIGN_GROUPS - 1) / MGPU_ALIGN_GROUPS) : (int)blockDim.x;
     const int w = first_walker + (live ? wl : 0);
+    const int nwarps = (int)(blockDim.x >> 5);
+    // Phase alignment is for loaded pores.  When the CTA's walkers are nearly empty most steps evaluate nothing, and a CTA-wide
+    // barrier would make every step as long as that of the one walker in sixteen that inserts (r03e: 51 against 100 M moves/s at
+    // zero loading): a CTA where fewer than half of the walkers hold four molecules runs free (bit 16 of phase_sync asks for this
+    // test; the counts are read once per launch).
+    bool free_run = false;
+    if (NT == 32 && (phase_sync & 16)) {
+        int loaded = 0;
+        if (live && (threadIdx.x & 31) == 0) {
+            int c = 0;
+            for (int r = 0; r < c_sys.nres; ++r) if (c_sys.active[r]) c += c_sys.count[(int64_t)w * MGPU_MAX_RES + r];
+            loaded = c >= 4;
+        }
+        const int n_loaded = __syncthreads_count(loaded);
+        const int n_live = min(ngroups, n_walkers - (int)blockIdx.x * ngroups);
+        free_run = 2 * n_loaded < n_live;
+    }
+    if (!live && (free_run || !(phase_sync & 15))) return;
+    {
+        // threads that meet at a phase barrier: the warps of this warp's alignment group (NT = 32) or the whole CTA (teams).
+        // The barrier set lives in the group's workspace (0 = not taken), so that the step loop carries no extra register:
+        // with phase_sync itself rewritten in a register the kernel ran 6 % slower (r03i: 26.0 against 27.7 M moves/s).
+        const int qthreads = free_run ? 0 : ((NT == 32) ? 32 * ((nwarps - (int)((threadIdx.x >> 5) & (MGPU_ALIGN_GROUPS - 1)) + MGPU_ALIGN_GROUPS - 1) / MGPU_ALIGN_GROUPS) : (int)blockDim.x);
+        if (Grp<NT>::tid() == 0) {
+            S.ws->sync_top = (phase_sync & 1) ? qthreads : 0; S.ws->sync_eval = (phase_sync & 2) ? qthreads : 0;
+            S.ws->sync_q = (phase_sync & 4) ? qthreads : 0; S.ws->sync_k = (phase_sync & 8) ? qthreads : 0;
+        }
+    }
     const int lane = Grp<NT>::tid();                    // index inside the walker's group; 0 plays the Fortran driver
     GroupWS &ws = *S.ws;
     if (live) {
@@ -1967,19 +1995,19 @@ __global__ void __launch_bounds__(MGPU_WBLOCK, 1) k_sweep(int first_walker, int 
         if (lane < MGPU_MAX_RES) { ws.loc.avgN[lane] = 0.0; ws.loc.avgN2[lane] = 0.0; }
         if (lane == 0) { ws.loc.avgE = 0.0; ws.loc.n_samples = 0; }
     }
-    if (lane == 0) { ws.sh.valid = 0; ws.sync_q = (phase_sync & 4) ? qthreads : 0; ws.sync_k = (phase_sync & 8) ? qthreads : 0; }
+    if (lane == 0) ws.sh.valid = 0;
     PairCount pc = { 0u, 0u, 0u, 0u };
     Grp<NT>::sync();
 
     for (long long step = 0; step < n_steps; ++step) {
-        if (phase_sync & 1) phase_barrier<NT>(qthreads);
-        if (!live) { if (phase_sync & 2) phase_barrier<NT>(qthreads); if (phase_sync & 4) phase_barrier<NT>(qthreads); if (phase_sync & 8) phase_barrier<NT>(qthreads); continue; }
+        if (ws.sync_top) phase_barrier<NT>(ws.sync_top);
+        if (!live) { if (ws.sync_eval) phase_barrier<NT>(ws.sync_eval); if (ws.sync_q) phase_barrier<NT>(ws.sync_q); if (ws.sync_k) phase_barrier<NT>(ws.sync_k); continue; }
         if (lane == 0) propose_step(w, ws, err);
         Grp<NT>::sync();
-        if (phase_sync & 2) phase_barrier<NT>(qthreads);
+        if (ws.sync_eval) phase_barrier<NT>(ws.sync_eval);
         const SweepShared &sh = ws.sh;
-        if (!sh.valid && (phase_sync & 4)) phase_barrier<NT>(qthreads);       // the barrier pair_sums would have taken
-        if (!sh.valid && (phase_sync & 8)) phase_barrier<NT>(qthreads);       // ... and the one before k-space
+        if (!sh.valid && ws.sync_q) phase_barrier<NT>(ws.sync_q);       // the barrier pair_sums would have taken
+        if (!sh.valid && ws.sync_k) phase_barrier<NT>(ws.sync_k);       // ... and the one before k-space
         if (sh.valid) {
             double e_old[6], e_new[6], hc_new[2];
             if (sh.kind == MGPU_KIND_SWAP) {
