@@ -413,6 +413,7 @@ int mgpu_init(const mgpu_system *sys)
             h.tri_thr_hi[d] = (int32_t)(bits >> 32);             // hi(|f|) >= hi(thr) is implied by |f| >= thr: a superset
         }
     }
+    h.tri_thr_min = std::min(h.tri_thr_hi[0], std::min(h.tri_thr_hi[1], h.tri_thr_hi[2]));
     // tri_lut[faces]: which listed vectors have to be tried when the lanes of a warp are near the faces in `faces` (bits 0-2 =
     // axes, bit 3 = some |g_d| >= 1.5, i.e. an atom far outside the cell).  Bit k = vector k; bit 31 = the complete search
     // (every vector, then the reference's 27 images if the winner leaves {-1,0,1}^3).  0 = the rounded image is the answer.

@@ -129,4 +129,7 @@ struct DevSys {
     double  *avg;                             // [W][MGPU_MAX_RES][4]
     MgpuTrial *trial;                         // [W]
     unsigned long long *pair_count;           // [3] pairs evaluated, LJ terms, Coulomb terms (all walkers)
+    // (appended, so that the offsets of everything above -- and with them the constant-bank loads the orthorhombic kernels
+    // were tuned with -- stay what they were)
+    int32_t tri_thr_min, tri_pad_;            // min of tri_thr_hi: "near some face that matters" in one compare (min_image_frac_fast)
 };

@@ -315,32 +315,38 @@ __device__ __noinline__ double min_image_frac_slow(double g0, double g1, double 
     }
     return fma(cx, cx, fma(cy, cy, cz * cz));
 }
-__device__ __forceinline__ double min_image_frac(double g0, double g1, double g2)
+// Branch-free part: the rounded image's squared length, and in `near` whether the rounded vector is near ANY face of the
+// fractional cube that matters to some listed vector (high word of max |f_d| against the smallest threshold: a superset, five
+// integer instructions).  The caller votes ONCE for all the pair chains of an iteration (HostPass::block); only warps with
+// a lane near a face work out which faces (frac_faces) and send the chains concerned through min_image_frac_slow with the
+// listed vectors tri_lut selects: a vector only matters near EVERY face of its tri_req set, so in a mildly tilted cell a
+// warp near one face tries one vector instead of the whole list (mgpu_init).  No branch in here -- not even on the cell's
+// triangular shape (three FMAs with zero coefficients are cheaper than a basic-block boundary in every chain): with a vote
+// and a call inside each chain the three chains of an iteration ran one after the other (r03b capture: 193 instructions
+// per pair, a third of the samples fixed-latency waits).  Vectors beyond the reference's 27 images (|g_d| >= 1.5) cannot
+// occur for probe atoms inside (-1/2, 3/2) of the cell, which HostPass::run checks once per pass.
+__device__ __forceinline__ double min_image_frac_fast(double g0, double g1, double g2, bool &near)
 {
     const double n0 = (g0 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC, n1 = (g1 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC,
                  n2 = (g2 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC;
     const double f0 = g0 - n0, f1 = g1 - n1, f2 = g2 - n2;                 // in [-1/2, 1/2]
-    double tx, ty, tz;
-    if (c_sys.tri_lower) {
-        tx = c_sys.H[0] * f0;
-        ty = fma(c_sys.H[3], f0, c_sys.H[4] * f1);
-        tz = fma(c_sys.H[6], f0, fma(c_sys.H[7], f1, c_sys.H[8] * f2));
-    } else {
-        tx = fma(c_sys.H[0], f0, fma(c_sys.H[1], f1, c_sys.H[2] * f2));
-        ty = fma(c_sys.H[3], f0, fma(c_sys.H[4], f1, c_sys.H[5] * f2));
-        tz = fma(c_sys.H[6], f0, fma(c_sys.H[7], f1, c_sys.H[8] * f2));
-    }
-    // faces of the fractional cube this lane's rounded vector is near (bits 0-2), bit 3: |g_d| >= 1.5 for some d (the rounded
-    // image is beyond the reference's 27).  The warp's union selects, through tri_lut, the listed vectors worth trying: a
-    // vector only matters near EVERY face of its tri_req set, so in a mildly tilted cell a warp near one face tries one
-    // vector instead of the whole list, and a warp near no relevant face none (mgpu_init).
+    const double tx = fma(c_sys.H[0], f0, fma(c_sys.H[1], f1, c_sys.H[2] * f2));
+    const double ty = fma(c_sys.H[3], f0, fma(c_sys.H[4], f1, c_sys.H[5] * f2));
+    const double tz = fma(c_sys.H[6], f0, fma(c_sys.H[7], f1, c_sys.H[8] * f2));
+    const int a0 = __double2hiint(f0) & 0x7fffffff, a1 = __double2hiint(f1) & 0x7fffffff, a2 = __double2hiint(f2) & 0x7fffffff;
+    near = max(a0, max(a1, a2)) >= c_sys.tri_thr_min;
+    return fma(tx, tx, fma(ty, ty, tz * tz));
+}
+// the faces (bits 0-2) the rounded vector is near, bit 3: |g_d| >= 1.5 for some d (index of tri_lut)
+__device__ __forceinline__ unsigned frac_faces(double g0, double g1, double g2)
+{
+    const double n0 = (g0 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC, n1 = (g1 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC,
+                 n2 = (g2 + MGPU_RINT_MAGIC) - MGPU_RINT_MAGIC;
+    const double f0 = g0 - n0, f1 = g1 - n1, f2 = g2 - n2;
     const int a0 = __double2hiint(f0) & 0x7fffffff, a1 = __double2hiint(f1) & 0x7fffffff, a2 = __double2hiint(f2) & 0x7fffffff;
     const int b0 = __double2hiint(g0) & 0x7fffffff, b1 = __double2hiint(g1) & 0x7fffffff, b2 = __double2hiint(g2) & 0x7fffffff;
-    const unsigned faces = (a0 >= c_sys.tri_thr_hi[0] ? 1u : 0u) | (a1 >= c_sys.tri_thr_hi[1] ? 2u : 0u) | (a2 >= c_sys.tri_thr_hi[2] ? 4u : 0u) |
-                           (max(b0, max(b1, b2)) >= 0x3ff80000 ? 8u : 0u);
-    const unsigned cand = c_sys.tri_lut[__reduce_or_sync(__activemask(), faces)];
-    if (cand) return min_image_frac_slow(g0, g1, g2, cand);
-    return fma(tx, tx, fma(ty, ty, tz * tz));
+    return (a0 >= c_sys.tri_thr_hi[0] ? 1u : 0u) | (a1 >= c_sys.tri_thr_hi[1] ? 2u : 0u) | (a2 >= c_sys.tri_thr_hi[2] ? 4u : 0u) |
+           (max(b0, max(b1, b2)) >= 0x3ff80000 ? 8u : 0u);
 }
 
 // Work counters for the roofline accounting: pairs evaluated, LJ terms inside the
@@ -586,7 +592,7 @@ struct HostPass {
     // are redone with the exact formulas when the block's smallest r^2 says there was one (e_x: their sum).
     // (bx, by, bz) = the probe atoms in the coordinates the targets are given in: Cartesian, or fractional (FRAC)
     template <int UU, bool FRAC>
-    __device__ __forceinline__ void block(const Atoms<UU> &A, const unsigned vmask, const double (&bx)[N], const double (&by)[N], const double (&bz)[N],
+    __device__ __forceinline__ void block(const Atoms<UU> &A, const unsigned vmask, const bool far_pass, const double (&bx)[N], const double (&by)[N], const double (&bz)[N],
                                           double &e_lj, double (&acc)[N], double2 &e_x, PairCount &pc) const
     {
         const double2 (&txy)[UU] = A.xy; const double2 (&tzq)[UU] = A.zq; const int (&tt)[UU] = A.tt;
@@ -594,18 +600,56 @@ struct HostPass {
         const bool all = (vmask == (1u << UU) - 1u);
         int hmin = 0x7fffffff;
         double sv[UU][N];
+        if (FRAC) {
+            // fractional framework coordinates: every chain's rounded image first (one basic block, the chains interleave),
+            // then ONE vote on the union of their faces; only warps near a relevant face look closer, chain by chain
+            bool near_any = far_pass;
+#pragma unroll
+            for (int u = 0; u < UU; ++u)
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    bool nr;
+                    sv[u][i] = min_image_frac_fast(txy[u].x - bx[i], txy[u].y - by[i], tzq[u].x - bz[i], nr);
+                    near_any |= nr;
+                }
+            if (__any_sync(__activemask(), near_any)) {
+#pragma unroll
+                for (int u = 0; u < UU; ++u)
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        const double g0 = txy[u].x - bx[i], g1 = txy[u].y - by[i], g2 = tzq[u].x - bz[i];
+                        const unsigned cand = c_sys.tri_lut[__reduce_or_sync(__activemask(), frac_faces(g0, g1, g2))];
+                        if (cand) sv[u][i] = min_image_frac_slow(g0, g1, g2, cand);
+                    }
+            }
+        } else if (TRI) {
+#pragma unroll
+            for (int u = 0; u < UU; ++u)
+#pragma unroll
+                for (int i = 0; i < N; ++i) sv[u][i] = min_image_r2<true>(txy[u].x - bx[i], txy[u].y - by[i], tzq[u].x - bz[i]);
+        }
+        // triclinic (large cells): whole warps are beyond the LJ cutoff -- one vote for all the chains of the iteration
+        bool lj_pass = (MODE & 1) != 0;
+        if ((MODE & 1) && TRI) {
+            double smin = 1.0e300;
+#pragma unroll
+            for (int u = 0; u < UU; ++u)
+#pragma unroll
+                for (int i = 0; i < N; ++i) smin = fmin(smin, (all || ((vmask >> u) & 1u)) ? sv[u][i] : 1.0e300);
+            lj_pass = __any_sync(__activemask(), smin < c_sys.rc2);
+        }
 #pragma unroll
         for (int u = 0; u < UU; ++u) {
             const bool val = (vmask >> u) & 1u;
 #pragma unroll
             for (int i = 0; i < N; ++i) {
-                double s = FRAC ? min_image_frac(txy[u].x - bx[i], txy[u].y - by[i], tzq[u].x - bz[i])
-                                : min_image_r2<TRI>(txy[u].x - bx[i], txy[u].y - by[i], tzq[u].x - bz[i]);
+                // (orthorhombic cells: the minimum image stays inside the chain, exactly as the loop was tuned -- r03)
+                double s = TRI ? sv[u][i] : min_image_r2<false>(txy[u].x - bx[i], txy[u].y - by[i], tzq[u].x - bz[i]);
                 if (!all) s = val ? s : 1.0e30;                                 // not a target: beyond every range (and (float)(s - centre) stays finite)
                 sv[u][i] = s;
                 const int hi = __double2hiint(s);
                 hmin = min(hmin, hi);
-                if ((MODE & 1) && (!TRI || __any_sync(__activemask(), s < c_sys.rc2))) {     // triclinic (large cells): whole warps are beyond the cutoff
+                if ((MODE & 1) && lj_pass) {
                     const double2 AB = ljAB[trow[i] + tt[u]];
                     const double y = rcp_fast(s), y3 = y * y * y;
                     const double e = (AB.x * y3 - AB.y) * y3;
@@ -672,10 +716,17 @@ struct HostPass {
                 bz[i] = fma(c_sys.Hinv[2], px[i], fma(c_sys.Hinv[5], py[i], c_sys.Hinv[8] * pz[i]));
             } else { bx[i] = px[i]; by[i] = py[i]; bz[i] = pz[i]; }
         }
+        // triclinic: a probe atom farther than half a cell outside the cell (host-provided geometries only) can put the rounded
+        // image beyond the reference's 27 -- then every pair of the pass takes the complete search
+        bool far_pass = false;
+        if (TRI) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) far_pass |= !(fabs(bx[i] - 0.5) < 1.0 && fabs(by[i] - 0.5) < 1.0 && fabs(bz[i] - 0.5) < 1.0);
+        }
         const int step = U * stride, reach = (U - 1) * stride;
         int j = t0;
         if (!MGPU_PF_HOSTU && U > 1) {
-            for (; j + reach < n; j += step) { Atoms<U> a; fetch<U>(a, j, stride); block<U, TRI>(a, (1u << U) - 1u, bx, by, bz, e_lj, acc, e_x, pc); }
+            for (; j + reach < n; j += step) { Atoms<U> a; fetch<U>(a, j, stride); block<U, TRI>(a, (1u << U) - 1u, far_pass, bx, by, bz, e_lj, acc, e_x, pc); }
         } else if (j + reach < n) {
             Atoms<U> cur;
             fetch<U>(cur, j, stride);
@@ -684,13 +735,13 @@ struct HostPass {
                 const bool more = jn + reach < n;
                 Atoms<U> nxt;
                 fetch<U>(nxt, more ? jn : j, stride);
-                block<U, TRI>(cur, (1u << U) - 1u, bx, by, bz, e_lj, acc, e_x, pc);
+                block<U, TRI>(cur, (1u << U) - 1u, far_pass, bx, by, bz, e_lj, acc, e_x, pc);
                 j = jn;
                 if (!more) break;
                 cur = nxt;
             }
         }
-        for (; j < n; j += stride) { Atoms<1> a1; fetch<1>(a1, j, stride); block<1, TRI>(a1, 1u, bx, by, bz, e_lj, acc, e_x, pc); }
+        for (; j < n; j += stride) { Atoms<1> a1; fetch<1>(a1, j, stride); block<1, TRI>(a1, 1u, far_pass, bx, by, bz, e_lj, acc, e_x, pc); }
         double e_c = e_x.y;
         if (MGPU_ACC_PER_ATOM) {
 #pragma unroll
@@ -812,7 +863,7 @@ struct HostPass {
                 A.tt[u] = ttype;
                 vm |= ok ? (1u << u) : 0u;
             }
-            block<U, false>(A, vm, px, py, pz, e_lj, acc, e_x, pc);
+            block<U, false>(A, vm, false, px, py, pz, e_lj, acc, e_x, pc);
         }
 
         double e_c = e_x.y;
