@@ -510,7 +510,7 @@ def main():
     t_ns, _ = timed_sweeps(ctl_head, W, 2, 1)
     t_ns = max_over_ranks(t_ns)
     no_sync = {"moves_per_s": float(W) * a.inner * 2 * world / t_ns,
-               "note": "mgpu_set_option(MGPU_OPT_PHASE_SYNC, 0): walkers of a CTA free-running (no per-quartet barrier)"}
+               "note": "mgpu_set_option(MGPU_OPT_PHASE_SYNC, 0): walkers of a CTA free-running (no phase-alignment barriers: the default takes one at the top of every MC step and one before the guest pass, CTA-wide)"}
     eng.set_option(OPT_PHASE_SYNC, 1 if a.phase_sync < 0 else a.phase_sync)
 
     # ---- e2e: the block-level C-ABI entry with HOST buffers (mgpu_block, pipelined) ---------------------

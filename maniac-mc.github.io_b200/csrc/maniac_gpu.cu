@@ -12,6 +12,9 @@
 #include <vector>
 #include <map>
 
+#ifndef MGPU_TRI_COLUMNS
+#define MGPU_TRI_COLUMNS 1        // triclinic cells: framework atoms in columns along the axis whose faces no single listed vector needs (see mgpu_init)
+#endif
 #ifndef MGPU_HILBERT
 #define MGPU_HILBERT 1            // framework atoms along a Hilbert curve (0: Z curve, round 1)
 #endif
@@ -554,17 +557,51 @@ int mgpu_init(const mgpu_system *sys)
         auto spread = [](uint32_t v) { v &= 1023u; v = (v | (v << 16)) & 0x030000FFu; v = (v | (v << 8)) & 0x0300F00Fu; v = (v | (v << 4)) & 0x030C30C3u; v = (v | (v << 2)) & 0x09249249u; return v; };
         auto curve_key = [&](uint32_t x, uint32_t y, uint32_t z) { return spread(x) | (spread(y) << 1) | (spread(z) << 2); };
 #endif
+        // Triclinic cells whose listed lattice vectors leave one axis free of single-face vectors (e.g. an xy tilt: the vectors
+        // that matter near ONE face are +-c1 and +-c2, none for the z faces): COLUMNS instead of compact clusters -- thin
+        // (about 4 A) along the axes whose faces matter, long along the free axis.  A warp iteration takes the candidate search
+        // of min_image_frac when any of its 32 atoms is within ~3 A of such a face: simulated on configs[4], 32 % of the
+        // iterations for Hilbert runs, 20 % for 16 x 16 columns (and 17 % instead of 13 % of them reach into the LJ cutoff
+        // sphere, which costs less than it saves).
+        int thin[3] = { 0, 0, 0 }, n_thin = 0, cols[3] = { 1, 1, 1 };
+        if (h.triclinic && h.tri_nrel > 0 && MGPU_TRI_COLUMNS) {
+            for (int k2 = 0; k2 < h.tri_nrel; ++k2) for (int d = 0; d < 3; ++d) if (g.tri_req[k2] == (1 << d)) thin[d] = 1;
+            n_thin = thin[0] + thin[1] + thin[2];
+            if (n_thin == 1 || n_thin == 2) {
+                long long ncol = 1;
+                for (int d = 0; d < 3; ++d) if (thin[d]) { cols[d] = std::max(1, (int)std::lround(metrics[d] / 4.25)); ncol *= cols[d]; }
+                while (ncol * 32 > n_host) {                       // keep at least one warp iteration per column
+                    ncol = 1;
+                    for (int d = 0; d < 3; ++d) if (thin[d]) { cols[d] = std::max(1, cols[d] - 1); ncol *= cols[d]; }
+                    if (ncol == 1) break;
+                }
+            } else n_thin = 0;
+        }
+        std::vector<uint64_t> key64(n_host);
         for (int k = 0; k < n_host; ++k) {
             const double r[3] = { hx[k].x - h.lo[0], hx[k].y - h.lo[1], hx[k].z - h.lo[2] };
             uint32_t q[3];
+            uint64_t col = 0;
             for (int d = 0; d < 3; ++d) {
                 double f = h.Hinv[0 * 3 + d] * r[0] + h.Hinv[1 * 3 + d] * r[1] + h.Hinv[2 * 3 + d] * r[2];   // Hinv = transposed inverse
                 f -= std::floor(f);
                 q[d] = (uint32_t)std::fmin(1023.0, f * 1024.0);
+                if (n_thin && thin[d]) {
+                    int b = std::min(cols[d] - 1, (int)(f * cols[d]));
+                    if (col & 1) b = cols[d] - 1 - b;              // serpentine: neighbouring columns follow each other
+                    col = col * cols[d] + b;
+                    q[d] = 0;                                      // the curve only runs along the free axes inside a column
+                }
             }
-            key[k] = { curve_key(q[0], q[1], q[2]), k };
+            uint32_t ck = curve_key(q[0], q[1], q[2]);
+            if (n_thin) {                                          // Z order of the free coordinates (monotone along a single free axis)
+                auto spread3 = [](uint32_t v) { v &= 1023u; v = (v | (v << 16)) & 0x030000FFu; v = (v | (v << 8)) & 0x0300F00Fu; v = (v | (v << 4)) & 0x030C30C3u; v = (v | (v << 2)) & 0x09249249u; return v; };
+                ck = spread3(q[0]) | (spread3(q[1]) << 1) | (spread3(q[2]) << 2);
+            }
+            key64[k] = (col << 32) | ck;
+            key[k] = { 0u, k };
         }
-        std::stable_sort(key.begin(), key.end());
+        std::stable_sort(key.begin(), key.end(), [&](const std::pair<uint32_t, int> &a, const std::pair<uint32_t, int> &b) { return key64[a.second] < key64[b.second]; });
         std::vector<double4> hx2(n_host); std::vector<int32_t> ht2(n_host), hm2(n_host); std::vector<double> hq2(n_host);
         for (int k = 0; k < n_host; ++k) { const int o = key[k].second; hx2[k] = hx[o]; ht2[k] = ht[o]; hm2[k] = hm[o]; hq2[k] = hq[o]; }
         hx.swap(hx2); ht.swap(ht2); hm.swap(hm2); hq.swap(hq2);
