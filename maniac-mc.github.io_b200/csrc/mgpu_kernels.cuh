@@ -292,20 +292,33 @@ __device__ __noinline__ double min_image_frac_slow(double g0, double g1, double 
     const double tx = fma(c_sys.H[0], f0, fma(c_sys.H[1], f1, c_sys.H[2] * f2));
     const double ty = fma(c_sys.H[3], f0, fma(c_sys.H[4], f1, c_sys.H[5] * f2));
     const double tz = fma(c_sys.H[6], f0, fma(c_sys.H[7], f1, c_sys.H[8] * f2));
-    double gain = 0.0, bsign = 0.0;
-    int bk = -1;
-    // cand (warp-uniform, c_sys.tri_lut): the listed vectors that can matter near the faces this warp's lanes are near --
-    // usually one.  A vector that cannot shorten t has gk >= 0 and loses against gain = 0, so trying it is harmless.
-    for (unsigned c = cand & 0x7fffffffu; c; c &= c - 1u) {
-        const int k = __ffs((int)c) - 1;
-        const double dot = fma(tx, c_sys.tri_rel[k][0], fma(ty, c_sys.tri_rel[k][1], tz * c_sys.tri_rel[k][2]));
-        const double gk = fma(-2.0, fabs(dot), c_sys.tri_len2[k]);
-        if (gk < gain) { gain = gk; bk = k; bsign = dot > 0.0 ? -1.0 : 1.0; }
-    }
+    // cand (warp-uniform, c_sys.tri_lut): the listed vectors that can matter near the faces this warp's lanes are near.
+    // A vector that cannot shorten t has gk >= 0 and loses against gain = 0, so trying it is harmless.
     double cx = tx, cy = ty, cz = tz, o0 = n0, o1 = n1, o2 = n2;
-    if (bk >= 0) {
-        cx = fma(bsign, c_sys.tri_rel[bk][0], tx); cy = fma(bsign, c_sys.tri_rel[bk][1], ty); cz = fma(bsign, c_sys.tri_rel[bk][2], tz);
-        o0 = fma(-bsign, c_sys.tri_m[bk][0], n0); o1 = fma(-bsign, c_sys.tri_m[bk][1], n1); o2 = fma(-bsign, c_sys.tri_m[bk][2], n2);
+    const unsigned cv = cand & 0x7fffffffu;
+    if ((cv & (cv - 1u)) == 0u && cv != 0u) {
+        // exactly one vector (the usual case in a mildly tilted cell): its data loaded once, applied by selects
+        const int k = __ffs((int)cv) - 1;
+        const double r0 = c_sys.tri_rel[k][0], r1 = c_sys.tri_rel[k][1], r2 = c_sys.tri_rel[k][2];
+        const double m0 = c_sys.tri_m[k][0], m1 = c_sys.tri_m[k][1], m2 = c_sys.tri_m[k][2];
+        const double dot = fma(tx, r0, fma(ty, r1, tz * r2));
+        const double gk = fma(-2.0, fabs(dot), c_sys.tri_len2[k]);
+        const double sg = (gk < 0.0) ? (dot > 0.0 ? -1.0 : 1.0) : 0.0;       // 0: the vector does not help this lane
+        cx = fma(sg, r0, tx); cy = fma(sg, r1, ty); cz = fma(sg, r2, tz);
+        o0 = fma(-sg, m0, n0); o1 = fma(-sg, m1, n1); o2 = fma(-sg, m2, n2);
+    } else {
+        double gain = 0.0, bsign = 0.0;
+        int bk = -1;
+        for (unsigned c = cv; c; c &= c - 1u) {
+            const int k = __ffs((int)c) - 1;
+            const double dot = fma(tx, c_sys.tri_rel[k][0], fma(ty, c_sys.tri_rel[k][1], tz * c_sys.tri_rel[k][2]));
+            const double gk = fma(-2.0, fabs(dot), c_sys.tri_len2[k]);
+            if (gk < gain) { gain = gk; bk = k; bsign = dot > 0.0 ? -1.0 : 1.0; }
+        }
+        if (bk >= 0) {
+            cx = fma(bsign, c_sys.tri_rel[bk][0], tx); cy = fma(bsign, c_sys.tri_rel[bk][1], ty); cz = fma(bsign, c_sys.tri_rel[bk][2], tz);
+            o0 = fma(-bsign, c_sys.tri_m[bk][0], n0); o1 = fma(-bsign, c_sys.tri_m[bk][1], n1); o2 = fma(-bsign, c_sys.tri_m[bk][2], n2);
+        }
     }
     if (c_sys.tri_nrel < 0 || fmax(fabs(o0), fmax(fabs(o1), fabs(o2))) > 1.0) {      // the literal search, on the raw Cartesian difference
         const double dx = fma(c_sys.H[0], g0, fma(c_sys.H[1], g1, c_sys.H[2] * g2));
