@@ -122,6 +122,20 @@ int mgpu_get_triclinic_candidates(int32_t *n);
 /* launch shape mgpu_sweep / mgpu_block would use for n_walkers walkers in flight: threads per walker (32, 64 or 128) and
  * walkers per CTA (one CTA per SM); see MGPU_OPT_SWEEP_TEAM */
 int mgpu_get_sweep_shape(int32_t n_walkers, int32_t *threads_per_walker, int32_t *walkers_per_cta);
+/* The two pieces of host-side planning behind the above, as pure functions that need no device (unit tests; neither has a
+ * counterpart in the reference):
+ *  - the launch shape for n_walkers on a GPU with sm_count SMs and warps_per_cta warps per sweep CTA (forced = the
+ *    MGPU_OPT_SWEEP_TEAM value);
+ *  - the triclinic minimum-image plan for a cell matrix (row major, cell vectors = COLUMNS as in geometry_utils.f90:263-280):
+ *    the lattice vectors C m that can beat the fractionally rounded image (n_vectors of them, -1 = too skewed, the literal
+ *    27-image search is kept; vectors[k][3] = C m, coefficients[k][3] = m, one of every +-m pair), faces[k] = the faces of the
+ *    fractional cube (bit d = axis d) a rounded vector has to be near for vector k to matter, thr_hi[3] = high word of the
+ *    |f_d| from which face d counts as near, lut[16] = vectors to try by the set of near faces (bit 3 = far outside the
+ *    cell, bit 31 of an entry = complete search).  Arrays hold up to 14 vectors. */
+int mgpu_plan_sweep_shape(int32_t n_walkers, int32_t sm_count, int32_t warps_per_cta, int32_t forced,
+                          int32_t *threads_per_walker, int32_t *walkers_per_cta);
+int mgpu_plan_triclinic(const double *matrix, int32_t *n_vectors, double *vectors, int32_t *coefficients, int32_t *faces,
+                        int32_t *thr_hi, uint32_t *lut);
 int mgpu_get_thermo(int32_t res, double *beta, double *lambda, double *mu_walker0);
 
 /* ---- per-walker state --------------------------------------------------------------- */

@@ -195,6 +195,79 @@ int rebuild(int first, int n)
     return 0;
 }
 int ensure_clean(int w) { if (g.dirty[w]) return rebuild(w, 1); return 0; }
+// ---- triclinic minimum image: which lattice vectors can beat the fractionally rounded image, and where (host-only math, also
+// behind mgpu_plan_triclinic so that it can be tested without a device) ----
+struct TriPlan {
+    int nrel = 0;                                  // listed vectors (one of every +-m pair); -1 = too skewed: literal 27-image search
+    double rel[MGPU_TRI_MAXREL][3], m[MGPU_TRI_MAXREL][3], len2[MGPU_TRI_MAXREL];
+    int req[MGPU_TRI_MAXREL];                      // faces (bit d = axis d) the rounded vector must be near for vector k to matter
+    double eps[3] = { 0.0, 0.0, 0.0 };             // largest such face distance per axis (fractional units)
+    double safe2 = 1e300;                          // a listed vector can only shorten t when |t|^2 > safe2 = min |C m|^2 / 4
+};
+static void plan_triclinic(const double M[3][3], TriPlan &tp)
+{
+    // lattice vectors that can beat the fractionally rounded image (min_image_r2<true>): m is relevant iff
+    // min over f in [-1/2,1/2]^3 of |C(f+m)|^2 - |C f|^2 = m.G.m - sum_d |(G m)_d| < 0, G = C^T C (C = columns of matrix)
+    double G[3][3];
+    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { G[a][b] = 0.0; for (int i = 0; i < 3; ++i) G[a][b] += M[i][a] * M[i][b]; }
+    int n = 0;
+    for (int a = -3; a <= 3 && n >= 0; ++a) for (int b = -3; b <= 3 && n >= 0; ++b) for (int c = -3; c <= 3; ++c) {
+        if (!a && !b && !c) continue;
+        if (a < 0 || (a == 0 && (b < 0 || (b == 0 && c < 0)))) continue;       // one of every +-m pair
+        const double m[3] = { (double)a, (double)b, (double)c };
+        double Gm[3], mGm = 0.0, s1 = 0.0;
+        for (int d = 0; d < 3; ++d) { Gm[d] = G[d][0] * m[0] + G[d][1] * m[1] + G[d][2] * m[2]; mGm += m[d] * Gm[d]; s1 += std::fabs(Gm[d]); }
+        if (!(mGm < s1 * (1.0 - 1e-13))) continue;
+        if (n == MGPU_TRI_MAXREL || std::abs(a) == 3 || std::abs(b) == 3 || std::abs(c) == 3) { n = -1; break; }   // very skewed cell: literal search
+        for (int i = 0; i < 3; ++i) { tp.rel[n][i] = M[i][0] * m[0] + M[i][1] * m[1] + M[i][2] * m[2]; tp.m[n][i] = m[i]; }
+        tp.len2[n] = tp.rel[n][0] * tp.rel[n][0] + tp.rel[n][1] * tp.rel[n][1] + tp.rel[n][2] * tp.rel[n][2];
+        ++n;
+    }
+    tp.nrel = n;
+    tp.safe2 = 1e300;
+    for (int k = 0; k < n; ++k) tp.safe2 = std::fmin(tp.safe2, 0.25 * tp.len2[k]);
+    // Gate of the candidate search in fractional space.  With f_d = +-(1/2 - u_d), u_d in [0, 1/2]:
+    //   |t|^2 - |t -+ C m|^2 = 2 |f . G m| - m.G.m  <=  s1 - m.G.m - 2 sum_d u_d |(G m)_d|,   s1 = sum_d |(G m)_d|,
+    // so m can only help when sum_d u_d |(G m)_d| < (s1 - m.G.m) / 2 =: D_m, hence u_d < D_m / |(G m)_d| for EVERY axis d
+    // with (G m)_d != 0.  Axes where that bound is below 1/2 are the faces the rounded vector has to be near for m to
+    // matter (req[k], a 3-bit set); eps[d] = the largest such bound of axis d over the listed vectors.
+    tp.eps[0] = tp.eps[1] = tp.eps[2] = 0.0;
+    for (int k = 0; k < n; ++k) {
+        double Gm[3], mGm = 0.0, s1 = 0.0;
+        for (int d = 0; d < 3; ++d) { Gm[d] = G[d][0] * tp.m[k][0] + G[d][1] * tp.m[k][1] + G[d][2] * tp.m[k][2]; mGm += tp.m[k][d] * Gm[d]; s1 += std::fabs(Gm[d]); }
+        tp.req[k] = 0;
+        for (int d = 0; d < 3; ++d) {
+            if (std::fabs(Gm[d]) == 0.0) continue;
+            const double e = 0.5 * (s1 - mGm) / std::fabs(Gm[d]) * (1.0 + 1e-9) + 1e-12;
+            if (e >= 0.5) continue;                                            // no constraint from this axis
+            tp.req[k] |= 1 << d;
+            tp.eps[d] = std::fmax(tp.eps[d], e);
+        }
+    }
+}
+// thr_hi[d]: high word of the |f_d| from which a listed vector can matter near face d; lut[faces]: which listed vectors have to
+// be tried when the lanes of a warp are near the faces in `faces` (bits 0-2 = axes, bit 3 = some |g_d| >= 1.5, i.e. an atom far
+// outside the cell).  Bit k = vector k; bit 31 = the complete search (every vector, then the reference's 27 images if the winner
+// leaves {-1,0,1}^3).  0 = the rounded image is the answer.
+static void plan_triclinic_gate(bool triclinic, int nrel, const int *req, const double *eps, int32_t thr_hi[3], uint32_t lut[16])
+{
+    for (int d = 0; d < 3; ++d) {
+        thr_hi[d] = (triclinic && nrel < 0) ? 0 : 0x7ff00000;      // very skewed cell: always the literal search; else never ...
+        if (triclinic && nrel > 0 && eps[d] > 0.0) {                // ... unless a listed vector can matter near this face
+            const double thr = std::fmax(0.0, 0.5 - eps[d]);
+            uint64_t bits; std::memcpy(&bits, &thr, 8);
+            thr_hi[d] = (int32_t)(bits >> 32);                      // hi(|f|) >= hi(thr) is implied by |f| >= thr: a superset
+        }
+    }
+    for (int f = 0; f < 16; ++f) {
+        uint32_t m = 0;
+        if (triclinic) {
+            if (nrel < 0 || (f & 8)) m = 0x80000000u | ((nrel > 0) ? ((1u << nrel) - 1u) : 0u);
+            else for (int k = 0; k < nrel; ++k) if ((req[k] & f) == req[k]) m |= 1u << k;
+        }
+        lut[f] = m;
+    }
+}
 // One launch of the device-resident drivers for walkers [first, first + n).  Shape = threads per walker x walkers per CTA
 // (one CTA per SM), chosen from the number of walkers in flight so that ONE wave covers every SM when the walkers allow it:
 //   * a team of four warps per walker (up to wgroups / 4 walkers per CTA) while the walkers fit such a wave,
@@ -205,27 +278,28 @@ int ensure_clean(int w) { if (g.dirty[w]) return rebuild(w, 1); return 0; }
 // spread over more GPUs are the case this is for.  MGPU_OPT_SWEEP_TEAM forces the threads per walker
 // (0: 32, 1: 128, 2: 64) with full CTAs.
 struct SweepShape { int nt, per_cta; };
-SweepShape sweep_shape(int n_total)
+// pure: slots = warps of a full sweep CTA, forced = MGPU_OPT_SWEEP_TEAM (also behind mgpu_plan_sweep_shape, for tests without a device)
+static SweepShape plan_sweep_shape(int n_total, int sm_count, int slots, int forced)
 {
-    const int slots = g.wgroups;                                  // warps of a sweep CTA
     int nt = 32;
     const bool can4 = slots * 32 >= MGPU_TEAM, can2 = slots * 32 >= MGPU_TEAM2;
-    if (g.sweep_team == 1 && can4) nt = MGPU_TEAM;
-    else if (g.sweep_team == 2 && can2) nt = MGPU_TEAM2;
-    else if (g.sweep_team < 0) {
-        if (can4 && (long long)n_total <= (long long)g.sm_count * (slots / 4)) nt = MGPU_TEAM;
-        else if (can2 && (long long)n_total <= (long long)g.sm_count * (slots / 2)) nt = MGPU_TEAM2;
+    if (forced == 1 && can4) nt = MGPU_TEAM;
+    else if (forced == 2 && can2) nt = MGPU_TEAM2;
+    else if (forced < 0) {
+        if (can4 && (long long)n_total <= (long long)sm_count * (slots / 4)) nt = MGPU_TEAM;
+        else if (can2 && (long long)n_total <= (long long)sm_count * (slots / 2)) nt = MGPU_TEAM2;
     }
     const int max_per = std::max(1, slots * 32 / nt);
     int per = max_per;
-    if (g.sweep_team < 0) {
-        const long long wave = (long long)max_per * g.sm_count;
+    if (forced < 0) {
+        const long long wave = (long long)max_per * sm_count;
         const long long rounds = (n_total + wave - 1) / wave;
-        per = (int)((n_total + rounds * g.sm_count - 1) / (rounds * g.sm_count));
+        per = (int)((n_total + rounds * sm_count - 1) / (rounds * sm_count));
         per = std::max(1, std::min(per, max_per));
     }
     return { nt, per };
 }
+SweepShape sweep_shape(int n_total) { return plan_sweep_shape(n_total, g.sm_count, g.wgroups, g.sweep_team); }
 // n_total: the walkers in flight together (the call's, when it is cut into slices on several streams)
 void launch_sweep(cudaStream_t st, int first, int n, long long n_steps, int trace_walker, mgpu_step_trace *d_trace, int n_total)
 {
@@ -343,44 +417,14 @@ int mgpu_init(const mgpu_system *sys)
     for (int d = 0; d < 3; ++d) { h.L[d] = M[d][d]; h.invL[d] = 1.0 / M[d][d]; }
     h.tri_nrel = 0; g.tri_listed = 0;
     if (h.triclinic) {
-        // lattice vectors that can beat the fractionally rounded image (min_image_r2<true>): m is relevant iff
-        // min over f in [-1/2,1/2]^3 of |C(f+m)|^2 - |C f|^2 = m.G.m - sum_d |(G m)_d| < 0, G = C^T C (C = columns of matrix)
-        double G[3][3];
-        for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) { G[a][b] = 0.0; for (int i = 0; i < 3; ++i) G[a][b] += M[i][a] * M[i][b]; }
-        int n = 0;
-        for (int a = -3; a <= 3 && n >= 0; ++a) for (int b = -3; b <= 3 && n >= 0; ++b) for (int c = -3; c <= 3; ++c) {
-            if (!a && !b && !c) continue;
-            if (a < 0 || (a == 0 && (b < 0 || (b == 0 && c < 0)))) continue;       // one of every +-m pair
-            const double m[3] = { (double)a, (double)b, (double)c };
-            double Gm[3], mGm = 0.0, s1 = 0.0;
-            for (int d = 0; d < 3; ++d) { Gm[d] = G[d][0] * m[0] + G[d][1] * m[1] + G[d][2] * m[2]; mGm += m[d] * Gm[d]; s1 += std::fabs(Gm[d]); }
-            if (!(mGm < s1 * (1.0 - 1e-13))) continue;
-            if (n == MGPU_TRI_MAXREL || std::abs(a) == 3 || std::abs(b) == 3 || std::abs(c) == 3) { n = -1; break; }   // very skewed cell: literal search
-            for (int i = 0; i < 3; ++i) { h.tri_rel[n][i] = M[i][0] * m[0] + M[i][1] * m[1] + M[i][2] * m[2]; h.tri_m[n][i] = m[i]; }
-            h.tri_len2[n] = h.tri_rel[n][0] * h.tri_rel[n][0] + h.tri_rel[n][1] * h.tri_rel[n][1] + h.tri_rel[n][2] * h.tri_rel[n][2];
-            ++n;
+        TriPlan tp;
+        plan_triclinic(M, tp);
+        h.tri_nrel = tp.nrel; h.tri_safe2 = tp.safe2;
+        for (int k = 0; k < std::max(tp.nrel, 0); ++k) {
+            for (int i = 0; i < 3; ++i) { h.tri_rel[k][i] = tp.rel[k][i]; h.tri_m[k][i] = tp.m[k][i]; }
+            h.tri_len2[k] = tp.len2[k]; g.tri_req[k] = tp.req[k];
         }
-        h.tri_nrel = n;
-        h.tri_safe2 = 1e300;
-        for (int k = 0; k < n; ++k) h.tri_safe2 = std::fmin(h.tri_safe2, 0.25 * h.tri_len2[k]);
-        // Gate of the candidate search in fractional space.  With f_d = +-(1/2 - u_d), u_d in [0, 1/2]:
-        //   |t|^2 - |t -+ C m|^2 = 2 |f . G m| - m.G.m  <=  s1 - m.G.m - 2 sum_d u_d |(G m)_d|,   s1 = sum_d |(G m)_d|,
-        // so m can only help when sum_d u_d |(G m)_d| < (s1 - m.G.m) / 2 =: D_m, hence u_d < D_m / |(G m)_d| for EVERY axis d
-        // with (G m)_d != 0.  Axes where that bound is below 1/2 are the faces the rounded vector has to be near for m to
-        // matter (tri_req[k], a 3-bit set); tri_eps[d] = the largest such bound of axis d over the listed vectors.
-        h.tri_eps[0] = h.tri_eps[1] = h.tri_eps[2] = 0.0;
-        for (int k = 0; k < n; ++k) {
-            double Gm[3], mGm = 0.0, s1 = 0.0;
-            for (int d = 0; d < 3; ++d) { Gm[d] = G[d][0] * h.tri_m[k][0] + G[d][1] * h.tri_m[k][1] + G[d][2] * h.tri_m[k][2]; mGm += h.tri_m[k][d] * Gm[d]; s1 += std::fabs(Gm[d]); }
-            g.tri_req[k] = 0;
-            for (int d = 0; d < 3; ++d) {
-                if (std::fabs(Gm[d]) == 0.0) continue;
-                const double e = 0.5 * (s1 - mGm) / std::fabs(Gm[d]) * (1.0 + 1e-9) + 1e-12;
-                if (e >= 0.5) continue;                                            // no constraint from this axis
-                g.tri_req[k] |= 1 << d;
-                h.tri_eps[d] = std::fmax(h.tri_eps[d], e);
-            }
-        }
+        for (int d = 0; d < 3; ++d) h.tri_eps[d] = tp.eps[d];
     }
     h.tri_lower = (M[0][1] == 0.0 && M[0][2] == 0.0 && M[1][2] == 0.0) ? 1 : 0;
     // ---- Ewald: setup_ewald, prepare_utils.f90:110-226 ----
@@ -408,26 +452,8 @@ int mgpu_init(const mgpu_system *sys)
         const double bound = (double)targets * MGPU_MAX_SITES * qmax * qmax * std::erfc(alpha * r_safe) / r_safe * EPS0_INV_real();
         if (rc <= r_safe && bound < 1.0e-12) { g.tri_listed = h.tri_nrel; h.tri_nrel = 0; }
     }
-    for (int d = 0; d < 3; ++d) {
-        h.tri_thr_hi[d] = (h.triclinic && h.tri_nrel < 0) ? 0 : 0x7ff00000;      // very skewed cell: always the literal search; else never ...
-        if (h.triclinic && h.tri_nrel > 0 && h.tri_eps[d] > 0.0) {                // ... unless a listed vector can matter near this face
-            const double thr = std::fmax(0.0, 0.5 - h.tri_eps[d]);
-            uint64_t bits; std::memcpy(&bits, &thr, 8);
-            h.tri_thr_hi[d] = (int32_t)(bits >> 32);             // hi(|f|) >= hi(thr) is implied by |f| >= thr: a superset
-        }
-    }
+    plan_triclinic_gate(h.triclinic != 0, h.tri_nrel, g.tri_req, h.tri_eps, h.tri_thr_hi, h.tri_lut);
     h.tri_thr_min = std::min(h.tri_thr_hi[0], std::min(h.tri_thr_hi[1], h.tri_thr_hi[2]));
-    // tri_lut[faces]: which listed vectors have to be tried when the lanes of a warp are near the faces in `faces` (bits 0-2 =
-    // axes, bit 3 = some |g_d| >= 1.5, i.e. an atom far outside the cell).  Bit k = vector k; bit 31 = the complete search
-    // (every vector, then the reference's 27 images if the winner leaves {-1,0,1}^3).  0 = the rounded image is the answer.
-    for (int f = 0; f < 16; ++f) {
-        uint32_t m = 0;
-        if (h.triclinic) {
-            if (h.tri_nrel < 0 || (f & 8)) m = 0x80000000u | ((h.tri_nrel > 0) ? ((1u << h.tri_nrel) - 1u) : 0u);
-            else for (int k = 0; k < h.tri_nrel; ++k) if ((g.tri_req[k] & f) == g.tri_req[k]) m |= 1u << k;
-        }
-        h.tri_lut[f] = m;
-    }
     for (int d = 0; d < 3; ++d) h.kmax[d] = f_nint(0.25 + metrics[d] * alpha * fprec / PI);
     h.kmax_max = std::max(h.kmax[0], std::max(h.kmax[1], h.kmax[2]));
     h.eps0_inv_real = EPS0_INV_real(); h.twopi = TWOPI; h.overlap = OVERLAP();
@@ -912,6 +938,34 @@ int mgpu_get_launch_info(int32_t *walkers_per_cta, int64_t *smem_bytes_per_cta, 
     return 0;
 }
 int mgpu_get_triclinic_candidates(int32_t *n) { NEED_READY(); *n = g.h.tri_nrel; return 0; }
+int mgpu_plan_sweep_shape(int32_t n_walkers, int32_t sm_count, int32_t warps_per_cta, int32_t forced,
+                          int32_t *threads_per_walker, int32_t *walkers_per_cta)
+{
+    if (n_walkers < 1 || sm_count < 1 || warps_per_cta < 1) return fail("mgpu_plan_sweep_shape: arguments must be positive");
+    const SweepShape sh = plan_sweep_shape(n_walkers, sm_count, warps_per_cta, forced);
+    if (threads_per_walker) *threads_per_walker = sh.nt;
+    if (walkers_per_cta) *walkers_per_cta = sh.per_cta;
+    return 0;
+}
+int mgpu_plan_triclinic(const double *matrix, int32_t *n_vectors, double *vectors, int32_t *coefficients, int32_t *faces,
+                        int32_t *thr_hi, uint32_t *lut)
+{
+    if (!matrix || !n_vectors) return fail("mgpu_plan_triclinic: null argument");
+    double M[3][3];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) M[i][j] = matrix[i * 3 + j];
+    TriPlan tp;
+    plan_triclinic(M, tp);
+    *n_vectors = tp.nrel;
+    for (int k = 0; k < std::max(tp.nrel, 0); ++k) {
+        for (int i = 0; i < 3; ++i) { if (vectors) vectors[k * 3 + i] = tp.rel[k][i]; if (coefficients) coefficients[k * 3 + i] = (int32_t)tp.m[k][i]; }
+        if (faces) faces[k] = tp.req[k];
+    }
+    int32_t th[3]; uint32_t lt[16];
+    plan_triclinic_gate(true, tp.nrel, tp.req, tp.eps, th, lt);
+    for (int d = 0; d < 3; ++d) if (thr_hi) thr_hi[d] = th[d];
+    for (int f = 0; f < 16; ++f) if (lut) lut[f] = lt[f];
+    return 0;
+}
 int mgpu_get_sweep_shape(int32_t n_walkers, int32_t *threads_per_walker, int32_t *walkers_per_cta)
 {
     NEED_READY();

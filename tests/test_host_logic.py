@@ -262,3 +262,83 @@ def test_topology_data_writer_roundtrips_through_the_data_reader(tmp_path, load)
     atoms = [ln.split() for ln in (tmp_path / "topology.data").read_text().splitlines()[i0:i0 + n_atoms]]
     q = np.array([float(r[3]) for r in atoms])
     assert abs(q.sum() - sum(res.nmol * res.charges.sum() for res in s.residues)) < 1e-5
+
+
+@pytest.mark.parametrize("n,forced,expect", [
+    (5, -1, (128, 1)), (450, -1, (128, 4)), (592, -1, (128, 4)), (593, -1, (64, 5)), (1024, -1, (64, 7)), (1184, -1, (64, 8)),
+    (1185, -1, (32, 9)), (2048, -1, (32, 14)), (2368, -1, (32, 16)), (4096, -1, (32, 14)), (4736, -1, (32, 16)),
+    (16384, -1, (32, 16)), (1000, 0, (32, 16)), (1000, 1, (128, 4)), (1000, 2, (64, 8))])
+def test_sweep_shape_plan(n, forced, expect):
+    """Launch shape of the device-resident drivers (mgpu_plan_sweep_shape = the pure part of mgpu_get_sweep_shape) on a
+    148-SM GPU with 16-warp CTAs: the widest team with which one wave of CTAs holds every walker, the fewest walkers per
+    CTA that need no extra round; forced shapes use full CTAs."""
+    from maniac_b200 import capi
+    L = capi.lib()
+    t, p = C.c_int32(0), C.c_int32(0)
+    assert L.mgpu_plan_sweep_shape(n, 148, 16, forced, C.byref(t), C.byref(p)) == 0
+    assert (t.value, p.value) == expect
+    assert t.value * p.value <= 512
+    if forced < 0:
+        per_wave = 148 * p.value
+        rounds = -(-n // per_wave)
+        full = 148 * (512 // t.value)
+        assert rounds == -(-n // full)                       # no more rounds than full CTAs would need ...
+        assert p.value == 1 or 148 * (p.value - 1) * rounds < n     # ... and one walker less per CTA would need one more
+
+
+def _tri_plan(M):
+    from maniac_b200 import capi
+    L = capi.lib()
+    n = C.c_int32(0)
+    vec = np.zeros((14, 3)); coef = np.zeros((14, 3), dtype=np.int32); faces = np.zeros(14, dtype=np.int32)
+    thr = np.zeros(3, dtype=np.int32); lut = np.zeros(16, dtype=np.uint32)
+    rc = L.mgpu_plan_triclinic(np.ascontiguousarray(M, dtype=np.float64).ctypes.data_as(C.POINTER(C.c_double)), C.byref(n),
+                               vec.ctypes.data_as(C.POINTER(C.c_double)), coef.ctypes.data_as(C.POINTER(C.c_int32)),
+                               faces.ctypes.data_as(C.POINTER(C.c_int32)), thr.ctypes.data_as(C.POINTER(C.c_int32)),
+                               lut.ctypes.data_as(C.POINTER(C.c_uint32)))
+    assert rc == 0
+    return n.value, vec, coef, faces, thr, lut
+
+
+@pytest.mark.parametrize("M", [
+    [[68.04, 0, 0], [3.0, 68.04, 0], [0, 0, 68.04]],                      # configs[4]: xy tilt, columns convention
+    [[30.0, 0, 0], [4.0, 28.0, 0], [-3.0, 5.0, 26.0]],                    # three tilts
+    [[30.0, 2.0, 1.0], [4.0, 28.0, -3.0], [-3.0, 5.0, 26.0]],             # not triangular
+    [[30.0, 0, 0], [14.9, 28.0, 0], [14.9, 13.9, 26.0]]])                 # LAMMPS' maximal skew
+def test_triclinic_plan_reproduces_the_27_image_search(M):
+    """The triclinic minimum image of the framework passes (min_image_frac_fast / _slow), replayed in numpy from the plan
+    mgpu_plan_triclinic hands the kernels -- rounded image, face test on the high words, tri_lut -> vectors to try, the
+    reference's 27-image search when the winning shift leaves {-1,0,1}^3 -- against the reference's definition: the
+    minimum over the 27 shifts of the raw difference vector (geometry_utils.f90:263-280), on random vectors."""
+    M = np.array(M, dtype=np.float64)
+    n, vec, coef, faces, thr_hi, lut = _tri_plan(M)
+    rng = np.random.default_rng(7)
+    g = rng.uniform(-1.0, 1.0, (200_000, 3))                              # differences of two points of the cell
+    shifts = np.array([[i, j, k] for i in (-1, 0, 1) for j in (-1, 0, 1) for k in (-1, 0, 1)], dtype=np.float64)
+    d = g @ M.T                                                           # raw Cartesian difference, cell vectors = columns
+    ref = np.min(((d[:, None, :] + (shifts @ M.T)[None, :, :]) ** 2).sum(-1), axis=1)
+    if n < 0:
+        assert (lut >> 31).all()                                          # too skewed: every pair takes the literal search
+        return
+    nn = np.rint(g); f = g - nn; t = f @ M.T
+    hi = (np.abs(f).view(np.int64) >> 32).astype(np.int64)
+    fb = ((hi[:, 0] >= thr_hi[0]) * 1 + (hi[:, 1] >= thr_hi[1]) * 2 + (hi[:, 2] >= thr_hi[2]) * 4).astype(int)
+    cand = lut[fb]
+    t2 = (t * t).sum(1)
+    best, shift = t2.copy(), np.zeros_like(t)
+    for k in range(n):
+        use = ((cand >> k) & 1).astype(bool)
+        dot = t @ vec[k]
+        gk = vec[k] @ vec[k] - 2 * np.abs(dot)
+        better = use & (t2 + gk < best)
+        sg = np.where(dot > 0, -1.0, 1.0)
+        best = np.where(better, t2 + gk, best)
+        shift = np.where(better[:, None], sg[:, None] * coef[k][None, :], shift)
+    o = nn - shift
+    fallback = np.abs(o).max(axis=1) > 1.0                                # beyond the reference's 27 images: literal search
+    got = np.where(fallback, ref, best)
+    assert np.max(np.abs(got - ref)) < 1e-9
+    assert fallback.mean() < 0.05
+    # the gate is doing something: in the tilted 68 A cell only a few per cent of the pairs look at any vector
+    if abs(M[0][0] - 68.04) < 1e-9:
+        assert n == 6 and (cand != 0).mean() < 0.12 and sorted(np.unique(faces[:n])) == [1, 2, 5, 6]
