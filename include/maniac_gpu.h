@@ -136,6 +136,9 @@ int mgpu_plan_sweep_shape(int32_t n_walkers, int32_t sm_count, int32_t warps_per
                           int32_t *threads_per_walker, int32_t *walkers_per_cta);
 int mgpu_plan_triclinic(const double *matrix, int32_t *n_vectors, double *vectors, int32_t *coefficients, int32_t *faces,
                         int32_t *thr_hi, uint32_t *lut);
+/*  - the order in which mgpu_init stores the static framework atoms (xyz[n_atoms][3] Cartesian, lo = cell origin): order[k] =
+ *    index of the atom stored k-th; columns[3] = bins per axis when the cell's plan leaves an axis free (1 = not binned). */
+int mgpu_plan_framework_order(const double *matrix, const double *lo, int32_t n_atoms, const double *xyz, int32_t *order, int32_t *columns);
 int mgpu_get_thermo(int32_t res, double *beta, double *lambda, double *mu_walker0);
 
 /* ---- per-walker state --------------------------------------------------------------- */

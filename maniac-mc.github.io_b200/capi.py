@@ -61,6 +61,7 @@ SIGNATURES = {
     "mgpu_get_sweep_shape": (C.c_int, [C.c_int32, _pi, _pi]),
     "mgpu_plan_sweep_shape": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _pi, _pi]),
     "mgpu_plan_triclinic": (C.c_int, [_pd, _pi, _pd, _pi, _pi, _pi, C.POINTER(C.c_uint32)]),
+    "mgpu_plan_framework_order": (C.c_int, [_pd, _pd, C.c_int32, _pd, _pi, _pi]),
     "mgpu_get_thermo": (C.c_int, [I, _pd, _pd, _pd]),
     "mgpu_set_molecule": (C.c_int, [I, I, I, _pd, _pd]),
     "mgpu_get_molecule": (C.c_int, [I, I, I, _pd, _pd]),

@@ -268,6 +268,111 @@ static void plan_triclinic_gate(bool triclinic, int nrel, const int *req, const 
         lut[f] = m;
     }
 }
+// prepare_simulation_box (geometry_utils.f90:148-200,293-361): cell edge lengths (cell vectors = COLUMNS of the matrix), volume
+// and the reference's "reciprocal" = transposed inverse, by the adjugate as the reference computes it.  Returns 1 when the
+// determinant is degenerate (the reference's own check).
+static int box_geometry(const double M[3][3], double metrics[3], double hinv[9], double *volume)
+{
+    auto colv = [&](int j, double v[3]) { for (int i = 0; i < 3; ++i) v[i] = M[i][j]; };
+    auto cross = [](const double a[3], const double b[3], double c[3]) {
+        c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0]; };
+    double a[3], b[3], c[3], bxc[3];
+    colv(0, a); colv(1, b); colv(2, c);
+    for (int j = 0; j < 3; ++j) { double v[3]; colv(j, v); metrics[j] = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+    cross(b, c, bxc);
+    *volume = std::fabs(a[0] * bxc[0] + a[1] * bxc[1] + a[2] * bxc[2]);
+    double adj[3][3], v1[3], v2[3], cr[3];
+    colv(1, v1); colv(2, v2); cross(v1, v2, cr); for (int i = 0; i < 3; ++i) adj[i][0] = cr[i];
+    colv(2, v1); colv(0, v2); cross(v1, v2, cr); for (int i = 0; i < 3; ++i) adj[i][1] = cr[i];
+    colv(0, v1); colv(1, v2); cross(v1, v2, cr); for (int i = 0; i < 3; ++i) adj[i][2] = cr[i];
+    colv(0, v1);
+    const double det = v1[0] * adj[0][0] + v1[1] * adj[1][0] + v1[2] * adj[2][0];
+    if (std::fabs(det) < 1.0) return 1;
+    const double rcp = 1.0 / det;
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) hinv[i * 3 + j] = rcp * adj[i][j];
+    return 0;
+}
+// Order of the static framework atoms (host-only; also behind mgpu_plan_framework_order for tests without a device).
+// Default: along a space-filling curve of the fractional coordinates, so that the 32 consecutive atoms a warp takes per
+// iteration sit in one small region and "beyond the LJ cutoff" / "no lattice vector can help" become warp-uniform facts.
+// hinv = the reference's "reciprocal" (transposed inverse: f_d = sum_j hinv[j*3+d] r_j); metrics = cell edge lengths;
+// req / nrel = the triclinic plan (columns only when `columns` is set); cols_out = bins per axis (1 = not binned).
+static void order_framework(int n_host, const double *xyz, const double lo[3], const double hinv[9], const double metrics[3],
+                            bool columns, const int *req, int nrel, std::vector<int> &order, int cols_out[3])
+{
+#if MGPU_HILBERT
+    // Hilbert curve (Skilling's transpose form, 10 bits per axis): unlike the Z curve it has no jumps, so EVERY run of 32
+    // consecutive atoms is one compact cluster -- with Z order a run that straddles a jump of the curve is two clusters
+    auto curve_key = [](uint32_t x, uint32_t y, uint32_t z) {
+        uint32_t X[3] = { x & 1023u, y & 1023u, z & 1023u };
+        const uint32_t Mb = 1u << 9;
+        for (uint32_t Q = Mb; Q > 1; Q >>= 1) {
+            const uint32_t P = Q - 1;
+            for (int i = 0; i < 3; ++i) {
+                if (X[i] & Q) X[0] ^= P;
+                else { const uint32_t t = (X[0] ^ X[i]) & P; X[0] ^= t; X[i] ^= t; }
+            }
+        }
+        for (int i = 1; i < 3; ++i) X[i] ^= X[i - 1];
+        uint32_t t = 0;
+        for (uint32_t Q = Mb; Q > 1; Q >>= 1) if (X[2] & Q) t ^= Q - 1;
+        for (int i = 0; i < 3; ++i) X[i] ^= t;
+        uint32_t k = 0;
+        for (int b = 9; b >= 0; --b) for (int i = 0; i < 3; ++i) k = (k << 1) | ((X[i] >> b) & 1u);
+        return k;
+    };
+#else
+    auto spread = [](uint32_t v) { v &= 1023u; v = (v | (v << 16)) & 0x030000FFu; v = (v | (v << 8)) & 0x0300F00Fu; v = (v | (v << 4)) & 0x030C30C3u; v = (v | (v << 2)) & 0x09249249u; return v; };
+    auto curve_key = [&](uint32_t x, uint32_t y, uint32_t z) { return spread(x) | (spread(y) << 1) | (spread(z) << 2); };
+#endif
+    // Triclinic cells whose listed lattice vectors leave one axis free of single-face vectors (e.g. an xy tilt: the vectors
+    // that matter near ONE face are +-c1 and +-c2, none for the z faces): COLUMNS instead of compact clusters -- thin
+    // (about 4 A) along the axes whose faces matter, long along the free axis.  A warp iteration takes the candidate search
+    // of the triclinic minimum image when any of its 32 atoms is within ~3 A of such a face: simulated on configs[4], 32 % of
+    // the iterations for Hilbert runs, 20 % for 16 x 16 columns (and 17 % instead of 13 % of them reach into the LJ cutoff
+    // sphere, which costs less than it saves).
+    int thin[3] = { 0, 0, 0 }, n_thin = 0, cols[3] = { 1, 1, 1 };
+    if (columns && nrel > 0 && MGPU_TRI_COLUMNS) {
+        for (int k2 = 0; k2 < nrel; ++k2) for (int d = 0; d < 3; ++d) if (req[k2] == (1 << d)) thin[d] = 1;
+        n_thin = thin[0] + thin[1] + thin[2];
+        if (n_thin == 1 || n_thin == 2) {
+            long long ncol = 1;
+            for (int d = 0; d < 3; ++d) if (thin[d]) { cols[d] = std::max(1, (int)std::lround(metrics[d] / 4.25)); ncol *= cols[d]; }
+            while (ncol * 32 > n_host) {                       // keep at least one warp iteration per column
+                ncol = 1;
+                for (int d = 0; d < 3; ++d) if (thin[d]) { cols[d] = std::max(1, cols[d] - 1); ncol *= cols[d]; }
+                if (ncol == 1) break;
+            }
+        } else n_thin = 0;
+    }
+    std::vector<uint64_t> key64(n_host);
+    for (int k = 0; k < n_host; ++k) {
+        const double r[3] = { xyz[(size_t)k * 3] - lo[0], xyz[(size_t)k * 3 + 1] - lo[1], xyz[(size_t)k * 3 + 2] - lo[2] };
+        uint32_t q[3];
+        uint64_t col = 0;
+        for (int d = 0; d < 3; ++d) {
+            double f = hinv[0 * 3 + d] * r[0] + hinv[1 * 3 + d] * r[1] + hinv[2 * 3 + d] * r[2];
+            f -= std::floor(f);
+            q[d] = (uint32_t)std::fmin(1023.0, f * 1024.0);
+            if (n_thin && thin[d]) {
+                int b = std::min(cols[d] - 1, (int)(f * cols[d]));
+                if (col & 1) b = cols[d] - 1 - b;              // serpentine: neighbouring columns follow each other
+                col = col * cols[d] + b;
+                q[d] = 0;                                      // the curve only runs along the free axes inside a column
+            }
+        }
+        uint32_t ck = curve_key(q[0], q[1], q[2]);
+        if (n_thin) {                                          // Z order of the free coordinates (monotone along a single free axis)
+            auto spread3 = [](uint32_t v) { v &= 1023u; v = (v | (v << 16)) & 0x030000FFu; v = (v | (v << 8)) & 0x0300F00Fu; v = (v | (v << 4)) & 0x030C30C3u; v = (v | (v << 2)) & 0x09249249u; return v; };
+            ck = spread3(q[0]) | (spread3(q[1]) << 1) | (spread3(q[2]) << 2);
+        }
+        key64[k] = (col << 32) | ck;
+    }
+    order.resize(n_host);
+    for (int k = 0; k < n_host; ++k) order[k] = k;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key64[a] < key64[b]; });
+    for (int d = 0; d < 3; ++d) cols_out[d] = n_thin ? cols[d] : 1;
+}
 // One launch of the device-resident drivers for walkers [first, first + n).  Shape = threads per walker x walkers per CTA
 // (one CTA per SM), chosen from the number of walkers in flight so that ONE wave covers every SM when the walkers allow it:
 //   * a team of four warps per walker (up to wgroups / 4 walkers per CTA) while the walkers fit such a wave,
@@ -394,26 +499,8 @@ int mgpu_init(const mgpu_system *sys)
         double mx = 0.0; for (double v : od) mx = std::fmax(mx, std::fabs(v));
         h.triclinic = mx > MGPU_ERR_TOL;
     }
-    auto colv = [&](int j, double v[3]) { for (int i = 0; i < 3; ++i) v[i] = M[i][j]; };
-    auto cross = [](const double a[3], const double b[3], double c[3]) {
-        c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0]; };
     double metrics[3];
-    {
-        double a[3], b[3], c[3], bxc[3];
-        colv(0, a); colv(1, b); colv(2, c);
-        for (int j = 0; j < 3; ++j) { double v[3]; colv(j, v); metrics[j] = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
-        cross(b, c, bxc);
-        h.volume = std::fabs(a[0] * bxc[0] + a[1] * bxc[1] + a[2] * bxc[2]);
-        double adj[3][3], v1[3], v2[3], cr[3];
-        colv(1, v1); colv(2, v2); cross(v1, v2, cr); for (int i = 0; i < 3; ++i) adj[i][0] = cr[i];
-        colv(2, v1); colv(0, v2); cross(v1, v2, cr); for (int i = 0; i < 3; ++i) adj[i][1] = cr[i];
-        colv(0, v1); colv(1, v2); cross(v1, v2, cr); for (int i = 0; i < 3; ++i) adj[i][2] = cr[i];
-        colv(0, v1);
-        const double det = v1[0] * adj[0][0] + v1[1] * adj[1][0] + v1[2] * adj[2][0];
-        if (std::fabs(det) < 1.0) return fail("Error: Determinant fell into denormal/underflow range");
-        const double rcp = 1.0 / det;
-        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) h.Hinv[i * 3 + j] = rcp * adj[i][j];
-    }
+    if (box_geometry(M, metrics, h.Hinv, &h.volume)) return fail("Error: Determinant fell into denormal/underflow range");
     for (int d = 0; d < 3; ++d) { h.L[d] = M[d][d]; h.invL[d] = 1.0 / M[d][d]; }
     h.tri_nrel = 0; g.tri_listed = 0;
     if (h.triclinic) {
@@ -551,85 +638,16 @@ int mgpu_init(const mgpu_system *sys)
         }
     }
     if (n_host > 64) {
-        // Static framework atoms in Morton (Z-curve) order of their fractional coordinates: the 32 consecutive atoms a warp
-        // takes per iteration then sit in one small region, so "beyond the LJ cutoff" / "no lattice candidate can help"
-        // become warp-uniform facts that whole iterations can act on (triclinic passes).  Sums are order-independent
-        // up to rounding; the host-host constant and S_host use the same permuted arrays.
-        std::vector<std::pair<uint32_t, int>> key(n_host);
-#if MGPU_HILBERT
-        // Hilbert curve (Skilling's transpose form, 10 bits per axis): unlike the Z curve it has no jumps, so EVERY run of 32
-        // consecutive atoms is one compact cluster -- with Z order 76 % of the warp-level pair evaluations of configs[4] had some
-        // lane near a face of the fractional cube (the rare path of min_image_frac), because a run that straddles a jump of
-        // the curve is two clusters
-        auto curve_key = [](uint32_t x, uint32_t y, uint32_t z) {
-            uint32_t X[3] = { x & 1023u, y & 1023u, z & 1023u };
-            const uint32_t Mb = 1u << 9;
-            for (uint32_t Q = Mb; Q > 1; Q >>= 1) {
-                const uint32_t P = Q - 1;
-                for (int i = 0; i < 3; ++i) {
-                    if (X[i] & Q) X[0] ^= P;
-                    else { const uint32_t t = (X[0] ^ X[i]) & P; X[0] ^= t; X[i] ^= t; }
-                }
-            }
-            for (int i = 1; i < 3; ++i) X[i] ^= X[i - 1];
-            uint32_t t = 0;
-            for (uint32_t Q = Mb; Q > 1; Q >>= 1) if (X[2] & Q) t ^= Q - 1;
-            for (int i = 0; i < 3; ++i) X[i] ^= t;
-            uint32_t k = 0;
-            for (int b = 9; b >= 0; --b) for (int i = 0; i < 3; ++i) k = (k << 1) | ((X[i] >> b) & 1u);
-            return k;
-        };
-#else
-        auto spread = [](uint32_t v) { v &= 1023u; v = (v | (v << 16)) & 0x030000FFu; v = (v | (v << 8)) & 0x0300F00Fu; v = (v | (v << 4)) & 0x030C30C3u; v = (v | (v << 2)) & 0x09249249u; return v; };
-        auto curve_key = [&](uint32_t x, uint32_t y, uint32_t z) { return spread(x) | (spread(y) << 1) | (spread(z) << 2); };
-#endif
-        // Triclinic cells whose listed lattice vectors leave one axis free of single-face vectors (e.g. an xy tilt: the vectors
-        // that matter near ONE face are +-c1 and +-c2, none for the z faces): COLUMNS instead of compact clusters -- thin
-        // (about 4 A) along the axes whose faces matter, long along the free axis.  A warp iteration takes the candidate search
-        // of min_image_frac when any of its 32 atoms is within ~3 A of such a face: simulated on configs[4], 32 % of the
-        // iterations for Hilbert runs, 20 % for 16 x 16 columns (and 17 % instead of 13 % of them reach into the LJ cutoff
-        // sphere, which costs less than it saves).
-        int thin[3] = { 0, 0, 0 }, n_thin = 0, cols[3] = { 1, 1, 1 };
-        if (h.triclinic && h.tri_nrel > 0 && MGPU_TRI_COLUMNS) {
-            for (int k2 = 0; k2 < h.tri_nrel; ++k2) for (int d = 0; d < 3; ++d) if (g.tri_req[k2] == (1 << d)) thin[d] = 1;
-            n_thin = thin[0] + thin[1] + thin[2];
-            if (n_thin == 1 || n_thin == 2) {
-                long long ncol = 1;
-                for (int d = 0; d < 3; ++d) if (thin[d]) { cols[d] = std::max(1, (int)std::lround(metrics[d] / 4.25)); ncol *= cols[d]; }
-                while (ncol * 32 > n_host) {                       // keep at least one warp iteration per column
-                    ncol = 1;
-                    for (int d = 0; d < 3; ++d) if (thin[d]) { cols[d] = std::max(1, cols[d] - 1); ncol *= cols[d]; }
-                    if (ncol == 1) break;
-                }
-            } else n_thin = 0;
-        }
-        std::vector<uint64_t> key64(n_host);
-        for (int k = 0; k < n_host; ++k) {
-            const double r[3] = { hx[k].x - h.lo[0], hx[k].y - h.lo[1], hx[k].z - h.lo[2] };
-            uint32_t q[3];
-            uint64_t col = 0;
-            for (int d = 0; d < 3; ++d) {
-                double f = h.Hinv[0 * 3 + d] * r[0] + h.Hinv[1 * 3 + d] * r[1] + h.Hinv[2 * 3 + d] * r[2];   // Hinv = transposed inverse
-                f -= std::floor(f);
-                q[d] = (uint32_t)std::fmin(1023.0, f * 1024.0);
-                if (n_thin && thin[d]) {
-                    int b = std::min(cols[d] - 1, (int)(f * cols[d]));
-                    if (col & 1) b = cols[d] - 1 - b;              // serpentine: neighbouring columns follow each other
-                    col = col * cols[d] + b;
-                    q[d] = 0;                                      // the curve only runs along the free axes inside a column
-                }
-            }
-            uint32_t ck = curve_key(q[0], q[1], q[2]);
-            if (n_thin) {                                          // Z order of the free coordinates (monotone along a single free axis)
-                auto spread3 = [](uint32_t v) { v &= 1023u; v = (v | (v << 16)) & 0x030000FFu; v = (v | (v << 8)) & 0x0300F00Fu; v = (v | (v << 4)) & 0x030C30C3u; v = (v | (v << 2)) & 0x09249249u; return v; };
-                ck = spread3(q[0]) | (spread3(q[1]) << 1) | (spread3(q[2]) << 2);
-            }
-            key64[k] = (col << 32) | ck;
-            key[k] = { 0u, k };
-        }
-        std::stable_sort(key.begin(), key.end(), [&](const std::pair<uint32_t, int> &a, const std::pair<uint32_t, int> &b) { return key64[a.second] < key64[b.second]; });
+        // Static framework atoms in an order that makes the 32 consecutive atoms of a warp iteration one small region (see
+        // order_framework): sums are order-independent up to rounding; the host-host constant and S_host use the same
+        // permuted arrays.
+        std::vector<double> xyz((size_t)n_host * 3);
+        for (int k = 0; k < n_host; ++k) { xyz[(size_t)k * 3] = hx[k].x; xyz[(size_t)k * 3 + 1] = hx[k].y; xyz[(size_t)k * 3 + 2] = hx[k].z; }
+        std::vector<int> order;
+        int cols[3];
+        order_framework(n_host, xyz.data(), h.lo, h.Hinv, metrics, h.triclinic && h.tri_nrel > 0, g.tri_req, h.tri_nrel, order, cols);
         std::vector<double4> hx2(n_host); std::vector<int32_t> ht2(n_host), hm2(n_host); std::vector<double> hq2(n_host);
-        for (int k = 0; k < n_host; ++k) { const int o = key[k].second; hx2[k] = hx[o]; ht2[k] = ht[o]; hm2[k] = hm[o]; hq2[k] = hq[o]; }
+        for (int k = 0; k < n_host; ++k) { const int o = order[k]; hx2[k] = hx[o]; ht2[k] = ht[o]; hm2[k] = hm[o]; hq2[k] = hq[o]; }
         hx.swap(hx2); ht.swap(ht2); hm.swap(hm2); hq.swap(hq2);
     }
     double4 *d_hx; int32_t *d_ht, *d_hm; double *d_eps, *d_sig, *d_ffW, *d_Shost, *d_hq, *d_ctab; int32_t *d_kx, *d_ky, *d_kz;
@@ -945,6 +963,23 @@ int mgpu_plan_sweep_shape(int32_t n_walkers, int32_t sm_count, int32_t warps_per
     const SweepShape sh = plan_sweep_shape(n_walkers, sm_count, warps_per_cta, forced);
     if (threads_per_walker) *threads_per_walker = sh.nt;
     if (walkers_per_cta) *walkers_per_cta = sh.per_cta;
+    return 0;
+}
+int mgpu_plan_framework_order(const double *matrix, const double *lo, int32_t n_atoms, const double *xyz, int32_t *order, int32_t *columns)
+{
+    if (!matrix || !lo || !xyz || !order || n_atoms < 1) return fail("mgpu_plan_framework_order: bad argument");
+    double M[3][3], metrics[3], hinv[9], vol;
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) M[i][j] = matrix[i * 3 + j];
+    if (box_geometry(M, metrics, hinv, &vol)) return fail("Error: Determinant fell into denormal/underflow range");
+    const double od[6] = { M[0][1], M[0][2], M[1][0], M[1][2], M[2][0], M[2][1] };
+    double mx = 0.0; for (double v : od) mx = std::fmax(mx, std::fabs(v));
+    TriPlan tp;
+    if (mx > MGPU_ERR_TOL) plan_triclinic(M, tp);
+    std::vector<int> ord;
+    int cols[3];
+    order_framework(n_atoms, xyz, lo, hinv, metrics, mx > MGPU_ERR_TOL && tp.nrel > 0, tp.req, tp.nrel, ord, cols);
+    for (int k = 0; k < n_atoms; ++k) order[k] = ord[k];
+    if (columns) for (int d = 0; d < 3; ++d) columns[d] = cols[d];
     return 0;
 }
 int mgpu_plan_triclinic(const double *matrix, int32_t *n_vectors, double *vectors, int32_t *coefficients, int32_t *faces,

@@ -342,3 +342,54 @@ def test_triclinic_plan_reproduces_the_27_image_search(M):
     # the gate is doing something: in the tilted 68 A cell only a few per cent of the pairs look at any vector
     if abs(M[0][0] - 68.04) < 1e-9:
         assert n == 6 and (cand != 0).mean() < 0.12 and sorted(np.unique(faces[:n])) == [1, 2, 5, 6]
+
+
+def _framework_order(matrix, lo, pos):
+    from maniac_b200 import capi
+    L = capi.lib()
+    pos = np.ascontiguousarray(pos, dtype=np.float64)
+    order = np.zeros(len(pos), dtype=np.int32); cols = np.zeros(3, dtype=np.int32)
+    pd, pi = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    rc = L.mgpu_plan_framework_order(np.ascontiguousarray(matrix, dtype=np.float64).ctypes.data_as(pd),
+                                     np.ascontiguousarray(lo, dtype=np.float64).ctypes.data_as(pd), len(pos),
+                                     pos.ctypes.data_as(pd), order.ctypes.data_as(pi), cols.ctypes.data_as(pi))
+    assert rc == 0
+    return order, cols
+
+
+def test_framework_order_clusters_and_columns(load):
+    """mgpu_init's order of the static framework atoms (mgpu_plan_framework_order): a permutation; in an orthorhombic cell the
+    32 atoms of a warp iteration form a compact cluster (Hilbert curve); in the tilted 68 A cell of configs[4] the atoms are
+    binned into 16 x 16 columns along the free z axis, and fewer warp iterations have an atom near a face that matters
+    (within tri_eps of |f_d| = 1/2 for d = x, y) than with compact clusters."""
+    from maniac_b200.workloads import mixture_supercell
+    base = load("zif8_co2_widom")
+    zif = [r for r in base.residues if not r.active][0]
+    pos0 = np.asarray(zif.com[0]) + np.asarray(zif.offset[0])
+    order0, cols0 = _framework_order(base.matrix, base.lo, pos0)
+    assert sorted(order0) == list(range(len(pos0))) and list(cols0) == [1, 1, 1]
+    cl = pos0[order0][: len(pos0) // 32 * 32].reshape(-1, 32, 3)
+    ext = (cl.max(axis=1) - cl.min(axis=1))
+    assert ext.mean() < 12.0                                   # 2208 atoms in (34 A)^3: a 32-atom box is ~8 A per edge
+
+    sm = mixture_supercell(base, reps=(2, 2, 2), tilt_xy=3.0, n_co2=4, n_n2=4)
+    fw = [r for r in sm.residues if not r.active][0]
+    pos = np.asarray(fw.com[0]) + np.asarray(fw.offset[0])
+    order, cols = _framework_order(sm.matrix, sm.lo, pos)
+    assert sorted(order) == list(range(len(pos))) and list(cols) == [16, 16, 1]
+    Cm = np.asarray(sm.matrix); f = (pos - np.asarray(sm.lo)) @ np.linalg.inv(Cm).T
+    f -= np.floor(f)
+    n, _, _, faces, thr_hi, _ = _tri_plan(Cm)
+    thr = 0.478                                                # 1/2 - tri_eps of this cell (test_triclinic_plan...)
+    rng = np.random.default_rng(3)
+
+    def near_fraction(o):
+        ff = f[o][: len(o) // 32 * 32]
+        hits = tot = 0
+        for _ in range(60):
+            gg = ff - rng.random(3); gg -= np.rint(gg)
+            near = (np.abs(gg[:, 0]) >= thr) | (np.abs(gg[:, 1]) >= thr)
+            hits += near.reshape(-1, 32).any(axis=1).sum(); tot += len(ff) // 32
+        return hits / tot
+    plain, _ = _framework_order(np.diag(np.diag(Cm)), sm.lo, pos)      # the same atoms ordered as in an untilted cell: compact clusters
+    assert near_fraction(order) < 0.24 < 0.27 < near_fraction(plain)
