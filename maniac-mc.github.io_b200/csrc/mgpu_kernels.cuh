@@ -4,19 +4,21 @@
 //                       new geometry in one pass over the targets) vs the host framework
 //                       and the walker's guests            (pairwise_energy_utils.f90:21-179,
 //                                                           geometry_utils.f90:210-284)
-// K2  kspace            1-D phase tables, dS(k), S_trial = S + dS, sum_k ffW |S_trial|^2
-//                                                          (ewald_phase.f90:205-312,
-//                                                           ewald_energy.f90:64-164)
+// K2  fill_trial_tables 1-D phase tables of the trial's charged atoms (charge folded in), dS(k),
+//     kspace_entries    S_trial = S + dS, sum_k ffW |S_trial|^2     (ewald_phase.f90:205-312,
+//                                                                   ewald_energy.f90:64-164)
 // K3  k_widom_batch     one warp per test insertion, K1 + K2 read-only
 // K4  k_total_energy    full recompute (energy_utils.f90:22-134, ewald_energy.f90:20-58)
 //     k_sweep           device-resident move drivers + Metropolis (translation.f90,
 //                       rotation.f90, creation.f90, deletion.f90, widom.f90,
-//                       monte_carlo.f90:50-99), ONE WARP PER WALKER
+//                       monte_carlo.f90:50-99), ONE WARP PER WALKER (or a team of two / four
+//                       warps when a launch has few walkers), the walkers of a CTA in phase
 //     k_trial           host-driven trials (compute_old/new_energy of monte_carlo_utils.f90),
 //                       one warp per task for large batches, one CTA per task otherwise
 //
 // Every energy routine is written once for a cooperating "group" of NT threads
-// (NT = 32: a warp, synchronised with __syncwarp; NT = MGPU_BLOCK: a CTA, __syncthreads).
+// (NT = 32: a warp, synchronised with __syncwarp; NT = 64 / 128: a team of warps with its own
+// named barrier; NT = MGPU_BLOCK: a CTA, __syncthreads).
 //
 // All arithmetic is IEEE binary64.  No tensor cores: nothing here is a dense contraction.
 // The per-pair erfc(alpha r)/r comes from a piecewise degree-6 polynomial in r^2 staged in
@@ -49,9 +51,9 @@ __constant__ DevSys c_sys;
 #ifndef MGPU_ALIGN_GROUPS
 #define MGPU_ALIGN_GROUPS 1               // phase-alignment groups per CTA (warp id mod this): 1 = every warp of the CTA meets at the barriers (measured best, r03c); 4 = the warps of one SM sub-partition (round 1); 8 = pairs
 #endif
-#ifndef MGPU_SWP_COUL
-#define MGPU_SWP_COUL 0                   // hand-pipelined Coulomb-only framework pass (HostPass::run_pipelined)
-#endif
+// (A hand-pipelined Coulomb-only framework pass -- geometry of the next atom and table part of the current one as two streams of
+// one loop body -- was measured in round 2 (r03a): ptxas serialises the three table chains on eight reused registers, no gain;
+// removed.)
 #ifndef MGPU_SCREEN_NOTHING
 #define MGPU_SCREEN_NOTHING 1
 #endif
@@ -68,9 +70,6 @@ __constant__ DevSys c_sys;
 // (N2's centre site: an LJ term with A = B = 0), removes the "nothing"-list screen (those pairs are simply evaluated).
 #ifndef MGPU_TRI_MERGED
 #define MGPU_TRI_MERGED 1
-#endif
-#ifndef MGPU_PF_KSPACE
-#define MGPU_PF_KSPACE 1
 #endif
 #ifndef MGPU_BLOCK
 #define MGPU_BLOCK 256                    // CTA-per-task kernels (NT = MGPU_BLOCK)
@@ -767,87 +766,6 @@ struct HostPass {
         e_lj_io = e_lj + e_x.x; e_c_io = e_c_io + e_c; pc_io = pc;
     }
 
-    // Coulomb-only framework pass (MODE 2, orthorhombic cell, one framework atom per thread and iteration), software
-    // pipelined BY HAND across iterations: the geometry of the NEXT atom (27 back-to-back FP64 instructions that saturate
-    // the pipe) and the table part of the CURRENT one (index -> LDS.128 gather -> conversions -> Horner chain: latency
-    // bound, r02k capture: 70-80 % of the samples on those lines wait for shared memory) are independent instruction
-    // streams inside one loop body, so the in-order issue of a warp always has one of them ready.  In run() / block()
-    // the two sit behind each other and the compiler keeps them there.  Same arithmetic per pair, same order of the sums.
-    __device__ __forceinline__ void run_pipelined(int t0, int stride, double &e_c_io, PairCount &pc_io) const
-    {
-        const double2 *ctab = smem_ctab<REP>();
-        const double2 *__restrict__ hxy = c_sys.host_xy;
-        const double2 *__restrict__ hzq = c_sys.host_zq;
-        double acc = 0.0;
-        const int n = c_sys.n_host;
-        int jfirst = 0x7fffffff, jlast = -1;                 // iterations that saw a pair below the table start (r < 1 A)
-        if (t0 < n) {
-            // the loop runs one round more than there are atoms: round k does the geometry of atom k and the table part of
-            // atom k - 1 (round 0: a dummy "atom" beyond every range, which reads the all-zero row)
-            double s_cur[N], q_cur = 0.0;
-#pragma unroll
-            for (int i = 0; i < N; ++i) s_cur[i] = 1.0e30;
-            int j = t0, jcur = t0;
-            double2 xy = __ldg(hxy + t0), zq = __ldg(hzq + t0);
-            for (;;) {
-                const bool have = j < n;
-                // stream B: geometry of atom j (in registers since the previous round), then its successor's loads go out
-                double s_nxt[N];
-                const double q_nxt = zq.y;
-#pragma unroll
-                for (int i = 0; i < N; ++i) s_nxt[i] = min_image_r2<false>(xy.x - px[i], xy.y - py[i], zq.x - pz[i]);
-                const int jn = j + stride;
-                { const int jc = jn < n ? jn : t0; xy = __ldg(hxy + jc); zq = __ldg(hzq + jc); }
-                // stream A: table part of atom jcur
-                int hmin = 0x7fffffff;
-#pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    const double sI = s_cur[i];
-                    const int hi = __double2hiint(sI);
-                    hmin = min(hmin, hi);
-                    const unsigned idx = min((unsigned)((hi >> (20 - MGPU_TAB_K)) - c_sys.tab_ibase), (unsigned)c_sys.tab_nint);
-                    const int chi = (hi & ~((1 << (20 - MGPU_TAB_K)) - 1)) | (1 << (19 - MGPU_TAB_K));
-                    const double uu = sI - __hiloint2double(chi, 0);
-                    const double2 *t = ctab + idx * (3 * REP);
-                    const double2 c01 = t[0], c23 = t[REP], c45 = t[2 * REP];
-                    const float uf = (float)uu;
-                    const float pf = fmaf(__int_as_float(__double2hiint(c45.y)), uf, __int_as_float(__double2loint(c45.y)));
-                    double p = (double)pf;
-                    p = fma(p, uu, c45.x);
-                    p = fma(p, uu, c23.y);
-                    p = fma(p, uu, c23.x);
-                    p = fma(p, uu, c01.y);
-                    p = fma(p, uu, c01.x);
-                    acc = fma(q[i] * q_cur, p, acc);
-                }
-                const bool hit = hmin < c_sys.tab_hi_lo;             // such pairs read the all-zero row; redone below
-                jfirst = min(jfirst, hit ? jcur : 0x7fffffff);
-                jlast = max(jlast, hit ? jcur : -1);
-                if (!have) break;
-#pragma unroll
-                for (int i = 0; i < N; ++i) s_cur[i] = s_nxt[i];
-                q_cur = q_nxt; jcur = j; j = jn;
-            }
-        }
-        double e_xc = 0.0;
-        for (int j = jfirst; j <= jlast; j += stride) {              // rare: pairs with r < 1 A (incl. overlap), exact formulas
-            const double2 xy = __ldg(hxy + j), zq = __ldg(hzq + j);
-#pragma unroll 1
-            for (int i = 0; i < N; ++i) {
-                const double sI = min_image_r2<false>(xy.x - px[i], xy.y - py[i], zq.x - pz[i]);
-                if (__double2hiint(sI) < c_sys.tab_hi_lo) {
-                    const double qq = q[i] * zq.y;
-                    e_xc += pair_exact(sI, 0.0, 0.0, qq, qq != 0.0).y;
-                }
-            }
-        }
-        if (t0 == 0) {                                               // work counters of the whole pass, once (SURVEY 8d accounting)
-            pc_io.geom += (unsigned)(N * n);
-            pc_io.coul += (unsigned)(n_charged() * c_sys.n_host_charged);
-        }
-        e_c_io = e_c_io + (e_xc + acc);
-    }
-
     // The same body against ONE atom (index b) of every molecule of a guest residue type of the
     // walker: targets are com[m] + off_b[m], m = t0, t0 + stride, ... < n (molecule index fastest
     // in memory, so the lanes' loads coalesce); tq / ttype are the target atom's charge (0 if tiny)
@@ -901,8 +819,7 @@ __device__ __forceinline__ void host_list(const Smem &S, const Probe &P, const d
     // chunks of at most 3 probe atoms: ~3 independent pair chains per thread fit the 128-register budget
     for (int base = 0; base < n; base += 3) {
         const int m = min(3, n - base);
-        if (m == 3 && MODE == 2 && !TRI && MGPU_SWP_COUL) { HostPass<TRI, MODE, 3, 1, REP> hp; hp.load(P, pos, list + base); hp.run_pipelined(t0, stride, e_c, pc); }
-        else if (m == 3) { HostPass<TRI, MODE, 3, MGPU_HOST_U3, REP> hp; hp.load(P, pos, list + base); hp.run(t0, stride, e_lj, e_c, pc); }
+        if (m == 3) { HostPass<TRI, MODE, 3, MGPU_HOST_U3, REP> hp; hp.load(P, pos, list + base); hp.run(t0, stride, e_lj, e_c, pc); }
         else if (m == 2) { HostPass<TRI, MODE, 2, 1, REP> hp; hp.load(P, pos, list + base); hp.run(t0, stride, e_lj, e_c, pc); }
         else { HostPass<TRI, MODE, 1, 3, REP> hp; hp.load(P, pos, list + base); hp.run(t0, stride, e_lj, e_c, pc); }
     }
@@ -1161,9 +1078,6 @@ __device__ __forceinline__ cplx phase_product(const double2 *tab, int a, int kx,
     return c_mul(c_mul(a1, a2), a3);
 }
 
-#ifndef MGPU_KSPACE_V2
-#define MGPU_KSPACE_V2 1                  // trial k-space pass on charge-folded entry tables, two k-vectors per thread and iteration
-#endif
 // The phase tables of ONE trial, as a list of ENTRIES: every atom of the probe whose charge is not exactly 0 (c_sys.qlist; the
 // others add exactly nothing to S(k) in the reference, q * phase), first in the new geometry, then in the old one.  The charge
 // is folded into the entry's x-table, with a minus sign for the old geometry, so that dS(k) = sum over entries of
@@ -1261,42 +1175,6 @@ __device__ double kspace_entries(const Smem &S, int ne, const double *__restrict
     return part[0] * c_sys.eps0_inv_real * c_sys.twopi / c_sys.volume;
 }
 
-// S_trial(k) = S(k) + dS(k) and E = sum_k ffW |S_trial|^2 * EPS0_INV_real * TWOPI / V.
-// S_out may be NULL (Widom: nothing is stored).
-template <int NT>
-__device__ double kspace(const Smem &S, const double *S_in, double *S_out)
-{
-    const Probe &P = S.ws->probe;
-    const int nk = c_sys.nk;
-    double part[1] = { 0.0 };
-    const int kind = P.kind, na = P.na;
-    // the next k-vector's index triple, weight and S(k) are in flight while this one is evaluated
-    int i = Grp<NT>::tid();
-    int kx = 0, ky = 0, kz = 0;
-    double w = 0.0, s_re = 0.0, s_im = 0.0;
-    if (i < nk) { kx = __ldg(c_sys.kx + i); ky = __ldg(c_sys.ky + i); kz = __ldg(c_sys.kz + i); w = __ldg(c_sys.ffW + i); s_re = S_in[i]; s_im = S_in[nk + i]; }
-    while (i < nk) {
-        const int in = i + NT, ip = in < nk ? in : i;
-        int nkx = 0, nky = 0, nkz = 0;
-        double nw = 0.0, n_re = 0.0, n_im = 0.0;
-        if (MGPU_PF_KSPACE) { nkx = __ldg(c_sys.kx + ip); nky = __ldg(c_sys.ky + ip); nkz = __ldg(c_sys.kz + ip); nw = __ldg(c_sys.ffW + ip); n_re = S_in[ip]; n_im = S_in[nk + ip]; }
-        double sr = 0.0, si = 0.0;
-        for (int a = 0; a < na; ++a) {
-            const double q = c_sys.charge[P.res][a];
-            if (q == 0.0) continue;                          // adds exactly nothing (and its tables were not filled)
-            if (kind != MGPU_KIND_DELETE) { const cplx pn = phase_product(S.tab_new, a, kx, ky, kz); sr += q * pn.re; si += q * pn.im; }
-            if (kind != MGPU_KIND_CREATE) { const cplx po = phase_product(S.tab_old, a, kx, ky, kz); sr -= q * po.re; si -= q * po.im; }
-        }
-        const double re = s_re + sr, im = s_im + si;
-        if (S_out) { S_out[i] = re; S_out[nk + i] = im; }
-        part[0] += w * (re * re + im * im);
-        if (!MGPU_PF_KSPACE && in < nk) { nkx = __ldg(c_sys.kx + in); nky = __ldg(c_sys.ky + in); nkz = __ldg(c_sys.kz + in); nw = __ldg(c_sys.ffW + in); n_re = S_in[in]; n_im = S_in[nk + in]; }
-        i = in; kx = nkx; ky = nky; kz = nkz; w = nw; s_re = n_re; s_im = n_im;
-    }
-    Grp<NT>::template sum<1>(part, S.ws->red);
-    return part[0] * c_sys.eps0_inv_real * c_sys.twopi / c_sys.volume;
-}
-
 // reciprocal_ewald_energy (ewald_energy.f90:139-164) of a stored S(k)
 template <int NT>
 __device__ double recip_energy(const double *Sk, double *red)
@@ -1383,16 +1261,9 @@ __device__ void evaluate_trial(const Smem &S, int w, bool store_S, double e_old[
         const int cur = c_sys.cur[w];
         const double *S_in = c_sys.S + ((int64_t)w * 2 + cur) * 2 * c_sys.nk;
         double *S_out = store_S ? c_sys.S + ((int64_t)w * 2 + (cur ^ 1)) * 2 * c_sys.nk : nullptr;
-        if (MGPU_KSPACE_V2) {
-            const int ne = fill_trial_tables<NT>(S, P);
-            Grp<NT>::sync();
-            recip_new = kspace_entries<NT>(S, ne, S_in, S_out);
-        } else {
-            if (P.has_old) fill_phase_tables(S.tab_old, P.po, P.na, Grp<NT>::tid(), NT, c_sys.charge[P.res]);
-            if (P.has_new) fill_phase_tables(S.tab_new, P.pn, P.na, Grp<NT>::tid(), NT, c_sys.charge[P.res]);
-            Grp<NT>::sync();
-            recip_new = kspace<NT>(S, S_in, S_out);
-        }
+        const int ne = fill_trial_tables<NT>(S, P);
+        Grp<NT>::sync();
+        recip_new = kspace_entries<NT>(S, ne, S_in, S_out);
     }
 #pragma unroll
     for (int i = 0; i < 6; ++i) { e_old[i] = 0.0; e_new[i] = 0.0; }
